@@ -1,0 +1,83 @@
+"""The oracle restatement vs. fixtures produced by the unmodified reference
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, relerr
+from oracle import npde, solvers
+
+
+@pytest.mark.parametrize("tag", ["npde_m5", "npde_m3"])
+def test_precompute_matches_reference(tag):
+    g = load_golden(tag)
+    pre = npde.precompute(g["Z"], float(g["sf"]), float(g["ell"]))
+    assert relerr(pre["Kzz"], g["Kzz"]) < 1e-14
+    assert relerr(pre["Kzzinv"], g["Kzzinv"]) < 1e-10
+    assert relerr(pre["KzzinvL"], g["KzzinvL"]) < 1e-10
+
+
+def test_inducing_grid_and_init_match_reference():
+    g = load_golden("npde_m5")
+    Z = npde.inducing_grid(g["Y"], 5)
+    assert np.array_equal(Z, g["Z"])
+    U0 = npde.gradient_matching_init(g["Y"], g["t"].astype(np.float64), Z, 1.0, 0.75)
+    assert relerr(U0, g["U0"]) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+@pytest.mark.parametrize("mode", ["discrete", "adjoint"])
+def test_closure_and_gradients_match_reference(method, mode):
+    g = load_golden("npde_m5")
+    loss, gU, gl, sol = npde.nlp_grad(g["U"], g["logsn"], g["Z"], 1.0, 0.75, g["x0"], g["t"], g["Y"],
+                                      method=method, grad_mode=mode)
+    assert relerr(sol, g[f"{method}_sol"]) < 1e-12
+    assert relerr(loss, g[f"{method}_loss"]) < 1e-12
+    assert relerr(gU, g[f"{method}_gU_{mode}"]) < 1e-10
+    assert relerr(gl, g[f"{method}_glogsn_{mode}"]) < 1e-12
+    sq = npde.nlp(g["U"], g["logsn"], sol, g["Y"], None, add_prior=False)
+    assert relerr(sq, g[f"{method}_sqerr"]) < 1e-12
+
+
+def test_m3_rk4():
+    g = load_golden("npde_m3")
+    for mode in ("discrete", "adjoint"):
+        loss, gU, gl, sol = npde.nlp_grad(g["U"], g["logsn"], g["Z"], 1.0, 0.75, g["x0"], g["t"], g["Y"],
+                                          grad_mode=mode)
+        assert relerr(sol, g["rk4_sol"]) < 1e-12
+        assert relerr(gU, g[f"rk4_gU_{mode}"]) < 1e-10
+
+
+def test_discrete_and_adjoint_gradients_differ():
+    """SURVEY.md hard part 1: the two gradient definitions are different functions."""
+    g = load_golden("npde_m5")
+    assert relerr(g["rk4_gU_discrete"], g["rk4_gU_adjoint"]) > 1e-6
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_step_size_grid_and_end_of_step_quirk(case):
+    g = load_golden("grid_options")
+    field = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    y0 = g["x0"][None]
+    t, h = g[f"{case}_t"], float(g[f"{case}_h"])
+    for method in ("euler", "midpoint", "rk4"):
+        sol = solvers.odeint_fixed(field, y0, t, method, step_size=h)[:, 0]
+        assert relerr(sol, g[f"{case}_{method}_sol"]) < 1e-12
+    w = g[f"{case}_w"][:, None]
+    gy0, gU = solvers.odeint_fixed_backward(field, y0, t, w, "rk4", step_size=h)
+    assert relerr(gU[0], g[f"{case}_rk4_gU"]) < 1e-10
+    assert relerr(gy0[0], g[f"{case}_rk4_gx0"]) < 1e-10
+
+
+def test_reversed_time():
+    g = load_golden("grid_options")
+    field = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    sol = solvers.odeint_fixed(field, g["x0"][None], g["rev_t"], "rk4")[:, 0]
+    assert relerr(sol, g["rev_rk4_sol"]) < 1e-12
+
+
+def test_output_map_is_end_of_step():
+    # SURVEY.md A.1 probe: dy/dt = 2t is not autonomous; use the published index logic instead:
+    t = np.array([0.0, 0.25, 0.7, 1.0])
+    t_, grid, sign = solvers.build_grid(t, np.float64, 0.5)
+    assert np.array_equal(grid, [0.0, 0.5, 1.0])
+    assert np.array_equal(solvers.output_map(t_, grid), [1, 2, 4])
