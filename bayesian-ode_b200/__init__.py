@@ -1,0 +1,15 @@
+"""bayesian_ode_b200 -- the B200-native (sm_100a) hot path of jaivardhankapoor/bayesian-ode.
+
+Public surface mirrors the reference:
+  odeint, odeint_adjoint          (torchdiffeq/__init__.py:1-2)
+  NPDEField / KernelRegression    (scripts/vanderpol/gp.py:56-71)
+  NPDEPosterior                   (loss_closure, gp.py:342-353)
+  samplers.*                      (samplers/{langevin,hamiltonian,stein}.py)
+All compute runs in hand-written CUDA behind the C ABI of include/bode_b200.h; there is no CPU path.
+"""
+from . import _lib
+from .fields import KernelRegression, NPDEField, rbf_kernel
+from .odeint import odeint, odeint_adjoint
+from .posterior import NPDEPosterior
+
+__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "rbf_kernel", "_lib"]

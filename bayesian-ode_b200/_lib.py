@@ -1,0 +1,95 @@
+"""ctypes binding of libbode_b200.so (the C ABI declared in include/bode_b200.h).
+
+PyTorch is used only for device memory and streams: tensors cross the boundary as raw
+device pointers.  There is no CPU fallback -- if the library is missing or a call fails
+this module raises."""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbode_b200.so")
+
+BODE_EULER, BODE_MIDPOINT, BODE_RK4 = 0, 1, 2
+METHODS = {"euler": BODE_EULER, "midpoint": BODE_MIDPOINT, "rk4": BODE_RK4}
+GRAD_DISCRETE, GRAD_ADJOINT = 0, 1
+
+
+class BodeError(RuntimeError):
+    pass
+
+
+class NpdeFieldStruct(C.Structure):
+    _fields_ = [
+        ("P", C.c_int32), ("m", C.c_int32), ("grid_mx", C.c_int32), ("grid_my", C.c_int32),
+        ("gx", C.c_double * 32), ("gy", C.c_double * 32), ("ell", C.c_double * 2),
+        ("Z", C.c_void_p), ("A", C.c_void_p), ("Ksym", C.c_void_p), ("U", C.c_void_p),
+    ]
+
+
+class GridStruct(C.Structure):
+    _fields_ = [
+        ("S", C.c_int32), ("T", C.c_int32), ("sign", C.c_float),
+        ("dt", C.c_void_p), ("obs_ptr", C.c_void_p), ("adj_dt", C.c_void_p), ("adj_ptr", C.c_void_p),
+    ]
+
+
+_lib = None
+
+# every symbol include/bode_b200.h declares: name -> (restype, argtypes)
+_P = C.c_void_p
+SYMBOLS = {
+    "bode_version": (C.c_int, []),
+    "bode_last_error": (C.c_char_p, []),
+    "bode_device_sm_count": (C.c_int, []),
+    "bode_npde_scratch_floats": (C.c_size_t, [C.c_int32] * 6),
+    "bode_npde_odeint": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "bode_npde_odeint_backward": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
+                                             _P, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
+    "bode_npde_nlp_grad": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
+                                      _P, C.c_int32, _P, _P, C.c_float, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+}
+
+
+def load():
+    """Load the shared library (once).  Raises BodeError when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BodeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C bayesian-ode_b200/csrc`. There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        msg = load().bode_last_error().decode("utf-8", "replace")
+        raise BodeError(f"libbode_b200 call failed (status {status}): {msg}")
+
+
+def ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor required at the C ABI"
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    if not torch.cuda.is_available():
+        raise BodeError("bayesian_ode_b200 needs a CUDA device (B200, sm_100a); there is no CPU path")
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise BodeError("expected CUDA tensors; the product has no CPU path")

@@ -1,0 +1,165 @@
+// Host side of the npde entry points: argument checks, parameter packing, kernel dispatch.
+#include "npde_solve.cuh"
+#include <math.h>
+
+namespace bode {
+
+// one translation unit per grid size keeps the build parallel; see npde_inst.cuh
+#define BODE_DECL_SEP(M)                                                                               \
+  int launch_sep_fwd_##M(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_sep_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+BODE_DECL_SEP(3)
+BODE_DECL_SEP(4)
+BODE_DECL_SEP(5)
+BODE_DECL_SEP(6)
+
+static int stages_of(int method) { return method == BODE_RK4 ? 4 : (method == BODE_MIDPOINT ? 2 : 1); }
+
+static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_grid* g, int method, int N,
+                       const float* y0, int y0_batched) {
+  BODE_REQUIRE(f && g, "null field/grid");
+  BODE_REQUIRE(f->P > 0 && f->m > 0 && N > 0, "P, m, N must be positive (P=%d m=%d N=%d)", f->P, f->m, N);
+  BODE_REQUIRE(g->S >= 0 && g->T >= 1, "bad grid S=%d T=%d", g->S, g->T);
+  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_RK4, "unknown method %d", method);
+  BODE_REQUIRE(f->U && f->A && y0, "null U/A/y0");
+  BODE_REQUIRE(g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
+  BODE_REQUIRE(f->ell[0] > 0 && f->ell[1] > 0, "ell must be positive");
+  memset(&prm, 0, sizeof(prm));
+  prm.P = f->P; prm.N = N; prm.S = g->S; prm.T = g->T; prm.m = f->m;
+  prm.y0_stride = y0_batched ? 2 * N : 0;
+  prm.sign = g->sign; prm.scale = 1.f;
+  const double LOG2E = 1.4426950408889634074, LN2 = 0.69314718055994530942;
+  const double c0 = sqrt(0.5 * LOG2E) / f->ell[0], c1 = sqrt(0.5 * LOG2E) / f->ell[1];
+  prm.c0 = (float)c0; prm.c1 = (float)c1;
+  prm.k0 = (float)(2.0 * LN2 * c0); prm.k1 = (float)(2.0 * LN2 * c1);
+  prm.U = f->U; prm.A = f->A; prm.Ksym = f->Ksym; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
+  prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr;
+  return BODE_OK;
+}
+
+static int fill_sep(NpdeKParams& prm, const bode_npde_field* f) {
+  BODE_REQUIRE(f->grid_mx == f->grid_my && f->grid_mx >= 3 && f->grid_mx <= 6 && f->grid_mx * f->grid_my == f->m,
+               "separable npde kernel supports square inducing grids 3x3..6x6 (got %dx%d, m=%d)", f->grid_mx, f->grid_my, f->m);
+  const double LOG2E = 1.4426950408889634074;
+  const double c0 = sqrt(0.5 * LOG2E) / f->ell[0], c1 = sqrt(0.5 * LOG2E) / f->ell[1];
+  for (int a = 0; a < f->grid_mx; ++a) prm.gxs[a] = (float)(c0 * f->gx[a]);
+  for (int b = 0; b < f->grid_my; ++b) prm.gys[b] = (float)(c1 * f->gy[b]);
+  return BODE_OK;
+}
+
+// CTA shape: ppc particles x N trajectories x G lanes, one warp unless N*G > 32.
+static int plan(NpdeKParams& prm, int G, int max_threads, dim3* grid, dim3* block) {
+  const int per_particle = prm.N * G;
+  BODE_REQUIRE(per_particle <= max_threads, "N*G=%d exceeds %d threads per CTA", per_particle, max_threads);
+  int ppc = 32 / per_particle;
+  if (ppc < 1) ppc = 1;
+  prm.ppc = ppc;
+  const int threads = ((ppc * per_particle + 31) / 32) * 32;
+  *block = dim3(threads);
+  *grid = dim3((prm.P + ppc - 1) / ppc);
+  return BODE_OK;
+}
+
+static int dispatch_fwd(const NpdeKParams& prm, int M, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  switch (M) {
+    case 3: return launch_sep_fwd_3(prm, method, grid, block, smem, st);
+    case 4: return launch_sep_fwd_4(prm, method, grid, block, smem, st);
+    case 5: return launch_sep_fwd_5(prm, method, grid, block, smem, st);
+    case 6: return launch_sep_fwd_6(prm, method, grid, block, smem, st);
+  }
+  set_error("no separable kernel for M=%d", M);
+  return BODE_ERR_UNSUPPORTED;
+}
+
+static int dispatch_grad(const NpdeKParams& prm, int M, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem,
+                         cudaStream_t st) {
+  switch (M) {
+    case 3: return launch_sep_grad_3(prm, method, inj, adj, grid, block, smem, st);
+    case 4: return launch_sep_grad_4(prm, method, inj, adj, grid, block, smem, st);
+    case 5: return launch_sep_grad_5(prm, method, inj, adj, grid, block, smem, st);
+    case 6: return launch_sep_grad_6(prm, method, inj, adj, grid, block, smem, st);
+  }
+  set_error("no separable kernel for M=%d", M);
+  return BODE_ERR_UNSUPPORTED;
+}
+
+static size_t scratch_floats(long long P, long long N, int S, int T, int method, int grad_mode) {
+  const long long npairs = P * N;
+  const long long slots = grad_mode == BODE_GRAD_ADJOINT ? (long long)T : (long long)S * stages_of(method);
+  return (size_t)(2 * npairs * (slots > 0 ? slots : 1));
+}
+
+static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, int grad_mode, int inj, int N,
+                    const float* y0, int y0_batched, NpdeKParams& prm, float* scratch, size_t scratch_n, cudaStream_t st) {
+  BODE_REQUIRE(grad_mode == BODE_GRAD_DISCRETE || grad_mode == BODE_GRAD_ADJOINT, "unknown grad_mode %d", grad_mode);
+  BODE_REQUIRE(grad_mode != BODE_GRAD_ADJOINT || g->T == 1 || (g->adj_dt && g->adj_ptr), "ADJOINT needs adj_dt/adj_ptr");
+  const size_t need = scratch_floats(f->P, N, g->S, g->T, method, grad_mode);
+  BODE_REQUIRE(scratch && scratch_n >= need, "scratch too small: have %zu floats, need %zu", scratch_n, need);
+  BODE_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "scratch must be 8-byte aligned");
+  prm.ck = reinterpret_cast<float2*>(scratch);
+  prm.npairs = (long long)f->P * N;
+  if (f->grid_mx > 0) {
+    int st_ = fill_sep(prm, f);
+    if (st_ != BODE_OK) return st_;
+    dim3 grid, block;
+    st_ = plan(prm, 1, 256, &grid, &block);
+    if (st_ != BODE_OK) return st_;
+    const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+    return dispatch_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
+  }
+  set_error("general (non-grid) inducing points: kernel not built in this version");
+  return BODE_ERR_UNSUPPORTED;
+}
+
+}  // namespace bode
+
+using namespace bode;
+
+extern "C" size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode) {
+  return scratch_floats(P, N, S, T, method, grad_mode);
+}
+
+extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
+                                int32_t y0_batched, float* sol, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = fill_common(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(sol, "null sol");
+  prm.sol = sol;
+  if (f->grid_mx > 0) {
+    st = fill_sep(prm, f);
+    if (st != BODE_OK) return st;
+    dim3 grid, block;
+    st = plan(prm, 1, 256, &grid, &block);
+    if (st != BODE_OK) return st;
+    const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
+    return dispatch_fwd(prm, f->grid_mx, method, grid, block, smem, (cudaStream_t)stream);
+  }
+  set_error("general (non-grid) inducing points: kernel not built in this version");
+  return BODE_ERR_UNSUPPORTED;
+}
+
+extern "C" int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
+                                         int32_t N, const float* y0, int32_t y0_batched, const float* gout, float* gU,
+                                         float* gy0, float* scratch, size_t scratch_n, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = fill_common(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(gout && gU, "null gout/gU");
+  prm.gout = gout; prm.gU = gU; prm.gy0 = gy0; prm.add_prior = 0;
+  return run_grad(f, g, method, grad_mode, INJ_GOUT, N, y0, y0_batched, prm, scratch, scratch_n, (cudaStream_t)stream);
+}
+
+extern "C" int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
+                                  const float* y0, int32_t y0_batched, const float* Y, const float* logsn, float scale,
+                                  int32_t add_prior, float* loss, float* sqerr, float* gU, float* glogsn, float* scratch,
+                                  size_t scratch_n, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = fill_common(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(Y && logsn && loss && sqerr && gU && glogsn, "null Y/logsn/outputs");
+  BODE_REQUIRE(!add_prior || f->Ksym, "add_prior needs Ksym");
+  prm.Y = Y; prm.logsn = logsn; prm.scale = scale; prm.add_prior = add_prior ? 1 : 0;
+  prm.loss = loss; prm.sqerr = sqerr; prm.gU = gU; prm.glogsn = glogsn;
+  return run_grad(f, g, method, grad_mode, INJ_LIK, N, y0, y0_batched, prm, scratch, scratch_n, (cudaStream_t)stream);
+}

@@ -1,0 +1,335 @@
+// Fused fixed-step ODE solve + Gaussian log-likelihood + reverse-mode gradient for the npde field.
+//
+// One launch per sampler step integrates every (particle, trajectory) pair forward, evaluates the
+// posterior closure (gp.py:342-353) and back-propagates through the solver, either as the exact
+// discrete adjoint (== autograd through torchdiffeq odeint, solvers.py:79-99 + fixed_grid.py) or as
+// the reference's continuous adjoint (adjoint.py:23-102).  The Field template argument supplies the
+// RHS / VJP for one pair; G = Field::G lanes cooperate on one pair (G = 1 for the separable field).
+#pragma once
+#include "npde_sep.cuh"
+
+namespace bode {
+
+enum { INJ_LIK = 0, INJ_GOUT = 1 };
+
+template <int METHOD> struct Stages { static constexpr int value = METHOD == BODE_RK4 ? 4 : (METHOD == BODE_MIDPOINT ? 2 : 1); };
+
+// W_p = A U_p for the ppc particles of this CTA (gp.py:70-71 hoisted out of the RHS: K(x,Z) (A U)).
+__device__ __forceinline__ void project_W(const NpdeKParams& prm, float* Us, float* Ws) {
+  const int m = prm.m, m2 = 2 * m, nout = prm.ppc * m2;
+  const long long base = (long long)blockIdx.x * nout, total = (long long)prm.P * m2;
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) Us[idx] = (base + idx < total) ? __ldg(prm.U + base + idx) : 0.f;
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2, j = r >> 1, d = r & 1;
+    const float* Uq = Us + q * m2 + d;
+    float acc = 0.f;
+    for (int k = 0; k < m; ++k) acc = fmaf(__ldg(prm.A + j * m + k), Uq[2 * k], acc);
+    Ws[idx] = acc;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------ one forward step (stores stage points)
+template <int METHOD, bool STORE, class Field>
+__device__ __forceinline__ float2 step_fwd(const NpdeKParams& prm, const Field& fld, float2 y, float dt,
+                                           float2* ckp, long long stride) {
+  const float sg = prm.sign;
+  if (METHOD == BODE_EULER) {
+    if (STORE) ckp[0] = y;
+    const float2 k1 = sg * fld.eval(prm, y);
+    return fma2(dt, k1, y);
+  } else if (METHOD == BODE_MIDPOINT) {
+    if (STORE) ckp[0] = y;
+    const float2 k1 = sg * fld.eval(prm, y);
+    const float2 y2 = fma2(0.5f * dt, k1, y);
+    if (STORE) ckp[stride] = y2;
+    const float2 k2 = sg * fld.eval(prm, y2);
+    return fma2(dt, k2, y);
+  } else {  // 3/8 rule, rk_common.py:72-78
+    if (STORE) ckp[0] = y;
+    const float2 k1 = sg * fld.eval(prm, y);
+    const float dt3 = dt * (1.f / 3.f);
+    const float2 y2 = fma2(dt3, k1, y);
+    if (STORE) ckp[stride] = y2;
+    const float2 k2 = sg * fld.eval(prm, y2);
+    const float2 y3 = fma2(dt, k2, fma2(-dt3, k1, y));
+    if (STORE) ckp[2 * stride] = y3;
+    const float2 k3 = sg * fld.eval(prm, y3);
+    const float2 y4 = fma2(dt, (k1 - k2) + k3, y);
+    if (STORE) ckp[3 * stride] = y4;
+    const float2 k4 = sg * fld.eval(prm, y4);
+    return fma2(dt * 0.125f, (k1 + k4) + 3.f * (k2 + k3), y);
+  }
+}
+
+// ------------------------------------------------------------------ discrete adjoint of one step
+template <int METHOD, class Field>
+__device__ __forceinline__ float2 step_bwd(const NpdeKParams& prm, Field& fld, float2 a, float dt,
+                                           const float2* ckp, long long stride, float2* y_start) {
+  const float sg = prm.sign;
+  if (METHOD == BODE_EULER) {
+    const float2 y1 = ckp[0];
+    *y_start = y1;
+    const float2 v1 = fld.template vjp<false>(prm, y1, (sg * dt) * a, 1.f, nullptr);
+    return a + v1;
+  } else if (METHOD == BODE_MIDPOINT) {
+    const float2 y1 = ckp[0], y2 = ckp[stride];
+    *y_start = y1;
+    const float2 v2 = fld.template vjp<false>(prm, y2, (sg * dt) * a, 1.f, nullptr);
+    const float2 v1 = fld.template vjp<false>(prm, y1, (sg * 0.5f * dt) * v2, 1.f, nullptr);
+    return (a + v2) + v1;
+  } else {
+    const float2 y1 = ckp[0], y2 = ckp[stride], y3 = ckp[2 * stride], y4 = ckp[3 * stride];
+    *y_start = y1;
+    const float dt3 = dt * (1.f / 3.f);
+    float2 kb1 = (dt * 0.125f) * a, kb2 = (dt * 0.375f) * a, kb3 = kb2;
+    float2 yb = a;
+    const float2 v4 = fld.template vjp<false>(prm, y4, sg * kb1, 1.f, nullptr);  // kb4 == initial kb1
+    yb = yb + v4;
+    kb1 = fma2(dt, v4, kb1);
+    kb2 = fma2(-dt, v4, kb2);
+    kb3 = fma2(dt, v4, kb3);
+    const float2 v3 = fld.template vjp<false>(prm, y3, sg * kb3, 1.f, nullptr);
+    yb = yb + v3;
+    kb1 = fma2(-dt3, v3, kb1);
+    kb2 = fma2(dt, v3, kb2);
+    const float2 v2 = fld.template vjp<false>(prm, y2, sg * kb2, 1.f, nullptr);
+    yb = yb + v2;
+    kb1 = fma2(dt3, v2, kb1);
+    const float2 v1 = fld.template vjp<false>(prm, y1, sg * kb1, 1.f, nullptr);
+    return yb + v1;
+  }
+}
+
+// ------------------------------------------------------------------ one step of the augmented reverse solve
+// adjoint.py:32-55 under the time reversal of misc.py:186-187:  d(y, a, g)/dtau = s_in * (f, -J^T a, -(df/dth)^T a)
+template <int METHOD, class Field>
+__device__ __forceinline__ void step_aug(const NpdeKParams& prm, Field& fld, float2& y, float2& a, float dt, float s_in) {
+  float2 f1, f2_, f3, f4;
+  if (METHOD == BODE_EULER) {
+    const float2 j1 = fld.template vjp<true>(prm, y, a, -s_in * dt, &f1);
+    y = fma2(s_in * dt, f1, y);
+    a = fma2(-s_in * dt, j1, a);
+  } else if (METHOD == BODE_MIDPOINT) {
+    const float2 j1 = fld.template vjp<true>(prm, y, a, 0.f, &f1);
+    const float h = 0.5f * dt * s_in;
+    const float2 y2 = fma2(h, f1, y), a2 = fma2(-h, j1, a);
+    const float2 j2 = fld.template vjp<true>(prm, y2, a2, -s_in * dt, &f2_);
+    y = fma2(s_in * dt, f2_, y);
+    a = fma2(-s_in * dt, j2, a);
+  } else {
+    const float h = s_in * dt, h3 = h * (1.f / 3.f);
+    const float2 j1 = fld.template vjp<true>(prm, y, a, -h * 0.125f, &f1);
+    const float2 y2 = fma2(h3, f1, y), a2 = fma2(-h3, j1, a);
+    const float2 j2 = fld.template vjp<true>(prm, y2, a2, -h * 0.375f, &f2_);
+    const float2 y3 = fma2(h, f2_, fma2(-h3, f1, y)), a3 = fma2(-h, j2, fma2(h3, j1, a));
+    const float2 j3 = fld.template vjp<true>(prm, y3, a3, -h * 0.375f, &f3);
+    const float2 y4 = fma2(h, (f1 - f2_) + f3, y), a4 = fma2(-h, (j1 - j2) + j3, a);
+    const float2 j4 = fld.template vjp<true>(prm, y4, a4, -h * 0.125f, &f4);
+    y = fma2(h * 0.125f, (f1 + f4) + 3.f * (f2_ + f3), y);
+    a = fma2(-h * 0.125f, (j1 + j4) + 3.f * (j2 + j3), a);
+  }
+}
+
+// ------------------------------------------------------------------ forward-only kernel: sol[T,P,N,2]
+template <class Field, int METHOD>
+__global__ void __launch_bounds__(Field::MAX_THREADS) npde_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
+  extern __shared__ float smem[];
+  constexpr int G = Field::G;
+  const int m2 = 2 * prm.m;
+  float* Us = smem;
+  float* Ws = smem + prm.ppc * m2;
+  project_W(prm, Us, Ws);
+  const int tid = threadIdx.x;
+  const int pairl = tid / G, lane = tid % G;
+  const int pl = pairl / prm.N, n = pairl % prm.N;
+  const int p = blockIdx.x * prm.ppc + pl;
+  if (pl >= prm.ppc || p >= prm.P) return;
+  Field fld;
+  fld.load_W(prm, Ws + pl * m2, lane);
+  const long long pair = (long long)p * prm.N + n;
+  const long long PN = (long long)prm.P * prm.N;
+  float2 y = reinterpret_cast<const float2*>(prm.y0)[(prm.y0_stride ? (long long)p * prm.N : 0) + n];
+  float2* sol = reinterpret_cast<float2*>(prm.sol);
+  if (lane == 0) sol[pair] = y;
+  for (int s = 0; s < prm.S; ++s) {
+    y = step_fwd<METHOD, false>(prm, fld, y, __ldg(prm.dt + s), nullptr, 0);
+    const int j1 = __ldg(prm.obs_ptr + s + 1);
+    for (int j = __ldg(prm.obs_ptr + s); j < j1; ++j)
+      if (lane == 0) sol[(long long)j * PN + pair] = y;
+  }
+}
+
+// ------------------------------------------------------------------ fused forward + closure + gradient kernel
+template <class Field, int METHOD, int INJ, int ADJ>
+__global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __grid_constant__ NpdeKParams prm) {
+  extern __shared__ float smem[];
+  constexpr int G = Field::G;
+  constexpr int STG = Stages<METHOD>::value;
+  const int m2 = 2 * prm.m;
+  const int N = prm.N, ppc = prm.ppc;
+  float* Us = smem;                      // [ppc][m2]   U of this CTA's particles
+  float* Ws = Us + ppc * m2;             // [ppc][m2]   W = A U, later sum_n gW
+  float* gWs = Ws + ppc * m2;            // [N][ppc][m2]
+  float* red = gWs + N * ppc * m2;       // [ppc*N][2]  sum of squared residuals per pair
+  project_W(prm, Us, Ws);
+
+  const int tid = threadIdx.x;
+  const int pairl = tid / G, lane = tid % G;
+  const int pl = pairl / N, n = pairl % N;
+  const int p = blockIdx.x * ppc + pl;
+  const bool active = pl < ppc && p < prm.P;
+  float r2x = 0.f, r2y = 0.f;
+  Field fld;
+  fld.zero_grad();
+  if (active) {
+    fld.load_W(prm, Ws + pl * m2, lane);
+    const long long pair = (long long)p * N + n;
+    const long long PN = (long long)prm.P * N;
+    const float2* Y2 = reinterpret_cast<const float2*>(prm.Y) + (long long)n * prm.T;   // Y[n][j]
+    const float2* go = reinterpret_cast<const float2*>(prm.gout) + pair;              // gout[j][pair]
+    float2 e2inv = f2(0.f, 0.f);
+    if (INJ == INJ_LIK) {
+      const float2 ls = reinterpret_cast<const float2*>(prm.logsn)[p];
+      e2inv = f2(expf(-2.f * ls.x), expf(-2.f * ls.y));
+    }
+    float2* ck = prm.ck + pair;
+    const long long stride = prm.npairs;
+
+    // ---------------- forward
+    float2 y = reinterpret_cast<const float2*>(prm.y0)[(prm.y0_stride ? (long long)p * N : 0) + n];
+    if (INJ == INJ_LIK) {
+      const float2 r = __ldg(Y2) - y;
+      r2x = r.x * r.x;
+      r2y = r.y * r.y;
+    }
+    if (ADJ == BODE_GRAD_ADJOINT && lane == 0) ck[0] = y;
+    for (int s = 0; s < prm.S; ++s) {
+      if (ADJ == BODE_GRAD_DISCRETE)
+        y = step_fwd<METHOD, true>(prm, fld, y, __ldg(prm.dt + s), ck + (long long)s * STG * stride, stride);
+      else
+        y = step_fwd<METHOD, false>(prm, fld, y, __ldg(prm.dt + s), nullptr, 0);
+      const int j1 = __ldg(prm.obs_ptr + s + 1);
+      for (int j = __ldg(prm.obs_ptr + s); j < j1; ++j) {
+        if (INJ == INJ_LIK) {
+          const float2 r = __ldg(Y2 + j) - y;
+          r2x = fmaf(r.x, r.x, r2x);
+          r2y = fmaf(r.y, r.y, r2y);
+        }
+        if (ADJ == BODE_GRAD_ADJOINT && lane == 0) ck[(long long)j * stride] = y;
+      }
+    }
+
+    // ---------------- backward
+    float2 a = f2(0.f, 0.f);
+    if (ADJ == BODE_GRAD_DISCRETE) {
+      float2 yend = y;
+      for (int s = prm.S - 1; s >= 0; --s) {
+        const int j0 = __ldg(prm.obs_ptr + s);
+        for (int j = __ldg(prm.obs_ptr + s + 1) - 1; j >= j0; --j) {
+          if (INJ == INJ_LIK) {
+            const float2 r = __ldg(Y2 + j) - yend;
+            a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
+          } else {
+            a = a + __ldg(go + (long long)j * PN);
+          }
+        }
+        a = step_bwd<METHOD>(prm, fld, a, __ldg(prm.dt + s), ck + (long long)s * STG * stride, stride, &yend);
+      }
+      if (INJ == INJ_LIK) {
+        const float2 r = __ldg(Y2) - yend;
+        a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
+      } else {
+        a = a + __ldg(go);
+      }
+    } else {
+      // continuous adjoint, adjoint.py:57-95: restart from the stored forward value at every t[i]
+      if (G > 1) __syncwarp();
+      const float s_in = -prm.sign;
+      {
+        const float2 yT = ck[(long long)(prm.T - 1) * stride];
+        if (INJ == INJ_LIK) {
+          const float2 r = __ldg(Y2 + prm.T - 1) - yT;
+          a = f2(-r.x * e2inv.x, -r.y * e2inv.y);
+        } else {
+          a = __ldg(go + (long long)(prm.T - 1) * PN);
+        }
+      }
+      for (int i = prm.T - 1; i >= 1; --i) {
+        float2 yy = ck[(long long)i * stride];
+        const int q1 = __ldg(prm.adj_ptr + i);
+        for (int q = __ldg(prm.adj_ptr + i - 1); q < q1; ++q)
+          step_aug<METHOD>(prm, fld, yy, a, __ldg(prm.adj_dt + q), s_in);
+        const float2 yp = ck[(long long)(i - 1) * stride];
+        if (INJ == INJ_LIK) {
+          const float2 r = __ldg(Y2 + i - 1) - yp;
+          a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
+        } else {
+          a = a + __ldg(go + (long long)(i - 1) * PN);
+        }
+      }
+    }
+    if (prm.gy0 != nullptr && lane == 0) reinterpret_cast<float2*>(prm.gy0)[pair] = prm.scale * a;
+  }
+
+  // ---------------- epilogue: reduce over trajectories, back-project gU = A^T gW (+ prior)
+  __syncthreads();   // everyone is done reading Ws
+  if (active) {
+    fld.store_gW(prm, gWs + (n * ppc + pl) * m2, lane);
+    if (lane == 0) {
+      red[pairl * 2 + 0] = r2x;
+      red[pairl * 2 + 1] = r2y;
+    }
+  }
+  __syncthreads();
+  const int nout = ppc * m2;
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int nn = 0; nn < N; ++nn) acc += gWs[nn * nout + idx];
+    Ws[idx] = acc;
+  }
+  __syncthreads();
+  const int m = prm.m;
+  float* pri = gWs;                      // reuse: prior partials [ppc][m2]
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2, k = r >> 1, d = r & 1;
+    const int pp = blockIdx.x * ppc + q;
+    if (pp >= prm.P) { pri[idx] = 0.f; continue; }
+    float acc = 0.f;
+    const float* Wq = Ws + q * m2 + d;
+    for (int j = 0; j < m; ++j) acc = fmaf(__ldg(prm.A + j * m + k), Wq[2 * j], acc);
+    float pr = 0.f;
+    if (prm.add_prior) {
+      const float* Uq = Us + q * m2 + d;
+      for (int j = 0; j < m; ++j) pr = fmaf(__ldg(prm.Ksym + k * m + j), Uq[2 * j], pr);
+      acc += pr;
+      pr *= 0.5f * Us[idx];
+    }
+    pri[idx] = pr;
+    prm.gU[(long long)pp * m2 + r] = prm.scale * acc;
+  }
+  if (INJ == INJ_LIK) {
+    __syncthreads();
+    if (tid < ppc) {
+      const int pp = blockIdx.x * ppc + tid;
+      if (pp < prm.P) {
+        float sx = 0.f, sy = 0.f, pr = 0.f;
+        for (int nn = 0; nn < N; ++nn) {
+          sx += red[(tid * N + nn) * 2 + 0];
+          sy += red[(tid * N + nn) * 2 + 1];
+        }
+        for (int j = 0; j < m2; ++j) pr += pri[tid * m2 + j];
+        const float2 ls = reinterpret_cast<const float2*>(prm.logsn)[pp];
+        const float ex = expf(-2.f * ls.x), ey = expf(-2.f * ls.y);
+        const float nt = (float)N * (float)prm.T;
+        prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
+        prm.sqerr[pp] = sx + sy;
+        prm.glogsn[pp * 2 + 0] = prm.scale * (nt - sx * ex);
+        prm.glogsn[pp * 2 + 1] = prm.scale * (nt - sy * ey);
+      }
+    }
+  }
+}
+
+}  // namespace bode

@@ -1,0 +1,132 @@
+"""Vector-field modules recognised by ``odeint`` and dispatched to the fused CUDA kernels.
+
+``NPDEField`` is the particle-batched counterpart of the reference's ``KernelRegression``
+(scripts/vanderpol/gp.py:56-71): f(x) = K(x, Z) . Kzz^-1 L . U  with an RBF kernel
+(gp.py:41-54).  Z, sf, ell are shared by all particles; ``U`` ([P, m, 2] or [m, 2]) and
+``logsn`` ([P, 2] or [2]) are the sampled parameters (gp.py:337).
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _sq_dist(X1, X2, ell):
+    # gp.py:49-54 (expanded form kept for the float64 host precompute)
+    X1 = X1 / ell
+    X1s = torch.sum(X1 ** 2, dim=-1).unsqueeze(-1)
+    X2 = X2 / ell
+    X2s = torch.sum(X2 ** 2, dim=-1).unsqueeze(-2)
+    return -2 * X1 @ X2.transpose(-1, -2) + X1s + X2s
+
+
+def rbf_kernel(X1, X2, sf, ell):
+    """gp.py:41-43."""
+    return sf ** 2 * torch.exp(-_sq_dist(X1, X2, ell) / 2)
+
+
+def _detect_grid(Z):
+    """Return (gx, gy) when Z[a*My+b] == (gx[a], gy[b]) exactly (the layout gp.py:315-318 builds)."""
+    Z = np.asarray(Z)
+    m = Z.shape[0]
+    gy = []
+    for b in range(m):
+        if b > 0 and Z[b, 0] != Z[0, 0]:
+            break
+        gy.append(Z[b, 1])
+    My = len(gy)
+    if My == 0 or m % My != 0:
+        return None
+    Mx = m // My
+    gx = Z[::My, 0]
+    gy = np.asarray(gy)
+    ok = np.array_equal(Z[:, 0], np.repeat(gx, My)) and np.array_equal(Z[:, 1], np.tile(gy, Mx))
+    if not ok or len(set(gx.tolist())) != Mx or len(set(gy.tolist())) != My:
+        return None
+    return gx, gy
+
+
+class NPDEField(torch.nn.Module):
+    """KernelRegression(U0, Zt, sf, ell, noise) for P particles (gp.py:56-71).
+
+    Arguments keep the reference's names and order.  ``U0`` is ``[m, 2]`` (one chain, exactly the
+    reference) or ``[P, m, 2]``.  The float64 constants (Kzz, Kzzinv, L, KzzinvL) are computed on the
+    host like the reference does (gp.py:64-67, float64 by gp.py:314) and kept as attributes; the
+    device copies the kernels read are fp32.
+    """
+
+    def __init__(self, U0, Zt, sf, ell, noise, device=None, stable_solve=False):
+        super().__init__()
+        _lib.require_cuda()
+        device = torch.device(device if device is not None else "cuda")
+        U0 = torch.as_tensor(U0)
+        self.batched = U0.dim() == 3
+        if U0.dim() not in (2, 3) or U0.shape[-1] != 2:
+            raise ValueError("U0 must be [m, 2] or [P, m, 2]")
+        U0 = U0 if self.batched else U0[None]
+        self.P, self.m = int(U0.shape[0]), int(U0.shape[1])
+        self.U = torch.nn.Parameter(U0.to(device=device, dtype=torch.float32).contiguous().clone(), requires_grad=True)
+        logsn = torch.zeros(self.P, 2, dtype=torch.float32, device=device) + math.log(noise)
+        self.logsn = torch.nn.Parameter(logsn, requires_grad=True)
+        self.sf = float(sf)
+        ell_t = torch.as_tensor(ell, dtype=torch.float64).reshape(-1)
+        self.ell = ell
+        self._ell2 = (float(ell_t[0]), float(ell_t[-1]))
+        Z64 = torch.as_tensor(Zt).detach().to("cpu", torch.float64)
+        if Z64.shape != (self.m, 2):
+            raise ValueError("Zt must be [m, 2] matching U0")
+        self.Z = Z64
+        ell64 = ell_t if ell_t.numel() > 1 else float(ell_t[0])
+        self.Kzz = rbf_kernel(Z64, Z64, self.sf, ell64)
+        self.L = torch.linalg.cholesky(self.Kzz)
+        if stable_solve:
+            # Kzz^-1 L == L^-T ; triangular solves stay accurate when cond(Kzz) ~ 1e14 (16x16 grids)
+            eye = torch.eye(self.m, dtype=torch.float64)
+            Linv = torch.linalg.solve_triangular(self.L, eye, upper=False)
+            self.KzzinvL = Linv.t().contiguous()
+            self.Kzzinv = Linv.t() @ Linv
+        else:
+            self.Kzzinv = self.Kzz.inverse()               # gp.py:65
+            self.KzzinvL = torch.mm(self.Kzzinv, self.L)   # gp.py:67
+        self._A = (self.sf ** 2 * self.KzzinvL).to(device, torch.float32).contiguous()
+        self._Ksym = (0.5 * (self.Kzzinv + self.Kzzinv.t())).to(device, torch.float32).contiguous()
+        self._Zdev = Z64.to(device, torch.float32).contiguous()
+        self.grid_axes = _detect_grid(Z64.numpy())
+
+    # -- plain evaluation f(t, X) with torch ops (plotting / inspection; not used by odeint) -------------
+    def forward(self, t, X):
+        X = torch.as_tensor(X, device=self.U.device, dtype=torch.float32)
+        Kxz = rbf_kernel(X, self._Zdev, 1.0, torch.tensor(self._ell2, device=X.device, dtype=torch.float32))
+        W = torch.einsum("jk,pkd->pjd", self._A, self.U)
+        if X.dim() == 2:
+            out = torch.einsum("nj,pjd->pnd", Kxz, W)
+            return out if self.batched else out[0]
+        return torch.einsum("pnj,pjd->pnd", Kxz, W)
+
+    # -- C-ABI description -------------------------------------------------------------------------------
+    def c_struct(self, U=None):
+        fs = _lib.NpdeFieldStruct()
+        fs.P, fs.m = self.P, self.m
+        if self.grid_axes is not None and len(self.grid_axes[0]) <= 32 and len(self.grid_axes[1]) <= 32:
+            gx, gy = self.grid_axes
+            fs.grid_mx, fs.grid_my = len(gx), len(gy)
+            for i, v in enumerate(gx):
+                fs.gx[i] = float(v)
+            for i, v in enumerate(gy):
+                fs.gy[i] = float(v)
+        else:
+            fs.grid_mx = fs.grid_my = 0
+        fs.ell[0], fs.ell[1] = self._ell2
+        fs.Z = self._Zdev.data_ptr()
+        fs.A = self._A.data_ptr()
+        fs.Ksym = self._Ksym.data_ptr()
+        U = self.U if U is None else U
+        assert U.is_cuda and U.is_contiguous() and U.dtype == torch.float32
+        fs.U = U.data_ptr()
+        return fs
+
+
+# the reference's name for the same object (gp.py:56)
+KernelRegression = NPDEField

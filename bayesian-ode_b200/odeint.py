@@ -1,0 +1,145 @@
+"""``odeint`` / ``odeint_adjoint`` with the reference's signatures, backed by the fused CUDA kernels.
+
+Replaces torchdiffeq/_impl/odeint.py:20-76 (``odeint``) and torchdiffeq/_impl/adjoint.py:105-133
+(``odeint_adjoint``) for field modules the library recognises (``NPDEField``; ``MLPField``).
+There is deliberately no generic-callable path and no CPU path: an unrecognised ``func`` raises.
+
+Gradients: ``odeint`` back-propagates the exact discrete adjoint of the solver (what autograd
+through the reference's ``odeint`` yields); ``odeint_adjoint`` reproduces the reference's continuous
+adjoint re-solved per observation interval with the same method (adjoint.py:57-95).
+"""
+import torch
+
+from . import _grid, _lib
+from .fields import NPDEField
+
+FIXED_GRID_METHODS = ("euler", "midpoint", "rk4")
+# methods of the reference registry (odeint.py:8-17) that are outside this hot path
+_UNBUILT = ("explicit_adams", "fixed_adams", "adams", "tsit5")
+SOLVERS = {"euler": "Euler", "midpoint": "Midpoint", "rk4": "RK4", "dopri5": "Dopri5Solver"}
+
+_SCRATCH = {}
+
+
+def _scratch(device, nfloats):
+    """Grow-only per-device scratch for solver checkpoints (kept resident between sampler steps)."""
+    buf = _SCRATCH.get(device)
+    if buf is None or buf.numel() < nfloats:
+        buf = torch.empty(max(int(nfloats), 1), dtype=torch.float32, device=device)
+        _SCRATCH[device] = buf
+    return buf
+
+
+def _grid_struct(g, with_adjoint):
+    gs = _lib.GridStruct()
+    gs.S, gs.T, gs.sign = g.S, g.T, g.sign
+    gs.dt = g.dt_dev.data_ptr()
+    gs.obs_ptr = g.obs_ptr_dev.data_ptr()
+    if with_adjoint and g.adj_dt_dev is not None:
+        gs.adj_dt = g.adj_dt_dev.data_ptr()
+        gs.adj_ptr = g.adj_ptr_dev.data_ptr()
+    return gs
+
+
+def _check_inputs(func, y0, t):
+    """misc.py:173-195 (tuple-isation and dtype checks; time reversal lives in _grid)."""
+    tensor_input = False
+    if torch.is_tensor(y0):
+        tensor_input = True
+        y0 = (y0,)
+    assert isinstance(y0, tuple), "y0 must be either a torch.Tensor or a tuple"
+    for y0_ in y0:
+        assert torch.is_tensor(y0_), "each element must be a torch.Tensor but received {}".format(type(y0_))
+    for y0_ in y0:
+        if not torch.is_floating_point(y0_):
+            raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0_.type()))
+    if not torch.is_floating_point(t):
+        raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
+    if len(y0) != 1:
+        raise NotImplementedError("the fused fields integrate a single state tensor; tuple states of length > 1 are not built")
+    return tensor_input, y0[0]
+
+
+def _norm_y0(field, y0):
+    """y0 [N,2] (shared by all particles) or [P,N,2] -> (contiguous fp32 device tensor, batched flag, N)."""
+    if y0.shape[-1] != 2 or y0.dim() not in (2, 3):
+        raise ValueError("y0 must be [N, 2] or [P, N, 2] for the 2-D npde field")
+    if y0.dim() == 3 and y0.shape[0] != field.P:
+        raise ValueError("y0 leading dimension must equal the number of particles")
+    _lib.require_cuda()
+    y = y0.to(device=field.U.device, dtype=torch.float32).contiguous()
+    return y, y0.dim() == 3, int(y0.shape[-2])
+
+
+class _NpdeOdeint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y0, U, field, g, method, grad_mode, batched, N):
+        lib = _lib.load()
+        sol = torch.empty((g.T, field.P, N, 2), dtype=torch.float32, device=U.device)
+        fs = field.c_struct(U.detach().contiguous())
+        gs = _grid_struct(g, False)
+        _lib.check(lib.bode_npde_odeint(fs, gs, method, N, _lib.ptr(y0), int(batched), _lib.ptr(sol), _lib.stream_ptr()))
+        ctx.save_for_backward(y0, U)
+        ctx.misc = (field, g, method, grad_mode, batched, N)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gout):
+        y0, U = ctx.saved_tensors
+        field, g, method, grad_mode, batched, N = ctx.misc
+        lib = _lib.load()
+        gout = gout.to(torch.float32).contiguous()
+        gU = torch.empty_like(U)
+        gy0 = torch.empty((field.P, N, 2), dtype=torch.float32, device=U.device)
+        nsc = lib.bode_npde_scratch_floats(field.P, N, g.S, g.T, method, grad_mode)
+        sc = _scratch(U.device, nsc)
+        fs = field.c_struct(U.detach().contiguous())
+        gs = _grid_struct(g, grad_mode == _lib.GRAD_ADJOINT)
+        _lib.check(lib.bode_npde_odeint_backward(fs, gs, method, grad_mode, N, _lib.ptr(y0), int(batched), _lib.ptr(gout),
+                                                 _lib.ptr(gU), _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+        if not batched:
+            gy0 = gy0.sum(0)
+        return gy0, gU, None, None, None, None, None, None
+
+
+def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
+    tensor_input, y0 = _check_inputs(func, y0, t)
+    if options is None:
+        options = {}
+    elif method is None:
+        raise ValueError("cannot supply `options` without specifying `method`")
+    if method is None:
+        method = "dopri5"
+    if method in _UNBUILT:
+        raise NotImplementedError("method '{}' of the reference registry is outside the B200 hot path".format(method))
+    solver_name = SOLVERS[method]          # KeyError for unknown methods, like odeint.py:71
+    if t.requires_grad:
+        raise NotImplementedError("gradients with respect to `t` are not built")
+    if isinstance(func, NPDEField):
+        if method in FIXED_GRID_METHODS:
+            opts = _grid.split_options(solver_name, options)
+            if opts["step_size"] is not None and opts["grid_constructor"] is not None:
+                raise ValueError("step_size and grid_constructor are exclusive arguments.")
+            y0c, batched, N = _norm_y0(func, y0)
+            g = _grid.cached(t, torch.float32, func.U.device, opts["step_size"], opts["grid_constructor"],
+                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=func, y0=(y0c,))
+            sol = _NpdeOdeint.apply(y0c, func.U, func, g, _lib.METHODS[method], grad_mode, batched, N)
+            if not func.batched:
+                sol = sol[:, 0]
+            return sol if tensor_input else (sol,)
+        raise NotImplementedError("method '{}' is not built for NPDEField yet".format(method))
+    raise TypeError(
+        "{}: `func` must be a field module of bayesian_ode_b200 (NPDEField / MLPField); got {}. The B200 build "
+        "has no generic-callable or CPU path.".format(who, type(func).__name__))
+
+
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """Same contract as torchdiffeq.odeint (odeint.py:20-76); output is time-major ``[T, (P,) N, 2]``."""
+    return _odeint_impl(func, y0, t, rtol, atol, method, options, _lib.GRAD_DISCRETE, "odeint")
+
+
+def odeint_adjoint(func, y0, t, rtol=1e-6, atol=1e-12, method=None, options=None):
+    """Same contract as torchdiffeq.odeint_adjoint (adjoint.py:105-133)."""
+    if not isinstance(func, torch.nn.Module):
+        raise ValueError("func is required to be an instance of nn.Module.")
+    return _odeint_impl(func, y0, t, rtol, atol, method, options, _lib.GRAD_ADJOINT, "odeint_adjoint")

@@ -1,0 +1,103 @@
+"""The posterior closure of the npde model as ONE fused launch per sampler step.
+
+``NPDEPosterior`` is the particle-batched counterpart of ``loss_closure`` in
+scripts/vanderpol/gp.py:342-353:
+
+    loss = sum (Y - x)^2 / (2 exp(logsn)^2) + numel(Y) * sum(logsn) / D + tr(U^T Kzz^-1 U) / 2
+    closure(add_prior=False) = sum (Y - x)^2
+
+It is a callable with the closure protocol the reference samplers expect (``closure()`` returns a loss
+whose ``backward()`` fills ``.grad``; ``closure(add_prior=False)`` returns the squared error), and it
+also exposes ``loss_and_grad_()`` -- the graph-capturable fast path the batched samplers call.
+"""
+import torch
+
+from . import _grid, _lib
+from .fields import NPDEField
+from .odeint import _grid_struct, _norm_y0, _scratch, odeint
+
+
+class _FusedNLP(torch.autograd.Function):
+    """loss[P] with precomputed gradients; backward scales them by the incoming per-particle cotangent."""
+
+    @staticmethod
+    def forward(ctx, U, logsn, post):
+        loss, gU, gl = post._launch(U.detach(), logsn.detach())
+        ctx.save_for_backward(gU, gl)
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        gU, gl = ctx.saved_tensors
+        return gU * gloss.view(-1, 1, 1), gl * gloss.view(-1, 1), None
+
+
+class NPDEPosterior:
+    def __init__(self, field, x0, t, Y, method="rk4", options=None, grad_mode="discrete", scale=1.0):
+        """field: NPDEField; x0 [N,2] or [P,N,2]; t [T]; Y [N,T,2] (gp.py:320); method/options as odeint.
+        grad_mode "discrete" (autograd-through-odeint semantics) or "adjoint" (odeint_adjoint, what gp.py:26
+        runs).  ``scale`` multiplies loss and gradients (pSGLD passes 1/N, langevin.py:528)."""
+        if not isinstance(field, NPDEField):
+            raise TypeError("NPDEPosterior needs an NPDEField")
+        if method not in _lib.METHODS:
+            raise NotImplementedError("NPDEPosterior is built for the fixed-grid methods euler/midpoint/rk4")
+        self.field = field
+        self.method = method
+        self.options = dict(options or {})
+        self.grad_mode = {"discrete": _lib.GRAD_DISCRETE, "adjoint": _lib.GRAD_ADJOINT}[grad_mode]
+        self.scale = float(scale)
+        dev = field.U.device
+        self.x0, self.x0_batched, self.N = _norm_y0(field, torch.as_tensor(x0))
+        self.t = torch.as_tensor(t)
+        self.Y = torch.as_tensor(Y).to(dev, torch.float32).contiguous()
+        if self.Y.shape != (self.N, self.t.numel(), 2):
+            raise ValueError("Y must be [N, T, 2]")
+        opts = _grid.split_options("NPDEPosterior", self.options)
+        self.grid = _grid.cached(self.t, torch.float32, dev, opts["step_size"], opts["grid_constructor"],
+                                 with_adjoint=self.grad_mode == _lib.GRAD_ADJOINT, func=field, y0=(self.x0,))
+        P = field.P
+        self.loss = torch.empty(P, dtype=torch.float32, device=dev)
+        self.sqerr = torch.empty(P, dtype=torch.float32, device=dev)
+        self.gU = torch.empty_like(field.U.data)
+        self.glogsn = torch.empty_like(field.logsn.data)
+        self.add_prior = True
+
+    # ------------------------------------------------------------------------------------------------
+    def set_data(self, x0=None, Y=None):
+        """Overwrite the resident observations in place (a new minibatch; keeps captured graphs valid)."""
+        if x0 is not None:
+            self.x0.copy_(x0, non_blocking=True)
+        if Y is not None:
+            self.Y.copy_(Y, non_blocking=True)
+
+    def _launch(self, U, logsn, out=None):
+        lib = _lib.load()
+        f = self.field
+        loss, sqerr, gU, gl = out if out is not None else (
+            torch.empty_like(self.loss), self.sqerr, torch.empty_like(self.gU), torch.empty_like(self.glogsn))
+        nsc = lib.bode_npde_scratch_floats(f.P, self.N, self.grid.S, self.grid.T, _lib.METHODS[self.method], self.grad_mode)
+        sc = _scratch(U.device, nsc)
+        fs = f.c_struct(U.contiguous())
+        gs = _grid_struct(self.grid, self.grad_mode == _lib.GRAD_ADJOINT)
+        _lib.check(lib.bode_npde_nlp_grad(
+            fs, gs, _lib.METHODS[self.method], self.grad_mode, self.N, _lib.ptr(self.x0), int(self.x0_batched),
+            _lib.ptr(self.Y), _lib.ptr(logsn.contiguous()), self.scale, int(self.add_prior),
+            _lib.ptr(loss), _lib.ptr(sqerr), _lib.ptr(gU), _lib.ptr(gl), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+        return loss, gU, gl
+
+    def loss_and_grad_(self):
+        """One fused launch: fills self.loss/self.sqerr/self.gU/self.glogsn in place (no autograd graph,
+        no allocation -> CUDA-graph capturable).  Returns (loss, gU, glogsn)."""
+        return self._launch(self.field.U.data, self.field.logsn.data, out=(self.loss, self.sqerr, self.gU, self.glogsn))
+
+    def __call__(self, add_prior=True):
+        f = self.field
+        if not add_prior:
+            with torch.no_grad():
+                sol = odeint(f, self.x0, self.t, method=self.method, options=self.options or None)
+                sol = sol if f.batched else sol[:, None]
+                r2 = (self.Y[None] - sol.permute(1, 2, 0, 3)) ** 2
+                out = r2.sum(dim=(1, 2, 3))
+            return out if f.batched else out[0]
+        loss = _FusedNLP.apply(f.U, f.logsn, self)
+        return loss if f.batched else loss[0]

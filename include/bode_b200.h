@@ -1,0 +1,125 @@
+/*
+ * bode_b200.h -- C ABI of the B200-native bayesian-ode hot path (libbode_b200.so).
+ *
+ * The reference (jaivardhankapoor/bayesian-ode) is pure Python and has no FFI; the
+ * entry points below are what a binding for its hot path would call.  Each one names
+ * the reference interface it replaces (file:line relative to the reference checkout).
+ * All pointers are DEVICE pointers (fp32 unless stated) except where marked HOST; all
+ * calls are asynchronous on `stream` (a cudaStream_t) and return 0 on success or a
+ * negative bode_status; bode_last_error() gives the message of the last failure on the
+ * calling thread.  No CPU fallback exists: without a CUDA device every compute entry
+ * point fails with BODE_ERR_CUDA.
+ *
+ * Layouts (row-major, leading index slowest):
+ *   U      [P, m, 2]   whitened inducing values per particle      (gp.py:59  KernelRegression.U)
+ *   logsn  [P, 2]      log noise std per particle                 (gp.py:60)
+ *   Z      [m, 2]      inducing locations, shared                 (gp.py:62)
+ *   A      [m, m]      sf^2 * Kzz^-1 L, shared                    (gp.py:67,70-71; sf^2 folded in)
+ *   Ksym   [m, m]      (Kzz^-1 + Kzz^-T)/2, shared                (prior term gp.py:350)
+ *   y0     [P, N, 2] or [N, 2] (y0_batched = 0)                   (odeint.py:20 y0)
+ *   sol    [T, P, N, 2]  time-major like torchdiffeq              (solvers.py:99)
+ *   Y      [N, T, 2]   observations                               (gp.py:320,345)
+ */
+#ifndef BODE_B200_H
+#define BODE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* bode_stream_t; /* cudaStream_t */
+
+enum bode_status {
+  BODE_OK = 0,
+  BODE_ERR_ARG = -1,         /* bad argument / unsupported shape */
+  BODE_ERR_CUDA = -2,        /* CUDA runtime error (incl. no device) */
+  BODE_ERR_UNSUPPORTED = -3
+};
+
+/* torchdiffeq SOLVERS registry entries on the hot path (odeint.py:8-17) */
+enum bode_method { BODE_EULER = 0, BODE_MIDPOINT = 1, BODE_RK4 = 2 /* 3/8 rule, fixed_grid.py:29 */ };
+
+/* which gradient (SURVEY.md hard part 1):
+ *   DISCRETE = autograd through odeint (exact reverse of the discretisation)
+ *   ADJOINT  = odeint_adjoint, adjoint.py:23-102 (per-interval restart, same method) */
+enum bode_grad_mode { BODE_GRAD_DISCRETE = 0, BODE_GRAD_ADJOINT = 1 };
+
+int bode_version(void);
+const char* bode_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int bode_device_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * npde field description: KernelRegression (gp.py:56-71) for P particles sharing Z/sf/ell.
+ * If the inducing points form a tensor grid (gp.py:315-318 always builds one) set
+ * grid_mx, grid_my > 0 and pass the axis coordinates: Z[a*grid_my+b] = (gx[a], gy[b]);
+ * the separable kernel is then used.  Otherwise set both to 0 and the general-Z kernel runs.
+ * ------------------------------------------------------------------------------------- */
+typedef struct bode_npde_field {
+  int32_t P;            /* particles / chains */
+  int32_t m;            /* inducing points */
+  int32_t grid_mx, grid_my;
+  double  gx[32];       /* HOST values, axis coordinates (separable case) */
+  double  gy[32];
+  double  ell[2];       /* length-scales (gp.py:49-54 broadcasts a scalar) */
+  const float* Z;       /* [m,2] */
+  const float* A;       /* [m,m] */
+  const float* Ksym;    /* [m,m]  (may be NULL when no prior term is requested) */
+  const float* U;       /* [P,m,2] */
+} bode_npde_field;
+
+/* Solver grid, precomputed on the host exactly as FixedGridODESolver.integrate does
+ * (solvers.py:79-97) in the state dtype:
+ *   dt[s]      = grid[s+1]-grid[s], s < S
+ *   obs_ptr[s] .. obs_ptr[s+1]  = output indices emitted after step s (output 0 is y0);
+ *                 every emitted value is the END-of-step state (solvers.py:93-96 quirk)
+ *   sign       = -1 when t was decreasing (misc.py:184-187), else +1
+ * For BODE_GRAD_ADJOINT the inner reverse solves (adjoint.py:81-84) use
+ *   adj_dt[adj_ptr[i-1] .. adj_ptr[i])  = step sizes of the solve from t[i] to t[i-1], i=1..T-1 */
+typedef struct bode_grid {
+  int32_t S, T;
+  float   sign;
+  const float*   dt;       /* [S] device */
+  const int32_t* obs_ptr;  /* [S+1] device */
+  const float*   adj_dt;   /* device, may be NULL unless ADJOINT */
+  const int32_t* adj_ptr;  /* [T] device, may be NULL unless ADJOINT */
+} bode_grid;
+
+/* scratch floats needed by the gradient entry points for (P particles, N trajectories) */
+size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
+
+/* odeint(func=KernelRegression, y0, t, method in {euler,midpoint,rk4}) forward
+ * replaces torchdiffeq/_impl/odeint.py:20-76 + solvers.py:79-99 + fixed_grid.py for the npde field.
+ * sol [T,P,N,2]. */
+int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, int32_t method,
+                     int32_t N, const float* y0, int32_t y0_batched,
+                     float* sol, bode_stream_t stream);
+
+/* backward of the above for an arbitrary downstream loss: given gout = dL/dsol [T,P,N,2]
+ * returns gU [P,m,2] (dL/dU) and optionally gy0 [P,N,2] (may be NULL).
+ * DISCRETE replaces autograd-through-odeint (gradient_tests.py:19-37);
+ * ADJOINT replaces OdeintAdjointMethod.backward (adjoint.py:23-102). */
+int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
+                              int32_t N, const float* y0, int32_t y0_batched,
+                              const float* gout, float* gU, float* gy0,
+                              float* scratch, size_t scratch_floats, bode_stream_t stream);
+
+/* fused posterior closure + gradient: loss_closure (gp.py:342-353) followed by loss.backward()
+ * for every particle in ONE launch:
+ *   loss[p]  = sum (Y-x)^2/(2 e^{2 logsn}) + N*T*sum_d logsn_d + tr(U^T Kzz^-1 U)/2   (x scale)
+ *   sqerr[p] = sum (Y-x)^2                     (closure(add_prior=False); not scaled)
+ *   gU, glogsn = gradients of loss (x scale).  scale = 1/N for pSGLD (langevin.py:528).
+ * add_prior=0 drops the prior term from loss and gU (likelihood terms stay). */
+int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
+                       int32_t N, const float* y0, int32_t y0_batched,
+                       const float* Y, const float* logsn, float scale, int32_t add_prior,
+                       float* loss, float* sqerr, float* gU, float* glogsn,
+                       float* scratch, size_t scratch_floats, bode_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BODE_B200_H */

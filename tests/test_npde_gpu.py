@@ -1,0 +1,173 @@
+"""Parity of the fused npde CUDA path (through the C ABI) against the reference goldens and the oracle.
+
+Tolerances (BASELINE.json north_star): trajectories <= 1e-5 relative (fp32 vs the fp64 reference, relative to
+max|y|), gradients <= 1e-4 relative, each gradient mode against ITS OWN reference gradient."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _field(g, P=None):
+    import bayesian_ode_b200 as bode
+    U = torch.from_numpy(g["U"] if P is None else g["U"][:P])
+    f = bode.NPDEField(U, torch.from_numpy(g["Z"]), float(g["sf"]), float(g["ell"]), 0.1)
+    f.logsn.data.copy_(torch.from_numpy(g["logsn"] if P is None else g["logsn"][:P]))
+    return f
+
+
+@pytest.mark.parametrize("tag", ["npde_m5", "npde_m3"])
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+def test_odeint_trajectories_match_reference(tag, method):
+    import bayesian_ode_b200 as bode
+    g = load_golden(tag)
+    if f"{method}_sol" not in g:
+        pytest.skip("no golden for this method")
+    f = _field(g)
+    with torch.no_grad():
+        sol = bode.odeint(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), method=method)
+    assert sol.shape == g[f"{method}_sol"].shape
+    assert relerr(sol.cpu().numpy(), g[f"{method}_sol"]) < TRAJ_TOL
+
+
+@pytest.mark.parametrize("method", ["euler", "midpoint", "rk4"])
+@pytest.mark.parametrize("mode", ["discrete", "adjoint"])
+def test_fused_closure_matches_reference(method, mode):
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    f = _field(g)
+    post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]),
+                              method=method, grad_mode=mode)
+    loss, gU, gl = post.loss_and_grad_()
+    torch.cuda.synchronize()
+    assert relerr(loss.cpu().numpy(), g[f"{method}_loss"]) < 1e-5
+    assert relerr(post.sqerr.cpu().numpy(), g[f"{method}_sqerr"]) < 1e-5
+    assert relerr(gU.cpu().numpy(), g[f"{method}_gU_{mode}"]) < GRAD_TOL
+    assert relerr(gl.cpu().numpy(), g[f"{method}_glogsn_{mode}"]) < GRAD_TOL
+
+
+def test_closure_protocol_backward_fills_grads():
+    """closure() -> loss.backward() -> p.grad, the protocol samplers/langevin.py:219-224 drives."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    f = _field(g)
+    post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]))
+    loss = post()
+    loss.sum().backward()
+    assert relerr(f.U.grad.cpu().numpy(), g["rk4_gU_discrete"]) < GRAD_TOL
+    assert relerr(f.logsn.grad.cpu().numpy(), g["rk4_glogsn_discrete"]) < GRAD_TOL
+    sq = post(add_prior=False)
+    assert relerr(sq.cpu().numpy(), g["rk4_sqerr"]) < 1e-5
+
+
+def test_single_chain_shapes_like_reference():
+    """U [m,2] (one chain) behaves exactly like the reference's KernelRegression: sol is [T,N,2], loss scalar."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    f = bode.NPDEField(torch.from_numpy(g["U"][0]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    f.logsn.data.copy_(torch.from_numpy(g["logsn"][:1]))
+    x0, t, Y = (torch.from_numpy(g[k]) for k in ("x0", "t", "Y"))
+    sol = bode.odeint_adjoint(f, x0, t, method="rk4")
+    assert sol.shape == (40, 5, 2)
+    assert relerr(sol.detach().cpu().numpy(), g["rk4_sol"][:, 0]) < TRAJ_TOL
+    loss = bode.NPDEPosterior(f, x0, t, Y, grad_mode="adjoint")()
+    assert loss.dim() == 0
+    loss.backward()
+    assert relerr(f.U.grad[0].cpu().numpy(), g["rk4_gU_adjoint"][0]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("mode", ["discrete", "adjoint"])
+def test_autograd_through_odeint_matches_reference(mode):
+    """Generic downstream loss written in torch ops; gradient flows back through the CUDA backward kernel."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    f = _field(g)
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
+    Y = torch.from_numpy(g["Y"]).cuda().float()
+    ode = bode.odeint if mode == "discrete" else bode.odeint_adjoint
+    xode = ode(f, x0, t, method="rk4").permute(1, 2, 0, 3)          # [P,N,T,2]
+    Kinv = f.Kzzinv.cuda().float()
+    loss = ((Y[None] - xode) ** 2 / (2 * torch.exp(f.logsn)[:, None, None, :] ** 2)).sum()
+    loss = loss + Y.numel() * f.logsn.sum() / 2
+    loss = loss + 0.5 * torch.einsum("pjd,jk,pkd->", f.U, Kinv, f.U)
+    loss.backward()
+    assert relerr(f.U.grad.cpu().numpy(), g[f"rk4_gU_{mode}"]) < GRAD_TOL
+    assert relerr(f.logsn.grad.cpu().numpy(), g[f"rk4_glogsn_{mode}"]) < GRAD_TOL
+
+
+@pytest.mark.parametrize("case", ["a", "b", "c"])
+def test_step_size_grid_quirk_and_gradients(case):
+    import bayesian_ode_b200 as bode
+    g = load_golden("grid_options")
+    f = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    t, h = torch.from_numpy(g[f"{case}_t"]), float(g[f"{case}_h"])
+    for method in ("euler", "midpoint", "rk4"):
+        with torch.no_grad():
+            sol = bode.odeint(f, torch.from_numpy(g["x0"]), t, method=method, options={"step_size": h})
+        assert relerr(sol.cpu().numpy(), g[f"{case}_{method}_sol"]) < TRAJ_TOL
+    x0 = torch.from_numpy(g["x0"]).cuda().float().requires_grad_(True)
+    sol = bode.odeint(f, x0, t, method="rk4", options={"step_size": h})
+    (sol * torch.from_numpy(g[f"{case}_w"]).cuda().float()).sum().backward()
+    assert relerr(f.U.grad.cpu().numpy(), g[f"{case}_rk4_gU"]) < GRAD_TOL
+    assert relerr(x0.grad.cpu().numpy(), g[f"{case}_rk4_gx0"]) < GRAD_TOL
+
+
+def test_reversed_time():
+    import bayesian_ode_b200 as bode
+    g = load_golden("grid_options")
+    f = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    with torch.no_grad():
+        sol = bode.odeint(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["rev_t"]), method="rk4")
+    assert relerr(sol.cpu().numpy(), g["rev_rk4_sol"]) < TRAJ_TOL
+
+
+def test_api_errors_like_reference():
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    f = _field(g)
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
+    with pytest.raises(ValueError):                      # odeint.py:65-66
+        bode.odeint(f, x0, t, options={"step_size": 0.1})
+    with pytest.raises(KeyError):                        # odeint.py:71
+        bode.odeint(f, x0, t, method="nope")
+    with pytest.raises(TypeError):                       # misc.py:189-193
+        bode.odeint(f, x0.long(), t, method="rk4")
+    with pytest.raises(ValueError):                      # adjoint.py:109-110
+        bode.odeint_adjoint(lambda t, y: y, x0, t, method="rk4")
+    with pytest.raises(TypeError):                       # no generic-callable path in this build
+        bode.odeint(lambda t, y: y, x0, t, method="rk4")
+    with pytest.raises(AssertionError):                  # misc.py:60
+        bode.odeint(f, x0, torch.tensor([0.0, 1.0, 0.5]), method="rk4")
+    with pytest.raises(ValueError):                      # solvers.py:53
+        bode.odeint(f, x0, t, method="rk4", options={"step_size": 0.1, "grid_constructor": lambda f, y, t: t})
+
+
+def test_full_size_against_oracle():
+    """BASELINE config sizes (P=4096 SVGD particles; P=1024 x 100 steps) vs the float64 oracle on a subsample,
+    plus determinism (bitwise-identical reruns)."""
+    import bayesian_ode_b200 as bode
+    from oracle import npde
+    g = load_golden("npde_m5")
+    rng = np.random.default_rng(0)
+    P = 4096
+    U = g["U0"][None] + 0.1 * rng.standard_normal((P, 25, 2))
+    logsn = np.log(0.1) + 0.05 * rng.standard_normal((P, 2))
+    f = bode.NPDEField(torch.from_numpy(U), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    f.logsn.data.copy_(torch.from_numpy(logsn))
+    post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]))
+    loss, gU, gl = (x.clone() for x in post.loss_and_grad_())
+    loss2, gU2, gl2 = post.loss_and_grad_()
+    assert torch.equal(loss, loss2) and torch.equal(gU, gU2) and torch.equal(gl, gl2)
+    idx = np.concatenate([np.arange(8), rng.choice(P, 56, replace=False), [P - 1]])
+    ol, ogU, ogl, _ = npde.nlp_grad(U[idx], logsn[idx], g["Z"], 1.0, 0.75, g["x0"], g["t"], g["Y"])
+    assert relerr(loss.cpu().numpy()[idx], ol) < 1e-5
+    # per-particle gradient error relative to that particle's gradient scale
+    err = np.abs(gU.cpu().numpy()[idx] - ogU).max(axis=(1, 2)) / np.abs(ogU).max(axis=(1, 2))
+    assert err.max() < GRAD_TOL
+    assert relerr(gl.cpu().numpy()[idx], ogl) < GRAD_TOL
