@@ -11,5 +11,6 @@ from . import _lib
 from .fields import KernelRegression, NPDEField, rbf_kernel
 from .odeint import odeint, odeint_adjoint
 from .posterior import NPDEPosterior
+from . import samplers
 
-__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "rbf_kernel", "_lib"]
+__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "rbf_kernel", "samplers", "_lib"]

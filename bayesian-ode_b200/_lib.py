@@ -24,7 +24,7 @@ class NpdeFieldStruct(C.Structure):
     _fields_ = [
         ("P", C.c_int32), ("m", C.c_int32), ("grid_mx", C.c_int32), ("grid_my", C.c_int32),
         ("gx", C.c_double * 32), ("gy", C.c_double * 32), ("ell", C.c_double * 2),
-        ("Z", C.c_void_p), ("A", C.c_void_p), ("Ksym", C.c_void_p), ("U", C.c_void_p),
+        ("Z", C.c_void_p), ("A", C.c_void_p), ("Ksym", C.c_void_p), ("U", C.c_void_p), ("U_stride", C.c_int64),
     ]
 
 
@@ -46,9 +46,25 @@ SYMBOLS = {
     "bode_npde_scratch_floats": (C.c_size_t, [C.c_int32] * 6),
     "bode_npde_odeint": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_npde_odeint_backward": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
-                                             _P, C.c_int32, _P, _P, _P, _P, C.c_size_t, _P]),
+                                             _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "bode_npde_nlp_grad": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
-                                      _P, C.c_int32, _P, _P, C.c_float, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P]),
+                                      _P, C.c_int32, _P, _P, C.c_int64, C.c_float, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
+                                      _P, C.c_size_t, _P]),
+    "bode_sgld_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
+    "bode_psgld_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
+    "bode_asghmc_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32,
+                                    C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
+    "bode_axpy": (C.c_int, [_P, _P, C.c_float, C.c_int64, _P, _P, _P]),
+    "bode_sampler_schedule": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _P]),
+    "bode_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint32, _P]),
+    "bode_svgd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
+    "bode_svgd_sqdist": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P, C.c_size_t,
+                                    C.POINTER(C.c_void_p), _P]),
+    "bode_svgd_hist_pass": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "bode_svgd_select_digit": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "bode_svgd_gamma": (C.c_int, [C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
+    "bode_svgd_phi": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, _P, _P,
+                                 _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
 }
 
 
@@ -81,6 +97,15 @@ def ptr(t):
         return None
     assert t.is_cuda and t.is_contiguous(), "device-contiguous tensor required at the C ABI"
     return C.c_void_p(t.data_ptr())
+
+
+def rows(t, inner):
+    """(pointer, row stride in floats) of a [P, ...] fp32 CUDA tensor whose trailing dims are dense with ``inner``
+    elements per particle -- e.g. a column block of a flat theta[P, d] buffer."""
+    assert t.is_cuda and t.dtype == torch.float32
+    if t.dim() >= 2 and t[0].is_contiguous() and t[0].numel() == inner:
+        return C.c_void_p(t.data_ptr()), int(t.stride(0)) if t.shape[0] > 1 else max(int(t.stride(0)), inner)
+    raise BodeError("tensor rows must be dense (got shape %s strides %s)" % (tuple(t.shape), t.stride()))
 
 
 def stream_ptr():

@@ -34,6 +34,8 @@ static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_gr
   prm.k0 = (float)(2.0 * LN2 * c0); prm.k1 = (float)(2.0 * LN2 * c1);
   prm.U = f->U; prm.A = f->A; prm.Ksym = f->Ksym; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
   prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr;
+  BODE_REQUIRE(f->U_stride >= 2 * f->m && (f->U_stride % 2) == 0, "U_stride=%lld must be even and >= 2m", (long long)f->U_stride);
+  prm.U_stride = f->U_stride;
   return BODE_OK;
 }
 
@@ -141,18 +143,20 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
 
 extern "C" int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
                                          int32_t N, const float* y0, int32_t y0_batched, const float* gout, float* gU,
-                                         float* gy0, float* scratch, size_t scratch_n, bode_stream_t stream) {
+                                         int64_t gU_stride, float* gy0, float* scratch, size_t scratch_n, bode_stream_t stream) {
   NpdeKParams prm;
   int st = fill_common(prm, f, g, method, N, y0, y0_batched);
   if (st != BODE_OK) return st;
   BODE_REQUIRE(gout && gU, "null gout/gU");
-  prm.gout = gout; prm.gU = gU; prm.gy0 = gy0; prm.add_prior = 0;
+  BODE_REQUIRE(gU_stride >= 2 * f->m, "gU_stride too small");
+  prm.gout = gout; prm.gU = gU; prm.gU_stride = gU_stride; prm.gy0 = gy0; prm.add_prior = 0;
   return run_grad(f, g, method, grad_mode, INJ_GOUT, N, y0, y0_batched, prm, scratch, scratch_n, (cudaStream_t)stream);
 }
 
 extern "C" int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
-                                  const float* y0, int32_t y0_batched, const float* Y, const float* logsn, float scale,
-                                  int32_t add_prior, float* loss, float* sqerr, float* gU, float* glogsn, float* scratch,
+                                  const float* y0, int32_t y0_batched, const float* Y, const float* logsn, int64_t logsn_stride,
+                                  float scale, int32_t add_prior, float* loss, float* sqerr, float* gU, int64_t gU_stride,
+                                  float* glogsn, int64_t glogsn_stride, float* scratch,
                                   size_t scratch_n, bode_stream_t stream) {
   NpdeKParams prm;
   int st = fill_common(prm, f, g, method, N, y0, y0_batched);
@@ -160,6 +164,9 @@ extern "C" int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, 
   BODE_REQUIRE(Y && logsn && loss && sqerr && gU && glogsn, "null Y/logsn/outputs");
   BODE_REQUIRE(!add_prior || f->Ksym, "add_prior needs Ksym");
   prm.Y = Y; prm.logsn = logsn; prm.scale = scale; prm.add_prior = add_prior ? 1 : 0;
+  BODE_REQUIRE(gU_stride >= 2 * f->m && logsn_stride >= 2 && glogsn_stride >= 2 && (logsn_stride % 2) == 0, "bad strides");
+  BODE_REQUIRE((reinterpret_cast<uintptr_t>(logsn) & 7) == 0, "logsn must be 8-byte aligned");
   prm.loss = loss; prm.sqerr = sqerr; prm.gU = gU; prm.glogsn = glogsn;
+  prm.logsn_stride = logsn_stride; prm.gU_stride = gU_stride; prm.glogsn_stride = glogsn_stride;
   return run_grad(f, g, method, grad_mode, INJ_LIK, N, y0, y0_batched, prm, scratch, scratch_n, (cudaStream_t)stream);
 }

@@ -24,6 +24,7 @@ struct NpdeKParams {
   const int *obs_ptr, *adj_ptr;
   float2* ck;
   long long npairs;
+  long long U_stride, logsn_stride, gU_stride, glogsn_stride;
   float *sol, *loss, *sqerr, *gU, *glogsn, *gy0;
 };
 

@@ -17,8 +17,11 @@ template <int METHOD> struct Stages { static constexpr int value = METHOD == BOD
 // W_p = A U_p for the ppc particles of this CTA (gp.py:70-71 hoisted out of the RHS: K(x,Z) (A U)).
 __device__ __forceinline__ void project_W(const NpdeKParams& prm, float* Us, float* Ws) {
   const int m = prm.m, m2 = 2 * m, nout = prm.ppc * m2;
-  const long long base = (long long)blockIdx.x * nout, total = (long long)prm.P * m2;
-  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) Us[idx] = (base + idx < total) ? __ldg(prm.U + base + idx) : 0.f;
+  const int p0 = blockIdx.x * prm.ppc;
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2;
+    Us[idx] = (p0 + q < prm.P) ? __ldg(prm.U + (long long)(p0 + q) * prm.U_stride + r) : 0.f;
+  }
   __syncthreads();
   for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
     const int q = idx / m2, r = idx - q * m2, j = r >> 1, d = r & 1;
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     const float2* go = reinterpret_cast<const float2*>(prm.gout) + pair;              // gout[j][pair]
     float2 e2inv = f2(0.f, 0.f);
     if (INJ == INJ_LIK) {
-      const float2 ls = reinterpret_cast<const float2*>(prm.logsn)[p];
+      const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)p * prm.logsn_stride);
       e2inv = f2(expf(-2.f * ls.x), expf(-2.f * ls.y));
     }
     float2* ck = prm.ck + pair;
@@ -307,7 +310,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
       pr *= 0.5f * Us[idx];
     }
     pri[idx] = pr;
-    prm.gU[(long long)pp * m2 + r] = prm.scale * acc;
+    prm.gU[(long long)pp * prm.gU_stride + r] = prm.scale * acc;
   }
   if (INJ == INJ_LIK) {
     __syncthreads();
@@ -320,13 +323,13 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
           sy += red[(tid * N + nn) * 2 + 1];
         }
         for (int j = 0; j < m2; ++j) pr += pri[tid * m2 + j];
-        const float2 ls = reinterpret_cast<const float2*>(prm.logsn)[pp];
+        const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)pp * prm.logsn_stride);
         const float ex = expf(-2.f * ls.x), ey = expf(-2.f * ls.y);
         const float nt = (float)N * (float)prm.T;
         prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
         prm.sqerr[pp] = sx + sy;
-        prm.glogsn[pp * 2 + 0] = prm.scale * (nt - sx * ex);
-        prm.glogsn[pp * 2 + 1] = prm.scale * (nt - sy * ey);
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = prm.scale * (nt - sx * ex);
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = prm.scale * (nt - sy * ey);
       }
     }
   }

@@ -1,0 +1,358 @@
+// SVGD interaction step (samplers/stein.py:12-34 RBFKernel, :75-86 phi), particle-sharded.
+//
+//   d2_ij  = ||x_i - x_j||^2                               (torch.cdist(X, Y) ** 2, stein.py:22)
+//   h      = median(d2 over ALL n*n entries) / (2 ln(n+1)) (np.median, stein.py:25-26; even count -> mean of the
+//                                                           two middle order statistics)
+//   gamma  = 1 / (1e-8 + 2 h)                              (stein.py:31, sigma = sqrt(h))
+//   K_ij   = exp(-gamma d2_ij)
+//   phi_i  = (1/n) [ sum_j K_ij s_j + 2 gamma ( (sum_j K_ij) x_i - sum_j K_ij x_j ) ]      
+//
+// Rows i are the LOCAL particles of this rank, columns j run over all n gathered particles.  The median is an
+// exact radix select on the fp32 bit patterns of d2 (order statistic choice is bit-exact and deterministic:
+// integer histograms only); with several ranks the per-pass histograms are summed by the caller (one small
+// all-reduce per pass) before bode_svgd_select_digit runs, so every rank selects the same element.
+#include "common.cuh"
+
+namespace bode {
+
+// ---------------------------------------------------------------- squared distances (difference form, fp32)
+constexpr int TS = 64;   // tile of 64 x 64 pairs per CTA, 4 x 4 per thread
+
+__global__ void __launch_bounds__(256) sqdist_kernel(const float* __restrict__ Xr, long long ldr, int nr,
+                                                     const float* __restrict__ Xc, long long ldc, int nc, int d,
+                                                     float* __restrict__ D2) {
+  extern __shared__ float sm[];
+  const int ldk = d | 1;                         // odd row pitch: conflict-free column reads
+  float* A = sm;                                 // [TS][ldk] rows
+  float* B = sm + TS * ldk;                      // [TS][ldk] cols
+  const int r0 = blockIdx.y * TS, c0 = blockIdx.x * TS;
+  for (int idx = threadIdx.x; idx < TS * d; idx += blockDim.x) {
+    const int i = idx / d, k = idx - i * d;
+    A[i * ldk + k] = (r0 + i < nr) ? __ldg(Xr + (long long)(r0 + i) * ldr + k) : 0.f;
+    B[i * ldk + k] = (c0 + i < nc) ? __ldg(Xc + (long long)(c0 + i) * ldc + k) : 0.f;
+  }
+  __syncthreads();
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  float acc[4][4] = {};
+  for (int k = 0; k < d; ++k) {
+    float a[4], b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { a[u] = A[(ty + 16 * u) * ldk + k]; b[u] = B[(tx + 16 * u) * ldk + k]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int v = 0; v < 4; ++v) { const float t = a[u] - b[v]; acc[u][v] = fmaf(t, t, acc[u][v]); }
+  }
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      const int r = r0 + ty + 16 * u, c = c0 + tx + 16 * v;
+      if (r < nr && c < nc) D2[(long long)r * nc + c] = acc[u][v];
+    }
+}
+
+// ---------------------------------------------------------------- exact median by radix select
+// state[0..1] = prefix bits of order statistics A, B ; state[2..3] (as 64-bit pairs) = remaining ranks
+struct SelState { unsigned int prefix[2]; unsigned int pad[2]; unsigned long long rank[2]; };
+
+__global__ void select_init_kernel(SelState* st, unsigned long long* hist, unsigned long long total) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    st->prefix[0] = st->prefix[1] = 0u;
+    st->rank[0] = (total - 1) / 2;             // lower middle (0-based, ascending)
+    st->rank[1] = total / 2;                   // upper middle; equal to rank[0] when total is odd
+  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 2048; i += gridDim.x * blockDim.x) hist[i] = 0ull;
+}
+
+// pass over bits [shift, shift+nbits): histogram of elements whose higher bits equal the running prefix
+__global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ D2, long long n, const SelState* __restrict__ st,
+                                                   int shift, int nbits, unsigned int himask, unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int sh[2][2048];
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) (&sh[0][0])[i] = 0u;
+  __syncthreads();
+  const unsigned int pa = st->prefix[0], pb = st->prefix[1];
+  const bool two = pa != pb;
+  const unsigned int dmask = (1u << nbits) - 1u;
+  const long long n4 = n >> 2;
+  const uint4* D4 = reinterpret_cast<const uint4*>(D2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 3; i += (long long)gridDim.x * blockDim.x) {
+    unsigned int v[4];
+    int cnt = 4;
+    if (i < n4) {
+      const uint4 q = __ldg(D4 + i);
+      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+    } else {
+      const long long e = (n4 << 2) + (i - n4);        // scalar tail elements
+      cnt = e < n ? 1 : 0;
+      if (cnt) v[0] = __float_as_uint(__ldg(D2 + e));
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (u >= cnt) break;
+      const unsigned int hi = v[u] & himask, dig = (v[u] >> shift) & dmask;
+      const int sel = hi == pa ? 0 : ((two && hi == pb) ? 1 : -1);
+      // warp-aggregate equal (histogram, digit) keys: d2 values cluster in a handful of top-bit buckets
+      const unsigned int key = sel < 0 ? 0xffffffffu : ((unsigned)sel << 16 | dig);
+      const unsigned int act = __activemask();
+      const unsigned int peers = __match_any_sync(act, key);
+      if (sel >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[sel][dig], __popc(peers));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
+    const unsigned int c = (&sh[0][0])[i];
+    if (c) atomicAdd(hist + i, (unsigned long long)c);
+  }
+}
+
+// one CTA: pick the digit holding each remaining rank, extend the prefixes, clear the histograms
+__global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsigned long long* hist, int shift, int nbits) {
+  __shared__ unsigned long long cum[2048];
+  __shared__ unsigned int newp[2];
+  __shared__ unsigned long long newr[2];
+  const int nb = 1 << nbits;
+  const bool two = st->prefix[0] != st->prefix[1];
+  for (int which = 0; which < 2; ++which) {
+    const unsigned long long* h = hist + ((which == 1 && two) ? 2048 : 0);
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) cum[i] = h[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {                     // 2048-entry serial scan: negligible next to the passes
+      unsigned long long run = 0, r = st->rank[which];
+      int dsel = nb - 1;
+      for (int i = 0; i < nb; ++i) {
+        if (r < run + cum[i]) { dsel = i; break; }
+        run += cum[i];
+      }
+      newp[which] = st->prefix[which] | ((unsigned)dsel << shift);
+      newr[which] = r - run;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    st->prefix[0] = newp[0]; st->prefix[1] = newp[1];
+    st->rank[0] = newr[0]; st->rank[1] = newr[1];
+  }
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
+}
+
+// out[0] = median, out[1] = gamma   (stein.py:25-31)
+__global__ void gamma_kernel(const SelState* st, int n, float sigma_fixed, float* out) {
+  const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
+  const float med = 0.5f * (a + b);
+  double s2;
+  if (sigma_fixed > 0.f) s2 = (double)sigma_fixed * (double)sigma_fixed;
+  else s2 = (double)med / (2.0 * log((double)n + 1.0));
+  out[0] = med;
+  out[1] = (float)(1.0 / (1e-8 + 2.0 * s2));
+}
+
+// ---------------------------------------------------------------- phi partials: K[rows, jslice] @ [S | X], row sums
+constexpr int PR = 32;      // rows per CTA
+constexpr int PJ = 64;      // columns per smem stage
+constexpr int CG = 8;       // column groups (threads along the feature axis)
+
+template <int CPT>          // features per thread; CG*CPT >= 2d
+__global__ void __launch_bounds__(128) phi_partial_kernel(const float* __restrict__ D2, int nr, int nc,
+                                                          const float* __restrict__ Xc, long long ldx,
+                                                          const float* __restrict__ Sc, long long lds, int d,
+                                                          const float* __restrict__ gam, int jsplit,
+                                                          float* __restrict__ part, float* __restrict__ rsum) {
+  extern __shared__ float sm[];
+  const int F = CG * CPT;                        // padded feature count (S then X)
+  float* Ks = sm;                                // [PR][PJ+1]
+  float* Vs = sm + PR * (PJ + 1);                // [PJ][F]
+  const float ngamma = -gam[1] * 1.4426950408889634f;
+  const int r0 = blockIdx.x * PR;
+  const int jper = ((nc + jsplit - 1) / jsplit + PJ - 1) / PJ * PJ;
+  const int jbeg = blockIdx.y * jper, jend = min(nc, jbeg + jper);
+  const int cg = threadIdx.x % CG, rg = threadIdx.x / CG;     // 16 row groups x 2 rows
+  float acc[2][CPT] = {};
+  float rs[2] = {0.f, 0.f};
+  for (int j0 = jbeg; j0 < jend; j0 += PJ) {
+    for (int idx = threadIdx.x; idx < PR * PJ; idx += blockDim.x) {
+      const int i = idx / PJ, j = idx - i * PJ;
+      float k = 0.f;
+      if (r0 + i < nr && j0 + j < jend) k = ex2(ngamma * __ldg(D2 + (long long)(r0 + i) * nc + j0 + j));
+      Ks[i * (PJ + 1) + j] = k;
+    }
+    for (int idx = threadIdx.x; idx < PJ * F; idx += blockDim.x) {
+      const int j = idx / F, c = idx - j * F;
+      float v = 0.f;
+      if (j0 + j < jend) {
+        if (c < d) v = __ldg(Sc + (long long)(j0 + j) * lds + c);
+        else if (c < 2 * d) v = __ldg(Xc + (long long)(j0 + j) * ldx + (c - d));
+      }
+      Vs[idx] = v;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int j = 0; j < PJ; ++j) {
+      const float k0 = Ks[(2 * rg) * (PJ + 1) + j], k1 = Ks[(2 * rg + 1) * (PJ + 1) + j];
+      rs[0] += k0; rs[1] += k1;
+      const float* v = Vs + j * F + cg * CPT;
+#pragma unroll
+      for (int c = 0; c < CPT; ++c) {
+        acc[0][c] = fmaf(k0, v[c], acc[0][c]);
+        acc[1][c] = fmaf(k1, v[c], acc[1][c]);
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int r = r0 + 2 * rg + u;
+    if (r >= nr) continue;
+    float* dst = part + ((long long)blockIdx.y * nr + r) * (2 * d);
+#pragma unroll
+    for (int c = 0; c < CPT; ++c) {
+      const int f = cg * CPT + c;
+      if (f < 2 * d) dst[f] = acc[u][c];
+    }
+    if (cg == 0) rsum[(long long)blockIdx.y * nr + r] = rs[u];
+  }
+}
+
+// phi = (KS + 2 gamma (rowsum * x_i - KX)) / n ; optional fused update theta_i += step * phi_i
+__global__ void phi_combine_kernel(const float* __restrict__ part, const float* __restrict__ rsum, int jsplit, int nr, int d,
+                                   const float* __restrict__ Xr, long long ldr, const float* __restrict__ gam, float inv_n,
+                                   float* __restrict__ phi, long long ldp, float* __restrict__ theta, long long ldt, float step) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nr * d) return;
+  const int r = (int)(idx / d), c = (int)(idx - (long long)r * d);
+  float ks = 0.f, kx = 0.f, rs = 0.f;
+  for (int s = 0; s < jsplit; ++s) {
+    const float* p = part + ((long long)s * nr + r) * (2 * d);
+    ks += p[c];
+    kx += p[d + c];
+    rs += rsum[(long long)s * nr + r];
+  }
+  const float x = Xr[(long long)r * ldr + c];
+  const float ph = (ks + 2.f * gam[1] * (rs * x - kx)) * inv_n;
+  if (phi) phi[(long long)r * ldp + c] = ph;
+  if (theta) theta[(long long)r * ldt + c] = fmaf(step, ph, theta[(long long)r * ldt + c]);
+}
+
+}  // namespace bode
+
+using namespace bode;
+
+extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t d) {
+  const size_t jsplit = 4;
+  size_t b = 0;
+  b += (size_t)n_rows * n_cols * sizeof(float);                 // d2
+  b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials + row sums
+  b += 2 * 2048 * sizeof(unsigned long long) + 256;             // histograms + select state
+  return b + 1024;
+}
+
+namespace {
+struct Ws {
+  float* d2; float* part; float* rsum; unsigned long long* hist; SelState* st;
+};
+Ws carve(void* ws, int nr, int nc, int d) {
+  Ws w;
+  char* p = (char*)ws;
+  w.d2 = (float*)p; p += (((size_t)nr * nc * sizeof(float)) + 255) / 256 * 256;
+  w.part = (float*)p; p += ((4 * (size_t)nr * 2 * d * sizeof(float)) + 255) / 256 * 256;
+  w.rsum = (float*)p; p += ((4 * (size_t)nr * sizeof(float)) + 255) / 256 * 256;
+  w.hist = (unsigned long long*)p; p += 2 * 2048 * sizeof(unsigned long long);
+  w.st = (SelState*)p;
+  return w;
+}
+}  // namespace
+
+/* d2[rows, cols] for the local rows, and reset of the select state; total = number of entries the median runs over
+ * (n*n for the whole job).  hist_out receives the device address of the 2x2048 uint64 histogram block so a multi-rank
+ * caller can all-reduce it between bode_svgd_hist_pass and bode_svgd_select_digit. */
+extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
+                                int32_t n_cols, int32_t d, uint64_t total_entries, void* workspace, size_t workspace_bytes,
+                                void** hist_out, bode_stream_t stream) {
+  BODE_REQUIRE(Xrows && Xcols && workspace, "null pointer");
+  BODE_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && d <= 512, "bad sizes");
+  BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
+  BODE_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t smem = 2 * (size_t)TS * (d | 1) * sizeof(float);
+  if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((n_cols + TS - 1) / TS, (n_rows + TS - 1) / TS);
+  sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2);
+  BODE_CUDA(cudaGetLastError());
+  select_init_kernel<<<4, 1024, 0, st>>>(w.st, w.hist, total_entries);
+  BODE_CUDA(cudaGetLastError());
+  if (hist_out) *hist_out = w.hist;
+  return BODE_OK;
+}
+
+/* pass = 0,1,2 over bit windows [20,31), [9,20), [0,9) of the fp32 pattern (d2 >= 0 so bit 31 is clear) */
+static void window(int pass, int* shift, int* nbits, unsigned int* himask) {
+  const int sh[3] = {20, 9, 0}, nb[3] = {11, 11, 9};
+  *shift = sh[pass]; *nbits = nb[pass];
+  *himask = pass == 0 ? 0u : (0xffffffffu << (sh[pass] + nb[pass]));
+}
+
+extern "C" int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+  BODE_REQUIRE(pass >= 0 && pass < 3 && workspace, "bad pass/workspace");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  int shift, nbits; unsigned int himask;
+  window(pass, &shift, &nbits, &himask);
+  const long long n = (long long)n_rows * n_cols;
+  int sms = bode_device_sm_count();
+  if (sms < 0) return BODE_ERR_CUDA;
+  long long blocks = (n / 4 + 511) / 512;
+  if (blocks > 4LL * sms) blocks = 4LL * sms;
+  if (blocks < 1) blocks = 1;
+  hist_kernel<<<(int)blocks, 512, 0, (cudaStream_t)stream>>>(w.d2, n, w.st, shift, nbits, himask, w.hist);
+  return check_cuda(cudaGetLastError(), "hist launch");
+}
+
+extern "C" int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+  BODE_REQUIRE(pass >= 0 && pass < 3 && workspace, "bad pass/workspace");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  int shift, nbits; unsigned int himask;
+  window(pass, &shift, &nbits, &himask);
+  select_digit_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w.st, w.hist, shift, nbits);
+  return check_cuda(cudaGetLastError(), "select launch");
+}
+
+/* med_gamma[0] = median(d2), med_gamma[1] = gamma; sigma > 0 fixes the bandwidth (RBFKernel(sigma), stein.py:13-16,28) */
+extern "C" int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
+                               float* med_gamma, bode_stream_t stream) {
+  BODE_REQUIRE(workspace && med_gamma && n_total > 0, "bad args");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  gamma_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(w.st, n_total, sigma, med_gamma);
+  return check_cuda(cudaGetLastError(), "gamma launch");
+}
+
+/* phi for the local rows (uses d2 left in the workspace by bode_svgd_sqdist).  phi may be NULL; when theta != NULL the
+ * update theta_i += step * phi_i is fused (the wrapped optimiser of stein.py descends -phi with lr = step). */
+extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
+                             const float* Scols, int64_t ld_sc, int32_t n_cols, int32_t d, int32_t n_total,
+                             const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
+                             int64_t ld_theta, float step, bode_stream_t stream) {
+  BODE_REQUIRE(Xrows && Xcols && Scols && med_gamma && workspace, "null pointer");
+  BODE_REQUIRE(d > 0 && 2 * d <= 8 * 32, "svgd phi kernel supports d <= 128 (got %d)", d);
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int jsplit = 4;
+  dim3 grid((n_rows + PR - 1) / PR, jsplit);
+  const int cpt = (2 * d + CG - 1) / CG;
+#define BODE_PHI(C)                                                                                              \
+  {                                                                                                              \
+    const size_t smem = ((size_t)PR * (PJ + 1) + (size_t)PJ * CG * C) * sizeof(float);                           \
+    if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(phi_partial_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+    phi_partial_kernel<C><<<grid, 128, smem, st>>>(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, med_gamma, jsplit, w.part, w.rsum); \
+  }
+  if (cpt <= 4) BODE_PHI(4)
+  else if (cpt <= 8) BODE_PHI(8)
+  else if (cpt <= 13) BODE_PHI(13)
+  else if (cpt <= 16) BODE_PHI(16)
+  else BODE_PHI(32)
+#undef BODE_PHI
+  BODE_CUDA(cudaGetLastError());
+  const long long tot = (long long)n_rows * d;
+  phi_combine_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(w.part, w.rsum, jsplit, n_rows, d, Xrows, ld_rows, med_gamma,
+                                                               1.f / (float)n_total, phi, ld_phi, theta, ld_theta, step);
+  return check_cuda(cudaGetLastError(), "phi combine launch");
+}

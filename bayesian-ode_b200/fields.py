@@ -67,9 +67,16 @@ class NPDEField(torch.nn.Module):
             raise ValueError("U0 must be [m, 2] or [P, m, 2]")
         U0 = U0 if self.batched else U0[None]
         self.P, self.m = int(U0.shape[0]), int(U0.shape[1])
-        self.U = torch.nn.Parameter(U0.to(device=device, dtype=torch.float32).contiguous().clone(), requires_grad=True)
-        logsn = torch.zeros(self.P, 2, dtype=torch.float32, device=device) + math.log(noise)
-        self.logsn = torch.nn.Parameter(logsn, requires_grad=True)
+        # One resident buffer theta[P, d] = [U_p (2m) | logsn_p (2)], particle-major; U and logsn are Parameters
+        # that VIEW its column blocks, so the sampler updates and the SVGD interaction run on the flat buffer
+        # while the reference's ``params = [kreg.U, kreg.logsn]`` (gp.py:337) keeps working.
+        self.d = 2 * self.m + 2
+        self.theta = torch.empty(self.P, self.d, dtype=torch.float32, device=device)
+        self.theta[:, :2 * self.m] = U0.to(device=device, dtype=torch.float32).reshape(self.P, -1)
+        self.theta[:, 2 * self.m:] = math.log(noise)
+        self.theta_grad = torch.zeros_like(self.theta)
+        self.U = torch.nn.Parameter(self.theta[:, :2 * self.m].view(self.P, self.m, 2), requires_grad=True)
+        self.logsn = torch.nn.Parameter(self.theta[:, 2 * self.m:], requires_grad=True)
         self.sf = float(sf)
         ell_t = torch.as_tensor(ell, dtype=torch.float64).reshape(-1)
         self.ell = ell
@@ -123,9 +130,16 @@ class NPDEField(torch.nn.Module):
         fs.A = self._A.data_ptr()
         fs.Ksym = self._Ksym.data_ptr()
         U = self.U if U is None else U
-        assert U.is_cuda and U.is_contiguous() and U.dtype == torch.float32
-        fs.U = U.data_ptr()
+        p, stride = _lib.rows(U, 2 * self.m)
+        fs.U = p.value
+        fs.U_stride = stride
         return fs
+
+    def bind_flat_grads(self):
+        """Point U.grad / logsn.grad at the column blocks of the flat ``theta_grad`` buffer."""
+        self.U.grad = self.theta_grad[:, :2 * self.m].view(self.P, self.m, 2)
+        self.logsn.grad = self.theta_grad[:, 2 * self.m:]
+        return self.theta_grad
 
 
 # the reference's name for the same object (gp.py:56)

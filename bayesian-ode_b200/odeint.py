@@ -76,7 +76,7 @@ class _NpdeOdeint(torch.autograd.Function):
     def forward(ctx, y0, U, field, g, method, grad_mode, batched, N):
         lib = _lib.load()
         sol = torch.empty((g.T, field.P, N, 2), dtype=torch.float32, device=U.device)
-        fs = field.c_struct(U.detach().contiguous())
+        fs = field.c_struct(U.detach())
         gs = _grid_struct(g, False)
         _lib.check(lib.bode_npde_odeint(fs, gs, method, N, _lib.ptr(y0), int(batched), _lib.ptr(sol), _lib.stream_ptr()))
         ctx.save_for_backward(y0, U)
@@ -89,14 +89,15 @@ class _NpdeOdeint(torch.autograd.Function):
         field, g, method, grad_mode, batched, N = ctx.misc
         lib = _lib.load()
         gout = gout.to(torch.float32).contiguous()
-        gU = torch.empty_like(U)
+        gU = torch.empty((field.P, field.m, 2), dtype=torch.float32, device=U.device)
         gy0 = torch.empty((field.P, N, 2), dtype=torch.float32, device=U.device)
         nsc = lib.bode_npde_scratch_floats(field.P, N, g.S, g.T, method, grad_mode)
         sc = _scratch(U.device, nsc)
-        fs = field.c_struct(U.detach().contiguous())
+        fs = field.c_struct(U.detach())
         gs = _grid_struct(g, grad_mode == _lib.GRAD_ADJOINT)
         _lib.check(lib.bode_npde_odeint_backward(fs, gs, method, grad_mode, N, _lib.ptr(y0), int(batched), _lib.ptr(gout),
-                                                 _lib.ptr(gU), _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+                                                 _lib.ptr(gU), 2 * field.m, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(),
+                                                 _lib.stream_ptr()))
         if not batched:
             gy0 = gy0.sum(0)
         return gy0, gU, None, None, None, None, None, None

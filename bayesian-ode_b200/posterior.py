@@ -58,8 +58,10 @@ class NPDEPosterior:
         P = field.P
         self.loss = torch.empty(P, dtype=torch.float32, device=dev)
         self.sqerr = torch.empty(P, dtype=torch.float32, device=dev)
-        self.gU = torch.empty_like(field.U.data)
-        self.glogsn = torch.empty_like(field.logsn.data)
+        # gradients land directly in the column blocks of the field's flat grad buffer
+        self.gtheta = field.theta_grad
+        self.gU = self.gtheta[:, :2 * field.m].view(P, field.m, 2)
+        self.glogsn = self.gtheta[:, 2 * field.m:]
         self.add_prior = True
 
     # ------------------------------------------------------------------------------------------------
@@ -73,16 +75,23 @@ class NPDEPosterior:
     def _launch(self, U, logsn, out=None):
         lib = _lib.load()
         f = self.field
-        loss, sqerr, gU, gl = out if out is not None else (
-            torch.empty_like(self.loss), self.sqerr, torch.empty_like(self.gU), torch.empty_like(self.glogsn))
+        if out is not None:
+            loss, sqerr, gU, gl = out
+        else:
+            gflat = torch.empty_like(self.gtheta)
+            loss, sqerr = torch.empty_like(self.loss), self.sqerr
+            gU, gl = gflat[:, :2 * f.m].view(f.P, f.m, 2), gflat[:, 2 * f.m:]
         nsc = lib.bode_npde_scratch_floats(f.P, self.N, self.grid.S, self.grid.T, _lib.METHODS[self.method], self.grad_mode)
         sc = _scratch(U.device, nsc)
-        fs = f.c_struct(U.contiguous())
+        fs = f.c_struct(U)
         gs = _grid_struct(self.grid, self.grad_mode == _lib.GRAD_ADJOINT)
+        lp, ls = _lib.rows(logsn, 2)
+        gUp, gUs = _lib.rows(gU, 2 * f.m)
+        glp, gls = _lib.rows(gl, 2)
         _lib.check(lib.bode_npde_nlp_grad(
             fs, gs, _lib.METHODS[self.method], self.grad_mode, self.N, _lib.ptr(self.x0), int(self.x0_batched),
-            _lib.ptr(self.Y), _lib.ptr(logsn.contiguous()), self.scale, int(self.add_prior),
-            _lib.ptr(loss), _lib.ptr(sqerr), _lib.ptr(gU), _lib.ptr(gl), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+            _lib.ptr(self.Y), lp, ls, self.scale, int(self.add_prior),
+            _lib.ptr(loss), _lib.ptr(sqerr), gUp, gUs, glp, gls, _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
         return loss, gU, gl
 
     def loss_and_grad_(self):

@@ -1,0 +1,215 @@
+"""Sampler base class and the flat-buffer plumbing shared by all B200 samplers.
+
+Mirrors samplers/sampler.py:9-21 (``Sampler(torch.optim.Optimizer)`` with a ``samples`` chain) and adds what
+particle-batched chains need: detection of parameters that are column blocks of one resident theta[P, d]
+buffer (NPDEField / MLPField lay them out that way) so an update is ONE fused launch over the flat buffer,
+an on-device chain store, and deferred (asynchronous) NaN reporting.
+"""
+import numpy as np
+import torch
+from torch.optim.optimizer import Optimizer
+
+from .. import _lib
+
+
+
+def _flat_base(tensors):
+    """If every tensor is a dense column block [P, ...] of one row-major [P, d] buffer and together they tile its
+    columns, return that buffer as a [P, d] view; else None."""
+    ts = list(tensors)
+    if not ts or any((not t.is_cuda) or t.dtype != torch.float32 or t.dim() < 2 for t in ts):
+        return None
+    st = ts[0].untyped_storage().data_ptr()
+    P, d = ts[0].shape[0], ts[0].stride(0)
+    blocks = []
+    for t in ts:
+        if t.untyped_storage().data_ptr() != st or t.shape[0] != P or (P > 1 and t.stride(0) != d):
+            return None
+        inner = t[0].numel()
+        if not t[0].is_contiguous():
+            return None
+        blocks.append((t.storage_offset(), inner))
+    blocks.sort()
+    off0 = blocks[0][0]
+    pos = off0
+    for o, n in blocks:
+        if o != pos:
+            return None
+        pos += n
+    if P == 1:
+        d = pos - off0
+    if pos - off0 != d:
+        return None
+    return torch.as_strided(ts[0], (P, d), (d, 1), off0)
+
+
+class ChainStore:
+    """List-like view of an on-device chain [num_samples, P, d]; entries materialise lazily in the reference's
+    format ``([[param arrays ...]], True)`` (langevin.py:243-245) so no per-sample D2H copy or sync happens."""
+
+    def __init__(self):
+        self._host = []           # entries appended the slow (reference) way
+        self._dev = None
+        self._count = 0
+        self._split = None
+
+    def reserve(self, n, flat, params):
+        self._dev = torch.empty((n,) + tuple(flat.shape), dtype=flat.dtype, device=flat.device)
+        self._count = 0
+        offs, pos = [], 0
+        for p in params:
+            inner = p[0].numel()
+            offs.append((pos, inner, tuple(p.shape)))
+            pos += inner
+        self._split = offs
+
+    def push_flat(self, flat):
+        self._dev[self._count].copy_(flat, non_blocking=True)
+        self._count += 1
+
+    def append(self, item):
+        self._host.append(item)
+
+    def device_tensor(self):
+        return None if self._dev is None else self._dev[:self._count]
+
+    def __len__(self):
+        return len(self._host) + self._count
+
+    def _entry(self, i):
+        if i < len(self._host):
+            return self._host[i]
+        row = self._dev[i - len(self._host)].cpu().numpy()
+        return ([[row[:, o:o + n].reshape(shape) for (o, n, shape) in self._split]], True)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self._entry(j) for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        return self._entry(i)
+
+    def __iter__(self):
+        return (self._entry(i) for i in range(len(self)))
+
+
+class Sampler(Optimizer):
+    """samplers/sampler.py:9-21.  ``self.samples`` holds the chain as ``[(params, accepted), ...]``."""
+
+    def __init__(self, params, defaults):
+        self.samples = ChainStore()
+        super().__init__(params, defaults)
+        self._plist = [p for g in self.param_groups for p in g["params"]]
+        _lib.require_cuda(*self._plist)
+        self._flat = _flat_base([p.data for p in self._plist])
+        self._flat_grad = None
+        self._status = torch.zeros(1, dtype=torch.int32, device=self._plist[0].device)
+        self._ctl_dev = None
+        self._step_index = 0
+        self.seed = int(defaults.get("seed", 0)) if isinstance(defaults, dict) else 0
+        self.check_finite = "sync"       # "sync": raise inside step() like the reference; "deferred": raise at check()
+
+    # ---- flat buffers ------------------------------------------------------------------------------------
+    def _grad_flat(self):
+        """The gradient as one [P, d] buffer matching ``self._flat`` (bound lazily: grads may be created by autograd)."""
+        if self._flat is None:
+            return None
+        grads = [p.grad for p in self._plist]
+        if any(g is None for g in grads):
+            return None
+        gf = _flat_base(grads)
+        if gf is None or gf.shape != self._flat.shape:
+            return None
+        return gf
+
+    def bind_flat_grads(self):
+        """Allocate one flat gradient buffer and make every ``p.grad`` a column-block view of it."""
+        if self._flat is None:
+            return None
+        gf = self._grad_flat()
+        if gf is not None:
+            return gf
+        gf = torch.zeros_like(self._flat)
+        base_off = self._flat.storage_offset()
+        d = self._flat.shape[1]
+        for p in self._plist:
+            o = p.data.storage_offset() - base_off
+            n = p[0].numel()
+            p.grad = gf[:, o:o + n].view(p.shape)
+        return gf
+
+    def zero_grad(self, set_to_none=False):
+        # in place, so flat-bound gradient views survive (the reference's torch version zeroed in place too)
+        with torch.no_grad():
+            for p in self._plist:
+                if p.grad is not None:
+                    p.grad.zero_()
+
+    def _tensors_for_launch(self):
+        """[(param, grad)] pairs a fused kernel can run on: the flat pair, or each contiguous tensor."""
+        gf = self._grad_flat()
+        if gf is not None:
+            return [(self._flat, gf)]
+        if self._flat is not None and all(p.grad is not None for p in self._plist):
+            # gradients were produced by plain autograd as separate tensors: pack them once into a flat buffer and
+            # rebind p.grad to its column blocks so later backward() calls accumulate in place
+            grads = [p.grad for p in self._plist]
+            for p in self._plist:
+                p.grad = None
+            gf = self.bind_flat_grads()
+            with torch.no_grad():
+                for p, g in zip(self._plist, grads):
+                    p.grad.copy_(g)
+            return [(self._flat, gf)]
+        out = []
+        for p in self._plist:
+            if p.grad is None:
+                continue
+            if not p.data.is_contiguous() or not p.grad.is_contiguous():
+                raise _lib.BodeError("sampler parameters must be contiguous or column blocks of one flat buffer")
+            out.append((p.data, p.grad))
+        return out
+
+    # ---- NaN reporting (langevin.py:184-185) -------------------------------------------------------------
+    def check(self):
+        if int(self._status.item()) != 0:
+            self._status.zero_()
+            raise ValueError("Encountered NaN/Inf in parameter")
+
+    def _after_step(self):
+        self._step_index += 1
+        if self.check_finite == "sync":
+            self.check()
+
+    # ---- device control block for graph replay -----------------------------------------------------------
+    def ctl(self):
+        """Device control block (bode_sampler_ctl, 8 x 32 bit).  ``schedule_()`` advances it on the device."""
+        if self._ctl_dev is None:
+            self._ctl_dev = torch.zeros(8, dtype=torch.int32, device=self._status.device)
+        return self._ctl_dev
+
+    def schedule_(self, kind=0, lr0=0.0, gamma=0.0, t0=0.0, alpha=0.0, burn_in_iters=0, resample_every=0):
+        """Enqueue the device-side schedule for the next iteration (graph-capturable; see bode_sampler_schedule)."""
+        _lib.check(_lib.load().bode_sampler_schedule(_lib.ptr(self.ctl()), int(kind), float(lr0), float(gamma), float(t0),
+                                                     float(alpha), int(burn_in_iters), int(resample_every), _lib.stream_ptr()))
+
+    def step(self):
+        raise NotImplementedError
+
+    def sample(self):
+        raise NotImplementedError
+
+    # ---- helpers shared by the sample() loops ----------------------------------------------------------
+    @staticmethod
+    def _backward(loss):
+        if loss.dim() == 0:
+            loss.backward()
+        else:
+            loss.backward(torch.ones_like(loss))      # independent chains: d(sum_p loss_p)/d theta_p
+
+    def _record(self, chain):
+        if self._flat is not None and chain._dev is not None:
+            chain.push_flat(self._flat)
+        else:
+            params = [[p.clone().detach().data.cpu().numpy() for p in group["params"]] for group in self.param_groups]
+            chain.append((params, True))

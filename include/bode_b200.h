@@ -13,6 +13,9 @@
  * Layouts (row-major, leading index slowest):
  *   U      [P, m, 2]   whitened inducing values per particle      (gp.py:59  KernelRegression.U)
  *   logsn  [P, 2]      log noise std per particle                 (gp.py:60)
+ *          U/logsn and their gradients carry an explicit per-particle stride (in floats) so that they can
+ *          be column blocks of one resident theta[P, d] / grad[P, d] buffer (d = 2m+2): the samplers and
+ *          the SVGD interaction then work on the flat buffers without any packing copies.
  *   Z      [m, 2]      inducing locations, shared                 (gp.py:62)
  *   A      [m, m]      sf^2 * Kzz^-1 L, shared                    (gp.py:67,70-71; sf^2 folded in)
  *   Ksym   [m, m]      (Kzz^-1 + Kzz^-T)/2, shared                (prior term gp.py:350)
@@ -68,7 +71,8 @@ typedef struct bode_npde_field {
   const float* Z;       /* [m,2] */
   const float* A;       /* [m,m] */
   const float* Ksym;    /* [m,m]  (may be NULL when no prior term is requested) */
-  const float* U;       /* [P,m,2] */
+  const float* U;       /* [P,m,2], particle p at U + p*U_stride */
+  int64_t U_stride;     /* floats between consecutive particles (>= 2m) */
 } bode_npde_field;
 
 /* Solver grid, precomputed on the host exactly as FixedGridODESolver.integrate does
@@ -104,7 +108,7 @@ int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, int32_t metho
  * ADJOINT replaces OdeintAdjointMethod.backward (adjoint.py:23-102). */
 int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
                               int32_t N, const float* y0, int32_t y0_batched,
-                              const float* gout, float* gU, float* gy0,
+                              const float* gout, float* gU, int64_t gU_stride, float* gy0,
                               float* scratch, size_t scratch_floats, bode_stream_t stream);
 
 /* fused posterior closure + gradient: loss_closure (gp.py:342-353) followed by loss.backward()
@@ -115,9 +119,79 @@ int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int3
  * add_prior=0 drops the prior term from loss and gU (likelihood terms stay). */
 int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,
                        int32_t N, const float* y0, int32_t y0_batched,
-                       const float* Y, const float* logsn, float scale, int32_t add_prior,
-                       float* loss, float* sqerr, float* gU, float* glogsn,
+                       const float* Y, const float* logsn, int64_t logsn_stride, float scale, int32_t add_prior,
+                       float* loss, float* sqerr, float* gU, int64_t gU_stride, float* glogsn, int64_t glogsn_stride,
                        float* scratch, size_t scratch_floats, bode_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Fused SG-MCMC parameter updates on flat buffers of n floats (theta[P*d] etc., 16-byte aligned).
+ * xi (and xi_resample) are optional INJECTED standard-normal draws for bit-parity runs; when NULL the
+ * kernel draws from counter-based Philox4x32-10 keyed on (seed, step).  *status (device int, may be
+ * NULL) gets bit 0 set when a parameter is non-finite on entry (langevin.py:184-185 -> ValueError).
+ * ------------------------------------------------------------------------------------- */
+
+/* Optional DEVICE-resident control block: when non-NULL its fields override the scalar arguments of the same name,
+ * so a captured CUDA graph can be replayed while the lr schedule / step counter / phase flags change. */
+typedef struct bode_sampler_ctl {
+  float    lr;        /* langevin.py:205-210 get_lr(t); for bode_axpy: alpha */
+  uint32_t step;      /* Philox stream index */
+  int32_t  burn_in;   /* aSGHMC */
+  int32_t  resample;  /* aSGHMC */
+  uint32_t next_iter; /* global iteration index the next bode_sampler_schedule call will publish */
+  uint32_t pad[3];
+} bode_sampler_ctl;
+
+/* Device-side schedule: publishes iteration it = ctl->next_iter into the control block and advances it, so a captured
+ * graph replays with NO host input:   step = it ;  lr = kind==1 ? lr0 / (t0 + alpha it)^gamma (langevin.py:205-210) : lr0 ;
+ * burn_in = it < burn_in_iters ;  resample = !burn_in && resample_every > 0 && (it+1) % resample_every == 0 (hamiltonian.py:81-83). */
+int bode_sampler_schedule(bode_sampler_ctl* ctl, int32_t kind, double lr0, double gamma, double t0, double alpha,
+                          uint32_t burn_in_iters, uint32_t resample_every, bode_stream_t stream);
+
+/* SGLD.step, samplers/langevin.py:173-202:  p <- p - lr (g + xi / sqrt(lr/2)) */
+int bode_sgld_step(float* p, const float* g, const float* xi, int64_t n, float lr, int32_t add_noise,
+                   uint64_t seed, uint32_t step, int32_t* status, const bode_sampler_ctl* ctl, bode_stream_t stream);
+
+/* pSGLD.step, samplers/langevin.py:457-500:  V <- a V + (1-a) g^2 ; G = 1/(lambda + sqrt V) ;
+ * p <- p - lr (G g + sqrt(G) xi / sqrt(lr/2)) */
+int bode_psgld_step(float* p, const float* g, float* V, const float* xi, int64_t n, float lr, float alpha,
+                    float lambda, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
+                    const bode_sampler_ctl* ctl, bode_stream_t stream);
+
+/* aSGHMC.step, samplers/hamiltonian.py:38-99 (state init tau=gbar=vhat=1, mom=0 is the caller's, :55-60).
+ * burn_in: adapt tau/gbar/vhat (:73-77, tau_inv from the OLD tau :70); resample: momentum <- N(0, min(1/minv, 10))
+ * from xi_resample (:81-83; the `iteration % k == 0` test is evaluated by the host). */
+int bode_asghmc_step(float* p, const float* g, float* tau, float* gbar, float* vhat, float* mom, const float* xi,
+                     const float* xi_resample, int64_t n, float lr, float mom_decay, float lambda, int32_t burn_in,
+                     int32_t resample, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
+                     const bode_sampler_ctl* ctl, bode_stream_t stream);
+
+/* p <- p + alpha x   (the SVGD particle update: the optimiser wrapped by stein.py:37-106 descends -phi) */
+int bode_axpy(float* p, const float* x, float alpha, int64_t n, int32_t* status, const bode_sampler_ctl* ctl,
+              bode_stream_t stream);
+
+/* out[i] ~ N(0,1) from the same Philox stream the samplers use (testing / momentum initialisation) */
+int bode_fill_normal(float* out, int64_t n, uint64_t seed, uint32_t step, bode_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * SVGD interaction, samplers/stein.py:12-34 (RBFKernel with median heuristic) and :75-86 (phi), for the
+ * LOCAL rows of a particle-sharded job against all gathered particles (columns).  Call order per step:
+ *   bode_svgd_sqdist -> for pass in 0..2: bode_svgd_hist_pass, [all-reduce *hist_out over ranks], bode_svgd_select_digit
+ *   -> bode_svgd_gamma -> bode_svgd_phi.       Everything stays on `stream`; no host synchronisation.
+ * The median is the exact order statistic of the fp32 d2 values (mean of the two middle ones for an even count,
+ * like np.median, stein.py:25-26), chosen by an integer radix select.
+ * ------------------------------------------------------------------------------------- */
+size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t d);
+int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
+                     int32_t n_cols, int32_t d, uint64_t total_entries, void* workspace, size_t workspace_bytes,
+                     void** hist_out, bode_stream_t stream);
+int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
+int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
+int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
+                    float* med_gamma, bode_stream_t stream);
+int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
+                  const float* Scols, int64_t ld_sc, int32_t n_cols, int32_t d, int32_t n_total,
+                  const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
+                  int64_t ld_theta, float step, bode_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -167,9 +167,139 @@ def gen_grid_options(data):
     save("grid_options", **out)
 
 
+def _replay_noise(seed, shapes):
+    """The reference draws Normal(0, std).sample() / torch.normal(0, std) per parameter in order; under the same
+    seed these are std * torch.randn(shape) bit for bit -- verified below by reproducing the updates."""
+    torch.manual_seed(seed)
+    return [torch.randn(sh) for sh in shapes]
+
+
+def gen_sampler_steps(data):
+    """SGLD / pSGLD / aSGHMC: per-step (params, grads, noise) -> (params', state') sequences from the reference."""
+    from samplers.langevin import SGLD, pSGLD
+    from samplers.hamiltonian import aSGHMC
+    from oracle import samplers as osamp
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    x0, t = data["x0"], data["t"]
+    out = {}
+
+    gg = torch.Generator().manual_seed(4242)
+
+    def fresh():
+        kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+        return kreg, None
+
+    def record(name, sampler, kreg, cl, nsteps, step_fn, shapes_fn):
+        """Synthetic (seeded) gradients stand in for closure().backward(): the update rules under test do not care
+        where the gradient came from, and real npde gradients make aSGHMC's momentum resampling diverge."""
+        rec = {k: [] for k in ("U", "logsn", "gU", "glogsn", "U_new", "logsn_new", "lr")}
+        noises = []
+        for i in range(nsteps):
+            kreg.U.grad = 50.0 * torch.randn(25, 2, generator=gg)
+            kreg.logsn.grad = 5.0 * torch.randn(2, generator=gg)
+            rec["U"].append(kreg.U.data.clone()); rec["logsn"].append(kreg.logsn.data.clone())
+            rec["gU"].append(kreg.U.grad.clone()); rec["glogsn"].append(kreg.logsn.grad.clone())
+            torch.manual_seed(1000 + i)
+            lr = step_fn(i)
+            rec["lr"].append(torch.tensor(float(lr)))
+            rec["U_new"].append(kreg.U.data.clone()); rec["logsn_new"].append(kreg.logsn.data.clone())
+            noises.append(_replay_noise(1000 + i, shapes_fn(i)))
+        for k, v in rec.items():
+            out[f"{name}_{k}"] = torch.stack(v)
+        return noises
+
+    # ---- SGLD (gen_configs.py: lr0=1e-4, gamma .51, t0 100, alpha .03)
+    kreg, cl = fresh()
+    smp = SGLD([kreg.U, kreg.logsn], lr0=1e-4, lr_gamma=0.51, lr_t0=100, lr_alpha=0.03)
+    def sgld_step(i):
+        lr = smp.get_lr(i); smp.step(lr=lr); return lr
+    noises = record("sgld", smp, kreg, cl, 4, sgld_step, lambda i: [(25, 2), (2,)])
+    out["sgld_xiU"] = torch.stack([n[0] for n in noises]); out["sgld_xilogsn"] = torch.stack([n[1] for n in noises])
+    for i in range(4):   # pin the noise-replay assumption
+        for nm, k in (("U", 0), ("logsn", 1)):
+            ref = out[f"sgld_{nm}_new"][i].numpy()
+            mine = osamp.sgld_step(out[f"sgld_{nm}"][i].numpy(), out[f"sgld_g{nm}"][i].numpy(), float(out["sgld_lr"][i]), noises[i][k].numpy())
+            assert np.abs(ref - mine).max() < 1e-13, "noise replay mismatch (sgld)"
+
+    # ---- pSGLD (gp.py:372-373: alpha .99, lambda 1e-8, N=5)
+    kreg, cl = fresh()
+    smp2 = pSGLD([kreg.U, kreg.logsn], lr0=5e-3, lr_gamma=0.51, lr_t0=100, lr_alpha=0.1, lambda_=1e-8, alpha=0.99, N=5)
+    def psgld_step(i):
+        lr = smp2.get_lr(i); smp2.step(lr=lr); return lr
+    noises = record("psgld", smp2, kreg, cl, 4, psgld_step, lambda i: [(25, 2), (2,)])
+    out["psgld_xiU"] = torch.stack([n[0] for n in noises]); out["psgld_xilogsn"] = torch.stack([n[1] for n in noises])
+    out["psgld_VU_final"] = smp2.state[kreg.U]["V"].clone(); out["psgld_Vlogsn_final"] = smp2.state[kreg.logsn]["V"].clone()
+    V = {"U": np.zeros((25, 2)), "logsn": np.zeros(2)}
+    for i in range(4):
+        for nm, k in (("U", 0), ("logsn", 1)):
+            mine, V[nm] = osamp.psgld_step(out[f"psgld_{nm}"][i].numpy(), out[f"psgld_g{nm}"][i].numpy(), V[nm],
+                                           float(out["psgld_lr"][i]), 0.99, 1e-8, noises[i][k].numpy())
+            assert np.abs(out[f"psgld_{nm}_new"][i].numpy() - mine).max() < 1e-12, "noise replay mismatch (psgld)"
+    assert np.abs(V["U"] - out["psgld_VU_final"].numpy()).max() < 1e-12
+
+    # ---- aSGHMC: 3 burn-in steps, then 4 sampling steps with resample_mom_every=2 (iteration 4 and 6 resample)
+    kreg, cl = fresh()
+    smp3 = aSGHMC([kreg.U, kreg.logsn], lr=1e-2, mom_decay=5e-2, lambda_=1e-5)
+    burn, k_res = 3, 2
+    def asghmc_step(i):
+        smp3.step(lr=1e-2, burn_in=i < burn, resample_mom_every=k_res); return 1e-2
+    def shapes(i):
+        res = (i >= burn) and ((i + 1) % k_res == 0)
+        return ([(25, 2)] * (2 if res else 1)) + ([(2,)] * (2 if res else 1))
+    noises = record("asghmc", smp3, kreg, cl, 7, asghmc_step, shapes)
+    xiU, xiL, xrU, xrL = [], [], [], []
+    for i, n in enumerate(noises):
+        res = len(n) == 4
+        xrU.append(n[0] if res else torch.zeros(25, 2)); xiU.append(n[1] if res else n[0])
+        xrL.append(n[2] if res else torch.zeros(2)); xiL.append(n[3] if res else n[1])
+    out.update(asghmc_xiU=torch.stack(xiU), asghmc_xilogsn=torch.stack(xiL), asghmc_xrU=torch.stack(xrU),
+               asghmc_xrlogsn=torch.stack(xrL), asghmc_burn=burn, asghmc_resample_every=k_res)
+    for nm, pt in (("U", kreg.U), ("logsn", kreg.logsn)):
+        for k in ("tau", "g", "v_hat", "momentum"):
+            out[f"asghmc_{k}_{nm}_final"] = smp3.state[pt][k].clone()
+    st = {"U": osamp.asghmc_init(np.zeros((25, 2))), "logsn": osamp.asghmc_init(np.zeros(2))}
+    for i in range(7):
+        for nm in ("U", "logsn"):
+            mine, st[nm] = osamp.asghmc_step(out[f"asghmc_{nm}"][i].numpy(), out[f"asghmc_g{nm}"][i].numpy(), st[nm], 1e-2, 5e-2, 1e-5,
+                                             i < burn, k_res, out[f"asghmc_xi{nm}"][i].numpy(), out[f"asghmc_xr{nm}"][i].numpy())
+            assert np.abs(out[f"asghmc_{nm}_new"][i].numpy() - mine).max() < 1e-12, ("noise replay mismatch (asghmc)", i, nm)
+    save("sampler_steps", **out)
+
+
+def gen_svgd(data):
+    """RBFKernel (stein.py:12-34) run unmodified; phi (stein.py:75-86) restated with the reference kernel + autograd
+    because the reference's SVGD.phi/step reference undefined names."""
+    from samplers.stein import RBFKernel
+    from oracle import samplers as osamp
+    Zt, Yt, U0 = make_model(data, 5)
+    g = torch.Generator().manual_seed(99)
+    out = {}
+    for n in (64, 257):
+        X = torch.cat([U0.reshape(1, -1) + 0.1 * torch.randn(n, 50, generator=g),
+                       np.log(0.1) + 0.05 * torch.randn(n, 2, generator=g)], 1)
+        S = torch.randn(n, 52, generator=g) * 3.0                      # stand-in scores
+        Kmod = RBFKernel()
+        Xr = X.clone().requires_grad_(True)
+        K_XX = Kmod(Xr, Xr.detach())
+        grad_K = -torch.autograd.grad(K_XX.sum(), Xr)[0]
+        phi = (K_XX.detach().matmul(S) + grad_K) / X.size(0)
+        d2 = (torch.cdist(X, X) ** 2).numpy()
+        med = np.median(d2)
+        out.update({f"n{n}_X": X, f"n{n}_S": S, f"n{n}_K": K_XX.detach(), f"n{n}_phi": phi, f"n{n}_median": med})
+        Ko, gam = osamp.rbf_kernel(X.numpy(), X.numpy())
+        assert np.abs(Ko - K_XX.detach().numpy()).max() < 1e-10
+        assert np.abs(osamp.svgd_phi(X.numpy(), S.numpy()) - phi.numpy()).max() < 1e-10 * np.abs(phi.numpy()).max() + 1e-12
+        Kf = RBFKernel(sigma=0.7)(X, X)
+        out[f"n{n}_K_sigma07"] = Kf
+    save("svgd", **out)
+
+
 if __name__ == "__main__":
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
     gen_npde(data, 5, 4, "npde_m5")
     gen_npde(data, 3, 2, "npde_m3", methods=("rk4",))
     gen_grid_options(data)
+    gen_sampler_steps(data)
+    gen_svgd(data)

@@ -1,0 +1,58 @@
+"""CPU: oracle sampler updates / SVGD kernel+phi vs fixtures produced by the reference's samplers/ package."""
+import numpy as np
+
+from conftest import load_golden, relerr
+from oracle import samplers as osamp
+
+
+def test_lr_schedule_matches_reference():
+    g = load_golden("sampler_steps")
+    for i in range(4):
+        assert osamp.get_lr(i, 1e-4, 0.51, 100, 0.03) == float(g["sgld_lr"][i])
+        assert osamp.get_lr(i, 5e-3, 0.51, 100, 0.1) == float(g["psgld_lr"][i])
+
+
+def test_sgld_steps():
+    g = load_golden("sampler_steps")
+    for i in range(4):
+        for nm in ("U", "logsn"):
+            out = osamp.sgld_step(g[f"sgld_{nm}"][i], g[f"sgld_g{nm}"][i], float(g["sgld_lr"][i]), g[f"sgld_xi{nm}"][i])
+            assert relerr(out, g[f"sgld_{nm}_new"][i]) < 1e-13
+
+
+def test_psgld_steps():
+    g = load_golden("sampler_steps")
+    V = {"U": np.zeros((25, 2)), "logsn": np.zeros(2)}
+    for i in range(4):
+        for nm in ("U", "logsn"):
+            out, V[nm] = osamp.psgld_step(g[f"psgld_{nm}"][i], g[f"psgld_g{nm}"][i], V[nm], float(g["psgld_lr"][i]), 0.99, 1e-8,
+                                          g[f"psgld_xi{nm}"][i])
+            assert relerr(out, g[f"psgld_{nm}_new"][i]) < 1e-12
+    assert relerr(V["U"], g["psgld_VU_final"]) < 1e-13
+
+
+def test_asghmc_steps_incl_resample_and_stale_tau_inv():
+    g = load_golden("sampler_steps")
+    burn, k = int(g["asghmc_burn"]), int(g["asghmc_resample_every"])
+    st = {"U": osamp.asghmc_init(np.zeros((25, 2))), "logsn": osamp.asghmc_init(np.zeros(2))}
+    for i in range(7):
+        for nm in ("U", "logsn"):
+            out, st[nm] = osamp.asghmc_step(g[f"asghmc_{nm}"][i], g[f"asghmc_g{nm}"][i], st[nm], 1e-2, 5e-2, 1e-5, i < burn, k,
+                                            g[f"asghmc_xi{nm}"][i], g[f"asghmc_xr{nm}"][i])
+            assert relerr(out, g[f"asghmc_{nm}_new"][i]) < 1e-12
+    for key in ("tau", "g", "v_hat", "momentum"):
+        assert relerr(st["U"][key], g[f"asghmc_{key}_U_final"]) < 1e-12
+
+
+def test_rbf_kernel_and_phi():
+    g = load_golden("svgd")
+    for n in (64, 257):
+        X, S = g[f"n{n}_X"], g[f"n{n}_S"]
+        K, gam = osamp.rbf_kernel(X, X)
+        assert relerr(K, g[f"n{n}_K"]) < 1e-10
+        assert relerr(np.median(osamp.sq_dists(X, X)), g[f"n{n}_median"]) < 1e-10
+        assert relerr(osamp.svgd_phi(X, S), g[f"n{n}_phi"]) < 1e-9
+        Kf, _ = osamp.rbf_kernel(X, X, sigma=0.7)
+        assert relerr(Kf, g[f"n{n}_K_sigma07"]) < 1e-10
+        rows = np.arange(5, 20)
+        assert relerr(osamp.svgd_phi(X, S, rows=rows), g[f"n{n}_phi"][rows]) < 1e-9

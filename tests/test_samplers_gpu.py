@@ -1,0 +1,222 @@
+"""GPU: fused sampler updates and the SVGD interaction (through the C ABI) vs the reference goldens / the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-6          # fp32 elementwise update vs the float64 reference
+
+
+def _single_chain_field():
+    import bayesian_ode_b200 as bode
+    g = load_golden("npde_m5")
+    return bode.NPDEField(torch.from_numpy(g["U0"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+
+
+def _set(f, U, logsn):
+    f.U.data.copy_(torch.from_numpy(U).view_as(f.U))
+    f.logsn.data.copy_(torch.from_numpy(logsn).view_as(f.logsn))
+
+
+def _setgrad(f, gU, gl):
+    f.bind_flat_grads()
+    f.U.grad.copy_(torch.from_numpy(gU).view_as(f.U))
+    f.logsn.grad.copy_(torch.from_numpy(gl).view_as(f.logsn))
+
+
+def _noise(g, key, i):
+    return [torch.from_numpy(g[f"{key}U"][i])[None], torch.from_numpy(g[f"{key}logsn"][i])[None]]
+
+
+def test_sgld_matches_reference_steps():
+    from bayesian_ode_b200.samplers import SGLD
+    g = load_golden("sampler_steps")
+    f = _single_chain_field()
+    smp = SGLD([f.U, f.logsn], lr0=1e-4, lr_gamma=0.51, lr_t0=100, lr_alpha=0.03)
+    assert smp._flat is not None and smp._flat.shape == (1, 52)
+    _set(f, g["sgld_U"][0], g["sgld_logsn"][0])
+    for i in range(4):
+        _setgrad(f, g["sgld_gU"][i], g["sgld_glogsn"][i])
+        lr = smp.get_lr(i)
+        assert lr == float(g["sgld_lr"][i])                      # schedule is host float64: bit-exact
+        smp.step(lr=lr, noise=_noise(g, "sgld_xi", i))
+        assert relerr(f.U.data.cpu().numpy()[0], g["sgld_U_new"][i]) < TOL
+        assert relerr(f.logsn.data.cpu().numpy()[0], g["sgld_logsn_new"][i]) < TOL
+
+
+def test_psgld_matches_reference_steps():
+    from bayesian_ode_b200.samplers import pSGLD
+    g = load_golden("sampler_steps")
+    f = _single_chain_field()
+    smp = pSGLD([f.U, f.logsn], lr0=5e-3, lr_gamma=0.51, lr_t0=100, lr_alpha=0.1, lambda_=1e-8, alpha=0.99, N=5)
+    _set(f, g["psgld_U"][0], g["psgld_logsn"][0])
+    for i in range(4):
+        _setgrad(f, g["psgld_gU"][i], g["psgld_glogsn"][i])
+        smp.step(lr=smp.get_lr(i), noise=_noise(g, "psgld_xi", i))
+        assert relerr(f.U.data.cpu().numpy()[0], g["psgld_U_new"][i]) < 1e-5
+        assert relerr(f.logsn.data.cpu().numpy()[0], g["psgld_logsn_new"][i]) < 1e-5
+    V = list(smp._V.values())[0].cpu().numpy()[0]
+    assert relerr(V[:50].reshape(25, 2), g["psgld_VU_final"]) < 1e-5
+
+
+def test_asghmc_matches_reference_steps():
+    from bayesian_ode_b200.samplers import aSGHMC
+    g = load_golden("sampler_steps")
+    burn, k = int(g["asghmc_burn"]), int(g["asghmc_resample_every"])
+    f = _single_chain_field()
+    smp = aSGHMC([f.U, f.logsn], lr=1e-2, mom_decay=5e-2, lambda_=1e-5)
+    _set(f, g["asghmc_U"][0], g["asghmc_logsn"][0])
+    for i in range(7):
+        _setgrad(f, g["asghmc_gU"][i], g["asghmc_glogsn"][i])
+        smp.step(lr=1e-2, burn_in=i < burn, resample_mom_every=k, noise=_noise(g, "asghmc_xi", i),
+                 noise_resample=_noise(g, "asghmc_xr", i))
+        assert relerr(f.U.data.cpu().numpy()[0], g["asghmc_U_new"][i]) < 1e-5, i
+        assert relerr(f.logsn.data.cpu().numpy()[0], g["asghmc_logsn_new"][i]) < 1e-5, i
+    st = list(smp._st.values())[0]
+    for key in ("tau", "g", "v_hat", "momentum"):
+        assert relerr(st[key].cpu().numpy()[0][:50].reshape(25, 2), g[f"asghmc_{key}_U_final"]) < 1e-5, key
+
+
+def test_non_flat_tensors_and_scalar_tail():
+    """Parameters that are NOT column blocks of one buffer take one launch per tensor; logsn (2 elements) exercises
+    the scalar tail of the vectorised kernel."""
+    from bayesian_ode_b200.samplers import SGLD
+    from oracle import samplers as osamp
+    rng = np.random.default_rng(3)
+    a = torch.nn.Parameter(torch.from_numpy(rng.standard_normal((7, 3))).float().cuda())
+    b = torch.nn.Parameter(torch.from_numpy(rng.standard_normal(2)).float().cuda())
+    smp = SGLD([a, b], lr0=1e-2, lr_gamma=0.5, lr_t0=1, lr_alpha=1)
+    assert smp._flat is None
+    ga, gb = rng.standard_normal((7, 3)), rng.standard_normal(2)
+    xa, xb = rng.standard_normal((7, 3)), rng.standard_normal(2)
+    a.grad, b.grad = torch.from_numpy(ga).float().cuda(), torch.from_numpy(gb).float().cuda()
+    a0, b0 = a.data.cpu().numpy().astype(np.float64), b.data.cpu().numpy().astype(np.float64)
+    smp.step(lr=0.01, noise=[torch.from_numpy(xa), torch.from_numpy(xb)])
+    assert relerr(a.data.cpu().numpy(), osamp.sgld_step(a0, ga, 0.01, xa)) < TOL
+    assert relerr(b.data.cpu().numpy(), osamp.sgld_step(b0, gb, 0.01, xb)) < TOL
+
+
+def test_nan_parameter_raises_like_reference():
+    from bayesian_ode_b200.samplers import SGLD
+    f = _single_chain_field()
+    smp = SGLD([f.U, f.logsn], lr0=1e-4, lr_gamma=0.51, lr_t0=100, lr_alpha=0.03)
+    f.bind_flat_grads()
+    f.U.data[0, 3, 1] = float("nan")
+    with pytest.raises(ValueError):                    # langevin.py:184-185
+        smp.step(lr=1e-4)
+
+
+def test_philox_normals_are_normal_and_counter_based():
+    import bayesian_ode_b200 as bode
+    lib = bode._lib.load()
+    n = 1 << 20
+    out = torch.empty(n, device="cuda")
+    st = bode._lib.stream_ptr()
+    bode._lib.check(lib.bode_fill_normal(bode._lib.ptr(out), n, 1234, 0, st))
+    x = out.double().cpu().numpy()
+    assert abs(x.mean()) < 5e-3 and abs(x.var() - 1) < 5e-3
+    assert abs((x ** 4).mean() - 3) < 0.05 and abs((x ** 3).mean()) < 0.02
+    out2 = torch.empty(n, device="cuda")
+    bode._lib.check(lib.bode_fill_normal(bode._lib.ptr(out2), n, 1234, 0, st))
+    assert torch.equal(out, out2)                       # same (seed, step) -> same stream
+    bode._lib.check(lib.bode_fill_normal(bode._lib.ptr(out2), n, 1234, 1, st))
+    assert abs(float((out * out2).mean())) < 5e-3       # different step -> independent stream
+    # in-kernel noise in SGLD: after one step with g = 0 the displacement is sqrt(2 lr) * N(0,1)
+    p = torch.zeros(n, device="cuda"); g = torch.zeros(n, device="cuda")
+    bode._lib.check(lib.bode_sgld_step(bode._lib.ptr(p), bode._lib.ptr(g), None, n, 1e-2, 1, 7, 0, None, None, st))
+    assert abs(float(p.var()) / (2 * 1e-2) - 1) < 1e-2
+
+
+@pytest.mark.parametrize("n", [64, 257])
+def test_rbf_kernel_matches_reference(n):
+    from bayesian_ode_b200.samplers import RBFKernel
+    g = load_golden("svgd")
+    X = torch.from_numpy(g[f"n{n}_X"]).float().cuda()
+    ker = RBFKernel()
+    K = ker(X, X)
+    assert relerr(K.cpu().numpy(), g[f"n{n}_K"]) < 1e-5
+    assert relerr(float(ker.last_median), g[f"n{n}_median"]) < 1e-5
+    Kf = RBFKernel(sigma=0.7)(X, X)
+    assert relerr(Kf.cpu().numpy(), g[f"n{n}_K_sigma07"]) < 1e-5
+
+
+@pytest.mark.parametrize("n", [64, 257])
+def test_svgd_phi_matches_reference(n):
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import SVGD
+    g = load_golden("svgd")
+    X, S = g[f"n{n}_X"], g[f"n{n}_S"]
+    f = bode.NPDEField(torch.from_numpy(X[:, :50].reshape(n, 25, 2)), torch.from_numpy(load_golden("npde_m5")["Z"]), 1.0, 0.75, 0.1)
+    f.logsn.data.copy_(torch.from_numpy(X[:, 50:]))
+    smp = SVGD([f.U, f.logsn], lr=1e-4)
+    f.bind_flat_grads().copy_(torch.from_numpy(-S))               # grad of the loss = -score
+    phi = smp.phi().clone()
+    assert relerr(phi.cpu().numpy(), g[f"n{n}_phi"]) < 1e-4
+    th0 = f.theta.clone()
+    smp.step()                                                    # theta += lr * phi  (descends -phi)
+    assert relerr((f.theta - th0).cpu().numpy(), 1e-4 * g[f"n{n}_phi"]) < 1e-3
+
+
+def test_median_selection_is_bit_exact_at_full_size():
+    """P = 4096 (BASELINE config 3): the selected order statistics equal np.median of the very d2 matrix the kernel
+    produced, bit for bit (even count -> mean of the two middle values); phi rows agree with the float64 oracle."""
+    from bayesian_ode_b200.samplers.stein import _Workspace
+    from oracle import samplers as osamp
+    g = load_golden("npde_m5")
+    rng = np.random.default_rng(5)
+    n, d = 4096, 52
+    X = np.concatenate([g["U0"].reshape(1, -1) + 0.1 * rng.standard_normal((n, 50)),
+                        np.log(0.1) + 0.05 * rng.standard_normal((n, 2))], 1)
+    S = 3.0 * rng.standard_normal((n, d))
+    Xd = torch.from_numpy(X).float().cuda()
+    ws = _Workspace(n, n, d, Xd.device)
+    ws.sqdist(Xd, n, Xd, n, d, n * n)
+    ws.median(n, n, d, n)
+    d2 = ws.d2(n, n).cpu().numpy()
+    med = float(ws.med_gamma[0])
+    assert np.float32(med) == np.median(d2)                       # bit-exact selection
+    assert abs(med - np.median(osamp.sq_dists(X[:512], X[:512]))) / med < 0.05    # sanity vs float64 on a subsample
+    assert np.array_equal(d2, d2.T) and np.all(np.diag(d2) == 0)
+    gam64 = 1.0 / (1e-8 + 2 * (np.median(d2.astype(np.float64)) / (2 * np.log(n + 1))))
+    assert abs(float(ws.med_gamma[1]) - gam64) / gam64 < 1e-6
+    # odd count (n*n odd): single middle element
+    n2 = 255
+    X2 = Xd[:n2].contiguous()
+    ws2 = _Workspace(n2, n2, d, Xd.device)
+    ws2.sqdist(X2, n2, X2, n2, d, n2 * n2)
+    ws2.median(n2, n2, d, n2)
+    assert np.float32(float(ws2.med_gamma[0])) == np.median(ws2.d2(n2, n2).cpu().numpy())
+    # phi on a row subset vs the oracle using the kernel's own gamma
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import SVGD
+    f = bode.NPDEField(torch.from_numpy(X[:, :50].reshape(n, 25, 2)), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    f.logsn.data.copy_(torch.from_numpy(X[:, 50:]))
+    smp = SVGD([f.U, f.logsn])
+    f.bind_flat_grads().copy_(torch.from_numpy(-S))
+    phi = smp.phi().cpu().numpy()
+    rows = np.concatenate([np.arange(4), rng.choice(n, 28, replace=False)])
+    Xf = f.theta.cpu().numpy().astype(np.float64)
+    ref = osamp.svgd_phi(Xf, S.astype(np.float32).astype(np.float64), rows=rows, gamma=float(smp._ws.med_gamma[1]))
+    assert relerr(phi[rows], ref) < 1e-4
+
+
+def test_sample_loop_fused_and_protocol_paths_agree():
+    """SGLD.sample() drives NPDEPosterior through the fused path; the autograd closure protocol gives the same chain
+    when the same noise stream is used (in-kernel Philox is a pure function of (seed, step, element))."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import SGLD
+    g = load_golden("npde_m5")
+    chains = []
+    for fused in (True, False):
+        f = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+        post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]))
+        smp = SGLD([f.U, f.logsn], lr0=1e-4, lr_gamma=0.51, lr_t0=100, lr_alpha=0.03, seed=11)
+        closure = post if fused else (lambda add_prior=True, post=post: post(add_prior))
+        chain = smp.sample(closure, num_samples=3, burn_in=2)
+        assert len(chain) == 3
+        params, accepted = chain[-1]
+        assert accepted is True and params[0][0].shape == (4, 25, 2) and params[0][1].shape == (4, 2)
+        chains.append(np.concatenate([params[0][0].reshape(4, -1), params[0][1]], 1))
+    assert relerr(chains[0], chains[1]) < 1e-6
