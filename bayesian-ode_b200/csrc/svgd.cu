@@ -156,7 +156,7 @@ template <int CPT>          // features per thread; CG*CPT >= 2d
 __global__ void __launch_bounds__(128) phi_partial_kernel(const float* __restrict__ D2, int nr, int nc,
                                                           const float* __restrict__ Xc, long long ldx,
                                                           const float* __restrict__ Sc, long long lds, int d,
-                                                          const float* __restrict__ gam, int jsplit,
+                                                          const float* __restrict__ gam, int jsplit, float ssign,
                                                           float* __restrict__ part, float* __restrict__ rsum) {
   extern __shared__ float sm[];
   const int F = CG * CPT;                        // padded feature count (S then X)
@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(128) phi_partial_kernel(const float* __restric
       const int j = idx / F, c = idx - j * F;
       float v = 0.f;
       if (j0 + j < jend) {
-        if (c < d) v = __ldg(Sc + (long long)(j0 + j) * lds + c);
+        if (c < d) v = ssign * __ldg(Sc + (long long)(j0 + j) * lds + c);
         else if (c < 2 * d) v = __ldg(Xc + (long long)(j0 + j) * ldx + (c - d));
       }
       Vs[idx] = v;
@@ -325,10 +325,11 @@ extern "C" int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int
   return check_cuda(cudaGetLastError(), "gamma launch");
 }
 
-/* phi for the local rows (uses d2 left in the workspace by bode_svgd_sqdist).  phi may be NULL; when theta != NULL the
+/* phi for the local rows (uses d2 left in the workspace by bode_svgd_sqdist).  Scols holds score_sign * score, so the
+ * gradient of the negative log posterior can be passed as is with score_sign = -1 (score = -grad loss).  phi may be NULL; when theta != NULL the
  * update theta_i += step * phi_i is fused (the wrapped optimiser of stein.py descends -phi with lr = step). */
 extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
-                             const float* Scols, int64_t ld_sc, int32_t n_cols, int32_t d, int32_t n_total,
+                             const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
                              const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                              int64_t ld_theta, float step, bode_stream_t stream) {
   BODE_REQUIRE(Xrows && Xcols && Scols && med_gamma && workspace, "null pointer");
@@ -342,7 +343,7 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
   {                                                                                                              \
     const size_t smem = ((size_t)PR * (PJ + 1) + (size_t)PJ * CG * C) * sizeof(float);                           \
     if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(phi_partial_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    phi_partial_kernel<C><<<grid, 128, smem, st>>>(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, med_gamma, jsplit, w.part, w.rsum); \
+    phi_partial_kernel<C><<<grid, 128, smem, st>>>(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, med_gamma, jsplit, score_sign, w.part, w.rsum); \
   }
   if (cpt <= 4) BODE_PHI(4)
   else if (cpt <= 8) BODE_PHI(8)

@@ -106,8 +106,7 @@ class SVGD(Sampler):
         self._ws = _Workspace(self.P_local, self.n_total, self.d, dev)
         self.phi_buf = torch.empty_like(self._flat)
         if self.world > 1:
-            self._send = torch.empty(self.P_local, 2 * self.d, dtype=torch.float32, device=dev)
-            self._gath = torch.empty(self.n_total, 2 * self.d, dtype=torch.float32, device=dev)
+            self._gath = torch.empty(2, self.n_total, self.d, dtype=torch.float32, device=dev)
 
     def phi(self, X=None, grad=None, update_lr=None):
         """stein.py:75-86 for the local rows.  Returns phi [P_local, d]; with ``update_lr`` the update is fused."""
@@ -118,26 +117,20 @@ class SVGD(Sampler):
             raise _lib.BodeError("SVGD.phi: gradients missing (call closure + backward, or pass grad=)")
         d, nl, nt = self.d, self.P_local, self.n_total
         if self.world > 1:
-            self._send[:, :d].copy_(X)
-            torch.neg(G, out=self._send[:, d:])
-            torch.distributed.all_gather_into_tensor(self._gath, self._send)
-            Xall, Sall = self._gath[:, :d], self._gath[:, d:]
+            # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
+            torch.distributed.all_gather_into_tensor(self._gath[0], X)
+            torch.distributed.all_gather_into_tensor(self._gath[1], G)
+            Xall, Gall = self._gath[0], self._gath[1]
         else:
-            Xall, Sall = X, None
+            Xall, Gall = X, G
         ws = self._ws
         ws.sqdist(X, nl, Xall, nt, d, nt * nt)
         ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
-        if Sall is None:
-            # single rank: scores are -grad; fold the sign into a scratch copy (one tiny elementwise op)
-            if not hasattr(self, "_score"):
-                self._score = torch.empty_like(X)
-            torch.neg(G, out=self._score)
-            Sall = self._score
         xr, xrs = _lib.rows(X, d)
         xc, xcs = _lib.rows(Xall, d)
-        sc, scs = _lib.rows(Sall, d)
+        sc, scs = _lib.rows(Gall, d)
         th = (xr, xrs) if update_lr is not None else (None, 0)
-        _lib.check(lib.bode_svgd_phi(xr, xrs, nl, xc, xcs, sc, scs, nt, d, nt, _lib.ptr(ws.med_gamma),
+        _lib.check(lib.bode_svgd_phi(xr, xrs, nl, xc, xcs, sc, scs, -1.0, nt, d, nt, _lib.ptr(ws.med_gamma),
                                      C.c_void_p(ws.base.data_ptr()), _lib.ptr(self.phi_buf), d, th[0], th[1],
                                      float(update_lr or 0.0), _lib.stream_ptr()))
         return self.phi_buf

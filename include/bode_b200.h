@@ -55,6 +55,10 @@ const char* bode_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int bode_device_sm_count(void);
 
+/* Measurement aid: register-resident chains for the non-tensor fp32 FMA peak (kind 0: 32*iters flop per thread)
+ * and the MUFU.EX2 peak (kind 1: 8*iters ex2 per thread); `ctas` CTAs of 256 threads.  Timed by the caller. */
+int bode_peak_kernel(int32_t kind, int32_t ctas, int32_t iters, float* scratch, bode_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * npde field description: KernelRegression (gp.py:56-71) for P particles sharing Z/sf/ell.
  * If the inducing points form a tensor grid (gp.py:315-318 always builds one) set
@@ -188,8 +192,9 @@ int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d,
 int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
                     float* med_gamma, bode_stream_t stream);
+/* Scols = score_sign * (grad log p): pass the loss gradient as is with score_sign = -1. */
 int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
-                  const float* Scols, int64_t ld_sc, int32_t n_cols, int32_t d, int32_t n_total,
+                  const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
                   const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                   int64_t ld_theta, float step, bode_stream_t stream);
 
