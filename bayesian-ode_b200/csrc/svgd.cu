@@ -20,7 +20,7 @@ constexpr int TS = 64;   // tile of 64 x 64 pairs per CTA, 4 x 4 per thread
 
 __global__ void __launch_bounds__(256) sqdist_kernel(const float* __restrict__ Xr, long long ldr, int nr,
                                                      const float* __restrict__ Xc, long long ldc, int nc, int d,
-                                                     float* __restrict__ D2) {
+                                                     float* __restrict__ D2, unsigned int* __restrict__ maxbits) {
   extern __shared__ float sm[];
   const int ldk = d | 1;                         // odd row pitch: conflict-free column reads
   float* A = sm;                                 // [TS][ldk] rows
@@ -50,22 +50,74 @@ __global__ void __launch_bounds__(256) sqdist_kernel(const float* __restrict__ X
       const int r = r0 + ty + 16 * u, c = c0 + tx + 16 * v;
       if (r < nr && c < nc) D2[(long long)r * nc + c] = acc[u][v];
     }
+  // largest d2 of the job (non-negative floats order like their bit patterns): positions the hot window of pass 0
+  float mx = 0.f;
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) mx = fmaxf(mx, acc[u][v]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(maxbits, __float_as_uint(mx));
 }
 
 // ---------------------------------------------------------------- exact median by radix select
 // state[0..1] = prefix bits of order statistics A, B ; state[2..3] (as 64-bit pairs) = remaining ranks
-struct SelState { unsigned int prefix[2]; unsigned int pad[2]; unsigned long long rank[2]; };
+struct SelState { unsigned int prefix[2]; unsigned int maxbits; unsigned int pad; unsigned long long rank[2]; };
 
 __global__ void select_init_kernel(SelState* st, unsigned long long* hist, unsigned long long total) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->prefix[0] = st->prefix[1] = 0u;
+    st->maxbits = 0u;
     st->rank[0] = (total - 1) / 2;             // lower middle (0-based, ascending)
     st->rank[1] = total / 2;                   // upper middle; equal to rank[0] when total is odd
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 2048; i += gridDim.x * blockDim.x) hist[i] = 0ull;
 }
 
-// pass over bits [shift, shift+nbits): histogram of elements whose higher bits equal the running prefix
+// Pass 0 (top 11 bits, every element participates): d2 values cluster in a few dozen exponent/mantissa buckets just
+// below the maximum, so plain shared atomics serialise.  The HOT buckets [top-HOTB+1, top] get one counter PER LANE
+// (column = lane id -> bank = lane: conflict-free within a warp); anything below the window takes the ordinary path.
+constexpr int HOTB = 64;
+
+__global__ void __launch_bounds__(512) hist0_kernel(const float* __restrict__ D2, long long n, const SelState* __restrict__ st,
+                                                    unsigned long long* __restrict__ hist) {
+  __shared__ unsigned int hot[HOTB][32];
+  __shared__ unsigned int cold[2048];
+  for (int i = threadIdx.x; i < HOTB * 32; i += blockDim.x) (&hot[0][0])[i] = 0u;
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) cold[i] = 0u;
+  __syncthreads();
+  const int top = (int)(st->maxbits >> 20), base = top - (HOTB - 1);
+  const int lane = threadIdx.x & 31;
+  const long long n4 = n >> 2;
+  const uint4* D4 = reinterpret_cast<const uint4*>(D2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(D4 + i);
+    const unsigned int v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int dig = (int)(v[u] >> 20), h = dig - base;
+      if (h >= 0 && h < HOTB) atomicAdd(&hot[h][lane], 1u);
+      else atomicAdd(&cold[dig & 2047], 1u);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - (n4 << 2))) {          // scalar tail
+    const int dig = (int)(__float_as_uint(__ldg(D2 + (n4 << 2) + threadIdx.x)) >> 20);
+    atomicAdd(&cold[dig & 2047], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2048; i += blockDim.x) {
+    unsigned int c = cold[i];
+    const int h = i - base;
+    if (h >= 0 && h < HOTB) {
+#pragma unroll 8
+      for (int l = 0; l < 32; ++l) c += hot[h][l];
+    }
+    if (c) atomicAdd(hist + i, (unsigned long long)c);
+  }
+}
+
+// Passes 1, 2 over bits [shift, shift+nbits): histogram of the (few) elements whose higher bits equal a running prefix
 __global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ D2, long long n, const SelState* __restrict__ st,
                                                    int shift, int nbits, unsigned int himask, unsigned long long* __restrict__ hist) {
   __shared__ unsigned int sh[2][2048];
@@ -76,28 +128,21 @@ __global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ D2,
   const unsigned int dmask = (1u << nbits) - 1u;
   const long long n4 = n >> 2;
   const uint4* D4 = reinterpret_cast<const uint4*>(D2);
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4 + 3; i += (long long)gridDim.x * blockDim.x) {
-    unsigned int v[4];
-    int cnt = 4;
-    if (i < n4) {
-      const uint4 q = __ldg(D4 + i);
-      v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
-    } else {
-      const long long e = (n4 << 2) + (i - n4);        // scalar tail elements
-      cnt = e < n ? 1 : 0;
-      if (cnt) v[0] = __float_as_uint(__ldg(D2 + e));
-    }
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(D4 + i);
+    const unsigned int v[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      if (u >= cnt) break;
       const unsigned int hi = v[u] & himask, dig = (v[u] >> shift) & dmask;
-      const int sel = hi == pa ? 0 : ((two && hi == pb) ? 1 : -1);
-      // warp-aggregate equal (histogram, digit) keys: d2 values cluster in a handful of top-bit buckets
-      const unsigned int key = sel < 0 ? 0xffffffffu : ((unsigned)sel << 16 | dig);
-      const unsigned int act = __activemask();
-      const unsigned int peers = __match_any_sync(act, key);
-      if (sel >= 0 && (int)(__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(&sh[sel][dig], __popc(peers));
+      if (hi == pa) atomicAdd(&sh[0][dig], 1u);
+      else if (two && hi == pb) atomicAdd(&sh[1][dig], 1u);
     }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - (n4 << 2))) {          // scalar tail
+    const unsigned int v = __float_as_uint(__ldg(D2 + (n4 << 2) + threadIdx.x));
+    const unsigned int hi = v & himask, dig = (v >> shift) & dmask;
+    if (hi == pa) atomicAdd(&sh[0][dig], 1u);
+    else if (two && hi == pb) atomicAdd(&sh[1][dig], 1u);
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
@@ -106,27 +151,43 @@ __global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ D2,
   }
 }
 
-// one CTA: pick the digit holding each remaining rank, extend the prefixes, clear the histograms
+// one CTA of 1024 threads: pick the digit holding each remaining rank (block-wide exclusive scan of the 2048 counts),
+// extend the prefixes, clear the histograms
 __global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsigned long long* hist, int shift, int nbits) {
-  __shared__ unsigned long long cum[2048];
+  __shared__ unsigned long long wsum[32];
   __shared__ unsigned int newp[2];
   __shared__ unsigned long long newr[2];
   const int nb = 1 << nbits;
   const bool two = st->prefix[0] != st->prefix[1];
+  const unsigned long long rank0 = st->rank[0], rank1 = st->rank[1];
+  const unsigned int pre0 = st->prefix[0], pre1 = st->prefix[1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   for (int which = 0; which < 2; ++which) {
     const unsigned long long* h = hist + ((which == 1 && two) ? 2048 : 0);
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) cum[i] = h[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {                     // 2048-entry serial scan: negligible next to the passes
-      unsigned long long run = 0, r = st->rank[which];
-      int dsel = nb - 1;
-      for (int i = 0; i < nb; ++i) {
-        if (r < run + cum[i]) { dsel = i; break; }
-        run += cum[i];
-      }
-      newp[which] = st->prefix[which] | ((unsigned)dsel << shift);
-      newr[which] = r - run;
+    const unsigned long long r = which ? rank1 : rank0;
+    const int i0 = 2 * threadIdx.x;
+    const unsigned long long c0 = i0 < nb ? h[i0] : 0ull, c1 = i0 + 1 < nb ? h[i0 + 1] : 0ull;
+    unsigned long long incl = c0 + c1;                          // inclusive scan over threads
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[lane] = w;                                           // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long excl = incl - (c0 + c1) + (wid ? wsum[wid - 1] : 0ull);   // count below bin i0
+    if (r >= excl && r < excl + c0) { newp[which] = (which ? pre1 : pre0) | ((unsigned)i0 << shift); newr[which] = r - excl; }
+    else if (r >= excl + c0 && r < excl + c0 + c1) { newp[which] = (which ? pre1 : pre0) | ((unsigned)(i0 + 1) << shift); newr[which] = r - excl - c0; }
     __syncthreads();
   }
   if (threadIdx.x == 0) {
@@ -147,74 +208,87 @@ __global__ void gamma_kernel(const SelState* st, int n, float sigma_fixed, float
   out[1] = (float)(1.0 / (1e-8 + 2.0 * s2));
 }
 
-// ---------------------------------------------------------------- phi partials: K[rows, jslice] @ [S | X], row sums
-constexpr int PR = 32;      // rows per CTA
-constexpr int PJ = 64;      // columns per smem stage
-constexpr int CG = 8;       // column groups (threads along the feature axis)
+// ---------------------------------------------------------------- phi partials: K[rows, jslice] @ [S | X | 1]
+// CTA = 64 rows x F features (F = 16*FT >= 2d+1; the trailing ones column yields the row sums), 128 threads, each an
+// 8 x FT register tile; per j the thread issues 2 LDS.128 (8 kernel values) + FT LDS for 8*FT FFMA.
+constexpr int PR = 64;      // rows per CTA
+constexpr int PJ = 32;      // columns per smem stage
+constexpr int KP = PR + 4;  // pitch of the transposed kernel tile (16-byte aligned rows)
+constexpr int MAXSPLIT = 16;
 
-template <int CPT>          // features per thread; CG*CPT >= 2d
-__global__ void __launch_bounds__(128) phi_partial_kernel(const float* __restrict__ D2, int nr, int nc,
+template <int FT>
+__global__ void __launch_bounds__(128, 3) phi_partial_kernel(const float* __restrict__ D2, int nr, int nc,
                                                           const float* __restrict__ Xc, long long ldx,
                                                           const float* __restrict__ Sc, long long lds, int d,
                                                           const float* __restrict__ gam, int jsplit, float ssign,
-                                                          float* __restrict__ part, float* __restrict__ rsum) {
-  extern __shared__ float sm[];
-  const int F = CG * CPT;                        // padded feature count (S then X)
-  float* Ks = sm;                                // [PR][PJ+1]
-  float* Vs = sm + PR * (PJ + 1);                // [PJ][F]
+                                                          float* __restrict__ part) {
+  extern __shared__ __align__(16) float sm[];
+  constexpr int F = 16 * FT;
+  float* Ks = sm;                                // [PJ][KP]   K^T tile
+  float* Vs = sm + PJ * KP;                      // [PJ][F]    [sign*G | X | 1 | 0..]
   const float ngamma = -gam[1] * 1.4426950408889634f;
   const int r0 = blockIdx.x * PR;
   const int jper = ((nc + jsplit - 1) / jsplit + PJ - 1) / PJ * PJ;
   const int jbeg = blockIdx.y * jper, jend = min(nc, jbeg + jper);
-  const int cg = threadIdx.x % CG, rg = threadIdx.x / CG;     // 16 row groups x 2 rows
-  float acc[2][CPT] = {};
-  float rs[2] = {0.f, 0.f};
+  const int fg = threadIdx.x & 15, rg = threadIdx.x >> 4;
+  float acc[8][FT] = {};
   for (int j0 = jbeg; j0 < jend; j0 += PJ) {
-    for (int idx = threadIdx.x; idx < PR * PJ; idx += blockDim.x) {
-      const int i = idx / PJ, j = idx - i * PJ;
-      float k = 0.f;
-      if (r0 + i < nr && j0 + j < jend) k = ex2(ngamma * __ldg(D2 + (long long)(r0 + i) * nc + j0 + j));
-      Ks[i * (PJ + 1) + j] = k;
+    // all global loads of the stage are issued before the first use (fixed trip counts, fully unrolled)
+    float kreg[PR * PJ / 128], vreg[4 * FT];
+#pragma unroll
+    for (int q = 0; q < PR * PJ / 128; ++q) {
+      const int idx = threadIdx.x + 128 * q, i = idx / PJ, j = idx - i * PJ;
+      kreg[q] = (r0 + i < nr && j0 + j < jend) ? __ldg(D2 + (long long)(r0 + i) * nc + j0 + j) : INFINITY;
     }
-    for (int idx = threadIdx.x; idx < PJ * F; idx += blockDim.x) {
-      const int j = idx / F, c = idx - j * F;
+#pragma unroll
+    for (int q = 0; q < 4 * FT; ++q) {
+      const int idx = threadIdx.x + 128 * q, j = idx / F, c = idx - j * F;
       float v = 0.f;
       if (j0 + j < jend) {
         if (c < d) v = ssign * __ldg(Sc + (long long)(j0 + j) * lds + c);
         else if (c < 2 * d) v = __ldg(Xc + (long long)(j0 + j) * ldx + (c - d));
+        else if (c == 2 * d) v = 1.f;
       }
-      Vs[idx] = v;
+      vreg[q] = v;
     }
-    __syncthreads();
-#pragma unroll 4
-    for (int j = 0; j < PJ; ++j) {
-      const float k0 = Ks[(2 * rg) * (PJ + 1) + j], k1 = Ks[(2 * rg + 1) * (PJ + 1) + j];
-      rs[0] += k0; rs[1] += k1;
-      const float* v = Vs + j * F + cg * CPT;
 #pragma unroll
-      for (int c = 0; c < CPT; ++c) {
-        acc[0][c] = fmaf(k0, v[c], acc[0][c]);
-        acc[1][c] = fmaf(k1, v[c], acc[1][c]);
-      }
+    for (int q = 0; q < PR * PJ / 128; ++q) {
+      const int idx = threadIdx.x + 128 * q, i = idx / PJ, j = idx - i * PJ;
+      Ks[j * KP + i] = ex2(ngamma * kreg[q]);                 // 2^(-inf) = 0 for out-of-range pairs
+    }
+#pragma unroll
+    for (int q = 0; q < 4 * FT; ++q) Vs[threadIdx.x + 128 * q] = vreg[q];
+    __syncthreads();
+#pragma unroll 2
+    for (int j = 0; j < PJ; ++j) {
+      const float4 ka = *reinterpret_cast<const float4*>(Ks + j * KP + 8 * rg);
+      const float4 kb = *reinterpret_cast<const float4*>(Ks + j * KP + 8 * rg + 4);
+      const float k[8] = {ka.x, ka.y, ka.z, ka.w, kb.x, kb.y, kb.z, kb.w};
+      float v[FT];
+#pragma unroll
+      for (int c = 0; c < FT; ++c) v[c] = Vs[j * F + fg * FT + c];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int c = 0; c < FT; ++c) acc[u][c] = fmaf(k[u], v[c], acc[u][c]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int u = 0; u < 2; ++u) {
-    const int r = r0 + 2 * rg + u;
+  for (int u = 0; u < 8; ++u) {
+    const int r = r0 + 8 * rg + u;
     if (r >= nr) continue;
-    float* dst = part + ((long long)blockIdx.y * nr + r) * (2 * d);
+    float* dst = part + ((long long)blockIdx.y * nr + r) * (2 * d + 1);
 #pragma unroll
-    for (int c = 0; c < CPT; ++c) {
-      const int f = cg * CPT + c;
-      if (f < 2 * d) dst[f] = acc[u][c];
+    for (int c = 0; c < FT; ++c) {
+      const int f = fg * FT + c;
+      if (f <= 2 * d) dst[f] = acc[u][c];
     }
-    if (cg == 0) rsum[(long long)blockIdx.y * nr + r] = rs[u];
   }
 }
 
 // phi = (KS + 2 gamma (rowsum * x_i - KX)) / n ; optional fused update theta_i += step * phi_i
-__global__ void phi_combine_kernel(const float* __restrict__ part, const float* __restrict__ rsum, int jsplit, int nr, int d,
+__global__ void phi_combine_kernel(const float* __restrict__ part, int jsplit, int nr, int d,
                                    const float* __restrict__ Xr, long long ldr, const float* __restrict__ gam, float inv_n,
                                    float* __restrict__ phi, long long ldp, float* __restrict__ theta, long long ldt, float step) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,10 +296,10 @@ __global__ void phi_combine_kernel(const float* __restrict__ part, const float* 
   const int r = (int)(idx / d), c = (int)(idx - (long long)r * d);
   float ks = 0.f, kx = 0.f, rs = 0.f;
   for (int s = 0; s < jsplit; ++s) {
-    const float* p = part + ((long long)s * nr + r) * (2 * d);
+    const float* p = part + ((long long)s * nr + r) * (2 * d + 1);
     ks += p[c];
     kx += p[d + c];
-    rs += rsum[(long long)s * nr + r];
+    rs += p[2 * d];
   }
   const float x = Xr[(long long)r * ldr + c];
   const float ph = (ks + 2.f * gam[1] * (rs * x - kx)) * inv_n;
@@ -238,24 +312,23 @@ __global__ void phi_combine_kernel(const float* __restrict__ part, const float* 
 using namespace bode;
 
 extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t d) {
-  const size_t jsplit = 4;
+  const size_t jsplit = MAXSPLIT;
   size_t b = 0;
   b += (size_t)n_rows * n_cols * sizeof(float);                 // d2
-  b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials + row sums
+  b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials (last column: row sums)
   b += 2 * 2048 * sizeof(unsigned long long) + 256;             // histograms + select state
   return b + 1024;
 }
 
 namespace {
 struct Ws {
-  float* d2; float* part; float* rsum; unsigned long long* hist; SelState* st;
+  float* d2; float* part; unsigned long long* hist; SelState* st;
 };
 Ws carve(void* ws, int nr, int nc, int d) {
   Ws w;
   char* p = (char*)ws;
   w.d2 = (float*)p; p += (((size_t)nr * nc * sizeof(float)) + 255) / 256 * 256;
-  w.part = (float*)p; p += ((4 * (size_t)nr * 2 * d * sizeof(float)) + 255) / 256 * 256;
-  w.rsum = (float*)p; p += ((4 * (size_t)nr * sizeof(float)) + 255) / 256 * 256;
+  w.part = (float*)p; p += ((MAXSPLIT * (size_t)nr * (2 * d + 1) * sizeof(float)) + 255) / 256 * 256;
   w.hist = (unsigned long long*)p; p += 2 * 2048 * sizeof(unsigned long long);
   w.st = (SelState*)p;
   return w;
@@ -277,9 +350,9 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   const size_t smem = 2 * (size_t)TS * (d | 1) * sizeof(float);
   if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n_cols + TS - 1) / TS, (n_rows + TS - 1) / TS);
-  sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2);
-  BODE_CUDA(cudaGetLastError());
   select_init_kernel<<<4, 1024, 0, st>>>(w.st, w.hist, total_entries);
+  BODE_CUDA(cudaGetLastError());
+  sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2, &w.st->maxbits);
   BODE_CUDA(cudaGetLastError());
   if (hist_out) *hist_out = w.hist;
   return BODE_OK;
@@ -303,7 +376,8 @@ extern "C" int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols,
   long long blocks = (n / 4 + 511) / 512;
   if (blocks > 4LL * sms) blocks = 4LL * sms;
   if (blocks < 1) blocks = 1;
-  hist_kernel<<<(int)blocks, 512, 0, (cudaStream_t)stream>>>(w.d2, n, w.st, shift, nbits, himask, w.hist);
+  if (pass == 0) hist0_kernel<<<(int)blocks, 512, 0, (cudaStream_t)stream>>>(w.d2, n, w.st, w.hist);
+  else hist_kernel<<<(int)blocks, 512, 0, (cudaStream_t)stream>>>(w.d2, n, w.st, shift, nbits, himask, w.hist);
   return check_cuda(cudaGetLastError(), "hist launch");
 }
 
@@ -333,27 +407,32 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
                              const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                              int64_t ld_theta, float step, bode_stream_t stream) {
   BODE_REQUIRE(Xrows && Xcols && Scols && med_gamma && workspace, "null pointer");
-  BODE_REQUIRE(d > 0 && 2 * d <= 8 * 32, "svgd phi kernel supports d <= 128 (got %d)", d);
+  BODE_REQUIRE(d > 0 && 2 * d + 1 <= 256, "svgd phi kernel supports d <= 127 (got %d)", d);
   Ws w = carve(workspace, n_rows, n_cols, d);
   cudaStream_t st = (cudaStream_t)stream;
-  const int jsplit = 4;
-  dim3 grid((n_rows + PR - 1) / PR, jsplit);
-  const int cpt = (2 * d + CG - 1) / CG;
+  const int rb = (n_rows + PR - 1) / PR;
+  int sms = bode_device_sm_count();
+  if (sms < 0) return BODE_ERR_CUDA;
+  int jsplit = (3 * sms) / rb;                          // one full wave at 3 resident CTAs per SM, never a tail wave
+  if (jsplit > MAXSPLIT) jsplit = MAXSPLIT;
+  if (jsplit > (n_cols + PJ - 1) / PJ) jsplit = (n_cols + PJ - 1) / PJ;
+  if (jsplit < 1) jsplit = 1;
+  dim3 grid(rb, jsplit);
+  const int ft = (2 * d + 1 + 15) / 16;
 #define BODE_PHI(C)                                                                                              \
   {                                                                                                              \
-    const size_t smem = ((size_t)PR * (PJ + 1) + (size_t)PJ * CG * C) * sizeof(float);                           \
-    if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(phi_partial_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-    phi_partial_kernel<C><<<grid, 128, smem, st>>>(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, med_gamma, jsplit, score_sign, w.part, w.rsum); \
+    const size_t smem = ((size_t)PJ * KP + (size_t)PJ * 16 * C) * sizeof(float);                                 \
+    phi_partial_kernel<C><<<grid, 128, smem, st>>>(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, med_gamma, jsplit, score_sign, w.part); \
   }
-  if (cpt <= 4) BODE_PHI(4)
-  else if (cpt <= 8) BODE_PHI(8)
-  else if (cpt <= 13) BODE_PHI(13)
-  else if (cpt <= 16) BODE_PHI(16)
-  else BODE_PHI(32)
+  if (ft <= 2) BODE_PHI(2)
+  else if (ft <= 4) BODE_PHI(4)
+  else if (ft <= 7) BODE_PHI(7)
+  else if (ft <= 10) BODE_PHI(10)
+  else BODE_PHI(16)
 #undef BODE_PHI
   BODE_CUDA(cudaGetLastError());
   const long long tot = (long long)n_rows * d;
-  phi_combine_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(w.part, w.rsum, jsplit, n_rows, d, Xrows, ld_rows, med_gamma,
+  phi_combine_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(w.part, jsplit, n_rows, d, Xrows, ld_rows, med_gamma,
                                                                1.f / (float)n_total, phi, ld_phi, theta, ld_theta, step);
   return check_cuda(cudaGetLastError(), "phi combine launch");
 }
