@@ -8,9 +8,9 @@ Public surface mirrors the reference:
 All compute runs in hand-written CUDA behind the C ABI of include/bode_b200.h; there is no CPU path.
 """
 from . import _lib
-from .fields import KernelRegression, NPDEField, rbf_kernel
+from .fields import KernelRegression, MLPField, NPDEField, rbf_kernel
 from .odeint import odeint, odeint_adjoint
-from .posterior import NPDEPosterior
+from .posterior import MLPPosterior, NPDEPosterior
 from . import samplers
 
-__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "rbf_kernel", "samplers", "_lib"]
+__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "MLPField", "MLPPosterior", "rbf_kernel", "samplers", "_lib"]

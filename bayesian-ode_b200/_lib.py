@@ -28,6 +28,10 @@ class NpdeFieldStruct(C.Structure):
     ]
 
 
+class MlpFieldStruct(C.Structure):
+    _fields_ = [("P", C.c_int32), ("H", C.c_int32), ("theta", C.c_void_p), ("theta_stride", C.c_int64)]
+
+
 class GridStruct(C.Structure):
     _fields_ = [
         ("S", C.c_int32), ("T", C.c_int32), ("sign", C.c_float),
@@ -51,6 +55,12 @@ SYMBOLS = {
     "bode_npde_nlp_grad": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
                                       _P, C.c_int32, _P, _P, C.c_int64, C.c_float, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                       _P, C.c_size_t, _P]),
+    "bode_mlp_odeint": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "bode_mlp_odeint_backward": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
+                                            _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
+    "bode_mlp_sse_grad": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
+                                     _P, C.c_int32, _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P, C.c_int64,
+                                     _P, C.c_size_t, _P]),
     "bode_sgld_step": (C.c_int, [_P, _P, _P, C.c_int64, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "bode_psgld_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "bode_asghmc_step": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32,

@@ -1,0 +1,85 @@
+// Host side of the MLP neural-ODE entry points (argument checks, parameter packing, dispatch on the hidden width).
+#include "npde_solve.cuh"
+#include <string.h>
+
+namespace bode {
+#define BODE_DECL_MLP(H)                                                                                                  \
+  size_t mlp_smem_bytes_##H(int N);                                                                                       \
+  int launch_mlp_fwd_##H(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);         \
+  int launch_mlp_grad_##H(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+BODE_DECL_MLP(20)
+BODE_DECL_MLP(64)
+
+static int mlp_fill(NpdeKParams& prm, const bode_mlp_field* f, const bode_grid* g, int method, int N, const float* y0, int y0_batched) {
+  BODE_REQUIRE(f && g, "null field/grid");
+  BODE_REQUIRE(f->H == 20 || f->H == 64, "MLP field is built for hidden widths 20 and 64 (got %d)", f->H);
+  BODE_REQUIRE(f->P > 0 && N > 0 && N <= 8, "need P > 0 and 1 <= N <= 8 trajectories (got P=%d N=%d)", f->P, N);
+  BODE_REQUIRE(g->S >= 0 && g->T >= 1, "bad grid S=%d T=%d", g->S, g->T);
+  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_RK4, "unknown method %d", method);
+  const int d = f->H * f->H + 6 * f->H + 2;
+  BODE_REQUIRE(f->theta && y0 && f->theta_stride >= d, "null theta/y0 or theta_stride < d=%d", d);
+  BODE_REQUIRE(g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
+  memset(&prm, 0, sizeof(prm));
+  prm.P = f->P; prm.N = N; prm.S = g->S; prm.T = g->T; prm.m = 0; prm.ppc = 1;
+  prm.y0_stride = y0_batched ? 2 * N : 0;
+  prm.sign = g->sign; prm.scale = 1.f;
+  prm.U = f->theta; prm.U_stride = f->theta_stride; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
+  prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr;
+  return BODE_OK;
+}
+
+static size_t mlp_smem(int H, int N) { return H == 20 ? mlp_smem_bytes_20(N) : mlp_smem_bytes_64(N); }
+
+static int mlp_grad(const bode_mlp_field* f, const bode_grid* g, int method, int grad_mode, int inj, int N, NpdeKParams& prm,
+                    float* scratch, size_t scratch_n, cudaStream_t st) {
+  BODE_REQUIRE(grad_mode == BODE_GRAD_DISCRETE || grad_mode == BODE_GRAD_ADJOINT, "unknown grad_mode %d", grad_mode);
+  BODE_REQUIRE(grad_mode != BODE_GRAD_ADJOINT || g->T == 1 || (g->adj_dt && g->adj_ptr), "ADJOINT needs adj_dt/adj_ptr");
+  const size_t need = bode_npde_scratch_floats(f->P, N, g->S, g->T, method, grad_mode);
+  BODE_REQUIRE(scratch && scratch_n >= need, "scratch too small: have %zu floats, need %zu", scratch_n, need);
+  prm.ck = reinterpret_cast<float2*>(scratch);
+  prm.npairs = (long long)f->P * N;
+  const dim3 grid(f->P), block(32 * N);
+  const size_t smem = mlp_smem(f->H, N);
+  if (f->H == 20) return launch_mlp_grad_20(prm, method, inj, grad_mode, grid, block, smem, st);
+  return launch_mlp_grad_64(prm, method, inj, grad_mode, grid, block, smem, st);
+}
+}  // namespace bode
+
+using namespace bode;
+
+extern "C" int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
+                               int32_t y0_batched, float* sol, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(sol, "null sol");
+  prm.sol = sol;
+  const dim3 grid(f->P), block(32 * N);
+  const size_t smem = mlp_smem(f->H, N);
+  if (f->H == 20) return launch_mlp_fwd_20(prm, method, grid, block, smem, (cudaStream_t)stream);
+  return launch_mlp_fwd_64(prm, method, grid, block, smem, (cudaStream_t)stream);
+}
+
+extern "C" int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
+                                        const float* y0, int32_t y0_batched, const float* gout, float* gtheta,
+                                        int64_t gtheta_stride, float* gy0, float* scratch, size_t scratch_n, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(gout && gtheta, "null gout/gtheta");
+  prm.gout = gout; prm.gU = gtheta; prm.gU_stride = gtheta_stride; prm.gy0 = gy0; prm.add_prior = 0;
+  return mlp_grad(f, g, method, grad_mode, INJ_GOUT, N, prm, scratch, scratch_n, (cudaStream_t)stream);
+}
+
+extern "C" int bode_mlp_sse_grad(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
+                                 const float* y0, int32_t y0_batched, const float* X, float lik_w, float reg, float scale,
+                                 int32_t add_prior, float* loss, float* sqerr, float* gtheta, int64_t gtheta_stride,
+                                 float* scratch, size_t scratch_n, bode_stream_t stream) {
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, g, method, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(X && loss && sqerr && gtheta, "null X/outputs");
+  prm.Y = X; prm.lik_w = lik_w; prm.reg = reg; prm.scale = scale; prm.add_prior = add_prior ? 1 : 0;
+  prm.loss = loss; prm.sqerr = sqerr; prm.gU = gtheta; prm.gU_stride = gtheta_stride;
+  return mlp_grad(f, g, method, grad_mode, INJ_LIK, N, prm, scratch, scratch_n, (cudaStream_t)stream);
+}

@@ -1,0 +1,60 @@
+// Instantiates the solver kernels for the MLP field with hidden width BODE_H (compiled once per width).
+#include "npde_solve.cuh"
+#include "mlp_field.cuh"
+
+namespace bode {
+
+#define BODE_CAT_(a, b) a##b
+#define BODE_CAT(a, b) BODE_CAT_(a, b)
+using MF = MlpField<BODE_H>;
+
+template <int METHOD>
+static int mlp_launch_fwd(const NpdeKParams& prm, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    int e = check_cuda(cudaFuncSetAttribute(npde_fwd_kernel<MF, METHOD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (e != BODE_OK) return e;
+  }
+  npde_fwd_kernel<MF, METHOD><<<grid, block, smem, st>>>(prm);
+  return check_cuda(cudaGetLastError(), "mlp fwd launch");
+}
+
+template <int METHOD, int INJ, int ADJ>
+static int mlp_launch_grad(const NpdeKParams& prm, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    int e = check_cuda(cudaFuncSetAttribute(npde_grad_kernel<MF, METHOD, INJ, ADJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (e != BODE_OK) return e;
+  }
+  npde_grad_kernel<MF, METHOD, INJ, ADJ><<<grid, block, smem, st>>>(prm);
+  return check_cuda(cudaGetLastError(), "mlp grad launch");
+}
+
+size_t BODE_CAT(mlp_smem_bytes_, BODE_H)(int N) { return sizeof(float) * (size_t)MF::smem_floats(N); }
+
+int BODE_CAT(launch_mlp_fwd_, BODE_H)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  switch (method) {
+    case BODE_EULER: return mlp_launch_fwd<BODE_EULER>(prm, grid, block, smem, st);
+    case BODE_MIDPOINT: return mlp_launch_fwd<BODE_MIDPOINT>(prm, grid, block, smem, st);
+    default: return mlp_launch_fwd<BODE_RK4>(prm, grid, block, smem, st);
+  }
+}
+
+template <int METHOD>
+static int mlp_launch_grad_m(const NpdeKParams& prm, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  if (inj == INJ_LIK) {
+    if (adj == BODE_GRAD_DISCRETE) return mlp_launch_grad<METHOD, INJ_LIK, BODE_GRAD_DISCRETE>(prm, grid, block, smem, st);
+    return mlp_launch_grad<METHOD, INJ_LIK, BODE_GRAD_ADJOINT>(prm, grid, block, smem, st);
+  }
+  if (adj == BODE_GRAD_DISCRETE) return mlp_launch_grad<METHOD, INJ_GOUT, BODE_GRAD_DISCRETE>(prm, grid, block, smem, st);
+  return mlp_launch_grad<METHOD, INJ_GOUT, BODE_GRAD_ADJOINT>(prm, grid, block, smem, st);
+}
+
+int BODE_CAT(launch_mlp_grad_, BODE_H)(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem,
+                                       cudaStream_t st) {
+  switch (method) {
+    case BODE_EULER: return mlp_launch_grad_m<BODE_EULER>(prm, inj, adj, grid, block, smem, st);
+    case BODE_MIDPOINT: return mlp_launch_grad_m<BODE_MIDPOINT>(prm, inj, adj, grid, block, smem, st);
+    default: return mlp_launch_grad_m<BODE_RK4>(prm, inj, adj, grid, block, smem, st);
+  }
+}
+
+}  // namespace bode

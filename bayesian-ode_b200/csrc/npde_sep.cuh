@@ -25,8 +25,11 @@ struct NpdeKParams {
   float2* ck;
   long long npairs;
   long long U_stride, logsn_stride, gU_stride, glogsn_stride;
+  float reg, lik_w;   // MLP closure: lik_w * sum (X - x)^2 + reg * sum theta^2
   float *sol, *loss, *sqerr, *gU, *glogsn, *gy0;
 };
+
+enum { INJ_LIK = 0, INJ_GOUT = 1 };
 
 __device__ __forceinline__ float2 f2(float x, float y) { return make_float2(x, y); }
 __device__ __forceinline__ float2 operator+(float2 a, float2 b) { return f2(a.x + b.x, a.y + b.y); }
@@ -41,6 +44,17 @@ struct SepField {
   float2 W[MX][MY];
   float2 gW[MX][MY];
 
+  static __device__ __forceinline__ void prologue(const NpdeKParams& prm, float* smem);
+  static __device__ __forceinline__ float2 lik_weight(const NpdeKParams& prm, int p) {
+    const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)p * prm.logsn_stride);
+    return f2(expf(-2.f * ls.x), expf(-2.f * ls.y));
+  }
+  template <int INJ>
+  static __device__ __forceinline__ void epilogue(const NpdeKParams& prm, float* smem, const SepField& fld, bool active, int pl,
+                                                  int n, int pairl, int lane, float r2x, float r2y);
+  __device__ __forceinline__ void load(const NpdeKParams& prm, const float* smem, int pl, int, int lane) {
+    load_W(prm, smem + (prm.ppc + pl) * 2 * prm.m, lane);      // Ws sits after Us in the CTA's shared memory
+  }
   __device__ __forceinline__ void load_W(const NpdeKParams&, const float* Wp, int) {
 #pragma unroll
     for (int a = 0; a < MX; ++a)

@@ -10,8 +10,6 @@
 
 namespace bode {
 
-enum { INJ_LIK = 0, INJ_GOUT = 1 };
-
 template <int METHOD> struct Stages { static constexpr int value = METHOD == BODE_RK4 ? 4 : (METHOD == BODE_MIDPOINT ? 2 : 1); };
 
 // W_p = A U_p for the ppc particles of this CTA (gp.py:70-71 hoisted out of the RHS: K(x,Z) (A U)).
@@ -135,22 +133,100 @@ __device__ __forceinline__ void step_aug(const NpdeKParams& prm, Field& fld, flo
   }
 }
 
+// ------------------------------------------------------------------ npde epilogue (shared by the npde field types)
+// reduce gW over trajectories (deterministic order), back-project gU = A^T gW (+ prior gp.py:350), closure values
+template <int INJ, class Field>
+__device__ __forceinline__ void npde_epilogue(const NpdeKParams& prm, float* smem, const Field& fld, bool active, int pl, int n,
+                                              int pairl, int lane, float r2x, float r2y) {
+  const int tid = threadIdx.x;
+  const int m2 = 2 * prm.m;
+  const int N = prm.N, ppc = prm.ppc;
+  float* Us = smem;                      // [ppc][m2]   U of this CTA's particles
+  float* Ws = Us + ppc * m2;             // [ppc][m2]   W = A U, later sum_n gW
+  float* gWs = Ws + ppc * m2;            // [N][ppc][m2]
+  float* red = gWs + N * ppc * m2;       // [ppc*N][2]  sum of squared residuals per pair
+  __syncthreads();   // everyone is done reading Ws
+  if (active) {
+    fld.store_gW(prm, gWs + (n * ppc + pl) * m2, lane);
+    if (lane == 0) {
+      red[pairl * 2 + 0] = r2x;
+      red[pairl * 2 + 1] = r2y;
+    }
+  }
+  __syncthreads();
+  const int nout = ppc * m2;
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int nn = 0; nn < N; ++nn) acc += gWs[nn * nout + idx];
+    Ws[idx] = acc;
+  }
+  __syncthreads();
+  const int m = prm.m;
+  float* pri = gWs;                      // reuse: prior partials [ppc][m2]
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2, k = r >> 1, d = r & 1;
+    const int pp = blockIdx.x * ppc + q;
+    if (pp >= prm.P) { pri[idx] = 0.f; continue; }
+    float acc = 0.f;
+    const float* Wq = Ws + q * m2 + d;
+    for (int j = 0; j < m; ++j) acc = fmaf(__ldg(prm.A + j * m + k), Wq[2 * j], acc);
+    float pr = 0.f;
+    if (prm.add_prior) {
+      const float* Uq = Us + q * m2 + d;
+      for (int j = 0; j < m; ++j) pr = fmaf(__ldg(prm.Ksym + k * m + j), Uq[2 * j], pr);
+      acc += pr;
+      pr *= 0.5f * Us[idx];
+    }
+    pri[idx] = pr;
+    prm.gU[(long long)pp * prm.gU_stride + r] = prm.scale * acc;
+  }
+  if (INJ == INJ_LIK) {
+    __syncthreads();
+    if (tid < ppc) {
+      const int pp = blockIdx.x * ppc + tid;
+      if (pp < prm.P) {
+        float sx = 0.f, sy = 0.f, pr = 0.f;
+        for (int nn = 0; nn < N; ++nn) {
+          sx += red[(tid * N + nn) * 2 + 0];
+          sy += red[(tid * N + nn) * 2 + 1];
+        }
+        for (int j = 0; j < m2; ++j) pr += pri[tid * m2 + j];
+        const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)pp * prm.logsn_stride);
+        const float ex = expf(-2.f * ls.x), ey = expf(-2.f * ls.y);
+        const float nt = (float)N * (float)prm.T;
+        prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
+        prm.sqerr[pp] = sx + sy;
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = prm.scale * (nt - sx * ex);
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = prm.scale * (nt - sy * ey);
+      }
+    }
+  }
+}
+
+template <int MX, int MY>
+__device__ __forceinline__ void SepField<MX, MY>::prologue(const NpdeKParams& prm, float* smem) {
+  project_W(prm, smem, smem + prm.ppc * 2 * prm.m);
+}
+template <int MX, int MY>
+template <int INJ>
+__device__ __forceinline__ void SepField<MX, MY>::epilogue(const NpdeKParams& prm, float* smem, const SepField& fld, bool active,
+                                                           int pl, int n, int pairl, int lane, float r2x, float r2y) {
+  npde_epilogue<INJ>(prm, smem, fld, active, pl, n, pairl, lane, r2x, r2y);
+}
+
 // ------------------------------------------------------------------ forward-only kernel: sol[T,P,N,2]
 template <class Field, int METHOD>
 __global__ void __launch_bounds__(Field::MAX_THREADS) npde_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   constexpr int G = Field::G;
-  const int m2 = 2 * prm.m;
-  float* Us = smem;
-  float* Ws = smem + prm.ppc * m2;
-  project_W(prm, Us, Ws);
+  Field::prologue(prm, smem);
   const int tid = threadIdx.x;
   const int pairl = tid / G, lane = tid % G;
   const int pl = pairl / prm.N, n = pairl % prm.N;
   const int p = blockIdx.x * prm.ppc + pl;
   if (pl >= prm.ppc || p >= prm.P) return;
   Field fld;
-  fld.load_W(prm, Ws + pl * m2, lane);
+  fld.load(prm, smem, pl, pairl, lane);
   const long long pair = (long long)p * prm.N + n;
   const long long PN = (long long)prm.P * prm.N;
   float2 y = reinterpret_cast<const float2*>(prm.y0)[(prm.y0_stride ? (long long)p * prm.N : 0) + n];
@@ -167,16 +243,11 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_fwd_kernel(const __gr
 // ------------------------------------------------------------------ fused forward + closure + gradient kernel
 template <class Field, int METHOD, int INJ, int ADJ>
 __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __grid_constant__ NpdeKParams prm) {
-  extern __shared__ float smem[];
+  extern __shared__ __align__(16) float smem[];
   constexpr int G = Field::G;
   constexpr int STG = Stages<METHOD>::value;
-  const int m2 = 2 * prm.m;
   const int N = prm.N, ppc = prm.ppc;
-  float* Us = smem;                      // [ppc][m2]   U of this CTA's particles
-  float* Ws = Us + ppc * m2;             // [ppc][m2]   W = A U, later sum_n gW
-  float* gWs = Ws + ppc * m2;            // [N][ppc][m2]
-  float* red = gWs + N * ppc * m2;       // [ppc*N][2]  sum of squared residuals per pair
-  project_W(prm, Us, Ws);
+  Field::prologue(prm, smem);
 
   const int tid = threadIdx.x;
   const int pairl = tid / G, lane = tid % G;
@@ -187,16 +258,13 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
   Field fld;
   fld.zero_grad();
   if (active) {
-    fld.load_W(prm, Ws + pl * m2, lane);
+    fld.load(prm, smem, pl, pairl, lane);
     const long long pair = (long long)p * N + n;
     const long long PN = (long long)prm.P * N;
     const float2* Y2 = reinterpret_cast<const float2*>(prm.Y) + (long long)n * prm.T;   // Y[n][j]
     const float2* go = reinterpret_cast<const float2*>(prm.gout) + pair;              // gout[j][pair]
-    float2 e2inv = f2(0.f, 0.f);
-    if (INJ == INJ_LIK) {
-      const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)p * prm.logsn_stride);
-      e2inv = f2(expf(-2.f * ls.x), expf(-2.f * ls.y));
-    }
+    float2 e2inv = f2(0.f, 0.f);                     // dL/dx = -e2inv * (Y - x)
+    if (INJ == INJ_LIK) e2inv = Field::lik_weight(prm, p);
     float2* ck = prm.ck + pair;
     const long long stride = prm.npairs;
 
@@ -276,63 +344,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     if (prm.gy0 != nullptr && lane == 0) reinterpret_cast<float2*>(prm.gy0)[pair] = prm.scale * a;
   }
 
-  // ---------------- epilogue: reduce over trajectories, back-project gU = A^T gW (+ prior)
-  __syncthreads();   // everyone is done reading Ws
-  if (active) {
-    fld.store_gW(prm, gWs + (n * ppc + pl) * m2, lane);
-    if (lane == 0) {
-      red[pairl * 2 + 0] = r2x;
-      red[pairl * 2 + 1] = r2y;
-    }
-  }
-  __syncthreads();
-  const int nout = ppc * m2;
-  for (int idx = tid; idx < nout; idx += blockDim.x) {
-    float acc = 0.f;
-    for (int nn = 0; nn < N; ++nn) acc += gWs[nn * nout + idx];
-    Ws[idx] = acc;
-  }
-  __syncthreads();
-  const int m = prm.m;
-  float* pri = gWs;                      // reuse: prior partials [ppc][m2]
-  for (int idx = tid; idx < nout; idx += blockDim.x) {
-    const int q = idx / m2, r = idx - q * m2, k = r >> 1, d = r & 1;
-    const int pp = blockIdx.x * ppc + q;
-    if (pp >= prm.P) { pri[idx] = 0.f; continue; }
-    float acc = 0.f;
-    const float* Wq = Ws + q * m2 + d;
-    for (int j = 0; j < m; ++j) acc = fmaf(__ldg(prm.A + j * m + k), Wq[2 * j], acc);
-    float pr = 0.f;
-    if (prm.add_prior) {
-      const float* Uq = Us + q * m2 + d;
-      for (int j = 0; j < m; ++j) pr = fmaf(__ldg(prm.Ksym + k * m + j), Uq[2 * j], pr);
-      acc += pr;
-      pr *= 0.5f * Us[idx];
-    }
-    pri[idx] = pr;
-    prm.gU[(long long)pp * prm.gU_stride + r] = prm.scale * acc;
-  }
-  if (INJ == INJ_LIK) {
-    __syncthreads();
-    if (tid < ppc) {
-      const int pp = blockIdx.x * ppc + tid;
-      if (pp < prm.P) {
-        float sx = 0.f, sy = 0.f, pr = 0.f;
-        for (int nn = 0; nn < N; ++nn) {
-          sx += red[(tid * N + nn) * 2 + 0];
-          sy += red[(tid * N + nn) * 2 + 1];
-        }
-        for (int j = 0; j < m2; ++j) pr += pri[tid * m2 + j];
-        const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)pp * prm.logsn_stride);
-        const float ex = expf(-2.f * ls.x), ey = expf(-2.f * ls.y);
-        const float nt = (float)N * (float)prm.T;
-        prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
-        prm.sqerr[pp] = sx + sy;
-        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = prm.scale * (nt - sx * ex);
-        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = prm.scale * (nt - sy * ey);
-      }
-    }
-  }
+  Field::template epilogue<INJ>(prm, smem, fld, active, pl, n, pairl, lane, r2x, r2y);
 }
 
 }  // namespace bode

@@ -142,5 +142,70 @@ class NPDEField(torch.nn.Module):
         return self.theta_grad
 
 
+class MLPField(torch.nn.Module):
+    """The notebook's ``NN(input_size=2, hidden_size=H)`` (notebooks/jai/nn.ipynb cell 4) for P particles:
+    Linear(2,H) - ELU - Linear(H,H) - ELU - Linear(H,2), weights U(-0.5, 0.5) (cell 4 ``init_normal``), biases with
+    nn.Linear's default U(-1/sqrt(fan_in), 1/sqrt(fan_in)).  Parameters are views of one flat theta[P, d] buffer in
+    ``parameters()`` order: W1 [P,H,2], b1 [P,H], W2 [P,H,H], b2 [P,H], W3 [P,2,H], b3 [P,2]."""
+
+    def __init__(self, P, hidden_size=64, input_size=2, device=None, generator=None, theta=None):
+        super().__init__()
+        _lib.require_cuda()
+        if input_size != 2:
+            raise ValueError("the fused MLP field integrates 2-D states")
+        if hidden_size not in (20, 64):
+            raise NotImplementedError("MLPField kernels are built for hidden_size 20 and 64")
+        device = torch.device(device if device is not None else "cuda")
+        H = self.H = int(hidden_size)
+        self.P = int(P)
+        self.batched = True
+        self.d = H * H + 6 * H + 2
+        self.theta = torch.empty(self.P, self.d, dtype=torch.float32, device=device)
+        if theta is not None:
+            self.theta.copy_(torch.as_tensor(theta).reshape(self.P, self.d))
+        else:
+            u = torch.rand(self.P, self.d, generator=generator, dtype=torch.float32)
+            lo = torch.empty(self.d)
+            shapes = self._blocks()
+            for name, (o, n, _), bound in zip(shapes, shapes.values(), (0.5, 2 ** -0.5, 0.5, H ** -0.5, 0.5, H ** -0.5)):
+                lo[o:o + n] = bound
+            self.theta.copy_((2 * u - 1) * lo)
+        self.theta_grad = torch.zeros_like(self.theta)
+        for name, (o, n, shp) in self._blocks().items():
+            setattr(self, name, torch.nn.Parameter(self.theta[:, o:o + n].view((self.P,) + shp), requires_grad=True))
+
+    def _blocks(self):
+        H = self.H
+        out, o = {}, 0
+        for name, shp in (("W1", (H, 2)), ("b1", (H,)), ("W2", (H, H)), ("b2", (H,)), ("W3", (2, H)), ("b3", (2,))):
+            n = 1
+            for s_ in shp:
+                n *= s_
+            out[name] = (o, n, shp)
+            o += n
+        return out
+
+    def forward(self, t, X):
+        X = torch.as_tensor(X, device=self.theta.device, dtype=torch.float32)
+        if X.dim() == 2:
+            X = X[None].expand(self.P, -1, -1)
+        h = torch.nn.functional.elu(torch.einsum("phd,pnd->pnh", self.W1, X) + self.b1[:, None])
+        h = torch.nn.functional.elu(torch.einsum("phk,pnk->pnh", self.W2, h) + self.b2[:, None])
+        return torch.einsum("pdh,pnh->pnd", self.W3, h) + self.b3[:, None]
+
+    def c_struct(self, theta=None):
+        fs = _lib.MlpFieldStruct()
+        fs.P, fs.H = self.P, self.H
+        th = self.theta if theta is None else theta
+        p, stride = _lib.rows(th, self.d)
+        fs.theta, fs.theta_stride = p.value, stride
+        return fs
+
+    def bind_flat_grads(self):
+        for name, (o, n, shp) in self._blocks().items():
+            getattr(self, name).grad = self.theta_grad[:, o:o + n].view((self.P,) + shp)
+        return self.theta_grad
+
+
 # the reference's name for the same object (gp.py:56)
 KernelRegression = NPDEField

@@ -11,7 +11,7 @@ adjoint re-solved per observation interval with the same method (adjoint.py:57-9
 import torch
 
 from . import _grid, _lib
-from .fields import NPDEField
+from .fields import MLPField, NPDEField
 
 FIXED_GRID_METHODS = ("euler", "midpoint", "rk4")
 # methods of the reference registry (odeint.py:8-17) that are outside this hot path
@@ -67,7 +67,7 @@ def _norm_y0(field, y0):
     if y0.dim() == 3 and y0.shape[0] != field.P:
         raise ValueError("y0 leading dimension must equal the number of particles")
     _lib.require_cuda()
-    y = y0.to(device=field.U.device, dtype=torch.float32).contiguous()
+    y = y0.to(device=field.theta.device, dtype=torch.float32).contiguous()
     return y, y0.dim() == 3, int(y0.shape[-2])
 
 
@@ -103,6 +103,40 @@ class _NpdeOdeint(torch.autograd.Function):
         return gy0, gU, None, None, None, None, None, None
 
 
+class _MlpOdeint(torch.autograd.Function):
+    """odeint for MLPField; the six parameter views enter as inputs so autograd routes d/dtheta back to each."""
+
+    @staticmethod
+    def forward(ctx, y0, field, g, method, grad_mode, batched, N, *params):
+        lib = _lib.load()
+        sol = torch.empty((g.T, field.P, N, 2), dtype=torch.float32, device=y0.device)
+        fs = field.c_struct()
+        gs = _grid_struct(g, False)
+        _lib.check(lib.bode_mlp_odeint(fs, gs, method, N, _lib.ptr(y0), int(batched), _lib.ptr(sol), _lib.stream_ptr()))
+        ctx.save_for_backward(y0)
+        ctx.misc = (field, g, method, grad_mode, batched, N)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gout):
+        (y0,) = ctx.saved_tensors
+        field, g, method, grad_mode, batched, N = ctx.misc
+        lib = _lib.load()
+        gout = gout.to(torch.float32).contiguous()
+        gth = torch.empty((field.P, field.d), dtype=torch.float32, device=y0.device)
+        gy0 = torch.empty((field.P, N, 2), dtype=torch.float32, device=y0.device)
+        nsc = lib.bode_npde_scratch_floats(field.P, N, g.S, g.T, method, grad_mode)
+        sc = _scratch(y0.device, nsc)
+        fs = field.c_struct()
+        gs = _grid_struct(g, grad_mode == _lib.GRAD_ADJOINT)
+        _lib.check(lib.bode_mlp_odeint_backward(fs, gs, method, grad_mode, N, _lib.ptr(y0), int(batched), _lib.ptr(gout),
+                                                _lib.ptr(gth), field.d, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+        if not batched:
+            gy0 = gy0.sum(0)
+        grads = tuple(gth[:, o:o + n].view((field.P,) + shp) for (o, n, shp) in field._blocks().values())
+        return (gy0, None, None, None, None, None, None) + grads
+
+
 def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
     tensor_input, y0 = _check_inputs(func, y0, t)
     if options is None:
@@ -129,6 +163,18 @@ def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
                 sol = sol[:, 0]
             return sol if tensor_input else (sol,)
         raise NotImplementedError("method '{}' is not built for NPDEField yet".format(method))
+    if isinstance(func, MLPField):
+        if method in FIXED_GRID_METHODS:
+            opts = _grid.split_options(solver_name, options)
+            if opts["step_size"] is not None and opts["grid_constructor"] is not None:
+                raise ValueError("step_size and grid_constructor are exclusive arguments.")
+            y0c, batched, N = _norm_y0(func, y0)
+            g = _grid.cached(t, torch.float32, func.theta.device, opts["step_size"], opts["grid_constructor"],
+                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=func, y0=(y0c,))
+            params = [getattr(func, k) for k in func._blocks()]
+            sol = _MlpOdeint.apply(y0c, func, g, _lib.METHODS[method], grad_mode, batched, N, *params)
+            return sol if tensor_input else (sol,)
+        raise NotImplementedError("method '{}' is not built for MLPField yet".format(method))
     raise TypeError(
         "{}: `func` must be a field module of bayesian_ode_b200 (NPDEField / MLPField); got {}. The B200 build "
         "has no generic-callable or CPU path.".format(who, type(func).__name__))

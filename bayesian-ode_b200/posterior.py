@@ -13,7 +13,7 @@ also exposes ``loss_and_grad_()`` -- the graph-capturable fast path the batched 
 import torch
 
 from . import _grid, _lib
-from .fields import NPDEField
+from .fields import MLPField, NPDEField
 from .odeint import _grid_struct, _norm_y0, _scratch, odeint
 
 
@@ -110,3 +110,78 @@ class NPDEPosterior:
             return out if f.batched else out[0]
         loss = _FusedNLP.apply(f.U, f.logsn, self)
         return loss if f.batched else loss[0]
+
+
+class _FusedSSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, post, *params):
+        loss, gth = post._launch()
+        ctx.save_for_backward(gth)
+        ctx.post = post
+        return loss
+
+    @staticmethod
+    def backward(ctx, gloss):
+        (gth,) = ctx.saved_tensors
+        f = ctx.post.field
+        g = gth * gloss.view(-1, 1)
+        return (None,) + tuple(g[:, o:o + n].view((f.P,) + shp) for (o, n, shp) in f._blocks().values())
+
+
+class MLPPosterior:
+    """``bayesian_closure`` of notebooks/jai/nn.ipynb cell 10 for P chains as one fused launch:
+    loss_p = lik_w * sum_rows sum (X[row] - odeint(net_p, x0[row], t))^2 + reg * sum theta_p^2   (reg = 0.5 in the notebook);
+    ``closure(add_prior=False)`` returns the squared error."""
+
+    def __init__(self, field, x0, t, X, method="rk4", options=None, grad_mode="discrete", reg=0.5, lik_w=1.0, scale=1.0):
+        if not isinstance(field, MLPField):
+            raise TypeError("MLPPosterior needs an MLPField")
+        if method not in _lib.METHODS:
+            raise NotImplementedError("MLPPosterior is built for the fixed-grid methods euler/midpoint/rk4")
+        self.field, self.method, self.options = field, method, dict(options or {})
+        self.grad_mode = {"discrete": _lib.GRAD_DISCRETE, "adjoint": _lib.GRAD_ADJOINT}[grad_mode]
+        self.reg, self.lik_w, self.scale = float(reg), float(lik_w), float(scale)
+        dev = field.theta.device
+        self.x0, self.x0_batched, self.N = _norm_y0(field, torch.as_tensor(x0))
+        self.t = torch.as_tensor(t)
+        self.Y = torch.as_tensor(X).to(dev, torch.float32).contiguous()
+        if self.Y.shape != (self.N, self.t.numel(), 2):
+            raise ValueError("X must be [N, T, 2]")
+        opts = _grid.split_options("MLPPosterior", self.options)
+        self.grid = _grid.cached(self.t, torch.float32, dev, opts["step_size"], opts["grid_constructor"],
+                                 with_adjoint=self.grad_mode == _lib.GRAD_ADJOINT, func=field, y0=(self.x0,))
+        self.loss = torch.empty(field.P, dtype=torch.float32, device=dev)
+        self.sqerr = torch.empty(field.P, dtype=torch.float32, device=dev)
+        self.gtheta = field.theta_grad
+        self.add_prior = True
+
+    def set_data(self, x0=None, Y=None):
+        if x0 is not None:
+            self.x0.copy_(x0, non_blocking=True)
+        if Y is not None:
+            self.Y.copy_(Y, non_blocking=True)
+
+    def _launch(self, out=None):
+        lib = _lib.load()
+        f = self.field
+        loss, gth = out if out is not None else (torch.empty_like(self.loss), torch.empty_like(self.gtheta))
+        m = _lib.METHODS[self.method]
+        nsc = lib.bode_npde_scratch_floats(f.P, self.N, self.grid.S, self.grid.T, m, self.grad_mode)
+        sc = _scratch(f.theta.device, nsc)
+        gs = _grid_struct(self.grid, self.grad_mode == _lib.GRAD_ADJOINT)
+        _lib.check(lib.bode_mlp_sse_grad(f.c_struct(), gs, m, self.grad_mode, self.N, _lib.ptr(self.x0), int(self.x0_batched),
+                                         _lib.ptr(self.Y), self.lik_w, self.reg, self.scale, int(self.add_prior), _lib.ptr(loss),
+                                         _lib.ptr(self.sqerr), _lib.ptr(gth), f.d, _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
+        return loss, gth
+
+    def loss_and_grad_(self):
+        loss, g = self._launch(out=(self.loss, self.gtheta))
+        return loss, g, None
+
+    def __call__(self, add_prior=True):
+        f = self.field
+        if not add_prior:
+            with torch.no_grad():
+                sol = odeint(f, self.x0, self.t, method=self.method, options=self.options or None)
+                return ((self.Y[None] - sol.permute(1, 2, 0, 3)) ** 2).sum(dim=(1, 2, 3))
+        return _FusedSSE.apply(self, *[getattr(f, k) for k in f._blocks()])

@@ -134,6 +134,32 @@ int bode_npde_nlp_grad(const bode_npde_field* f, const bode_grid* g, int32_t met
  * NULL) gets bit 0 set when a parameter is non-finite on entry (langevin.py:184-185 -> ValueError).
  * ------------------------------------------------------------------------------------- */
 
+/* ---------------------------------------------------------------------------------------
+ * MLP neural-ODE field (notebooks/jai/nn.ipynb cell 4: Linear(2,H)-ELU-Linear(H,H)-ELU-Linear(H,2)), one weight set
+ * per particle.  theta[p] = [W1 (H x 2) | b1 (H) | W2 (H x H) | b2 (H) | W3 (2 x H) | b3 (2)]  (parameters() order),
+ * d = H^2 + 6H + 2; built for H = 20 (notebook) and H = 64 (BASELINE config 4); N <= 8 trajectories.
+ * Scratch size: bode_npde_scratch_floats(P, N, S, T, method, grad_mode).
+ * ------------------------------------------------------------------------------------- */
+typedef struct bode_mlp_field {
+  int32_t P, H;
+  const float* theta;     /* [P, d], particle p at theta + p*theta_stride */
+  int64_t theta_stride;
+} bode_mlp_field;
+
+/* odeint(net, x0, t, method) forward for every particle and trajectory row (nn.ipynb cell 10 loops rows) */
+int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
+                    int32_t y0_batched, float* sol, bode_stream_t stream);
+/* its backward for an arbitrary dL/dsol [T,P,N,2]: gtheta [P,d] (+ optional gy0 [P,N,2]) */
+int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
+                             const float* y0, int32_t y0_batched, const float* gout, float* gtheta,
+                             int64_t gtheta_stride, float* gy0, float* scratch, size_t scratch_floats, bode_stream_t stream);
+/* fused bayesian_closure (nn.ipynb cell 10) + backward:  loss = lik_w * sum (X - x)^2 + reg * sum theta^2  (x scale);
+ * sqerr = sum (X - x)^2;  X is [N,T,2]. */
+int bode_mlp_sse_grad(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
+                      const float* y0, int32_t y0_batched, const float* X, float lik_w, float reg, float scale,
+                      int32_t add_prior, float* loss, float* sqerr, float* gtheta, int64_t gtheta_stride,
+                      float* scratch, size_t scratch_floats, bode_stream_t stream);
+
 /* Optional DEVICE-resident control block: when non-NULL its fields override the scalar arguments of the same name,
  * so a captured CUDA graph can be replayed while the lr schedule / step counter / phase flags change. */
 typedef struct bode_sampler_ctl {

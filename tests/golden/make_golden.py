@@ -295,6 +295,60 @@ def gen_svgd(data):
     save("svgd", **out)
 
 
+class NN(torch.nn.Module):
+    """notebooks/jai/nn.ipynb cell 4, verbatim structure."""
+
+    def __init__(self, input_size, hidden_size=10):
+        super(NN, self).__init__()
+        nn = torch.nn
+        self.layers = nn.Sequential(
+            nn.Linear(input_size, hidden_size), nn.ELU(),
+            nn.Linear(int(hidden_size * 1.0), int(hidden_size * 1.0)), nn.ELU(),
+            nn.Linear(hidden_size, input_size))
+
+    def forward(self, t, x):
+        size = x.size()
+        x = x.view(-1)
+        x = self.layers(x)
+        x = x.view(size)
+        return x
+
+
+def gen_mlp(data):
+    """MLP field: per-row odeint (nn.ipynb cell 10 loops over trajectory rows), rk4, autograd and adjoint gradients."""
+    x0, t = data["x0"], data["t"]
+    Xt = torch.from_numpy(data["X"])
+    out = dict(x0=x0, t=t, X=Xt)
+    for H, P in ((20, 3), (64, 2)):
+        torch.manual_seed(100 + H)
+        thetas, sols, losses, sqs, gd, ga = [], [], [], [], [], []
+        for p in range(P):
+            net = NN(2, H)
+            for m_ in net.modules():
+                if isinstance(m_, torch.nn.Linear):
+                    torch.nn.init.uniform_(m_.weight, a=-0.5, b=0.5)          # nn.ipynb cell 4 init_normal
+            params = list(net.parameters())
+            thetas.append(torch.cat([q.detach().reshape(-1) for q in params]))
+            for mode, odeint in (("d", torchdiffeq.odeint), ("a", torchdiffeq.odeint_adjoint)):
+                net.zero_grad()
+                loss = 0
+                rows = []
+                for r in range(x0.size(0)):
+                    xode = odeint(net, x0[r], t, method="rk4")
+                    rows.append(xode.detach())
+                    loss = loss + torch.sum((Xt[r] - xode) ** 2)
+                sq = loss.detach().clone()
+                loss = loss + 0.5 * sum([torch.sum(q ** 2) for q in params])
+                loss.backward()
+                g = torch.cat([q.grad.reshape(-1) for q in params])
+                (gd if mode == "d" else ga).append(g)
+            sols.append(torch.stack(rows, 1))               # [T,N,2]
+            losses.append(loss.detach()); sqs.append(sq)
+        out.update({f"h{H}_theta": torch.stack(thetas), f"h{H}_sol": torch.stack(sols, 1), f"h{H}_loss": torch.stack(losses),
+                    f"h{H}_sqerr": torch.stack(sqs), f"h{H}_g_discrete": torch.stack(gd), f"h{H}_g_adjoint": torch.stack(ga)})
+    save("mlp", **out)
+
+
 if __name__ == "__main__":
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
@@ -303,3 +357,4 @@ if __name__ == "__main__":
     gen_grid_options(data)
     gen_sampler_steps(data)
     gen_svgd(data)
+    gen_mlp(data)

@@ -81,3 +81,25 @@ def test_output_map_is_end_of_step():
     t_, grid, sign = solvers.build_grid(t, np.float64, 0.5)
     assert np.array_equal(grid, [0.0, 0.5, 1.0])
     assert np.array_equal(solvers.output_map(t_, grid), [1, 2, 4])
+
+
+@pytest.mark.parametrize("H", [20, 64])
+@pytest.mark.parametrize("mode", ["discrete", "adjoint"])
+def test_mlp_field_closure_and_gradients_match_reference(H, mode):
+    from oracle import mlp
+    g = load_golden("mlp")
+    loss, gr, sq, sol = mlp.sse_grad(g[f"h{H}_theta"], H, g["x0"], g["t"], g["X"], grad_mode=mode)
+    assert relerr(sol, g[f"h{H}_sol"]) < 1e-12
+    assert relerr(loss, g[f"h{H}_loss"]) < 1e-12
+    assert relerr(sq, g[f"h{H}_sqerr"]) < 1e-12
+    assert relerr(gr, g[f"h{H}_g_{mode}"]) < 1e-10
+
+
+def test_torch_port_used_as_cpu_baseline_matches_reference():
+    """oracle/ref_torch.py (the timed CPU baseline) computes the same trajectories as the reference."""
+    import torch
+    from oracle import ref_torch
+    g = load_golden("npde_m5")
+    kreg = ref_torch.KReg(torch.from_numpy(g["U"][0]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    xode = ref_torch.odeint_rk4(kreg, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]))
+    assert relerr(xode.detach().numpy(), g["rk4_sol"][:, 0]) < 1e-12
