@@ -9,7 +9,7 @@ All compute runs in hand-written CUDA behind the C ABI of include/bode_b200.h; t
 """
 from . import _lib
 from .fields import KernelRegression, MLPField, NPDEField, rbf_kernel
-from .odeint import odeint, odeint_adjoint
+from .odeint import last_dopri5_stats, odeint, odeint_adjoint
 from .posterior import MLPPosterior, NPDEPosterior
 from . import samplers
 

@@ -32,6 +32,11 @@ class MlpFieldStruct(C.Structure):
     _fields_ = [("P", C.c_int32), ("H", C.c_int32), ("theta", C.c_void_p), ("theta_stride", C.c_int64)]
 
 
+class Dopri5Opts(C.Structure):
+    _fields_ = [("t", C.c_void_p), ("rtol", C.c_double), ("atol", C.c_double), ("safety", C.c_double), ("ifactor", C.c_double),
+                ("dfactor", C.c_double), ("max_num_steps", C.c_int32), ("user_first_step", C.c_int32), ("stats", C.c_void_p)]
+
+
 class GridStruct(C.Structure):
     _fields_ = [
         ("S", C.c_int32), ("T", C.c_int32), ("sign", C.c_float),
@@ -56,6 +61,8 @@ SYMBOLS = {
                                       _P, C.c_int32, _P, _P, C.c_int64, C.c_float, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64,
                                       _P, C.c_size_t, _P]),
     "bode_mlp_odeint": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
+    "bode_npde_dopri5": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
+    "bode_mlp_dopri5": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_mlp_odeint_backward": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
                                             _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "bode_mlp_sse_grad": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,

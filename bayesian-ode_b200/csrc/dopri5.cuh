@@ -1,0 +1,146 @@
+// Adaptive Dormand-Prince 5(4) forward solve, one independent step-size controller per (particle, trajectory) pair
+// -- the "batched-step variant" of torchdiffeq's Dopri5Solver (dopri5.py:58-122): the reference notebook integrates one
+// trajectory row per odeint call (nn.ipynb cell 10), so every pair reproduces the control flow of its own reference call:
+//   tableau / DPS_C_MID            dopri5.py:11-36
+//   initial step (order 4)         misc.py:84-143  (dopri5.py:79-82: ANY user first_step becomes 0.01)
+//   stage loop, FSAL, error        rk_common.py:22-61
+//   error ratio, accept            misc.py:146-157, dopri5.py:109     (mean over the elements of the state tensor)
+//   step-size controller           misc.py:160-170 (float64 t, dt; applied after accepted AND rejected steps)
+//   dense output                   interp.py:5-65  (outputs are interpolated; dt is never clipped to hit t[i])
+// t and dt are float64 like the reference's controller; the state is fp32.
+#pragma once
+#include "npde_solve.cuh"
+
+namespace bode {
+
+struct Dopri5Params {
+  const double* t;        // [T] (already sign-normalised: increasing)
+  float rtol, atol;
+  int user_first_step;    // dopri5.py:81-82
+  double safety, ifactor, dfactor;
+  int max_num_steps;
+  int* stats;             // [P*N][3]: accepted, rejected, status bits (1 max_num_steps, 2 dt underflow, 4 non-finite state)
+};
+
+__device__ __forceinline__ float rms2(float2 v) { return sqrtf(0.5f * (v.x * v.x + v.y * v.y)); }
+__device__ __forceinline__ float2 div2(float2 a, float2 b) { return f2(a.x / b.x, a.y / b.y); }
+
+template <class Field>
+__global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __grid_constant__ NpdeKParams prm,
+                                                                       const __grid_constant__ Dopri5Params dp) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int G = Field::G;
+  Field::prologue(prm, smem);
+  const int tid = threadIdx.x;
+  const int pairl = tid / G, lane = tid % G;
+  const int pl = pairl / prm.N, n = pairl % prm.N;
+  const int p = blockIdx.x * prm.ppc + pl;
+  if (pl >= prm.ppc || p >= prm.P) return;
+  Field fld;
+  fld.load(prm, smem, pl, pairl, lane);
+  const long long pair = (long long)p * prm.N + n;
+  const long long PN = (long long)prm.P * prm.N;
+  float2* sol = reinterpret_cast<float2*>(prm.sol);
+  const float sg = prm.sign;
+  // tableau (dopri5.py:11-31)
+  const float B21 = 1.f / 5, B31 = 3.f / 40, B32 = 9.f / 40, B41 = 44.f / 45, B42 = -56.f / 15, B43 = 32.f / 9;
+  const float B51 = (float)(19372.0 / 6561), B52 = (float)(-25360.0 / 2187), B53 = (float)(64448.0 / 6561), B54 = (float)(-212.0 / 729);
+  const float B61 = (float)(9017.0 / 3168), B62 = (float)(-355.0 / 33), B63 = (float)(46732.0 / 5247), B64 = (float)(49.0 / 176),
+              B65 = (float)(-5103.0 / 18656);
+  const float C1 = (float)(35.0 / 384), C3 = (float)(500.0 / 1113), C4 = (float)(125.0 / 192), C5 = (float)(-2187.0 / 6784), C6 = (float)(11.0 / 84);
+  const float E1 = (float)(35.0 / 384 - 1951.0 / 21600), E3 = (float)(500.0 / 1113 - 22642.0 / 50085), E4 = (float)(125.0 / 192 - 451.0 / 720),
+              E5 = (float)(-2187.0 / 6784 + 12231.0 / 42400), E6 = (float)(11.0 / 84 - 649.0 / 6300), E7 = (float)(-1.0 / 60);
+  const float M1 = (float)(6025192743.0 / 30085553152.0 / 2), M3 = (float)(51252292925.0 / 65400821598.0 / 2),
+              M4 = (float)(-2691868925.0 / 45128329728.0 / 2), M5 = (float)(187940372067.0 / 1594534317056.0 / 2),
+              M6 = (float)(-1776094331.0 / 19743644256.0 / 2), M7 = (float)(11237099.0 / 235043384.0 / 2);
+
+  float2 y = reinterpret_cast<const float2*>(prm.y0)[(prm.y0_stride ? (long long)p * prm.N : 0) + n];
+  if (lane == 0) sol[pair] = y;
+  int n_acc = 0, n_rej = 0, status = 0;
+  if (prm.T > 1) {
+    float2 f = sg * fld.eval(prm, y);
+    // ---- first step (misc.py:84-143), state dtype arithmetic
+    double dt;
+    if (dp.user_first_step) {
+      dt = 0.01;
+    } else {
+      const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
+      const float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
+      const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+      const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
+      const float d2 = rms2(div2(f1 - f, scale)) / h0;
+      float h1;
+      if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+      else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
+      dt = (double)fminf(100.f * h0, h1);
+    }
+    double t0 = dp.t[0], t1 = dp.t[0];
+    float2 ca = y, cb = y, cc = y, cd = y, ce = y;       // interp_coeff = [y0]*5 (dopri5.py:83)
+    for (int i = 1; i < prm.T; ++i) {
+      const double next_t = dp.t[i];
+      int n_steps = 0;
+      while (next_t > t1) {
+        if (n_steps >= dp.max_num_steps) { status |= 1; break; }
+        const double ts = t1;                            // start of the attempted step
+        if (!(ts + dt > ts)) { status |= 2; break; }
+        if (!(fabsf(y.x) <= 3.4028234e38f && fabsf(y.y) <= 3.4028234e38f)) { status |= 4; break; }
+        const float h = (float)dt;
+        const float2 k1 = f;
+        const float2 k2 = sg * fld.eval(prm, fma2(h * B21, k1, y));
+        const float2 k3 = sg * fld.eval(prm, fma2(h * B32, k2, fma2(h * B31, k1, y)));
+        const float2 k4 = sg * fld.eval(prm, fma2(h * B43, k3, fma2(h * B42, k2, fma2(h * B41, k1, y))));
+        const float2 k5 = sg * fld.eval(prm, fma2(h * B54, k4, fma2(h * B53, k3, fma2(h * B52, k2, fma2(h * B51, k1, y)))));
+        const float2 k6 = sg * fld.eval(prm, fma2(h * B65, k5, fma2(h * B64, k4, fma2(h * B63, k3, fma2(h * B62, k2, fma2(h * B61, k1, y))))));
+        const float2 y1 = fma2(h * C6, k6, fma2(h * C5, k5, fma2(h * C4, k4, fma2(h * C3, k3, fma2(h * C1, k1, y)))));
+        const float2 k7 = sg * fld.eval(prm, y1);        // FSAL: f1 = k[-1]
+        const float2 err = fma2(h * E7, k7, fma2(h * E6, k6, fma2(h * E5, k5, fma2(h * E4, k4, fma2(h * E3, k3, (h * E1) * k1)))));
+        const float2 tol = f2(dp.atol + dp.rtol * fmaxf(fabsf(y.x), fabsf(y1.x)), dp.atol + dp.rtol * fmaxf(fabsf(y.y), fabsf(y1.y)));
+        const float2 er = div2(err, tol);
+        const float ratio = 0.5f * (er.x * er.x + er.y * er.y);
+        const bool accept = ratio <= 1.f;
+        if (accept) {
+          const float2 ymid = fma2(h * M7, k7, fma2(h * M6, k6, fma2(h * M5, k5, fma2(h * M4, k4, fma2(h * M3, k3, fma2(h * M1, k1, y))))));
+          // interp.py:21-35
+          ca = fma2(16.f, ymid, fma2(-8.f, y1, fma2(-8.f, y, fma2(2.f * h, k7, (-2.f * h) * k1))));
+          cb = fma2(-32.f, ymid, fma2(14.f, y1, fma2(18.f, y, fma2(-3.f * h, k7, (5.f * h) * k1))));
+          cc = fma2(16.f, ymid, fma2(-5.f, y1, fma2(-11.f, y, fma2(h, k7, (-4.f * h) * k1))));
+          cd = h * k1;
+          ce = y;
+          y = y1;
+          f = k7;
+          t0 = ts;
+          t1 = ts + dt;
+          ++n_acc;
+        } else {
+          t0 = ts;                                         // rk_state.t0 := start of the rejected attempt (dopri5.py:121)
+          ++n_rej;
+        }
+        // misc.py:160-170
+        double factor;
+        if (ratio == 0.f) {
+          dt = dt * dp.ifactor;
+        } else {
+          const double dfac = ratio < 1.f ? 1.0 : dp.dfactor;
+          const double er5 = pow((double)sqrtf(ratio), 0.2);     // sqrt in the ratio's dtype, then ** (1/5) in float64
+          factor = fmax(1.0 / dp.ifactor, fmin(er5 / dp.safety, 1.0 / dfac));
+          dt = dt / factor;
+        }
+        ++n_steps;
+      }
+      if (status) break;
+      // interp.py:38-65 in the state dtype
+      const float ft0 = (float)t0, ft1 = (float)t1, ft = (float)next_t;
+      const float x = (ft - ft0) / (ft1 - ft0);
+      const float x2 = x * x, x3 = x2 * x, x4 = x3 * x;
+      const float2 out = ((((x4 * ca) + (x3 * cb)) + (x2 * cc)) + (x * cd)) + ce;
+      if (lane == 0) sol[(long long)i * PN + pair] = out;
+    }
+  }
+  if (lane == 0 && dp.stats) {
+    dp.stats[pair * 3 + 0] = n_acc;
+    dp.stats[pair * 3 + 1] = n_rej;
+    dp.stats[pair * 3 + 2] = status;
+  }
+}
+
+}  // namespace bode

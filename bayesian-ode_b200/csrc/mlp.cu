@@ -1,12 +1,16 @@
 // Host side of the MLP neural-ODE entry points (argument checks, parameter packing, dispatch on the hidden width).
 #include "npde_solve.cuh"
+#include "dopri5.cuh"
 #include <string.h>
+
+int fill_dopri5(bode::Dopri5Params& dp, const bode_dopri5_opts* o);
 
 namespace bode {
 #define BODE_DECL_MLP(H)                                                                                                  \
   size_t mlp_smem_bytes_##H(int N);                                                                                       \
   int launch_mlp_fwd_##H(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);         \
-  int launch_mlp_grad_##H(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+  int launch_mlp_grad_##H(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_mlp_dopri5_##H(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
 BODE_DECL_MLP(20)
 BODE_DECL_MLP(64)
 
@@ -15,10 +19,10 @@ static int mlp_fill(NpdeKParams& prm, const bode_mlp_field* f, const bode_grid* 
   BODE_REQUIRE(f->H == 20 || f->H == 64, "MLP field is built for hidden widths 20 and 64 (got %d)", f->H);
   BODE_REQUIRE(f->P > 0 && N > 0 && N <= 8, "need P > 0 and 1 <= N <= 8 trajectories (got P=%d N=%d)", f->P, N);
   BODE_REQUIRE(g->S >= 0 && g->T >= 1, "bad grid S=%d T=%d", g->S, g->T);
-  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_RK4, "unknown method %d", method);
+  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_DOPRI5, "unknown method %d", method);
   const int d = f->H * f->H + 6 * f->H + 2;
   BODE_REQUIRE(f->theta && y0 && f->theta_stride >= d, "null theta/y0 or theta_stride < d=%d", d);
-  BODE_REQUIRE(g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
+  BODE_REQUIRE(method == BODE_DOPRI5 || g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
   memset(&prm, 0, sizeof(prm));
   prm.P = f->P; prm.N = N; prm.S = g->S; prm.T = g->T; prm.m = 0; prm.ppc = 1;
   prm.y0_stride = y0_batched ? 2 * N : 0;
@@ -58,6 +62,24 @@ extern "C" int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int3
   const size_t smem = mlp_smem(f->H, N);
   if (f->H == 20) return launch_mlp_fwd_20(prm, method, grid, block, smem, (cudaStream_t)stream);
   return launch_mlp_fwd_64(prm, method, grid, block, smem, (cudaStream_t)stream);
+}
+
+extern "C" int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                               const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(sol, "null sol");
+  prm.sol = sol;
+  Dopri5Params dp;
+  st = fill_dopri5(dp, o);
+  if (st != BODE_OK) return st;
+  const dim3 grid(f->P), block(32 * N);
+  const size_t smem = mlp_smem(f->H, N);
+  if (f->H == 20) return launch_mlp_dopri5_20(prm, dp, grid, block, smem, (cudaStream_t)stream);
+  return launch_mlp_dopri5_64(prm, dp, grid, block, smem, (cudaStream_t)stream);
 }
 
 extern "C" int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,

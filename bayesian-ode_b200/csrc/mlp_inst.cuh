@@ -1,6 +1,7 @@
 // Instantiates the solver kernels for the MLP field with hidden width BODE_H (compiled once per width).
 #include "npde_solve.cuh"
 #include "mlp_field.cuh"
+#include "dopri5.cuh"
 
 namespace bode {
 
@@ -26,6 +27,16 @@ static int mlp_launch_grad(const NpdeKParams& prm, dim3 grid, dim3 block, size_t
   }
   npde_grad_kernel<MF, METHOD, INJ, ADJ><<<grid, block, smem, st>>>(prm);
   return check_cuda(cudaGetLastError(), "mlp grad launch");
+}
+
+int BODE_CAT(launch_mlp_dopri5_, BODE_H)(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    int e = check_cuda(cudaFuncSetAttribute(dopri5_fwd_kernel<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (e != BODE_OK) return e;
+  }
+  dopri5_fwd_kernel<MF><<<grid, block, smem, st>>>(prm, dp);
+  return check_cuda(cudaGetLastError(), "mlp dopri5 launch");
 }
 
 size_t BODE_CAT(mlp_smem_bytes_, BODE_H)(int N) { return sizeof(float) * (size_t)MF::smem_floats(N); }

@@ -1,5 +1,6 @@
 // Host side of the npde entry points: argument checks, parameter packing, kernel dispatch.
 #include "npde_solve.cuh"
+#include "dopri5.cuh"
 #include <math.h>
 
 namespace bode {
@@ -7,7 +8,8 @@ namespace bode {
 // one translation unit per grid size keeps the build parallel; see npde_inst.cuh
 #define BODE_DECL_SEP(M)                                                                               \
   int launch_sep_fwd_##M(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
-  int launch_sep_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+  int launch_sep_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_sep_dopri5_##M(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
 BODE_DECL_SEP(3)
 BODE_DECL_SEP(4)
 BODE_DECL_SEP(5)
@@ -20,9 +22,9 @@ static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_gr
   BODE_REQUIRE(f && g, "null field/grid");
   BODE_REQUIRE(f->P > 0 && f->m > 0 && N > 0, "P, m, N must be positive (P=%d m=%d N=%d)", f->P, f->m, N);
   BODE_REQUIRE(g->S >= 0 && g->T >= 1, "bad grid S=%d T=%d", g->S, g->T);
-  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_RK4, "unknown method %d", method);
+  BODE_REQUIRE(method >= BODE_EULER && method <= BODE_DOPRI5, "unknown method %d", method);
   BODE_REQUIRE(f->U && f->A && y0, "null U/A/y0");
-  BODE_REQUIRE(g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
+  BODE_REQUIRE(method == BODE_DOPRI5 || g->S == 0 || (g->dt && g->obs_ptr), "null dt/obs_ptr");
   BODE_REQUIRE(f->ell[0] > 0 && f->ell[1] > 0, "ell must be positive");
   memset(&prm, 0, sizeof(prm));
   prm.P = f->P; prm.N = N; prm.S = g->S; prm.T = g->T; prm.m = f->m;
@@ -139,6 +141,43 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
   }
   set_error("general (non-grid) inducing points: kernel not built in this version");
   return BODE_ERR_UNSUPPORTED;
+}
+
+int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o) {
+  BODE_REQUIRE(o && o->t, "null dopri5 options / t");
+  BODE_REQUIRE(o->rtol > 0 && o->atol >= 0 && o->safety > 0 && o->ifactor > 0 && o->dfactor > 0, "bad dopri5 tolerances/factors");
+  dp.t = o->t; dp.rtol = (float)o->rtol; dp.atol = (float)o->atol; dp.user_first_step = o->user_first_step;
+  dp.safety = o->safety; dp.ifactor = o->ifactor; dp.dfactor = o->dfactor;
+  dp.max_num_steps = o->max_num_steps > 0 ? o->max_num_steps : 2147483647;
+  dp.stats = o->stats;
+  return BODE_OK;
+}
+
+extern "C" int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                                const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = fill_common(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(sol, "null sol");
+  prm.sol = sol;
+  Dopri5Params dp;
+  st = fill_dopri5(dp, o);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(f->grid_mx > 0, "general (non-grid) inducing points: kernel not built in this version");
+  st = fill_sep(prm, f);
+  if (st != BODE_OK) return st;
+  dim3 grid, block;
+  st = plan(prm, 1, 256, &grid, &block);
+  if (st != BODE_OK) return st;
+  const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
+  switch (f->grid_mx) {
+    case 3: return launch_sep_dopri5_3(prm, dp, grid, block, smem, (cudaStream_t)stream);
+    case 4: return launch_sep_dopri5_4(prm, dp, grid, block, smem, (cudaStream_t)stream);
+    case 5: return launch_sep_dopri5_5(prm, dp, grid, block, smem, (cudaStream_t)stream);
+    default: return launch_sep_dopri5_6(prm, dp, grid, block, smem, (cudaStream_t)stream);
+  }
 }
 
 extern "C" int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,

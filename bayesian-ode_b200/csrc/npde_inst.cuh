@@ -1,5 +1,6 @@
 // Instantiates the separable npde kernels for one grid size BODE_M (compiled once per size).
 #include "npde_solve.cuh"
+#include "dopri5.cuh"
 #include <string.h>
 
 namespace bode {
@@ -19,6 +20,12 @@ static int launch_grad_m(const NpdeKParams& prm, dim3 grid, dim3 block, size_t s
   using F = SepField<BODE_M, BODE_M>;
   npde_grad_kernel<F, METHOD, INJ, ADJ><<<grid, block, smem, st>>>(prm);
   return check_cuda(cudaGetLastError(), "npde_grad_kernel launch");
+}
+
+int BODE_CAT(launch_sep_dopri5_, BODE_M)(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem,
+                                         cudaStream_t st) {
+  dopri5_fwd_kernel<SepField<BODE_M, BODE_M>><<<grid, block, smem, st>>>(prm, dp);
+  return check_cuda(cudaGetLastError(), "dopri5 launch");
 }
 
 int BODE_CAT(launch_sep_fwd_, BODE_M)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {

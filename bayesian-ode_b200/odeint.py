@@ -137,6 +137,57 @@ class _MlpOdeint(torch.autograd.Function):
         return (gy0, None, None, None, None, None, None) + grads
 
 
+_last_dopri5_stats = None
+
+
+def last_dopri5_stats():
+    """[P, N, 3] int32 (accepted steps, rejected steps, status bits) of the most recent dopri5 call (diagnostics)."""
+    return _last_dopri5_stats
+
+
+def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
+    """Dopri5Solver forward (dopri5.py:58-122) with one controller per (particle, trajectory) pair.  The result is not
+    differentiable in this build (the gradient through adaptive steps is a next-round item)."""
+    global _last_dopri5_stats
+    import warnings
+    lib = _lib.load()
+    options = dict(options or {})
+    known = {k: options.pop(k) for k in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps") if k in options}
+    if len(options) > 0:
+        warnings.warn("Dopri5Solver: Unexpected arguments {}".format(options))          # misc.py:79-81
+    y0c, batched, N = _norm_y0(func, y0)
+    dev = y0c.device
+    t64 = t.detach().to("cpu", torch.float64)
+    sign = 1.0
+    if t64.numel() > 1 and bool((t64[1:] < t64[:-1]).all()):                               # misc.py:184-187
+        t64, sign = -t64, -1.0
+    assert t64.numel() < 2 or bool((t64[1:] > t64[:-1]).all()), "t must be strictly increasing or decrasing"
+    tdev = t64.to(dev)
+    T = int(t64.numel())
+    stats = torch.zeros((func.P, N, 3), dtype=torch.int32, device=dev)
+    o = _lib.Dopri5Opts()
+    o.t = tdev.data_ptr()
+    o.rtol, o.atol = float(rtol), float(atol)
+    o.safety, o.ifactor, o.dfactor = float(known.get("safety", 0.9)), float(known.get("ifactor", 10.0)), float(known.get("dfactor", 0.2))
+    o.max_num_steps = int(min(known.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
+    o.user_first_step = int(known.get("first_step") is not None)
+    o.stats = stats.data_ptr()
+    sol = torch.empty((T, func.P, N, 2), dtype=torch.float32, device=dev)
+    if isinstance(func, NPDEField):
+        st = lib.bode_npde_dopri5(func.c_struct(func.U.detach()), o, T, sign, N, _lib.ptr(y0c), int(batched), _lib.ptr(sol), _lib.stream_ptr())
+    else:
+        st = lib.bode_mlp_dopri5(func.c_struct(), o, T, sign, N, _lib.ptr(y0c), int(batched), _lib.ptr(sol), _lib.stream_ptr())
+    _lib.check(st)
+    flags = int(stats[..., 2].max().item())              # dopri5.py:89,100-102 assert on these conditions
+    _last_dopri5_stats = stats
+    assert not (flags & 1), "max_num_steps exceeded"
+    assert not (flags & 2), "underflow in dt"
+    assert not (flags & 4), "non-finite values in state `y`"
+    if isinstance(func, NPDEField) and not func.batched:
+        sol = sol[:, 0]
+    return sol if tensor_input else (sol,)
+
+
 def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
     tensor_input, y0 = _check_inputs(func, y0, t)
     if options is None:
@@ -162,7 +213,7 @@ def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
             if not func.batched:
                 sol = sol[:, 0]
             return sol if tensor_input else (sol,)
-        raise NotImplementedError("method '{}' is not built for NPDEField yet".format(method))
+        return _dopri5(func, y0, t, rtol, atol, options, tensor_input)
     if isinstance(func, MLPField):
         if method in FIXED_GRID_METHODS:
             opts = _grid.split_options(solver_name, options)
@@ -174,7 +225,7 @@ def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
             params = [getattr(func, k) for k in func._blocks()]
             sol = _MlpOdeint.apply(y0c, func, g, _lib.METHODS[method], grad_mode, batched, N, *params)
             return sol if tensor_input else (sol,)
-        raise NotImplementedError("method '{}' is not built for MLPField yet".format(method))
+        return _dopri5(func, y0, t, rtol, atol, options, tensor_input)
     raise TypeError(
         "{}: `func` must be a field module of bayesian_ode_b200 (NPDEField / MLPField); got {}. The B200 build "
         "has no generic-callable or CPU path.".format(who, type(func).__name__))

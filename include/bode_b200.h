@@ -43,7 +43,7 @@ enum bode_status {
 };
 
 /* torchdiffeq SOLVERS registry entries on the hot path (odeint.py:8-17) */
-enum bode_method { BODE_EULER = 0, BODE_MIDPOINT = 1, BODE_RK4 = 2 /* 3/8 rule, fixed_grid.py:29 */ };
+enum bode_method { BODE_EULER = 0, BODE_MIDPOINT = 1, BODE_RK4 = 2 /* 3/8 rule, fixed_grid.py:29 */, BODE_DOPRI5 = 3 };
 
 /* which gradient (SURVEY.md hard part 1):
  *   DISCRETE = autograd through odeint (exact reverse of the discretisation)
@@ -95,6 +95,23 @@ typedef struct bode_grid {
   const float*   adj_dt;   /* device, may be NULL unless ADJOINT */
   const int32_t* adj_ptr;  /* [T] device, may be NULL unless ADJOINT */
 } bode_grid;
+
+/* Adaptive Dormand-Prince 5(4), Dopri5Solver (dopri5.py:58-122), ONE step-size controller per (particle, trajectory)
+ * pair -- each pair reproduces the control flow of its own reference odeint call (the notebook integrates one row per
+ * call).  t is float64 like the reference's controller (solvers.py:28) and already increasing (pass sign = -1 and the
+ * negated times for decreasing t, misc.py:184-187).  Defaults of odeint / Dopri5Solver: rtol 1e-7, atol 1e-9, safety .9,
+ * ifactor 10, dfactor .2, max_num_steps 2^31-1 per output time; user_first_step != 0 reproduces dopri5.py:81-82 (0.01).
+ * stats (optional, device int32 [P*N][3]) receives accepted steps, rejected steps and status bits
+ * (1 = max_num_steps exceeded, 2 = dt underflow, 4 = non-finite state; dopri5.py:89,100-102 assert on these). */
+typedef struct bode_dopri5_opts {
+  const double* t;      /* [T] device */
+  double rtol, atol, safety, ifactor, dfactor;
+  int32_t max_num_steps, user_first_step;
+  int32_t* stats;
+} bode_dopri5_opts;
+
+int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                     const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream);
 
 /* scratch floats needed by the gradient entry points for (P particles, N trajectories) */
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
@@ -149,6 +166,9 @@ typedef struct bode_mlp_field {
 /* odeint(net, x0, t, method) forward for every particle and trajectory row (nn.ipynb cell 10 loops rows) */
 int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
                     int32_t y0_batched, float* sol, bode_stream_t stream);
+/* odeint(net, x0, t, method='dopri5') forward, per-pair controller (see bode_dopri5_opts) */
+int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                    const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream);
 /* its backward for an arbitrary dL/dsol [T,P,N,2]: gtheta [P,d] (+ optional gy0 [P,N,2]) */
 int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
                              const float* y0, int32_t y0_batched, const float* gout, float* gtheta,

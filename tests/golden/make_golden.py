@@ -349,6 +349,49 @@ def gen_mlp(data):
     save("mlp", **out)
 
 
+class _Counted(torch.nn.Module):
+    def __init__(self, inner):
+        super().__init__()
+        self.inner, self.nfe = inner, 0
+
+    def forward(self, t, y):
+        self.nfe += 1
+        return self.inner(t, y)
+
+
+def gen_dopri5(data):
+    """Adaptive dopri5 through the reference, one odeint call per trajectory row (per-row controller)."""
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    x0, t = data["x0"], data["t"]
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    torch.manual_seed(120)
+    net = NN(2, 20)
+    for m_ in net.modules():
+        if isinstance(m_, torch.nn.Linear):
+            torch.nn.init.uniform_(m_.weight, a=-0.5, b=0.5)
+    out = dict(x0=x0, t=t, U=U0, Z=Zt, theta=torch.cat([q.detach().reshape(-1) for q in net.parameters()]))
+    cases = {"default": dict(), "loose": dict(rtol=1e-5, atol=1e-7), "firststep": dict(rtol=1e-5, atol=1e-7, options=dict(first_step=0.5))}
+    for name, kw in cases.items():
+        for fname, fobj, mk in (("npde", kreg, lambda r: x0[r:r + 1]), ("mlp", net, lambda r: x0[r])):
+            sols, nfes = [], []
+            for r in range(x0.size(0)):
+                cf = _Counted(fobj)
+                with torch.no_grad():
+                    sol = torchdiffeq.odeint(cf, mk(r), t, method="dopri5" if "options" in kw else None, **kw)
+                sols.append(sol.reshape(len(t), 2)); nfes.append(cf.nfe)
+            out[f"{name}_{fname}_sol"] = torch.stack(sols, 1)          # [T,N,2]
+            out[f"{name}_{fname}_nfe"] = np.array(nfes)
+    trev = torch.linspace(3., 0., 7)
+    sols = []
+    for r in range(x0.size(0)):
+        with torch.no_grad():
+            sols.append(torchdiffeq.odeint(kreg, x0[r:r + 1], trev, rtol=1e-5, atol=1e-7).reshape(7, 2))
+    out["rev_t"] = trev
+    out["rev_npde_sol"] = torch.stack(sols, 1)
+    save("dopri5", **out)
+
+
 if __name__ == "__main__":
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
@@ -358,3 +401,4 @@ if __name__ == "__main__":
     gen_sampler_steps(data)
     gen_svgd(data)
     gen_mlp(data)
+    gen_dopri5(data)

@@ -1,0 +1,94 @@
+"""GPU: adaptive dopri5 (per-pair controller) through the C ABI vs the reference goldens and the float32 oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def _fields(g):
+    import bayesian_ode_b200 as bode
+    fn = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    fm = bode.MLPField(1, hidden_size=20, theta=torch.from_numpy(g["theta"])[None])
+    return fn, fm
+
+
+@pytest.mark.parametrize("case,kw", [("default", {}), ("loose", dict(rtol=1e-5, atol=1e-7)),
+                                     ("firststep", dict(rtol=1e-5, atol=1e-7, method="dopri5", options=dict(first_step=0.5)))])
+def test_dopri5_matches_reference(case, kw):
+    """fp32 state vs the float64 reference: trajectories to 1e-5 relative (the north_star bar) at the reference's own
+    tolerances; the number of attempted steps stays within 25% of the reference's (the controller sees fp32 rounding,
+    and one flipped borderline accept changes every later step size)."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("dopri5")
+    fn, fm = _fields(g)
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
+    for fname, f in (("npde", fn), ("mlp", fm)):
+        sol = bode.odeint(f, x0, t, **kw)                        # method=None -> dopri5 (odeint.py:68-69)
+        sol = sol if sol.dim() == 3 else sol[:, 0]
+        tol = 1e-5 if case == "default" else 1e-4      # the solver itself only controls the error to rtol
+        assert relerr(sol.cpu().numpy(), g[f"{case}_{fname}_sol"]) < tol, (fname, case)
+        st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
+        attempted_ref = (g[f"{case}_{fname}_nfe"] - (1 if case == "firststep" else 2)) / 6.0
+        assert np.all(st[:, 2] == 0)
+        assert np.all(np.abs(st[:, 0] + st[:, 1] - attempted_ref) <= np.maximum(3, 0.25 * attempted_ref)), (st, attempted_ref)
+
+
+def test_dopri5_control_flow_matches_float32_oracle():
+    """Same dtype on both sides (float32 state, float64 t/dt): accepted/rejected counts agree with the NumPy oracle for
+    most rows -- a borderline accept can flip on the last ulp because the device field uses FMA contraction and
+    MUFU.EX2 where NumPy does not (allowed: 2 rows of 5) -- and the trajectories agree to the solver tolerance."""
+    import bayesian_ode_b200 as bode
+    from oracle import dopri5, npde
+    g = load_golden("dopri5")
+    fn, _ = _fields(g)
+    fo = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    sol = bode.odeint(fn, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), rtol=1e-5, atol=1e-7)
+    st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
+    same = 0
+    for r in range(5):
+        f32 = lambda y: fo.f(y[None, None].astype(np.float64))[0, 0]
+        so, so_st = dopri5.odeint_dopri5(f32, g["x0"][r].astype(np.float32), g["t"], rtol=1e-5, atol=1e-7)
+        same += int(st[r, 0] == so_st["accepted"] and st[r, 1] == so_st["rejected"])
+        assert relerr(sol[:, r].cpu().numpy(), so) < 1e-4
+    assert same >= 3, st
+
+
+def test_dopri5_reversed_time_and_errors():
+    import bayesian_ode_b200 as bode
+    g = load_golden("dopri5")
+    fn, _ = _fields(g)
+    x0 = torch.from_numpy(g["x0"])
+    sol = bode.odeint(fn, x0, torch.from_numpy(g["rev_t"]), rtol=1e-5, atol=1e-7)
+    assert relerr(sol.cpu().numpy(), g["rev_npde_sol"]) < 1e-4
+    with pytest.raises(AssertionError):                      # dopri5.py:89 max_num_steps
+        bode.odeint(fn, x0, torch.from_numpy(g["t"]), method="dopri5", options=dict(max_num_steps=2))
+    with pytest.warns(UserWarning):                          # misc.py:79-81
+        bode.odeint(fn, x0, torch.from_numpy(g["t"]), rtol=1e-4, atol=1e-6, method="dopri5", options=dict(bogus=1))
+
+
+def test_dopri5_config4_sizes_run():
+    """BASELINE config 4 shape: 2-64-64-2 MLP, many chains, per-pair adaptive stepping, finite output and sane step counts."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("dopri5")
+    f = bode.MLPField(512, hidden_size=64, generator=torch.Generator().manual_seed(0))
+    sol = bode.odeint(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), rtol=1e-5, atol=1e-7)
+    assert sol.shape == (40, 512, 5, 2) and bool(torch.isfinite(sol).all())
+    st = bode.last_dopri5_stats()
+    assert int(st[..., 2].max()) == 0 and int(st[..., 0].min()) >= 5
+
+
+def test_dopri5_zero_field_takes_the_ratio_zero_branch():
+    """U = 0 -> f = 0 exactly on both sides: err = 0, ratio == 0 -> dt *= ifactor (misc.py:162-163), h0 = 1e-6 branch of
+    the initial step (misc.py:119-120); arithmetic is exact so the step counts must equal the oracle's bit for bit."""
+    import bayesian_ode_b200 as bode
+    from oracle import dopri5
+    g = load_golden("dopri5")
+    fn = bode.NPDEField(torch.zeros(25, 2), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    sol = bode.odeint(fn, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]))
+    st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
+    so, so_st = dopri5.odeint_dopri5(lambda y: np.zeros_like(y), g["x0"][0].astype(np.float32), g["t"])
+    assert np.all(st[:, 0] == so_st["accepted"]) and np.all(st[:, 1] == so_st["rejected"])
+    assert np.array_equal(sol[:, 0].cpu().numpy(), so)

@@ -103,3 +103,28 @@ def test_torch_port_used_as_cpu_baseline_matches_reference():
     kreg = ref_torch.KReg(torch.from_numpy(g["U"][0]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
     xode = ref_torch.odeint_rk4(kreg, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]))
     assert relerr(xode.detach().numpy(), g["rk4_sol"][:, 0]) < 1e-12
+
+
+@pytest.mark.parametrize("case,kw", [("default", {}), ("loose", dict(rtol=1e-5, atol=1e-7)),
+                                     ("firststep", dict(rtol=1e-5, atol=1e-7, first_step=0.5))])
+def test_dopri5_oracle_matches_reference_trajectories_and_nfe(case, kw):
+    """Per-row adaptive solves: identical number of function evaluations (accept/reject + controller logic) and
+    trajectories to 1e-8 for the npde and the MLP field; the first_step quirk (dopri5.py:81-82) included."""
+    from oracle import dopri5, mlp
+    g = load_golden("dopri5")
+    fn = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    fm = mlp.MLPField(g["theta"][None], 20)
+    for fname, fld in (("npde", fn), ("mlp", fm)):
+        for r in range(5):
+            sol, st = dopri5.odeint_dopri5(lambda y: fld.f(y[None, None])[0, 0], g["x0"][r], g["t"], **kw)
+            assert st["nfe"] == g[f"{case}_{fname}_nfe"][r]
+            assert relerr(sol, g[f"{case}_{fname}_sol"][:, r]) < 1e-8
+
+
+def test_dopri5_oracle_reversed_time():
+    from oracle import dopri5
+    g = load_golden("dopri5")
+    fn = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    for r in range(5):
+        sol, _ = dopri5.odeint_dopri5(lambda y: fn.f(y[None, None])[0, 0], g["x0"][r], g["rev_t"], rtol=1e-5, atol=1e-7)
+        assert relerr(sol, g["rev_npde_sol"][:, r]) < 1e-8
