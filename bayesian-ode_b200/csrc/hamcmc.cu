@@ -1,0 +1,233 @@
+// HAMCMC: L-BFGS-preconditioned Langevin (samplers/langevin.py:619-1107; Simsekli et al. 2016 via the product-form BFGS of
+// Zhang & Sutton), one CTA per chain, bug-compatible with the reference (see oracle/samplers.py::HAMCMC for the list):
+//   warm-up  step_without_metric  :941-964  theta <- theta - lr g - lr n, history append (:902-939) and the start-up pairs
+//   metric   step                 :966-1000 base = params[M-1]; (Hg, Sn) = _compute_vector_prod(g, n) (:717-860);
+//                                           theta_new = base - lr Hg - lr Sn; _update_metric_vars (:862-900)
+// The reference materialises d x d outer products and B0 = eye(d)/H_gamma; here every operator is applied as dot + axpy over
+// length-d vectors (O(K^2 d) per step), each thread owning a fixed strided slice so elementwise updates need no barrier and
+// only the dot products synchronise the CTA.
+#include "common.cuh"
+
+namespace bode {
+
+struct HamcmcArgs {
+  int P, d, M;                     // M = memory + 1
+  float *hist_theta, *hist_grad;   // [P][2M-1][d]
+  float *pair_s, *pair_y;          // [P][M-1][d]
+  float* work;                     // [P][4(M-1)+2][d]  u, v, p, q, z, z2
+  int* meta;                       // [P][4]  n_hist, head, K, pair_head
+  float* theta; long long ld_theta;
+  const float* grad; long long ld_grad;
+  const float* xi;                 // [P][d] injected standard normals or null
+  float lr, H_gamma, trust_reg;
+  int mode, add_params, add_noise;
+  unsigned long long seed; unsigned int step;
+  int* status;
+};
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[w] = v;
+  __syncthreads();
+  float t = 0.f;
+  for (int i = 0; i < nw; ++i) t += red[i];       // fixed order: deterministic
+  return t;
+}
+
+__device__ __forceinline__ float bdot(const float* a, const float* b, int d, float* red) {
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) acc = fmaf(a[e], b[e], acc);
+  return block_sum(acc, red);
+}
+
+// minimal Philox for in-kernel noise (same generator as samplers.cu)
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned int idx, unsigned int step) {
+  unsigned int c0 = idx >> 1, c1 = step, c2 = 0x4a3cu, c3 = 0x5eedu, a = (unsigned int)seed, b = (unsigned int)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned int hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned int hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ a; c1 = lo1; c2 = hi0 ^ c3 ^ b; c3 = lo0;
+    a += 0x9E3779B9u; b += 0xBB67AE85u;
+  }
+  const float u1 = (float)(c0 >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);
+  const float u2 = (float)(c1 >> 8) * (1.0f / 16777216.0f) + (0.5f / 16777216.0f);
+  const float r = sqrtf(-2.f * __logf(u1));
+  float s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return (idx & 1) ? r * s : r * c;
+}
+
+__global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
+  __shared__ float red[8];
+  const int p = blockIdx.x, d = a.d, M = a.M, cap = 2 * M - 1;
+  float* ht = a.hist_theta + (long long)p * cap * d;
+  float* hg = a.hist_grad + (long long)p * cap * d;
+  float* ps = a.pair_s + (long long)p * (M - 1) * d;
+  float* py = a.pair_y + (long long)p * (M - 1) * d;
+  float* wk = a.work + (long long)p * (4 * (M - 1) + 2) * d;
+  float *U = wk, *V = wk + (M - 1) * d, *Pp = wk + 2 * (M - 1) * d, *Q = wk + 3 * (M - 1) * d;
+  float *z = wk + 4 * (M - 1) * d, *z2 = z + d;
+  int* meta = a.meta + 4 * p;
+  float* th = a.theta + (long long)p * a.ld_theta;
+  const float* g = a.grad + (long long)p * a.ld_grad;
+  const float nscale = rsqrtf(0.5f * a.lr);
+  int bad = 0;
+  auto noise_at = [&](int e) -> float {
+    const float x = a.xi ? a.xi[(long long)p * d + e] : philox_normal(a.seed, (unsigned)(p * d + e), a.step);
+    return x * nscale;
+  };
+
+  if (a.mode == 0) {
+    // ---------------- step_without_metric (:941-964)
+    int n_hist = meta[0];
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+      float t = th[e];
+      bad |= !(fabsf(t) <= 3.4028234e38f);
+      t = fmaf(-a.lr, g[e], t);
+      if (a.add_noise) t = fmaf(-a.lr, noise_at(e), t);
+      th[e] = t;
+      if (a.add_params && n_hist < cap) {
+        ht[(long long)n_hist * d + e] = t;          // theta AFTER the update, gradient from BEFORE it (:954-961)
+        hg[(long long)n_hist * d + e] = g[e];
+      }
+    }
+    if (a.add_params && n_hist < cap) ++n_hist;
+    int K = meta[2];
+    if (a.add_params && n_hist == cap && meta[0] == cap - 1) {
+      // history just became full: start-up pairs i <-> i+M with the 1e-4 curvature filter (:924-935)
+      __syncthreads();
+      K = 0;
+      for (int i = 0; i < M - 1; ++i) {
+        float sy = 0.f, ss = 0.f;
+        for (int e = threadIdx.x; e < d; e += blockDim.x) {
+          const float s = ht[(long long)(i + M) * d + e] - ht[(long long)i * d + e];
+          const float y = hg[(long long)(i + M) * d + e] - hg[(long long)i * d + e] + a.trust_reg * s;
+          z[e] = s; z2[e] = y;
+          sy = fmaf(s, y, sy); ss = fmaf(s, s, ss);
+        }
+        sy = block_sum(sy, red);
+        ss = block_sum(ss, red);
+        if (sy > 1e-4f * ss) {
+          for (int e = threadIdx.x; e < d; e += blockDim.x) { ps[(long long)K * d + e] = z[e]; py[(long long)K * d + e] = z2[e]; }
+          ++K;
+        }
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { meta[0] = n_hist; meta[1] = 0; meta[2] = K; meta[3] = 0; }
+  } else {
+    // ---------------- metric step (:966-1000)
+    const int head = meta[1], K = meta[2], phead = meta[3];
+    const float B0 = 1.f / a.H_gamma, C0 = sqrtf(B0), S0 = rsqrtf(B0);
+    const float* base = ht + (long long)((head + M - 1) % cap) * d;
+    const float* gbase = hg + (long long)((head + M - 1) % cap) * d;
+    int nu = 0;
+    for (int i = 0; i < K; ++i) {
+      const float* s = ps + (long long)((phead + i) % K) * d;
+      const float* y = py + (long long)((phead + i) % K) * d;
+      const float sy = bdot(s, y, d, red);
+      if (sy < 0.f) continue;                                           // :825-829
+      if (nu == 0) {
+        for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = B0 * s[e];
+      } else {
+        for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = s[e];
+        for (int j = nu - 1; j >= 0; --j) {                             // C^T z (:760-777)
+          const float c = bdot(z, V + (long long)j * d, d, red);
+          for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = fmaf(-c, U[(long long)j * d + e], z[e]);
+        }
+        for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] *= C0 * C0;   // C0 applied by C^T and again by C (:751,776)
+        for (int j = 0; j < nu; ++j) {                                  // C z (:750-757)
+          const float c = bdot(z, U + (long long)j * d, d, red);
+          for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = fmaf(-c, V[(long long)j * d + e], z[e]);
+        }
+      }
+      const float sBs = bdot(s, z, d, red);
+      const float cq = sqrtf(sy / sBs), cu = sqrtf(sBs / sy), isy = 1.f / sy, isBs = 1.f / sBs;
+      for (int e = threadIdx.x; e < d; e += blockDim.x) {
+        Q[(long long)nu * d + e] = cq * z[e] - y[e];
+        Pp[(long long)nu * d + e] = s[e] * isy;
+        U[(long long)nu * d + e] = cu + z[e];                            // scalar + vector (:846)
+        V[(long long)nu * d + e] = s[e] * isBs;
+      }
+      ++nu;
+    }
+    // Hg = S (S^T g)   (:808-815) ; Sn = S n (:856)
+    for (int e = threadIdx.x; e < d; e += blockDim.x) { z[e] = g[e]; z2[e] = S0 * noise_at(e); }
+    if (nu == 0) {
+      for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = z[e] / B0;
+    } else {
+      for (int j = nu - 1; j >= 0; --j) {
+        const float c = bdot(z, Q + (long long)j * d, d, red);
+        for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = fmaf(-c, Pp[(long long)j * d + e], z[e]);
+      }
+      for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] *= S0 * S0;
+      for (int j = 0; j < nu; ++j) {
+        const float c = bdot(z, Pp + (long long)j * d, d, red);
+        for (int e = threadIdx.x; e < d; e += blockDim.x) z[e] = fmaf(-c, Q[(long long)j * d + e], z[e]);
+      }
+    }
+    for (int j = 0; j < nu; ++j) {
+      const float c = bdot(z2, Pp + (long long)j * d, d, red);
+      for (int e = threadIdx.x; e < d; e += blockDim.x) z2[e] = fmaf(-c, Q[(long long)j * d + e], z2[e]);
+    }
+    // theta_new = base - lr Hg - lr Sn ; s/y of the refresh pair (:862-873)
+    float sy = 0.f, ss = 0.f;
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {
+      float t = fmaf(-a.lr, z[e], base[e]);
+      if (a.add_noise) t = fmaf(-a.lr, z2[e], t);
+      bad |= !(fabsf(t) <= 3.4028234e38f);
+      const float s = t - base[e];
+      const float y = g[e] - gbase[e] + a.trust_reg * s;
+      z[e] = s; z2[e] = y;
+      th[e] = t;
+      sy = fmaf(s, y, sy); ss = fmaf(s, s, ss);
+    }
+    sy = block_sum(sy, red);
+    ss = block_sum(ss, red);
+    int np_head = phead;
+    if (sy > 1e-8f * ss && K > 0) {                                      // append + pop(0): the oldest pair is replaced
+      for (int e = threadIdx.x; e < d; e += blockDim.x) { ps[(long long)phead * d + e] = z[e]; py[(long long)phead * d + e] = z2[e]; }
+      np_head = (phead + 1) % K;
+    }
+    __syncthreads();                                                     // base/gbase fully consumed before the ring moves
+    for (int e = threadIdx.x; e < d; e += blockDim.x) {                  // history: append new, pop oldest
+      ht[(long long)head * d + e] = th[e];
+      hg[(long long)head * d + e] = g[e];
+    }
+    if (threadIdx.x == 0) { meta[1] = (head + 1) % cap; meta[3] = np_head; }
+  }
+  if (bad && a.status) atomicOr(a.status, 1);
+}
+
+}  // namespace bode
+
+using namespace bode;
+
+/* floats needed for: which 0 -> hist_theta (= hist_grad), 1 -> pair_s (= pair_y), 2 -> work */
+extern "C" size_t bode_hamcmc_floats(int32_t P, int32_t d, int32_t memory, int32_t which) {
+  const size_t M = (size_t)memory + 1, pd = (size_t)P * d;
+  if (which == 0) return pd * (2 * M - 1);
+  if (which == 1) return pd * (M - 1);
+  return pd * (4 * (M - 1) + 2);
+}
+
+extern "C" int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* hist_theta, float* hist_grad, float* pair_s,
+                                float* pair_y, float* work, int32_t* meta, float* theta, int64_t ld_theta, const float* grad,
+                                int64_t ld_grad, const float* xi, float lr, float H_gamma, float trust_reg, int32_t metric_step,
+                                int32_t add_params, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
+                                bode_stream_t stream) {
+  BODE_REQUIRE(P > 0 && d > 0 && memory >= 1, "bad sizes P=%d d=%d memory=%d", P, d, memory);
+  BODE_REQUIRE(hist_theta && hist_grad && pair_s && pair_y && work && meta && theta && grad, "null pointer");
+  BODE_REQUIRE(lr > 0 && H_gamma > 0, "lr and H_gamma must be positive");
+  HamcmcArgs a = {};
+  a.P = P; a.d = d; a.M = memory + 1; a.hist_theta = hist_theta; a.hist_grad = hist_grad; a.pair_s = pair_s; a.pair_y = pair_y;
+  a.work = work; a.meta = meta; a.theta = theta; a.ld_theta = ld_theta; a.grad = grad; a.ld_grad = ld_grad; a.xi = xi;
+  a.lr = lr; a.H_gamma = H_gamma; a.trust_reg = trust_reg; a.mode = metric_step ? 1 : 0; a.add_params = add_params;
+  a.add_noise = add_noise; a.seed = seed; a.step = step; a.status = status;
+  hamcmc_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(a);
+  return check_cuda(cudaGetLastError(), "hamcmc launch");
+}

@@ -138,3 +138,114 @@ class pSGLD(_LangevinBase):
                                            int(bool(group["add_noise"])), self.seed + k, self._step_index,
                                            _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
+
+
+class HAMCMC(_LangevinBase):
+    """langevin.py:619-1107: L-BFGS-preconditioned Langevin dynamics (marked DEBUG in the reference and reproduced as is).
+    HAMCMC(params, memory=5, lr0=, lr_gamma=, lr_t0=, lr_alpha=, trust_reg=1.0, H_gamma=1.0, add_noise=True).
+    Every chain (row of the flat theta[P, d] buffer, or the concatenation of the parameter tensors for a single chain)
+    keeps its own history window and (s, y) pairs on the device; one CTA per chain applies the product-form BFGS."""
+
+    def __init__(self, params, memory=5, **kwargs):
+        defaults = kwargs
+        defaults.setdefault("add_noise", True)
+        super().__init__(params, defaults)
+        g0 = self.param_groups[0]
+        g0.setdefault("trust_reg", 1e0)
+        g0.setdefault("H_gamma", 1e0)
+        self.loss = None
+        self.memory = memory + 1                       # langevin.py:645
+        self._user_memory = int(memory)
+        self._hs = None
+
+    # -- flat view of the chain state ---------------------------------------------------------------------
+    def _chain_buffers(self):
+        """(theta [P,d], grad [P,d], scatter_back) -- the flat buffers, or packed copies for free-standing tensors
+        (one chain, parameters_to_vector order, langevin.py:944)."""
+        gf = self._grad_flat()
+        if self._flat is not None and gf is not None:
+            return self._flat, gf, None
+        if self._flat is not None:
+            self._tensors_for_launch()
+            return self._flat, self._grad_flat(), None
+        th = torch.cat([p.data.reshape(-1) for p in self._plist])[None].contiguous()
+        gr = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in self._plist])[None].contiguous()
+
+        def scatter():
+            o = 0
+            for p in self._plist:
+                n = p.numel()
+                p.data.copy_(th[0, o:o + n].view_as(p))
+                o += n
+        return th, gr, scatter
+
+    def _state(self, P, d, dev):
+        if self._hs is None:
+            lib = _lib.load()
+            z = lambda w: torch.zeros(lib.bode_hamcmc_floats(P, d, self._user_memory, w), dtype=torch.float32, device=dev)
+            self._hs = dict(ht=z(0), hg=z(0), ps=z(1), py=z(1), wk=z(2), meta=torch.zeros(P, 4, dtype=torch.int32, device=dev))
+        return self._hs
+
+    def _launch(self, lr, metric, add_params, add_noise, noise):
+        lib = _lib.load()
+        th, gr, scatter = self._chain_buffers()
+        P, d = th.shape
+        hs = self._state(P, d, th.device)
+        g0 = self.param_groups[0]
+        xi = None
+        if noise is not None:
+            xi = torch.as_tensor(noise).to(th.device, torch.float32).reshape(P, d).contiguous()
+        _lib.check(lib.bode_hamcmc_step(P, d, self._user_memory, _lib.ptr(hs["ht"]), _lib.ptr(hs["hg"]), _lib.ptr(hs["ps"]),
+                                        _lib.ptr(hs["py"]), _lib.ptr(hs["wk"]), _lib.ptr(hs["meta"]), _lib.ptr(th), d, _lib.ptr(gr), d,
+                                        _lib.ptr(xi), float(lr), float(g0["H_gamma"]), float(g0["trust_reg"]), int(metric),
+                                        int(add_params), int(add_noise), self.seed, self._step_index, _lib.ptr(self._status),
+                                        _lib.stream_ptr()))
+        if scatter is not None:
+            scatter()
+        self._after_step()
+
+    def step_without_metric(self, lr, update_metric=True, add_noise=True, add_params=False, noise=None):
+        self._launch(lr, False, add_params and update_metric, add_noise, noise)
+
+    def step(self, lr, use_old_lbfgs=False, add_noise=True, noise=None):
+        if use_old_lbfgs:
+            raise NotImplementedError("the dense-BFGS + Cholesky variant (langevin.py:669-715) is not built")
+        self._launch(lr, True, False, add_noise, noise)
+
+    def n_pairs(self):
+        return None if self._hs is None else self._hs["meta"][:, 2].clone()
+
+    def sample(self, closure, num_samples=1000, burn_in=100, print_iters=True, print_loss=False, use_metric=True,
+               use_old_lbfgs=False, add_noise=True, thinning=1):
+        """langevin.py:1057-1107; returns (chain, logp_array) like the reference."""
+        chain = self.samples
+        logp_array = []
+        fused = hasattr(closure, "loss_and_grad_") and self._flat is not None
+        if fused:
+            if self._grad_flat() is None and hasattr(closure.field, "bind_flat_grads"):
+                closure.field.bind_flat_grads()
+            chain.reserve((num_samples + thinning - 1) // thinning, self._flat, self._plist)
+        for i in range(burn_in + num_samples):
+            if fused:
+                self.loss = closure.loss_and_grad_()[0]
+            else:
+                self.zero_grad()
+                self.loss = closure()
+                self._backward(self.loss)
+            lr = self.get_lr(i)
+            if i < burn_in and i < self.memory * 2 - 1 + 100:                 # langevin.py:1068-1069
+                self.step_without_metric(lr=lr, add_noise=add_noise, add_params=(i >= 100))
+            elif use_metric:
+                self.step(lr=lr, use_old_lbfgs=use_old_lbfgs, add_noise=add_noise)
+            else:
+                self.step_without_metric(lr=lr, update_metric=use_metric, add_noise=add_noise)
+            logp_array.append(-self.loss.detach())
+            if i >= burn_in and (i - burn_in) % thinning == 0:
+                self._record(chain)
+            if print_iters:
+                tag, k = ("Burn-in", i + 1) if i < burn_in else ("Sample", i - burn_in + 1)
+                if print_loss:
+                    print("{} iter {:04d} | loss {:.06f}".format(tag, k, float(closure(add_prior=False).sum())))
+                else:
+                    print("{} iter {:04d}".format(tag, k))
+        return chain, logp_array

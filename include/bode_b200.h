@@ -215,6 +215,19 @@ int bode_asghmc_step(float* p, const float* g, float* tau, float* gbar, float* v
                      int32_t resample, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
                      const bode_sampler_ctl* ctl, bode_stream_t stream);
 
+/* HAMCMC, samplers/langevin.py:619-1107 (L-BFGS-preconditioned Langevin), one CTA per chain, bug-compatible.
+ * State buffers (caller-owned, zero-initialised, sizes from bode_hamcmc_floats; meta is int32 [P][4]):
+ *   hist_theta/hist_grad [P][2M-1][d] (M = memory+1, :645), pair_s/pair_y [P][M-1][d], work [P][4(M-1)+2][d].
+ * metric_step = 0: step_without_metric (:941-964), add_params stores (theta_new, grad) and builds the start-up pairs when the
+ *   2M-1 window fills (:902-939);  metric_step = 1: step (:966-1000) = _compute_vector_prod (:717-860) + _update_metric_vars
+ *   (:862-900).  The warm-up schedule (first 2M-1+100 burn-in iterations, add_params from 100; :1068-1069) is the host's. */
+size_t bode_hamcmc_floats(int32_t P, int32_t d, int32_t memory, int32_t which);
+int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* hist_theta, float* hist_grad, float* pair_s,
+                     float* pair_y, float* work, int32_t* meta, float* theta, int64_t ld_theta, const float* grad,
+                     int64_t ld_grad, const float* xi, float lr, float H_gamma, float trust_reg, int32_t metric_step,
+                     int32_t add_params, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
+                     bode_stream_t stream);
+
 /* p <- p + alpha x   (the SVGD particle update: the optimiser wrapped by stein.py:37-106 descends -phi) */
 int bode_axpy(float* p, const float* x, float alpha, int64_t n, int32_t* status, const bode_sampler_ctl* ctl,
               bode_stream_t stream);

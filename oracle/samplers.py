@@ -78,3 +78,94 @@ def svgd_phi(X, score, sigma=None, rows=None, gamma=None):
         gamma = median_bandwidth(sq_dists(X, X), n) if sigma is None else 1.0 / (1e-8 + 2 * sigma ** 2)
     K = np.exp(-gamma * d2)
     return (K @ score + 2 * gamma * (K.sum(1)[:, None] * Xr - K @ X)) / n
+
+
+class HAMCMC:
+    """samplers/langevin.py:619-1000 restated for ONE chain with a flat parameter vector (float64 NumPy), bug-compatible:
+    history of 2M-1 (theta, grad) entries with M = memory+1 (:645), theta stored AFTER the warm-up update but the gradient
+    taken BEFORE it (:954-961), (s, y) pairs i <-> i+M with y += trust_reg*s and the 1e-4 curvature filter at start-up
+    (:924-935), base point params[M-1] (:970), product-form BFGS with u = sqrt(sBs/sy) + Bs -- a scalar added to a
+    vector -- (:846), pair refresh with the 1e-8 filter (:871-882; a chain that starts with zero pairs never gains one)."""
+
+    def __init__(self, memory=5, H_gamma=1.0, trust_reg=1.0):
+        self.M = memory + 1
+        self.H_gamma, self.trust_reg = H_gamma, trust_reg
+        self.params, self.grads, self.s, self.y = [], [], [], []
+
+    def step_without_metric(self, theta, grad, lr, xi, add_noise=True, add_params=False):
+        new = theta + (-lr) * grad
+        if add_noise:
+            new = new + (-lr) * (xi * (1.0 / np.sqrt(0.5 * lr)))
+        if add_params:
+            self.params.append(new.copy())
+            self.grads.append(grad.copy())
+        M = self.M
+        if len(self.params) >= 2 * M - 1:
+            for i in range(M - 1):
+                si = -self.params[i] + self.params[i + M]
+                yi = -self.grads[i] + self.grads[i + M] + self.trust_reg * si
+                if si @ yi > 1e-4 * (si @ si):
+                    self.s.append(si)
+                    self.y.append(yi)
+        return new
+
+    def vector_prod(self, grad, noise):
+        B0 = 1.0 / self.H_gamma
+        C0, S0 = np.sqrt(B0), 1.0 / np.sqrt(B0)
+        u, v, p, q = [], [], [], []
+
+        def Cz(z):
+            z = C0 * z
+            for i in range(len(u)):
+                z = z - v[i] * (z @ u[i])
+            return z
+
+        def CTz(z):
+            for i in reversed(range(len(u))):
+                z = z - u[i] * (z @ v[i])
+            return C0 * z
+
+        def Sz(z):
+            z = S0 * z
+            for i in range(len(u)):
+                z = z - q[i] * (z @ p[i])
+            return z
+
+        def STz(z):
+            for i in reversed(range(len(u))):
+                z = z - p[i] * (z @ q[i])
+            return S0 * z
+
+        for s, y in zip(self.s, self.y):
+            sy = s @ y
+            if sy < 0:
+                continue
+            Bs = B0 * s if len(u) == 0 else Cz(CTz(s))
+            sBs = s @ Bs
+            q.append(np.sqrt(sy / sBs) * Bs - y)
+            p.append(s / sy)
+            u.append(np.sqrt(sBs / sy) + Bs)           # scalar + vector, as in the reference
+            v.append(s / sBs)
+        Hg = grad / B0 if len(u) == 0 else Sz(STz(grad))
+        return Hg, Sz(noise)
+
+    def step(self, grad, lr, xi, add_noise=True):
+        M = self.M
+        base = self.params[M - 1]
+        noise = xi * (1.0 / np.sqrt(0.5 * lr))
+        Hg, Sn = self.vector_prod(grad, noise)
+        new = base + (-lr) * Hg
+        if add_noise:
+            new = new + (-lr) * Sn
+        self.params.append(new.copy())
+        self.grads.append(grad.copy())
+        si = -self.params[M - 1] + self.params[2 * M - 1]
+        yi = -self.grads[M - 1] + self.grads[2 * M - 1] + self.trust_reg * si
+        if si @ yi > 1e-8 * (si @ si):
+            self.s.append(si)
+            self.y.append(yi)
+            self.s.pop(0)
+            self.y.pop(0)
+        self.params.pop(0)
+        self.grads.pop(0)
+        return new

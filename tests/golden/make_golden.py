@@ -392,6 +392,57 @@ def gen_dopri5(data):
     save("dopri5", **out)
 
 
+def gen_hamcmc():
+    """HAMCMC (langevin.py:619-1107) on a convex quadratic with two parameter tensors; noise replayed per step."""
+    import io, contextlib
+    from samplers.langevin import HAMCMC
+    from oracle import samplers as osamp
+    g = torch.Generator().manual_seed(5)
+    d = 10
+    Q = torch.randn(d, d, generator=g)
+    Aq = Q @ Q.t() / d + 0.5 * torch.eye(d)
+    a = torch.nn.Parameter(torch.randn(3, 2, generator=g))
+    b = torch.nn.Parameter(torch.randn(4, generator=g))
+
+    def closure(add_prior=True):
+        th = torch.cat([a.reshape(-1), b.reshape(-1)])
+        return 0.5 * th @ (Aq @ th)
+
+    memory = 2
+    smp = HAMCMC([a, b], memory=memory, lr0=5e-2, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3, H_gamma=1.0, trust_reg=1.0)
+    M = memory + 1
+    nsteps = 100 + 2 * M - 1 + 8
+    thetas, grads, xis, lrs = [torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).clone()], [], [], []
+    with contextlib.redirect_stdout(io.StringIO()):
+        for i in range(nsteps):
+            smp.zero_grad()
+            smp.loss = closure()
+            smp.loss.backward()
+            grads.append(torch.cat([a.grad.reshape(-1), b.grad.reshape(-1)]).clone())
+            lr = smp.get_lr(i)
+            torch.manual_seed(7000 + i)
+            if i < 2 * M - 1 + 100:
+                smp.step_without_metric(lr=lr, add_noise=True, add_params=(i >= 100))
+            else:
+                smp.step(lr=lr, add_noise=True)
+            torch.manual_seed(7000 + i)
+            xis.append(torch.randn(d))
+            lrs.append(lr)
+            thetas.append(torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).clone())
+    out = dict(A=Aq, theta=torch.stack(thetas), grad=torch.stack(grads), xi=torch.stack(xis), lr=np.array(lrs), memory=memory,
+               n_pairs=len(smp.state["memory"]["param_diff"]))
+    # pin the oracle restatement (and the noise replay) right here
+    orc = osamp.HAMCMC(memory=memory, H_gamma=1.0, trust_reg=1.0)
+    for i in range(nsteps):
+        th, gr, xi = out["theta"][i].numpy(), out["grad"][i].numpy(), out["xi"][i].numpy()
+        if i < 2 * M - 1 + 100:
+            new = orc.step_without_metric(th, gr, lrs[i], xi, add_params=(i >= 100))
+        else:
+            new = orc.step(gr, lrs[i], xi)
+        assert np.abs(new - out["theta"][i + 1].numpy()).max() < 1e-10, ("hamcmc oracle mismatch", i)
+    save("hamcmc", **out)
+
+
 if __name__ == "__main__":
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
@@ -402,3 +453,4 @@ if __name__ == "__main__":
     gen_svgd(data)
     gen_mlp(data)
     gen_dopri5(data)
+    gen_hamcmc()

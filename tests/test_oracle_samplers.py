@@ -56,3 +56,18 @@ def test_rbf_kernel_and_phi():
         assert relerr(Kf, g[f"n{n}_K_sigma07"]) < 1e-10
         rows = np.arange(5, 20)
         assert relerr(osamp.svgd_phi(X, S, rows=rows), g[f"n{n}_phi"][rows]) < 1e-9
+
+
+def test_hamcmc_oracle_matches_reference_run():
+    """113 reference iterations (100 SGLD warm-up, 5 history-filling, 8 metric steps) incl. the u = scalar + vector quirk."""
+    g = load_golden("hamcmc")
+    memory = int(g["memory"])
+    M = memory + 1
+    orc = osamp.HAMCMC(memory=memory, H_gamma=1.0, trust_reg=1.0)
+    for i in range(g["grad"].shape[0]):
+        if i < 2 * M - 1 + 100:
+            new = orc.step_without_metric(g["theta"][i], g["grad"][i], float(g["lr"][i]), g["xi"][i], add_params=(i >= 100))
+        else:
+            new = orc.step(g["grad"][i], float(g["lr"][i]), g["xi"][i])
+        assert relerr(new, g["theta"][i + 1]) < 1e-10, i
+    assert len(orc.s) == int(g["n_pairs"])

@@ -222,3 +222,44 @@ def test_sample_loop_fused_and_protocol_paths_agree():
         assert accepted is True and params[0][0].shape == (4, 25, 2) and params[0][1].shape == (4, 2)
         chains.append(np.concatenate([params[0][0].reshape(4, -1), params[0][1]], 1))
     assert relerr(chains[0], chains[1]) < 1e-6
+
+
+def test_hamcmc_matches_reference_run():
+    """HAMCMC on the reference's own 113-step run (two free-standing parameter tensors, injected noise, gradients of the
+    same quadratic computed by autograd on the device): warm-up, history fill, start-up pairs, 8 metric steps."""
+    from bayesian_ode_b200.samplers import HAMCMC
+    g = load_golden("hamcmc")
+    memory = int(g["memory"])
+    M = memory + 1
+    A = torch.from_numpy(g["A"]).float().cuda()
+    th0 = torch.from_numpy(g["theta"][0]).float().cuda()
+    a = torch.nn.Parameter(th0[:6].reshape(3, 2).clone())
+    b = torch.nn.Parameter(th0[6:].clone())
+    smp = HAMCMC([a, b], memory=memory, lr0=5e-2, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3, H_gamma=1.0, trust_reg=1.0)
+    for i in range(g["grad"].shape[0]):
+        smp.zero_grad()
+        th = torch.cat([a.reshape(-1), b.reshape(-1)])
+        (0.5 * th @ (A @ th)).backward()
+        lr = smp.get_lr(i)
+        assert lr == float(g["lr"][i])
+        if i < 2 * M - 1 + 100:
+            smp.step_without_metric(lr=lr, add_params=(i >= 100), noise=g["xi"][i])
+        else:
+            smp.step(lr=lr, noise=g["xi"][i])
+        got = torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).cpu().numpy()
+        assert relerr(got, g["theta"][i + 1]) < (2e-5 if i < 105 else 5e-4), i
+    assert int(smp.n_pairs()[0]) == int(g["n_pairs"])
+
+
+def test_hamcmc_batched_chains_on_npde():
+    """P chains on the flat theta buffer: sample() drives warm-up -> metric steps through the fused closure."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import HAMCMC
+    g = load_golden("npde_m5")
+    f = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]))
+    smp = HAMCMC([f.U, f.logsn], memory=2, lr0=1e-6, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3)
+    chain, logp = smp.sample(post, num_samples=3, burn_in=108, print_iters=False)
+    assert len(chain) == 3 and len(logp) == 111
+    assert bool(torch.isfinite(f.theta).all())
+    assert smp._hs["meta"][:, 0].tolist() == [5, 5, 5, 5]
