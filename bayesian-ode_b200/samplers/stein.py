@@ -44,6 +44,24 @@ class RBFKernel(torch.nn.Module):
         return torch.exp(-mg[1] * d2)
 
 
+def radix_select_protocol(hist_pass, allreduce, select_digit, passes=3):
+    """The exact-median protocol every rank runs in lock-step: for each radix pass, histogram the local block, SUM the
+    histograms over ranks (the only communication: 2 x 2048 counters), then pick the digit -- so all ranks extend the
+    same prefix and end with the same order statistics.  ``allreduce`` is None on a single rank."""
+    for ps in range(passes):
+        hist_pass(ps)
+        if allreduce is not None:
+            allreduce()
+        select_digit(ps)
+
+
+def shard_range(n, rank, world):
+    """Contiguous block of particles / chains owned by ``rank``."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
 class _Workspace:
     def __init__(self, nr, nc, d, device):
         lib = _lib.load()
@@ -70,11 +88,10 @@ class _Workspace:
         lib = _lib.load()
         w = C.c_void_p(self.base.data_ptr())
         if sigma is None:
-            for ps in range(3):
-                _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr()))
-                if group is not None:
-                    torch.distributed.all_reduce(self._hist, group=group if group is not True else None)
-                _lib.check(lib.bode_svgd_select_digit(ps, nr, nc, d, w, _lib.stream_ptr()))
+            radix_select_protocol(
+                lambda ps: _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr())),
+                None if group is None else (lambda: torch.distributed.all_reduce(self._hist, group=group if group is not True else None)),
+                lambda ps: _lib.check(lib.bode_svgd_select_digit(ps, nr, nc, d, w, _lib.stream_ptr())))
         _lib.check(lib.bode_svgd_gamma(n_total, float(sigma or 0.0), nr, nc, d, w, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
 
     def d2(self, nr, nc):
