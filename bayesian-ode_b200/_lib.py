@@ -79,7 +79,8 @@ SYMBOLS = {
     "bode_sampler_schedule": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _P]),
     "bode_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint32, _P]),
     "bode_svgd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
-    "bode_svgd_sqdist": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_uint64, _P, C.c_size_t,
+    "bode_svgd_set_tensor_cores": (C.c_int, [C.c_int32]),
+    "bode_svgd_sqdist": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, C.c_size_t,
                                     C.POINTER(C.c_void_p), _P]),
     "bode_svgd_hist_pass": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bode_svgd_select_digit": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

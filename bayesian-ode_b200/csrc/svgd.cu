@@ -15,6 +15,17 @@
 
 namespace bode {
 
+// tensor-core path (svgd_tc.cu)
+int svgd_tc_supported(int d);
+int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, cudaStream_t st);
+int svgd_tc_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
+                 float* D2, unsigned int* maxbits, cudaStream_t st);
+int svgd_tc_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
+                const float* gam, float gsign, int jsplit, float* part, cudaStream_t st);
+int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* Xr, long long ldr, const float* mu, const float* gam,
+                    float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t st);
+static int g_tensor_cores = 1;
+
 // ---------------------------------------------------------------- squared distances (difference form, fp32)
 constexpr int TS = 64;   // tile of 64 x 64 pairs per CTA, 4 x 4 per thread
 
@@ -317,12 +328,13 @@ extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int3
   b += (size_t)n_rows * n_cols * sizeof(float);                 // d2
   b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials (last column: row sums)
   b += 2 * 2048 * sizeof(unsigned long long) + 256;             // histograms + select state
+  b += 256;                                                     // column means (tensor-core path)
   return b + 1024;
 }
 
 namespace {
 struct Ws {
-  float* d2; float* part; unsigned long long* hist; SelState* st;
+  float* d2; float* part; unsigned long long* hist; SelState* st; float* mu;
 };
 Ws carve(void* ws, int nr, int nc, int d) {
   Ws w;
@@ -330,7 +342,8 @@ Ws carve(void* ws, int nr, int nc, int d) {
   w.d2 = (float*)p; p += (((size_t)nr * nc * sizeof(float)) + 255) / 256 * 256;
   w.part = (float*)p; p += ((MAXSPLIT * (size_t)nr * (2 * d + 1) * sizeof(float)) + 255) / 256 * 256;
   w.hist = (unsigned long long*)p; p += 2 * 2048 * sizeof(unsigned long long);
-  w.st = (SelState*)p;
+  w.st = (SelState*)p; p += 256;
+  w.mu = (float*)p;
   return w;
 }
 }  // namespace
@@ -339,8 +352,8 @@ Ws carve(void* ws, int nr, int nc, int d) {
  * (n*n for the whole job).  hist_out receives the device address of the 2x2048 uint64 histogram block so a multi-rank
  * caller can all-reduce it between bode_svgd_hist_pass and bode_svgd_select_digit. */
 extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
-                                int32_t n_cols, int32_t d, uint64_t total_entries, void* workspace, size_t workspace_bytes,
-                                void** hist_out, bode_stream_t stream) {
+                                int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
+                                size_t workspace_bytes, void** hist_out, bode_stream_t stream) {
   BODE_REQUIRE(Xrows && Xcols && workspace, "null pointer");
   BODE_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && d <= 512, "bad sizes");
   BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
@@ -352,10 +365,25 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   dim3 grid((n_cols + TS - 1) / TS, (n_rows + TS - 1) / TS);
   select_init_kernel<<<4, 1024, 0, st>>>(w.st, w.hist, total_entries);
   BODE_CUDA(cudaGetLastError());
-  sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2, &w.st->maxbits);
-  BODE_CUDA(cudaGetLastError());
+  if (g_tensor_cores && svgd_tc_supported(d)) {
+    // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles
+    int e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, st);
+    if (e != BODE_OK) return e;
+    e = svgd_tc_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.d2, &w.st->maxbits, st);
+    if (e != BODE_OK) return e;
+  } else {
+    sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2, &w.st->maxbits);
+    BODE_CUDA(cudaGetLastError());
+  }
   if (hist_out) *hist_out = w.hist;
   return BODE_OK;
+}
+
+/* 1 (default): Gram and K@[S|X|1] on tcgen05 tensor cores (3xTF32) when d <= 56; 0: FP32-pipe kernels */
+extern "C" int bode_svgd_set_tensor_cores(int32_t on) {
+  const int old = g_tensor_cores;
+  g_tensor_cores = on ? 1 : 0;
+  return old;
 }
 
 /* pass = 0,1,2 over bit windows [20,31), [9,20), [0,9) of the fp32 pattern (d2 >= 0 so bit 31 is clear) */
@@ -417,6 +445,16 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
   if (jsplit > MAXSPLIT) jsplit = MAXSPLIT;
   if (jsplit > (n_cols + PJ - 1) / PJ) jsplit = (n_cols + PJ - 1) / PJ;
   if (jsplit < 1) jsplit = 1;
+  if (g_tensor_cores && svgd_tc_supported(d)) {
+    int js = (2 * sms) / ((n_rows + 127) / 128);        // ~2 CTAs per SM, one wave
+    if (js > MAXSPLIT) js = MAXSPLIT;
+    if (js > (n_cols + 31) / 32) js = (n_cols + 31) / 32;
+    if (js < 1) js = 1;
+    int e = svgd_tc_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, js, w.part, st);
+    if (e != BODE_OK) return e;
+    return svgd_tc_combine(w.part, js, n_rows, d, Xrows, ld_rows, w.mu, med_gamma, 1.f / (float)n_total, phi, ld_phi, theta, ld_theta,
+                           step, st);
+  }
   dim3 grid(rb, jsplit);
   const int ft = (2 * d + 1 + 15) / 16;
 #define BODE_PHI(C)                                                                                              \

@@ -1,0 +1,489 @@
+// SVGD contractions on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+//   gram_d2_tc_kernel   d2_ij = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j      (xc = x - column mean; stein.py:22 cdist^2)
+//   phi_tc_kernel       part[i, :] = sum_j 2^(-g d2_ij) [ -grad_j | xc_j | 1 ]   (stein.py:75-86, K @ [S | X | 1])
+//
+// fp32 parity needs more than TF32's 10-bit mantissa, so every fp32 operand is split x = hi + lo (hi = top 19 bits) and each
+// product is issued as three MMAs  hi*hi + hi*lo + lo*hi  (3xTF32, ~2^-21 relative).  Operand tiles are produced by the
+// CUDA cores straight into shared memory in the canonical no-swizzle UMMA layout (8-row x 16-byte core matrices), one
+// elected thread issues the MMAs, completion comes back through tcgen05.commit on an mbarrier, the epilogue reads the
+// accumulators with tcgen05.ld (one TMEM lane = one output row per thread).  No TMA: the A operand of the second
+// contraction (exp of a distance tile) does not exist in memory, and the first one needs the centred/split transform.
+#include "common.cuh"
+
+namespace bode {
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// bounded wait: a wrong descriptor must fail the launch, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  for (int spin = 0; spin < (1 << 26); ++spin) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, no swizzle (cute/arch/mma_sm100_desc.hpp SmemDescriptor): addr>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version 1 at [46,48), layout type 0 at [61,64)
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor (InstrDescriptor): c=F32 [4,6), a=TF32 [7,10), b=TF32 [10,13), a_major 15, b_major 16, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+  hi = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+  lo = x - hi;
+}
+
+// K-major operand tile [ROWS x KCH*4] in core-matrix order: [kchunk][row/8][row%8][16 B]; SBO = 128 B, LBO = ROWS*16 B
+template <int ROWS>
+__device__ __forceinline__ uint32_t kmajor_off(int row, int kchunk) { return (uint32_t)((kchunk * (ROWS / 8) + (row >> 3)) * 128 + (row & 7) * 16); }
+
+// ---------------------------------------------------------------- column means (deterministic tree per column)
+__global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ X, long long ld, int n, int d, float* __restrict__ mu) {
+  __shared__ float red[256];
+  const int c = blockIdx.x;
+  float acc = 0.f;
+  for (int r = threadIdx.x; r < n; r += 256) acc += X[(long long)r * ld + c];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) mu[c] = red[0] / (float)n;
+}
+
+// ---------------------------------------------------------------- d2 tile = Gram on tensor cores
+constexpr int GT = 128;       // output tile per CTA: GT rows x GN columns (two CTAs per SM by shared memory)
+constexpr int GN = 64;
+
+template <int KP>             // K padded to a multiple of 8 (d <= KP)
+__global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict__ Xr, long long ldr, int nr, int row_offset,
+                                                         const float* __restrict__ Xc, long long ldc, int nc, int d,
+                                                         const float* __restrict__ mu, float* __restrict__ D2,
+                                                         unsigned int* __restrict__ maxbits) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr int KCH = KP / 4;                       // 16-byte chunks along K
+  constexpr uint32_t TILE_A = GT * KP * 4, TILE_B = GN * KP * 4;
+  unsigned char* sAh = smraw;
+  unsigned char* sAl = sAh + TILE_A;
+  unsigned char* sBh = sAl + TILE_A;
+  unsigned char* sBl = sBh + TILE_B;
+  float* ni = reinterpret_cast<float*>(sBl + TILE_B);
+  float* nj = ni + GT;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(nj + GN);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.y * GT, c0 = blockIdx.x * GN;
+
+  if (warp == 0) tmem_alloc(tslot, GN);
+  if (tid == 0) mbar_init(bar, 1);
+  // operand tiles.  Fast path (d and the row strides multiples of 4): every 16-byte chunk of the canonical layout is one
+  // aligned float4 of a row, so the loads are fully coalesced; the row norms are then summed from shared memory.
+  const bool vec = ((d & 3) == 0) && ((ldr & 3) == 0) && ((ldc & 3) == 0) && ((((uintptr_t)Xr | (uintptr_t)Xc | (uintptr_t)mu) & 15) == 0);
+  if (vec) {
+    const int dch = d >> 2;
+    for (int idx = tid; idx < GT * KCH; idx += 128) {
+      const int row = idx / KCH, kc = idx - row * KCH;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc < dch && r0 + row < nr) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(Xr + (long long)(r0 + row) * ldr) + kc);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + kc);
+        v = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+      }
+      float h[4], l[4];
+      split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+      const uint32_t off = kmajor_off<GT>(row, kc);
+      *reinterpret_cast<float4*>(sAh + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(sAl + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    for (int idx = tid; idx < GN * KCH; idx += 128) {
+      const int row = idx / KCH, kc = idx - row * KCH;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kc < dch && c0 + row < nc) {
+        const float4 x = __ldg(reinterpret_cast<const float4*>(Xc + (long long)(c0 + row) * ldc) + kc);
+        const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + kc);
+        v = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
+      }
+      float h[4], l[4];
+      split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+      const uint32_t off = kmajor_off<GN>(row, kc);
+      *reinterpret_cast<float4*>(sBh + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(sBl + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+    __syncthreads();
+    {
+      float sa = 0.f, sb = 0.f;
+      for (int kc = 0; kc < KCH; ++kc) {
+        const float4 h = *reinterpret_cast<const float4*>(sAh + kmajor_off<GT>(tid, kc));
+        const float4 l = *reinterpret_cast<const float4*>(sAl + kmajor_off<GT>(tid, kc));
+        const float a0 = h.x + l.x, a1 = h.y + l.y, a2 = h.z + l.z, a3 = h.w + l.w;
+        sa = fmaf(a0, a0, sa); sa = fmaf(a1, a1, sa); sa = fmaf(a2, a2, sa); sa = fmaf(a3, a3, sa);
+        if (tid < GN) {
+          const float4 hb = *reinterpret_cast<const float4*>(sBh + kmajor_off<GN>(tid, kc));
+          const float4 lb = *reinterpret_cast<const float4*>(sBl + kmajor_off<GN>(tid, kc));
+          const float b0 = hb.x + lb.x, b1 = hb.y + lb.y, b2 = hb.z + lb.z, b3 = hb.w + lb.w;
+          sb = fmaf(b0, b0, sb); sb = fmaf(b1, b1, sb); sb = fmaf(b2, b2, sb); sb = fmaf(b3, b3, sb);
+        }
+      }
+      ni[tid] = sa;
+      if (tid < GN) nj[tid] = sb;
+    }
+  } else {
+    // general path: thread t owns row t of both tiles
+    float sa = 0.f, sb = 0.f;
+    const bool va = r0 + tid < nr, vb = tid < GN && c0 + tid < nc;
+    const float* xa = Xr + (long long)(r0 + tid) * ldr;
+    const float* xb = Xc + (long long)(c0 + tid) * ldc;
+#pragma unroll 2
+    for (int kc = 0; kc < KCH; ++kc) {
+      float a[4], b[4], ah[4], al[4], bh[4], bl[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int k = 4 * kc + q;
+        const float m = k < d ? __ldg(mu + k) : 0.f;
+        a[q] = (va && k < d) ? __ldg(xa + k) - m : 0.f;
+        b[q] = (vb && k < d) ? __ldg(xb + k) - m : 0.f;
+        sa = fmaf(a[q], a[q], sa);
+        sb = fmaf(b[q], b[q], sb);
+        split_tf32(a[q], ah[q], al[q]);
+        split_tf32(b[q], bh[q], bl[q]);
+      }
+      const uint32_t off = kmajor_off<GT>(tid, kc);
+      *reinterpret_cast<float4*>(sAh + off) = make_float4(ah[0], ah[1], ah[2], ah[3]);
+      *reinterpret_cast<float4*>(sAl + off) = make_float4(al[0], al[1], al[2], al[3]);
+      if (tid < GN) {
+        const uint32_t offb = kmajor_off<GN>(tid, kc);
+        *reinterpret_cast<float4*>(sBh + offb) = make_float4(bh[0], bh[1], bh[2], bh[3]);
+        *reinterpret_cast<float4*>(sBl + offb) = make_float4(bl[0], bl[1], bl[2], bl[3]);
+      }
+    }
+    ni[tid] = sa;
+    if (tid < GN) nj[tid] = sb;
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  if (tid == 0) {
+    constexpr uint32_t idesc = idesc_tf32(GT, GN, 0, 0);
+    constexpr uint32_t LBO = GT * 16, LBOB = GN * 16, SBO = 128;
+    uint32_t acc = 0;
+#pragma unroll 1
+    for (int pass = 0; pass < 3; ++pass) {
+      const uint32_t a0 = smem_u32(pass == 2 ? sAl : sAh), b0 = smem_u32(pass == 1 ? sBl : sBh);
+#pragma unroll 1
+      for (int ks = 0; ks < KP / 8; ++ks) {
+        umma_tf32(tmem, smem_desc(a0 + ks * 2 * LBO, LBO, SBO), smem_desc(b0 + ks * 2 * LBOB, LBOB, SBO), idesc, acc);
+        acc = 1;
+      }
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  // epilogue: TMEM lane (row) = 32*warp + lane -> d2 values -> shared staging (operand tiles are dead) -> coalesced rows
+  float* stage = reinterpret_cast<float*>(smraw);                  // [GT][GN+4]
+  constexpr int SP = GN + 4;
+  const int row = r0 + tid;
+  const float nrow = ni[tid];
+  float mx = 0.f;
+#pragma unroll 1
+  for (int cb = 0; cb < GN; cb += 8) {
+    float s[8];
+    tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + cb, s);
+    float o[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int col = c0 + cb + q;
+      float v = fmaxf(fmaf(-2.f, s[q], nrow + nj[cb + q]), 0.f);
+      if (row + row_offset == col) v = 0.f;                     // cdist(x, x) = 0 on the diagonal
+      o[q] = v;
+      if (row < nr && col < nc) mx = fmaxf(mx, v);
+    }
+    *reinterpret_cast<float4*>(stage + tid * SP + cb) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(stage + tid * SP + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+  }
+  __syncthreads();
+  if ((nc & 3) == 0 && c0 + GN <= nc) {
+    for (int idx = tid; idx < GT * (GN / 4); idx += 128) {
+      const int rr = idx / (GN / 4), c4 = idx - rr * (GN / 4);
+      if (r0 + rr < nr)
+        *reinterpret_cast<float4*>(D2 + (long long)(r0 + rr) * nc + c0 + 4 * c4) = *reinterpret_cast<const float4*>(stage + rr * SP + 4 * c4);
+    }
+  } else {
+    for (int idx = tid; idx < GT * GN; idx += 128) {
+      const int rr = idx / GN, cc = idx - rr * GN;
+      if (r0 + rr < nr && c0 + cc < nc) D2[(long long)(r0 + rr) * nc + c0 + cc] = stage[rr * SP + cc];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) atomicMax(maxbits, __float_as_uint(mx));
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, GN);
+}
+
+// ---------------------------------------------------------------- phi partials on tensor cores
+constexpr int PT = 128;       // rows per CTA
+constexpr int PK = 32;        // j per stage (4 MMA k-steps)
+
+template <int NF>             // padded feature count, multiple of 16, >= 2d+1
+__global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D2, int nr, int nc, const float* __restrict__ Xc,
+                                                     long long ldx, const float* __restrict__ Gc, long long ldg, int d,
+                                                     const float* __restrict__ mu, const float* __restrict__ gam, float gsign,
+                                                     int jsplit, float* __restrict__ part) {
+  extern __shared__ __align__(128) unsigned char smraw[];
+  constexpr uint32_t A_B = PT * PK * 4, B_B = PK * NF * 4;
+  unsigned char* sAh = smraw;
+  unsigned char* sAl = sAh + A_B;
+  unsigned char* sBh = sAl + A_B;
+  unsigned char* sBl = sBh + B_B;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBl + B_B);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+  constexpr uint32_t TCOLS = NF <= 32 ? 32 : (NF <= 64 ? 64 : (NF <= 128 ? 128 : 256));
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int r0 = blockIdx.x * PT;
+  const int jper = ((nc + jsplit - 1) / jsplit + PK - 1) / PK * PK;
+  const int jbeg = blockIdx.y * jper, jend = min(nc, jbeg + jper);
+  const float ngamma = -gam[1] * 1.4426950408889634f;
+
+  if (warp == 0) tmem_alloc(tslot, TCOLS);
+  if (tid == 0) mbar_init(bar, 1);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  constexpr uint32_t idesc = idesc_tf32(PT, NF, 0, 0);              // A and B both K-major (B holds V^T)
+  constexpr uint32_t A_LBO = PT * 16, A_SBO = 128;                   // [kchunk][row/8][row%8][16B]
+  constexpr uint32_t B_LBO = NF * 16, B_SBO = 128;
+  uint32_t phase = 0, acc = 0;
+  const int row = r0 + tid;
+  constexpr int NV = NF * (PK / 4);                                  // 16-byte chunks of V^T per stage
+  constexpr int NQ = (NV + 127) / 128;
+  const float* vsrc[NQ];
+  long long vld[NQ];
+  float vscale[NQ], vadd[NQ];
+  int vjc[NQ], voff[NQ];
+#pragma unroll
+  for (int q = 0; q < NQ; ++q) {
+    const int slot = tid + 128 * q;
+    const int jc = slot / NF, f = slot - jc * NF;
+    vjc[q] = jc;
+    voff[q] = slot < NV ? (int)kmajor_off<NF>(f, jc) : -1;
+    vsrc[q] = nullptr; vld[q] = 0; vscale[q] = 0.f; vadd[q] = 0.f;
+    if (slot < NV) {
+      if (f < d) { vsrc[q] = Gc + f; vld[q] = ldg; vscale[q] = gsign; }
+      else if (f < 2 * d) { vsrc[q] = Xc + (f - d); vld[q] = ldx; vscale[q] = 1.f; vadd[q] = -__ldg(mu + f - d); }
+      else if (f == 2 * d) { vadd[q] = 1.f; }
+    }
+  }
+  for (int j0 = jbeg; j0 < jend; j0 += PK) {
+    // ---- A: K[row][j0..j0+31] = 2^(-g d2), split hi/lo
+    float4 dv[PK / 4];
+#pragma unroll
+    for (int kc = 0; kc < PK / 4; ++kc) {
+      const int j = j0 + 4 * kc;
+      if (row < nr && j + 4 <= jend && ((nc & 3) == 0)) {
+        dv[kc] = __ldg(reinterpret_cast<const float4*>(D2 + (long long)row * nc + j));
+      } else {
+        float t[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) t[q] = (row < nr && j + q < jend) ? __ldg(D2 + (long long)row * nc + j + q) : INFINITY;
+        dv[kc] = make_float4(t[0], t[1], t[2], t[3]);
+      }
+    }
+    // ---- B: V^T[f][j] = [gsign*G | X - mu | 1 | 0]^T, K-major like A (thread <-> (feature f, 4 consecutive j)); the
+    //      per-slot source pointer / scale / offset are loop invariant, so the loads are branch free and all in flight
+    float4 vv[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      float t[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = j0 + 4 * vjc[q] + e;
+        const bool ok = j < jend;
+        const float raw = (ok && vsrc[q]) ? __ldg(vsrc[q] + (long long)j * vld[q]) : 0.f;
+        t[e] = ok ? fmaf(vscale[q], raw, vadd[q]) : 0.f;
+      }
+      vv[q] = make_float4(t[0], t[1], t[2], t[3]);
+    }
+    if (acc) {                                                       // previous stage's MMAs must have drained smem
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+#pragma unroll
+    for (int kc = 0; kc < PK / 4; ++kc) {
+      const float k4[4] = {ex2(ngamma * dv[kc].x), ex2(ngamma * dv[kc].y), ex2(ngamma * dv[kc].z), ex2(ngamma * dv[kc].w)};
+      float h[4], l[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) split_tf32(k4[q], h[q], l[q]);
+      const uint32_t off = kmajor_off<PT>(tid, kc);
+      *reinterpret_cast<float4*>(sAh + off) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(sAl + off) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (voff[q] >= 0) {
+        float h[4], l[4];
+        split_tf32(vv[q].x, h[0], l[0]); split_tf32(vv[q].y, h[1], l[1]); split_tf32(vv[q].z, h[2], l[2]); split_tf32(vv[q].w, h[3], l[3]);
+        *reinterpret_cast<float4*>(sBh + voff[q]) = make_float4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<float4*>(sBl + voff[q]) = make_float4(l[0], l[1], l[2], l[3]);
+      }
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    if (tid == 0) {
+#pragma unroll 1
+      for (int pass = 0; pass < 3; ++pass) {
+        const uint32_t a0 = smem_u32(pass == 2 ? sAl : sAh), b0 = smem_u32(pass == 1 ? sBl : sBh);
+#pragma unroll
+        for (int ks = 0; ks < PK / 8; ++ks) {
+          umma_tf32(tmem, smem_desc(a0 + ks * 2 * A_LBO, A_LBO, A_SBO), smem_desc(b0 + ks * 2 * B_LBO, B_LBO, B_SBO), idesc, acc);
+          acc = 1;
+        }
+      }
+      umma_commit(bar);
+    }
+    acc = 1;
+  }
+  if (acc) {
+    mbar_wait(bar, phase);
+    tc_fence_after();
+  }
+  // ---- epilogue: one TMEM lane per thread = one output row
+  if (jbeg < jend) {
+#pragma unroll 1
+    for (int cb = 0; cb < NF; cb += 8) {
+      float s[8];
+      tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + cb, s);
+      if (row < nr) {
+        float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+          if (cb + q <= 2 * d) dst[cb + q] = s[q];
+      }
+    }
+  } else if (row < nr) {
+    float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
+    for (int f = 0; f <= 2 * d; ++f) dst[f] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// combine with centred positions: phi = (KS + 2 g (rowsum (x_i - mu) - K(X - mu))) / n
+__global__ void phi_combine_tc_kernel(const float* __restrict__ part, int jsplit, int nr, int d, const float* __restrict__ Xr,
+                                      long long ldr, const float* __restrict__ mu, const float* __restrict__ gam, float inv_n,
+                                      float* __restrict__ phi, long long ldp, float* __restrict__ theta, long long ldt, float step) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)nr * d) return;
+  const int r = (int)(idx / d), c = (int)(idx - (long long)r * d);
+  float ks = 0.f, kx = 0.f, rs = 0.f;
+  for (int s = 0; s < jsplit; ++s) {
+    const float* p = part + ((long long)s * nr + r) * (2 * d + 1);
+    ks += p[c];
+    kx += p[d + c];
+    rs += p[2 * d];
+  }
+  const float x = Xr[(long long)r * ldr + c];
+  const float ph = (ks + 2.f * gam[1] * (rs * (x - mu[c]) - kx)) * inv_n;
+  if (phi) phi[(long long)r * ldp + c] = ph;
+  if (theta) theta[(long long)r * ldt + c] = fmaf(step, ph, theta[(long long)r * ldt + c]);
+}
+
+// ---------------------------------------------------------------- host launchers (called from svgd.cu)
+int svgd_tc_supported(int d) { return d >= 1 && d <= 56; }
+
+int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, cudaStream_t st) {
+  colmean_kernel<<<d, 256, 0, st>>>(X, ld, n, d, mu);
+  return check_cuda(cudaGetLastError(), "colmean launch");
+}
+
+int svgd_tc_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
+                 float* D2, unsigned int* maxbits, cudaStream_t st) {
+  constexpr int KP = 56;
+  const size_t smem = 2 * (size_t)(GT + GN) * KP * 4 + (GT + GN) * 4 + 64;
+  BODE_CUDA(cudaFuncSetAttribute(gram_d2_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((nc + GN - 1) / GN, (nr + GT - 1) / GT);
+  gram_d2_tc_kernel<KP><<<grid, 128, smem, st>>>(Xr, ldr, nr, row_offset, Xc, ldc, nc, d, mu, D2, maxbits);
+  return check_cuda(cudaGetLastError(), "gram tc launch");
+}
+
+int svgd_tc_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
+                const float* gam, float gsign, int jsplit, float* part, cudaStream_t st) {
+  constexpr int NF = 112;
+  const size_t smem = 2 * (size_t)PT * PK * 4 + 2 * (size_t)PK * NF * 4 + 64;
+  BODE_CUDA(cudaFuncSetAttribute(phi_tc_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((nr + PT - 1) / PT, jsplit);
+  phi_tc_kernel<NF><<<grid, 128, smem, st>>>(D2, nr, nc, Xc, ldx, Gc, ldg, d, mu, gam, gsign, jsplit, part);
+  return check_cuda(cudaGetLastError(), "phi tc launch");
+}
+
+int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* Xr, long long ldr, const float* mu, const float* gam,
+                    float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t st) {
+  const long long tot = (long long)nr * d;
+  phi_combine_tc_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(part, jsplit, nr, d, Xr, ldr, mu, gam, inv_n, phi, ldp, theta, ldt, step);
+  return check_cuda(cudaGetLastError(), "phi combine tc launch");
+}
+
+}  // namespace bode

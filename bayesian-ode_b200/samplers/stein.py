@@ -36,7 +36,7 @@ class RBFKernel(torch.nn.Module):
         Y = Y.detach().to(torch.float32).contiguous()
         n, m, d = X.shape[0], Y.shape[0], X.shape[1]
         ws = _Workspace(n, m, d, X.device)
-        ws.sqdist(X, n, Y, m, d, n * m)
+        ws.sqdist(X, n, Y, m, d, n * m, row_offset=0 if (n == m and (X.data_ptr() == Y.data_ptr() or torch.equal(X, Y))) else -1)
         ws.median(n, m, d, X.shape[0], self.sigma)
         d2 = ws.d2(n, m)
         mg = ws.med_gamma
@@ -74,11 +74,11 @@ class _Workspace:
         self.hist_ptr = C.c_void_p()
         self._hist = None
 
-    def sqdist(self, Xr, nr, Xc, nc, d, total):
+    def sqdist(self, Xr, nr, Xc, nc, d, total, row_offset=-1):
         lib = _lib.load()
         rp, rs = _lib.rows(Xr, d)
         cp, cs = _lib.rows(Xc, d)
-        _lib.check(lib.bode_svgd_sqdist(rp, rs, nr, cp, cs, nc, d, int(total), C.c_void_p(self.base.data_ptr()), self.nbytes,
+        _lib.check(lib.bode_svgd_sqdist(rp, rs, nr, cp, cs, nc, d, int(row_offset), int(total), C.c_void_p(self.base.data_ptr()), self.nbytes,
                                         C.byref(self.hist_ptr), _lib.stream_ptr()))
         if self._hist is None:
             off = self.hist_ptr.value - self.base.data_ptr()
@@ -141,7 +141,7 @@ class SVGD(Sampler):
         else:
             Xall, Gall = X, G
         ws = self._ws
-        ws.sqdist(X, nl, Xall, nt, d, nt * nt)
+        ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl)
         ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
         xr, xrs = _lib.rows(X, d)
         xc, xcs = _lib.rows(Xall, d)

@@ -282,7 +282,7 @@ def run_b200(args, wl):
         nl, nt = P_gpu, P_total
         Xall = smp._gath[0] if world > 1 else X
         Gall = smp._gath[1] if world > 1 else field.theta_grad
-        sq_ms = statistics.median(event_ms(torch, lambda: ws.sqdist(X, nl, Xall, nt, d, nt * nt), 10, flush=flush))
+        sq_ms = statistics.median(event_ms(torch, lambda: ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=rank * nl), 10, flush=flush))
         med_ms = statistics.median(event_ms(torch, lambda: ws.median(nl, nt, d, nt, None, group=True if world > 1 else None), 10))
         xr, xrs = bode._lib.rows(X, d); xc, xcs = bode._lib.rows(Xall, d); sc, scs = bode._lib.rows(Gall, d)
         import ctypes as C
@@ -290,12 +290,19 @@ def run_b200(args, wl):
                                                            C.c_void_p(ws.base.data_ptr()), bode._lib.ptr(smp.phi_buf), d, None, 0, 0.0,
                                                            bode._lib.stream_ptr()))
         phi_ms = statistics.median(event_ms(torch, phi_fn, 10, flush=flush))
-        kernels.append(dict(name="svgd sqdist_kernel", ms=sq_ms, bound="fp32", achieved=2.0 * nl * nt * d / (sq_ms * 1e-3) / 1e12,
-                            peak=peaks["fp32_fma_tflops"], unit="TFLOP/s"))
+        tc = bool(lib.bode_svgd_set_tensor_cores(1)) and d <= 56
+        lib.bode_svgd_set_tensor_cores(int(tc))
+        tpeak = None
+        if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+            tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops")
+        tpeak = (tpeak or 1590.0) / 2.0          # tf32 dense = half the bf16 rate; no measured tf32 figure exists
+        kernels.append(dict(name="svgd gram d2 (3xTF32 tcgen05)" if tc else "svgd sqdist_kernel", ms=sq_ms, bound="tensor" if tc else "fp32",
+                            achieved=2.0 * nl * nt * d / (sq_ms * 1e-3) / 1e12, peak=tpeak if tc else peaks["fp32_fma_tflops"], unit="TFLOP/s"))
         kernels.append(dict(name="svgd exact median (3 radix passes over d2)", ms=med_ms, bound="hbm",
                             achieved=3.0 * nl * nt * 4 / (med_ms * 1e-3) / 1e9, peak=None, unit="GB/s"))
-        kernels.append(dict(name="svgd phi_partial+combine (K@[S|X])", ms=phi_ms, bound="fp32",
-                            achieved=4.0 * nl * nt * d / (phi_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"], unit="TFLOP/s"))
+        kernels.append(dict(name="svgd phi K@[S|X|1] (3xTF32 tcgen05) + combine" if tc else "svgd phi_partial+combine (K@[S|X])", ms=phi_ms,
+                            bound="tensor" if tc else "fp32", achieved=4.0 * nl * nt * d / (phi_ms * 1e-3) / 1e12,
+                            peak=tpeak if tc else peaks["fp32_fma_tflops"], unit="TFLOP/s"))
     hbm_peak = None
     mp_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak_src = "fallback (B200_PROFILING.md)"
@@ -311,7 +318,8 @@ def run_b200(args, wl):
     roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"], traffic=None,
                     kernel=dom["name"], kernel_ms=dom["ms"],
                     peak_source=("fp32 FMA-chain microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 figure)"
-                                 if dom["bound"] == "fp32" else peak_src))
+                                 if dom["bound"] == "fp32" else ("half of MEASURED_PEAKS.json bf16_tflops (tf32 dense rate); algorithmic flops, "
+                                                                 "the kernel issues 3 MMAs per product" if dom["bound"] == "tensor" else peak_src)))
 
     # ---- end to end through the public API with HOST buffers: H2D of this step's observations, step, D2H of the loss
     loss_host = torch.empty(P_gpu, dtype=torch.float32).pin_memory()

@@ -245,8 +245,12 @@ int bode_fill_normal(float* out, int64_t n, uint64_t seed, uint32_t step, bode_s
  * ------------------------------------------------------------------------------------- */
 size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t d);
 int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
-                     int32_t n_cols, int32_t d, uint64_t total_entries, void* workspace, size_t workspace_bytes,
-                     void** hist_out, bode_stream_t stream);
+                     int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
+                     size_t workspace_bytes, void** hist_out, bode_stream_t stream);
+/* row_offset = index of local row 0 among the columns (rank * P_local); -1 when rows and columns are unrelated sets.
+ * bode_svgd_set_tensor_cores(1) (default) runs the two contractions as 3xTF32 tcgen05.mma (d <= 56); 0 selects the FP32-pipe
+ * kernels.  Returns the previous setting. */
+int bode_svgd_set_tensor_cores(int32_t on);
 int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
