@@ -15,6 +15,20 @@ BODE_DECL_SEP(4)
 BODE_DECL_SEP(5)
 BODE_DECL_SEP(6)
 
+#define BODE_DECL_GEN(J)                                                                                              \
+  int launch_gen_fwd_##J(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);         \
+  int launch_gen_grad_##J(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_gen_dopri5_##J(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+BODE_DECL_GEN(1)
+BODE_DECL_GEN(2)
+BODE_DECL_GEN(4)
+BODE_DECL_GEN(8)
+
+static bool use_sep(const bode_npde_field* f) {
+  return f->grid_mx == f->grid_my && f->grid_mx >= 3 && f->grid_mx <= 6 && f->grid_mx * f->grid_my == f->m;
+}
+static int gen_jpl(int m) { return m <= 32 ? 1 : (m <= 64 ? 2 : (m <= 128 ? 4 : 8)); }
+
 static int stages_of(int method) { return method == BODE_RK4 ? 4 : (method == BODE_MIDPOINT ? 2 : 1); }
 
 static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_grid* g, int method, int N,
@@ -35,7 +49,7 @@ static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_gr
   prm.c0 = (float)c0; prm.c1 = (float)c1;
   prm.k0 = (float)(2.0 * LN2 * c0); prm.k1 = (float)(2.0 * LN2 * c1);
   prm.U = f->U; prm.A = f->A; prm.Ksym = f->Ksym; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
-  prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr;
+  prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr; prm.Z = f->Z;
   BODE_REQUIRE(f->U_stride >= 2 * f->m && (f->U_stride % 2) == 0, "U_stride=%lld must be even and >= 2m", (long long)f->U_stride);
   prm.U_stride = f->U_stride;
   return BODE_OK;
@@ -102,17 +116,26 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
   BODE_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 7) == 0, "scratch must be 8-byte aligned");
   prm.ck = reinterpret_cast<float2*>(scratch);
   prm.npairs = (long long)f->P * N;
-  if (f->grid_mx > 0) {
+  dim3 grid, block;
+  if (use_sep(f)) {
     int st_ = fill_sep(prm, f);
     if (st_ != BODE_OK) return st_;
-    dim3 grid, block;
     st_ = plan(prm, 1, 256, &grid, &block);
     if (st_ != BODE_OK) return st_;
     const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
     return dispatch_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
   }
-  set_error("general (non-grid) inducing points: kernel not built in this version");
-  return BODE_ERR_UNSUPPORTED;
+  // general inducing locations (or a grid outside 3x3..6x6): lane-sliced kernel, one warp per (particle, trajectory)
+  BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
+  int st_ = plan(prm, 32, 256, &grid, &block);
+  if (st_ != BODE_OK) return st_;
+  const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+  switch (gen_jpl(f->m)) {
+    case 1: return launch_gen_grad_1(prm, method, inj, grad_mode, grid, block, smem, st);
+    case 2: return launch_gen_grad_2(prm, method, inj, grad_mode, grid, block, smem, st);
+    case 4: return launch_gen_grad_4(prm, method, inj, grad_mode, grid, block, smem, st);
+    default: return launch_gen_grad_8(prm, method, inj, grad_mode, grid, block, smem, st);
+  }
 }
 
 }  // namespace bode
@@ -130,17 +153,25 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
   if (st != BODE_OK) return st;
   BODE_REQUIRE(sol, "null sol");
   prm.sol = sol;
-  if (f->grid_mx > 0) {
+  dim3 grid, block;
+  if (use_sep(f)) {
     st = fill_sep(prm, f);
     if (st != BODE_OK) return st;
-    dim3 grid, block;
     st = plan(prm, 1, 256, &grid, &block);
     if (st != BODE_OK) return st;
     const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
     return dispatch_fwd(prm, f->grid_mx, method, grid, block, smem, (cudaStream_t)stream);
   }
-  set_error("general (non-grid) inducing points: kernel not built in this version");
-  return BODE_ERR_UNSUPPORTED;
+  BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
+  st = plan(prm, 32, 256, &grid, &block);
+  if (st != BODE_OK) return st;
+  const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
+  switch (gen_jpl(f->m)) {
+    case 1: return launch_gen_fwd_1(prm, method, grid, block, smem, (cudaStream_t)stream);
+    case 2: return launch_gen_fwd_2(prm, method, grid, block, smem, (cudaStream_t)stream);
+    case 4: return launch_gen_fwd_4(prm, method, grid, block, smem, (cudaStream_t)stream);
+    default: return launch_gen_fwd_8(prm, method, grid, block, smem, (cudaStream_t)stream);
+  }
 }
 
 int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o) {
@@ -165,10 +196,21 @@ extern "C" int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts
   Dopri5Params dp;
   st = fill_dopri5(dp, o);
   if (st != BODE_OK) return st;
-  BODE_REQUIRE(f->grid_mx > 0, "general (non-grid) inducing points: kernel not built in this version");
+  dim3 grid, block;
+  if (!use_sep(f)) {
+    BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
+    st = plan(prm, 32, 256, &grid, &block);
+    if (st != BODE_OK) return st;
+    const size_t smemg = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
+    switch (gen_jpl(f->m)) {
+      case 1: return launch_gen_dopri5_1(prm, dp, grid, block, smemg, (cudaStream_t)stream);
+      case 2: return launch_gen_dopri5_2(prm, dp, grid, block, smemg, (cudaStream_t)stream);
+      case 4: return launch_gen_dopri5_4(prm, dp, grid, block, smemg, (cudaStream_t)stream);
+      default: return launch_gen_dopri5_8(prm, dp, grid, block, smemg, (cudaStream_t)stream);
+    }
+  }
   st = fill_sep(prm, f);
   if (st != BODE_OK) return st;
-  dim3 grid, block;
   st = plan(prm, 1, 256, &grid, &block);
   if (st != BODE_OK) return st;
   const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;

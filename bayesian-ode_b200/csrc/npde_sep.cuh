@@ -20,7 +20,7 @@ struct NpdeKParams {
   float c0, c1;   // sqrt(log2(e)/2) / ell_d
   float k0, k1;   // 2 ln2 c_d     (d kappa / dx = -k * delta * kappa)
   float gxs[16], gys[16];  // c0*gx[a], c1*gy[b]
-  const float *U, *logsn, *A, *Ksym, *y0, *dt, *Y, *gout, *adj_dt;
+  const float *U, *logsn, *A, *Ksym, *y0, *dt, *Y, *gout, *adj_dt, *Z;
   const int *obs_ptr, *adj_ptr;
   float2* ck;
   long long npairs;

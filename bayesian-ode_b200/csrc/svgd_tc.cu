@@ -136,30 +136,44 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
   const bool vec = ((d & 3) == 0) && ((ldr & 3) == 0) && ((ldc & 3) == 0) && ((((uintptr_t)Xr | (uintptr_t)Xc | (uintptr_t)mu) & 15) == 0);
   if (vec) {
     const int dch = d >> 2;
-    for (int idx = tid; idx < GT * KCH; idx += 128) {
-      const int row = idx / KCH, kc = idx - row * KCH;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kc < dch && r0 + row < nr) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(Xr + (long long)(r0 + row) * ldr) + kc);
-        const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + kc);
-        v = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-      }
+    // all loads of the CTA's operand rows are issued before the first use (fixed trip counts: KCH and KCH/2 per thread)
+    constexpr int NA = GT * KCH / 128, NB = GN * KCH / 128;
+    static_assert(GT * KCH % 128 == 0 && GN * KCH % 128 == 0, "tile chunks must divide evenly over 128 threads");
+    float4 xa[NA], xb[NB], ma[NA], mb[NB];
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const bool ok = kc < dch && r0 + row < nr;
+      const int rr = min(r0 + row, nr - 1), kk = min(kc, dch - 1);
+      xa[q] = __ldg(reinterpret_cast<const float4*>(Xr + (long long)rr * ldr) + kk);
+      ma[q] = __ldg(reinterpret_cast<const float4*>(mu) + kk);
+      if (!ok) { xa[q] = make_float4(0.f, 0.f, 0.f, 0.f); ma[q] = xa[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const bool ok = kc < dch && c0 + row < nc;
+      const int rr = min(c0 + row, nc - 1), kk = min(kc, dch - 1);
+      xb[q] = __ldg(reinterpret_cast<const float4*>(Xc + (long long)rr * ldc) + kk);
+      mb[q] = __ldg(reinterpret_cast<const float4*>(mu) + kk);
+      if (!ok) { xb[q] = make_float4(0.f, 0.f, 0.f, 0.f); mb[q] = xb[q]; }
+    }
+#pragma unroll
+    for (int q = 0; q < NA; ++q) {
+      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
       float h[4], l[4];
-      split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+      split_tf32(xa[q].x - ma[q].x, h[0], l[0]); split_tf32(xa[q].y - ma[q].y, h[1], l[1]);
+      split_tf32(xa[q].z - ma[q].z, h[2], l[2]); split_tf32(xa[q].w - ma[q].w, h[3], l[3]);
       const uint32_t off = kmajor_off<GT>(row, kc);
       *reinterpret_cast<float4*>(sAh + off) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(sAl + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
-    for (int idx = tid; idx < GN * KCH; idx += 128) {
-      const int row = idx / KCH, kc = idx - row * KCH;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (kc < dch && c0 + row < nc) {
-        const float4 x = __ldg(reinterpret_cast<const float4*>(Xc + (long long)(c0 + row) * ldc) + kc);
-        const float4 m = __ldg(reinterpret_cast<const float4*>(mu) + kc);
-        v = make_float4(x.x - m.x, x.y - m.y, x.z - m.z, x.w - m.w);
-      }
+#pragma unroll
+    for (int q = 0; q < NB; ++q) {
+      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
       float h[4], l[4];
-      split_tf32(v.x, h[0], l[0]); split_tf32(v.y, h[1], l[1]); split_tf32(v.z, h[2], l[2]); split_tf32(v.w, h[3], l[3]);
+      split_tf32(xb[q].x - mb[q].x, h[0], l[0]); split_tf32(xb[q].y - mb[q].y, h[1], l[1]);
+      split_tf32(xb[q].z - mb[q].z, h[2], l[2]); split_tf32(xb[q].w - mb[q].w, h[3], l[3]);
       const uint32_t off = kmajor_off<GN>(row, kc);
       *reinterpret_cast<float4*>(sBh + off) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(sBl + off) = make_float4(l[0], l[1], l[2], l[3]);
@@ -326,21 +340,23 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
     const int jc = slot / NF, f = slot - jc * NF;
     vjc[q] = jc;
     voff[q] = slot < NV ? (int)kmajor_off<NF>(f, jc) : -1;
-    vsrc[q] = nullptr; vld[q] = 0; vscale[q] = 0.f; vadd[q] = 0.f;
+    vsrc[q] = Gc; vld[q] = 0; vscale[q] = 0.f; vadd[q] = 0.f;            // padding / ones columns read a dummy word, scale 0
     if (slot < NV) {
       if (f < d) { vsrc[q] = Gc + f; vld[q] = ldg; vscale[q] = gsign; }
       else if (f < 2 * d) { vsrc[q] = Xc + (f - d); vld[q] = ldx; vscale[q] = 1.f; vadd[q] = -__ldg(mu + f - d); }
       else if (f == 2 * d) { vadd[q] = 1.f; }
     }
   }
+  const bool avec = (nc & 3) == 0;
   for (int j0 = jbeg; j0 < jend; j0 += PK) {
     // ---- A: K[row][j0..j0+31] = 2^(-g d2), split hi/lo
     float4 dv[PK / 4];
 #pragma unroll
     for (int kc = 0; kc < PK / 4; ++kc) {
       const int j = j0 + 4 * kc;
-      if (row < nr && j + 4 <= jend && ((nc & 3) == 0)) {
-        dv[kc] = __ldg(reinterpret_cast<const float4*>(D2 + (long long)row * nc + j));
+      if (avec && j + 4 <= jend) {
+        dv[kc] = __ldg(reinterpret_cast<const float4*>(D2 + (long long)min(row, nr - 1) * nc + j));
+        if (row >= nr) dv[kc] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       } else {
         float t[4];
 #pragma unroll
@@ -358,7 +374,7 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
       for (int e = 0; e < 4; ++e) {
         const int j = j0 + 4 * vjc[q] + e;
         const bool ok = j < jend;
-        const float raw = (ok && vsrc[q]) ? __ldg(vsrc[q] + (long long)j * vld[q]) : 0.f;
+        const float raw = __ldg(vsrc[q] + (long long)min(j, jend - 1) * vld[q]);     // always a valid address: no branch
         t[e] = ok ? fmaf(vscale[q], raw, vadd[q]) : 0.f;
       }
       vv[q] = make_float4(t[0], t[1], t[2], t[3]);
