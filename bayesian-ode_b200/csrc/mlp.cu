@@ -43,7 +43,8 @@ static int mlp_grad(const bode_mlp_field* f, const bode_grid* g, int method, int
   prm.ck = reinterpret_cast<float2*>(scratch);
   prm.npairs = (long long)f->P * N;
   const dim3 grid(f->P), block(32 * N);
-  const size_t smem = mlp_smem(f->H, N);
+  prm.stage_off = (int)((mlp_smem(f->H, N) / sizeof(float) + 3) & ~(size_t)3);
+  const size_t smem = sizeof(float) * ((size_t)prm.stage_off + ((2 * (size_t)prm.S + 2) & ~(size_t)1) + 2 * (size_t)N * prm.T + 2);
   if (f->H == 20) return launch_mlp_grad_20(prm, method, inj, grad_mode, grid, block, smem, st);
   return launch_mlp_grad_64(prm, method, inj, grad_mode, grid, block, smem, st);
 }

@@ -101,6 +101,9 @@ static int dispatch_grad(const NpdeKParams& prm, int M, int method, int inj, int
   return BODE_ERR_UNSUPPORTED;
 }
 
+// staged dt[S] | obs_ptr[S+1] | Y[N,T,2] after the field's own shared-memory region
+static size_t stage_floats(const NpdeKParams& prm) { return (size_t)((2 * prm.S + 2) & ~1) + 2 * (size_t)prm.N * prm.T + 2; }
+
 static size_t scratch_floats(long long P, long long N, int S, int T, int method, int grad_mode) {
   const long long npairs = P * N;
   const long long slots = grad_mode == BODE_GRAD_ADJOINT ? (long long)T : (long long)S * stages_of(method);
@@ -122,14 +125,18 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
     if (st_ != BODE_OK) return st_;
     st_ = plan(prm, 1, 256, &grid, &block);
     if (st_ != BODE_OK) return st_;
-    const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+    prm.stage_off = (int)(((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2 + 3) & ~(size_t)3);
+    const size_t smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
+    BODE_REQUIRE(smem <= 48 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
     return dispatch_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
   }
   // general inducing locations (or a grid outside 3x3..6x6): lane-sliced kernel, one warp per (particle, trajectory)
   BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
   int st_ = plan(prm, 32, 256, &grid, &block);
   if (st_ != BODE_OK) return st_;
-  const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+  prm.stage_off = (int)(((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2 + 3) & ~(size_t)3);
+  const size_t smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
+  BODE_REQUIRE(smem <= 48 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
   switch (gen_jpl(f->m)) {
     case 1: return launch_gen_grad_1(prm, method, inj, grad_mode, grid, block, smem, st);
     case 2: return launch_gen_grad_2(prm, method, inj, grad_mode, grid, block, smem, st);

@@ -25,6 +25,7 @@ struct NpdeKParams {
   float2* ck;
   long long npairs;
   long long U_stride, logsn_stride, gU_stride, glogsn_stride;
+  int stage_off;      // float offset in dynamic shared memory of the staged dt[S] | obs_ptr[S+1] | Y[N,T,2]
   float reg, lik_w;   // MLP closure: lik_w * sum (X - x)^2 + reg * sum theta^2
   float *sol, *loss, *sqerr, *gU, *glogsn, *gy0;
 };

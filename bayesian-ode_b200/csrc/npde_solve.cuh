@@ -65,23 +65,29 @@ __device__ __forceinline__ float2 step_fwd(const NpdeKParams& prm, const Field& 
 }
 
 // ------------------------------------------------------------------ discrete adjoint of one step
+template <int METHOD>
+__device__ __forceinline__ void load_stage_points(float2 (&ys)[Stages<METHOD>::value], const float2* ckp, long long stride) {
+#pragma unroll
+  for (int i = 0; i < Stages<METHOD>::value; ++i) ys[i] = ckp[(long long)i * stride];
+}
+
 template <int METHOD, class Field>
 __device__ __forceinline__ float2 step_bwd(const NpdeKParams& prm, Field& fld, float2 a, float dt,
-                                           const float2* ckp, long long stride, float2* y_start) {
+                                           const float2 (&ys)[Stages<METHOD>::value], float2* y_start) {
   const float sg = prm.sign;
   if (METHOD == BODE_EULER) {
-    const float2 y1 = ckp[0];
+    const float2 y1 = ys[0];
     *y_start = y1;
     const float2 v1 = fld.template vjp<false>(prm, y1, (sg * dt) * a, 1.f, nullptr);
     return a + v1;
   } else if (METHOD == BODE_MIDPOINT) {
-    const float2 y1 = ckp[0], y2 = ckp[stride];
+    const float2 y1 = ys[0], y2 = ys[1];
     *y_start = y1;
     const float2 v2 = fld.template vjp<false>(prm, y2, (sg * dt) * a, 1.f, nullptr);
     const float2 v1 = fld.template vjp<false>(prm, y1, (sg * 0.5f * dt) * v2, 1.f, nullptr);
     return (a + v2) + v1;
   } else {
-    const float2 y1 = ckp[0], y2 = ckp[stride], y3 = ckp[2 * stride], y4 = ckp[3 * stride];
+    const float2 y1 = ys[0], y2 = ys[1], y3 = ys[METHOD == BODE_RK4 ? 2 : 0], y4 = ys[METHOD == BODE_RK4 ? 3 : 0];
     *y_start = y1;
     const float dt3 = dt * (1.f / 3.f);
     float2 kb1 = (dt * 0.125f) * a, kb2 = (dt * 0.375f) * a, kb3 = kb2;
@@ -247,6 +253,14 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
   constexpr int G = Field::G;
   constexpr int STG = Stages<METHOD>::value;
   const int N = prm.N, ppc = prm.ppc;
+  // solver grid and observations staged once per CTA: every later access is a short-latency shared-memory read
+  float* sdt = smem + prm.stage_off;
+  int* sptr = reinterpret_cast<int*>(sdt + prm.S);
+  float2* sY = reinterpret_cast<float2*>(sdt + ((2 * prm.S + 2) & ~1));
+  for (int i = threadIdx.x; i < prm.S; i += blockDim.x) sdt[i] = __ldg(prm.dt + i);
+  for (int i = threadIdx.x; i <= prm.S; i += blockDim.x) sptr[i] = prm.S > 0 ? __ldg(prm.obs_ptr + i) : 1;
+  if (INJ == INJ_LIK)
+    for (int i = threadIdx.x; i < N * prm.T; i += blockDim.x) sY[i] = __ldg(reinterpret_cast<const float2*>(prm.Y) + i);
   Field::prologue(prm, smem);
 
   const int tid = threadIdx.x;
@@ -261,7 +275,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     fld.load(prm, smem, pl, pairl, lane);
     const long long pair = (long long)p * N + n;
     const long long PN = (long long)prm.P * N;
-    const float2* Y2 = reinterpret_cast<const float2*>(prm.Y) + (long long)n * prm.T;   // Y[n][j]
+    const float2* Y2 = sY + n * prm.T;                                                  // Y[n][j] (shared)
     const float2* go = reinterpret_cast<const float2*>(prm.gout) + pair;              // gout[j][pair]
     float2 e2inv = f2(0.f, 0.f);                     // dL/dx = -e2inv * (Y - x)
     if (INJ == INJ_LIK) e2inv = Field::lik_weight(prm, p);
@@ -271,20 +285,20 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     // ---------------- forward
     float2 y = reinterpret_cast<const float2*>(prm.y0)[(prm.y0_stride ? (long long)p * N : 0) + n];
     if (INJ == INJ_LIK) {
-      const float2 r = __ldg(Y2) - y;
+      const float2 r = Y2[0] - y;
       r2x = r.x * r.x;
       r2y = r.y * r.y;
     }
     if (ADJ == BODE_GRAD_ADJOINT && lane == 0) ck[0] = y;
     for (int s = 0; s < prm.S; ++s) {
       if (ADJ == BODE_GRAD_DISCRETE)
-        y = step_fwd<METHOD, true>(prm, fld, y, __ldg(prm.dt + s), ck + (long long)s * STG * stride, stride);
+        y = step_fwd<METHOD, true>(prm, fld, y, sdt[s], ck + (long long)s * STG * stride, stride);
       else
-        y = step_fwd<METHOD, false>(prm, fld, y, __ldg(prm.dt + s), nullptr, 0);
-      const int j1 = __ldg(prm.obs_ptr + s + 1);
-      for (int j = __ldg(prm.obs_ptr + s); j < j1; ++j) {
+        y = step_fwd<METHOD, false>(prm, fld, y, sdt[s], nullptr, 0);
+      const int j1 = sptr[s + 1];
+      for (int j = sptr[s]; j < j1; ++j) {
         if (INJ == INJ_LIK) {
-          const float2 r = __ldg(Y2 + j) - y;
+          const float2 r = Y2[j] - y;
           r2x = fmaf(r.x, r.x, r2x);
           r2y = fmaf(r.y, r.y, r2y);
         }
@@ -296,20 +310,27 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     float2 a = f2(0.f, 0.f);
     if (ADJ == BODE_GRAD_DISCRETE) {
       float2 yend = y;
+      float2 ys[STG], yn[STG];
+      if (G > 1) __syncwarp();
+      if (prm.S > 0) load_stage_points<METHOD>(ys, ck + (long long)(prm.S - 1) * STG * stride, stride);
       for (int s = prm.S - 1; s >= 0; --s) {
-        const int j0 = __ldg(prm.obs_ptr + s);
-        for (int j = __ldg(prm.obs_ptr + s + 1) - 1; j >= j0; --j) {
+        // software prefetch: the stage points of step s-1 travel from L2 while step s is differentiated
+        if (s > 0) load_stage_points<METHOD>(yn, ck + (long long)(s - 1) * STG * stride, stride);
+        const int j0 = sptr[s];
+        for (int j = sptr[s + 1] - 1; j >= j0; --j) {
           if (INJ == INJ_LIK) {
-            const float2 r = __ldg(Y2 + j) - yend;
+            const float2 r = Y2[j] - yend;
             a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
           } else {
             a = a + __ldg(go + (long long)j * PN);
           }
         }
-        a = step_bwd<METHOD>(prm, fld, a, __ldg(prm.dt + s), ck + (long long)s * STG * stride, stride, &yend);
+        a = step_bwd<METHOD>(prm, fld, a, sdt[s], ys, &yend);
+#pragma unroll
+        for (int i = 0; i < STG; ++i) ys[i] = yn[i];
       }
       if (INJ == INJ_LIK) {
-        const float2 r = __ldg(Y2) - yend;
+        const float2 r = Y2[0] - yend;
         a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
       } else {
         a = a + __ldg(go);
@@ -321,7 +342,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
       {
         const float2 yT = ck[(long long)(prm.T - 1) * stride];
         if (INJ == INJ_LIK) {
-          const float2 r = __ldg(Y2 + prm.T - 1) - yT;
+          const float2 r = Y2[prm.T - 1] - yT;
           a = f2(-r.x * e2inv.x, -r.y * e2inv.y);
         } else {
           a = __ldg(go + (long long)(prm.T - 1) * PN);
@@ -334,7 +355,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
           step_aug<METHOD>(prm, fld, yy, a, __ldg(prm.adj_dt + q), s_in);
         const float2 yp = ck[(long long)(i - 1) * stride];
         if (INJ == INJ_LIK) {
-          const float2 r = __ldg(Y2 + i - 1) - yp;
+          const float2 r = Y2[i - 1] - yp;
           a = f2(fmaf(-r.x, e2inv.x, a.x), fmaf(-r.y, e2inv.y, a.y));
         } else {
           a = a + __ldg(go + (long long)(i - 1) * PN);
