@@ -178,6 +178,10 @@ def run_b200(args, wl):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL prints its version there) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -229,13 +233,24 @@ def run_b200(args, wl):
     for _ in range(3):
         step()
     torch.cuda.synchronize()
-    use_graph = world == 1 and not args.no_graph
+    use_graph = not args.no_graph
     run = step
     if use_graph:
-        gph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gph):
-            step()
-        run = gph.replay
+        try:
+            gph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gph):
+                step()
+            run = gph.replay
+        except Exception as e:                                   # e.g. NCCL capture unsupported: fall back to eager launches
+            print("cuda graph capture failed (%s); running eagerly" % str(e).splitlines()[0], file=sys.stderr)
+            use_graph = False
+            run = step
+            torch.cuda.synchronize()
+    if world > 1:
+        flag = torch.tensor([int(use_graph)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0 and use_graph:
+            use_graph, run = False, step
 
     flush_buf = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device="cuda")              # 256 MiB > 126 MB L2
 
@@ -349,8 +364,7 @@ def run_b200(args, wl):
     assert bool(torch.isfinite(loss_host).all()), "non-finite loss at the end of the run"
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world, dist)
         return
     cb = None
     if world == 1 and not args.no_cpu_baseline:
@@ -367,9 +381,22 @@ def run_b200(args, wl):
         "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk,
         "wall_s_timed_region": round(t_wall, 3),
     }
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    _finish(world, dist)
+
+
+def _finish(world, dist):
+    """Multi-rank teardown.  A captured graph that contains NCCL kernels keeps the communicator busy and
+    destroy_process_group() was seen to block on it, so after a final barrier the ranks leave without it."""
     if world > 1:
-        dist.destroy_process_group()
+        import torch
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
