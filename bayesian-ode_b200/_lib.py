@@ -63,6 +63,16 @@ SYMBOLS = {
     "bode_mlp_odeint": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_npde_dopri5": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_mlp_dopri5": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32, _P, _P]),
+    "bode_dopri5_scratch_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "bode_npde_dopri5_backward": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32,
+                                             _P, _P, C.c_int64, _P, _P, C.c_size_t, C.c_int32, _P]),
+    "bode_npde_dopri5_nlp_grad": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32,
+                                             _P, _P, C.c_int64, C.c_float, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, _P, C.c_size_t,
+                                             C.c_int32, _P]),
+    "bode_mlp_dopri5_backward": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32,
+                                            _P, _P, C.c_int64, _P, _P, C.c_size_t, C.c_int32, _P]),
+    "bode_mlp_dopri5_sse_grad": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(Dopri5Opts), C.c_int32, C.c_float, C.c_int32, _P, C.c_int32,
+                                            _P, C.c_float, C.c_float, C.c_float, C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_size_t, C.c_int32, _P]),
     "bode_mlp_odeint_backward": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
                                             _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),
     "bode_mlp_sse_grad": (C.c_int, [C.POINTER(MlpFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,

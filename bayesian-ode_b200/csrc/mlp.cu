@@ -4,13 +4,16 @@
 #include <string.h>
 
 int fill_dopri5(bode::Dopri5Params& dp, const bode_dopri5_opts* o);
+int carve_dopri5_rec(bode::Dopri5Rec& rec, float* scratch, size_t scratch_n, long long npairs, int T, int max_rec);
 
 namespace bode {
 #define BODE_DECL_MLP(H)                                                                                                  \
   size_t mlp_smem_bytes_##H(int N);                                                                                       \
   int launch_mlp_fwd_##H(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);         \
   int launch_mlp_grad_##H(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
-  int launch_mlp_dopri5_##H(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+  int launch_mlp_dopri5_##H(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_mlp_dopri5_grad_##H(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid, dim3 block, \
+                                 size_t smem, cudaStream_t st);
 BODE_DECL_MLP(20)
 BODE_DECL_MLP(64)
 
@@ -81,6 +84,49 @@ extern "C" int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* 
   const size_t smem = mlp_smem(f->H, N);
   if (f->H == 20) return launch_mlp_dopri5_20(prm, dp, grid, block, smem, (cudaStream_t)stream);
   return launch_mlp_dopri5_64(prm, dp, grid, block, smem, (cudaStream_t)stream);
+}
+
+static int mlp_dopri5_grad(const bode_mlp_field* f, const bode_dopri5_opts* o, int T, int N, NpdeKParams& prm, int inj, float* scratch,
+                           size_t scratch_n, int max_rec, cudaStream_t st) {
+  Dopri5Params dp;
+  int e = fill_dopri5(dp, o);
+  if (e != BODE_OK) return e;
+  Dopri5Rec rec;
+  e = carve_dopri5_rec(rec, scratch, scratch_n, (long long)f->P * N, T, max_rec);
+  if (e != BODE_OK) return e;
+  prm.npairs = (long long)f->P * N;
+  const dim3 grid(f->P), block(32 * N);
+  const size_t smem = mlp_smem(f->H, N);
+  if (f->H == 20) return launch_mlp_dopri5_grad_20(prm, dp, rec, inj, grid, block, smem, st);
+  return launch_mlp_dopri5_grad_64(prm, dp, rec, inj, grid, block, smem, st);
+}
+
+extern "C" int bode_mlp_dopri5_backward(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                                        const float* y0, int32_t y0_batched, const float* gout, float* gtheta, int64_t gtheta_stride,
+                                        float* gy0, float* scratch, size_t scratch_n, int32_t max_rec_steps, bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(gout && gtheta, "null gout/gtheta");
+  prm.gout = gout; prm.gU = gtheta; prm.gU_stride = gtheta_stride; prm.gy0 = gy0; prm.add_prior = 0;
+  return mlp_dopri5_grad(f, o, T, N, prm, INJ_GOUT, scratch, scratch_n, max_rec_steps, (cudaStream_t)stream);
+}
+
+extern "C" int bode_mlp_dopri5_sse_grad(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                                        const float* y0, int32_t y0_batched, const float* X, float lik_w, float reg, float scale,
+                                        int32_t add_prior, float* loss, float* sqerr, float* gtheta, int64_t gtheta_stride,
+                                        float* scratch, size_t scratch_n, int32_t max_rec_steps, bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = mlp_fill(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(X && loss && sqerr && gtheta, "null X/outputs");
+  prm.Y = X; prm.lik_w = lik_w; prm.reg = reg; prm.scale = scale; prm.add_prior = add_prior ? 1 : 0;
+  prm.loss = loss; prm.sqerr = sqerr; prm.gU = gtheta; prm.gU_stride = gtheta_stride;
+  return mlp_dopri5_grad(f, o, T, N, prm, INJ_LIK, scratch, scratch_n, max_rec_steps, (cudaStream_t)stream);
 }
 
 extern "C" int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,

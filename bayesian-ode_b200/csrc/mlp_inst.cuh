@@ -39,6 +39,19 @@ int BODE_CAT(launch_mlp_dopri5_, BODE_H)(const NpdeKParams& prm, const Dopri5Par
   return check_cuda(cudaGetLastError(), "mlp dopri5 launch");
 }
 
+int BODE_CAT(launch_mlp_dopri5_grad_, BODE_H)(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid,
+                                              dim3 block, size_t smem, cudaStream_t st) {
+  if (smem > 48 * 1024) {
+    int e = check_cuda(cudaFuncSetAttribute(dopri5_grad_kernel<MF, INJ_LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (e != BODE_OK) return e;
+    e = check_cuda(cudaFuncSetAttribute(dopri5_grad_kernel<MF, INJ_GOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
+    if (e != BODE_OK) return e;
+  }
+  if (inj == INJ_LIK) dopri5_grad_kernel<MF, INJ_LIK><<<grid, block, smem, st>>>(prm, dp, rec);
+  else dopri5_grad_kernel<MF, INJ_GOUT><<<grid, block, smem, st>>>(prm, dp, rec);
+  return check_cuda(cudaGetLastError(), "mlp dopri5 grad launch");
+}
+
 size_t BODE_CAT(mlp_smem_bytes_, BODE_H)(int N) { return sizeof(float) * (size_t)MF::smem_floats(N); }
 
 int BODE_CAT(launch_mlp_fwd_, BODE_H)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {

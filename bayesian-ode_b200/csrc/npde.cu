@@ -9,7 +9,9 @@ namespace bode {
 #define BODE_DECL_SEP(M)                                                                               \
   int launch_sep_fwd_##M(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
   int launch_sep_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
-  int launch_sep_dopri5_##M(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+  int launch_sep_dopri5_##M(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_sep_dopri5_grad_##M(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid, dim3 block, \
+                                 size_t smem, cudaStream_t st);
 BODE_DECL_SEP(3)
 BODE_DECL_SEP(4)
 BODE_DECL_SEP(5)
@@ -18,7 +20,9 @@ BODE_DECL_SEP(6)
 #define BODE_DECL_GEN(J)                                                                                              \
   int launch_gen_fwd_##J(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);         \
   int launch_gen_grad_##J(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
-  int launch_gen_dopri5_##J(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+  int launch_gen_dopri5_##J(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_gen_dopri5_grad_##J(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid, dim3 block, \
+                                 size_t smem, cudaStream_t st);
 BODE_DECL_GEN(1)
 BODE_DECL_GEN(2)
 BODE_DECL_GEN(4)
@@ -227,6 +231,89 @@ extern "C" int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts
     case 5: return launch_sep_dopri5_5(prm, dp, grid, block, smem, (cudaStream_t)stream);
     default: return launch_sep_dopri5_6(prm, dp, grid, block, smem, (cudaStream_t)stream);
   }
+}
+
+int carve_dopri5_rec(bode::Dopri5Rec& rec, float* scratch, size_t scratch_n, long long npairs, int T, int max_rec) {
+  BODE_REQUIRE(max_rec >= 1, "max_rec_steps must be >= 1");
+  const size_t need = bode_dopri5_scratch_floats((int32_t)npairs, 1, T, max_rec);
+  BODE_REQUIRE(scratch && scratch_n >= need, "dopri5 scratch too small: have %zu floats, need %zu", scratch_n, need);
+  BODE_REQUIRE((reinterpret_cast<uintptr_t>(scratch) & 15) == 0, "dopri5 scratch must be 16-byte aligned");
+  rec.outs = reinterpret_cast<float4*>(scratch);
+  rec.steps = reinterpret_cast<float2*>(scratch + 4 * (size_t)T * npairs);
+  rec.max_rec = max_rec;
+  return BODE_OK;
+}
+
+extern "C" size_t bode_dopri5_scratch_floats(int32_t P, int32_t N, int32_t T, int32_t max_rec_steps) {
+  const size_t npairs = (size_t)P * N;
+  return 4 * (size_t)T * npairs + 14 * (size_t)max_rec_steps * npairs;
+}
+
+static int npde_dopri5_grad(const bode_npde_field* f, const bode_dopri5_opts* o, int T, float sign, int N, const float* y0, int y0_batched,
+                            NpdeKParams& prm, int inj, float* scratch, size_t scratch_n, int max_rec, cudaStream_t st) {
+  Dopri5Params dp;
+  int e = fill_dopri5(dp, o);
+  if (e != BODE_OK) return e;
+  Dopri5Rec rec;
+  e = carve_dopri5_rec(rec, scratch, scratch_n, (long long)f->P * N, T, max_rec);
+  if (e != BODE_OK) return e;
+  prm.npairs = (long long)f->P * N;
+  dim3 grid, block;
+  if (use_sep(f)) {
+    e = fill_sep(prm, f);
+    if (e != BODE_OK) return e;
+    e = plan(prm, 1, 256, &grid, &block);
+    if (e != BODE_OK) return e;
+    const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+    switch (f->grid_mx) {
+      case 3: return launch_sep_dopri5_grad_3(prm, dp, rec, inj, grid, block, smem, st);
+      case 4: return launch_sep_dopri5_grad_4(prm, dp, rec, inj, grid, block, smem, st);
+      case 5: return launch_sep_dopri5_grad_5(prm, dp, rec, inj, grid, block, smem, st);
+      default: return launch_sep_dopri5_grad_6(prm, dp, rec, inj, grid, block, smem, st);
+    }
+  }
+  BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
+  e = plan(prm, 32, 256, &grid, &block);
+  if (e != BODE_OK) return e;
+  const size_t smem = sizeof(float) * ((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2);
+  switch (gen_jpl(f->m)) {
+    case 1: return launch_gen_dopri5_grad_1(prm, dp, rec, inj, grid, block, smem, st);
+    case 2: return launch_gen_dopri5_grad_2(prm, dp, rec, inj, grid, block, smem, st);
+    case 4: return launch_gen_dopri5_grad_4(prm, dp, rec, inj, grid, block, smem, st);
+    default: return launch_gen_dopri5_grad_8(prm, dp, rec, inj, grid, block, smem, st);
+  }
+}
+
+extern "C" int bode_npde_dopri5_backward(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                                         const float* y0, int32_t y0_batched, const float* gout, float* gU, int64_t gU_stride,
+                                         float* gy0, float* scratch, size_t scratch_n, int32_t max_rec_steps, bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = fill_common(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(gout && gU && gU_stride >= 2 * f->m, "null gout/gU or bad stride");
+  prm.gout = gout; prm.gU = gU; prm.gU_stride = gU_stride; prm.gy0 = gy0; prm.add_prior = 0;
+  return npde_dopri5_grad(f, o, T, sign, N, y0, y0_batched, prm, INJ_GOUT, scratch, scratch_n, max_rec_steps, (cudaStream_t)stream);
+}
+
+extern "C" int bode_npde_dopri5_nlp_grad(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                                         const float* y0, int32_t y0_batched, const float* Y, const float* logsn, int64_t logsn_stride,
+                                         float scale, int32_t add_prior, float* loss, float* sqerr, float* gU, int64_t gU_stride,
+                                         float* glogsn, int64_t glogsn_stride, float* scratch, size_t scratch_n, int32_t max_rec_steps,
+                                         bode_stream_t stream) {
+  bode_grid g = {};
+  g.S = 0; g.T = T; g.sign = sign;
+  NpdeKParams prm;
+  int st = fill_common(prm, f, &g, BODE_DOPRI5, N, y0, y0_batched);
+  if (st != BODE_OK) return st;
+  BODE_REQUIRE(Y && logsn && loss && sqerr && gU && glogsn, "null Y/logsn/outputs");
+  BODE_REQUIRE(!add_prior || f->Ksym, "add_prior needs Ksym");
+  BODE_REQUIRE(gU_stride >= 2 * f->m && logsn_stride >= 2 && glogsn_stride >= 2 && (logsn_stride % 2) == 0, "bad strides");
+  prm.Y = Y; prm.logsn = logsn; prm.scale = scale; prm.add_prior = add_prior ? 1 : 0;
+  prm.loss = loss; prm.sqerr = sqerr; prm.gU = gU; prm.glogsn = glogsn;
+  prm.logsn_stride = logsn_stride; prm.gU_stride = gU_stride; prm.glogsn_stride = glogsn_stride;
+  return npde_dopri5_grad(f, o, T, sign, N, y0, y0_batched, prm, INJ_LIK, scratch, scratch_n, max_rec_steps, (cudaStream_t)stream);
 }
 
 extern "C" int bode_npde_odeint_backward(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t grad_mode,

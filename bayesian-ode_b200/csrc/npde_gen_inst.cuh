@@ -21,6 +21,13 @@ int BODE_CAT(launch_gen_dopri5_, BODE_JPL)(const NpdeKParams& prm, const Dopri5P
   return check_cuda(cudaGetLastError(), "gen dopri5 launch");
 }
 
+int BODE_CAT(launch_gen_dopri5_grad_, BODE_JPL)(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid,
+                                                dim3 block, size_t smem, cudaStream_t st) {
+  if (inj == INJ_LIK) dopri5_grad_kernel<GF, INJ_LIK><<<grid, block, smem, st>>>(prm, dp, rec);
+  else dopri5_grad_kernel<GF, INJ_GOUT><<<grid, block, smem, st>>>(prm, dp, rec);
+  return check_cuda(cudaGetLastError(), "gen dopri5 grad launch");
+}
+
 template <int METHOD>
 static int gen_fwd(const NpdeKParams& prm, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   npde_fwd_kernel<GF, METHOD><<<grid, block, smem, st>>>(prm);

@@ -28,6 +28,13 @@ int BODE_CAT(launch_sep_dopri5_, BODE_M)(const NpdeKParams& prm, const Dopri5Par
   return check_cuda(cudaGetLastError(), "dopri5 launch");
 }
 
+int BODE_CAT(launch_sep_dopri5_grad_, BODE_M)(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid,
+                                              dim3 block, size_t smem, cudaStream_t st) {
+  if (inj == INJ_LIK) dopri5_grad_kernel<SepField<BODE_M, BODE_M>, INJ_LIK><<<grid, block, smem, st>>>(prm, dp, rec);
+  else dopri5_grad_kernel<SepField<BODE_M, BODE_M>, INJ_GOUT><<<grid, block, smem, st>>>(prm, dp, rec);
+  return check_cuda(cudaGetLastError(), "dopri5 grad launch");
+}
+
 int BODE_CAT(launch_sep_fwd_, BODE_M)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   switch (method) {
     case BODE_EULER: return launch_fwd_m<BODE_EULER>(prm, grid, block, smem, st);

@@ -145,12 +145,12 @@ def last_dopri5_stats():
     return _last_dopri5_stats
 
 
-def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
-    """Dopri5Solver forward (dopri5.py:58-122) with one controller per (particle, trajectory) pair.  The result is not
-    differentiable in this build (the gradient through adaptive steps is a next-round item)."""
-    global _last_dopri5_stats
+DOPRI5_MAX_REC_STEPS = 256      # accepted steps recorded per (particle, trajectory) pair for the gradient
+
+
+def dopri5_setup(func, y0, t, rtol, atol, options):
+    """Normalise the dopri5 call (dopri5.py:60-75 options, misc.py:184-187 time reversal) into the C-ABI structures."""
     import warnings
-    lib = _lib.load()
     options = dict(options or {})
     known = {k: options.pop(k) for k in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps") if k in options}
     if len(options) > 0:
@@ -159,11 +159,10 @@ def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
     dev = y0c.device
     t64 = t.detach().to("cpu", torch.float64)
     sign = 1.0
-    if t64.numel() > 1 and bool((t64[1:] < t64[:-1]).all()):                               # misc.py:184-187
+    if t64.numel() > 1 and bool((t64[1:] < t64[:-1]).all()):
         t64, sign = -t64, -1.0
     assert t64.numel() < 2 or bool((t64[1:] > t64[:-1]).all()), "t must be strictly increasing or decrasing"
     tdev = t64.to(dev)
-    T = int(t64.numel())
     stats = torch.zeros((func.P, N, 3), dtype=torch.int32, device=dev)
     o = _lib.Dopri5Opts()
     o.t = tdev.data_ptr()
@@ -172,17 +171,80 @@ def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
     o.max_num_steps = int(min(known.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
     o.user_first_step = int(known.get("first_step") is not None)
     o.stats = stats.data_ptr()
-    sol = torch.empty((T, func.P, N, 2), dtype=torch.float32, device=dev)
-    if isinstance(func, NPDEField):
-        st = lib.bode_npde_dopri5(func.c_struct(func.U.detach()), o, T, sign, N, _lib.ptr(y0c), int(batched), _lib.ptr(sol), _lib.stream_ptr())
-    else:
-        st = lib.bode_mlp_dopri5(func.c_struct(), o, T, sign, N, _lib.ptr(y0c), int(batched), _lib.ptr(sol), _lib.stream_ptr())
-    _lib.check(st)
-    flags = int(stats[..., 2].max().item())              # dopri5.py:89,100-102 assert on these conditions
+    return dict(o=o, tdev=tdev, T=int(t64.numel()), sign=sign, y0=y0c, batched=batched, N=N, stats=stats)
+
+
+def dopri5_check(stats, sync=True):
+    """dopri5.py:89,100-102 assert on these conditions; bit 8 = more accepted steps than the gradient record holds."""
+    global _last_dopri5_stats
     _last_dopri5_stats = stats
+    if not sync:
+        return
+    flags = 0
+    for b in (1, 2, 4, 8):
+        if bool(((stats[..., 2] & b) != 0).any()):
+            flags |= b
     assert not (flags & 1), "max_num_steps exceeded"
     assert not (flags & 2), "underflow in dt"
     assert not (flags & 4), "non-finite values in state `y`"
+    assert not (flags & 8), "more than DOPRI5_MAX_REC_STEPS accepted steps: raise bayesian_ode_b200.odeint.DOPRI5_MAX_REC_STEPS"
+
+
+class _Dopri5Odeint(torch.autograd.Function):
+    """Adaptive forward; backward = discrete adjoint of the accepted steps with frozen step sizes (one fused launch that
+    redoes the solve, records it and sweeps back)."""
+
+    @staticmethod
+    def forward(ctx, y0c, func, cfg, *params):
+        lib = _lib.load()
+        T, N = cfg["T"], cfg["N"]
+        sol = torch.empty((T, func.P, N, 2), dtype=torch.float32, device=y0c.device)
+        if isinstance(func, NPDEField):
+            st = lib.bode_npde_dopri5(func.c_struct(func.U.detach()), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]),
+                                      _lib.ptr(sol), _lib.stream_ptr())
+        else:
+            st = lib.bode_mlp_dopri5(func.c_struct(), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]), _lib.ptr(sol),
+                                     _lib.stream_ptr())
+        _lib.check(st)
+        dopri5_check(cfg["stats"])
+        ctx.save_for_backward(y0c)
+        ctx.misc = (func, cfg)
+        return sol
+
+    @staticmethod
+    def backward(ctx, gout):
+        (y0c,) = ctx.saved_tensors
+        func, cfg = ctx.misc
+        lib = _lib.load()
+        T, N = cfg["T"], cfg["N"]
+        gout = gout.to(torch.float32).contiguous()
+        gy0 = torch.empty((func.P, N, 2), dtype=torch.float32, device=y0c.device)
+        nsc = lib.bode_dopri5_scratch_floats(func.P, N, T, DOPRI5_MAX_REC_STEPS)
+        sc = _scratch(y0c.device, nsc)
+        if isinstance(func, NPDEField):
+            g = torch.empty((func.P, func.m, 2), dtype=torch.float32, device=y0c.device)
+            st = lib.bode_npde_dopri5_backward(func.c_struct(func.U.detach()), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]),
+                                               _lib.ptr(gout), _lib.ptr(g), 2 * func.m, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(),
+                                               DOPRI5_MAX_REC_STEPS, _lib.stream_ptr())
+            grads = (g,)
+        else:
+            g = torch.empty((func.P, func.d), dtype=torch.float32, device=y0c.device)
+            st = lib.bode_mlp_dopri5_backward(func.c_struct(), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]), _lib.ptr(gout),
+                                              _lib.ptr(g), func.d, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), DOPRI5_MAX_REC_STEPS,
+                                              _lib.stream_ptr())
+            grads = tuple(g[:, o:o + n].view((func.P,) + shp) for (o, n, shp) in func._blocks().values())
+        _lib.check(st)
+        dopri5_check(cfg["stats"])
+        if not cfg["batched"]:
+            gy0 = gy0.sum(0)
+        return (gy0, None, None) + grads
+
+
+def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
+    """Dopri5Solver (dopri5.py:58-122) with one controller per (particle, trajectory) pair."""
+    cfg = dopri5_setup(func, y0, t, rtol, atol, options)
+    params = [func.U] if isinstance(func, NPDEField) else [getattr(func, k) for k in func._blocks()]
+    sol = _Dopri5Odeint.apply(cfg["y0"], func, cfg, *params)
     if isinstance(func, NPDEField) and not func.batched:
         sol = sol[:, 0]
     return sol if tensor_input else (sol,)

@@ -113,6 +113,21 @@ typedef struct bode_dopri5_opts {
 int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
                      const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream);
 
+/* dopri5 gradients: discrete adjoint of the ACCEPTED steps and of the dense-output evaluation with the accepted step sizes
+ * frozen (equals odeint_adjoint(dopri5) to ~1e-5 at tight tolerance; autograd through the reference's controller is not a
+ * usable gradient).  The solve is redone inside the call (one launch = adaptive forward + record + reverse sweep).
+ * scratch: bode_dopri5_scratch_floats(P, N, T, max_rec_steps) floats, 16-byte aligned; a pair that accepts more than
+ * max_rec_steps steps sets status bit 8 in stats and contributes no gradient. */
+size_t bode_dopri5_scratch_floats(int32_t P, int32_t N, int32_t T, int32_t max_rec_steps);
+int bode_npde_dopri5_backward(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                              const float* y0, int32_t y0_batched, const float* gout, float* gU, int64_t gU_stride,
+                              float* gy0, float* scratch, size_t scratch_floats, int32_t max_rec_steps, bode_stream_t stream);
+int bode_npde_dopri5_nlp_grad(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                              const float* y0, int32_t y0_batched, const float* Y, const float* logsn, int64_t logsn_stride,
+                              float scale, int32_t add_prior, float* loss, float* sqerr, float* gU, int64_t gU_stride,
+                              float* glogsn, int64_t glogsn_stride, float* scratch, size_t scratch_floats, int32_t max_rec_steps,
+                              bode_stream_t stream);
+
 /* scratch floats needed by the gradient entry points for (P particles, N trajectories) */
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
 
@@ -169,6 +184,13 @@ int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method,
 /* odeint(net, x0, t, method='dopri5') forward, per-pair controller (see bode_dopri5_opts) */
 int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
                     const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream);
+int bode_mlp_dopri5_backward(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                             const float* y0, int32_t y0_batched, const float* gout, float* gtheta, int64_t gtheta_stride,
+                             float* gy0, float* scratch, size_t scratch_floats, int32_t max_rec_steps, bode_stream_t stream);
+int bode_mlp_dopri5_sse_grad(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
+                             const float* y0, int32_t y0_batched, const float* X, float lik_w, float reg, float scale,
+                             int32_t add_prior, float* loss, float* sqerr, float* gtheta, int64_t gtheta_stride,
+                             float* scratch, size_t scratch_floats, int32_t max_rec_steps, bode_stream_t stream);
 /* its backward for an arbitrary dL/dsol [T,P,N,2]: gtheta [P,d] (+ optional gy0 [P,N,2]) */
 int bode_mlp_odeint_backward(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t grad_mode, int32_t N,
                              const float* y0, int32_t y0_batched, const float* gout, float* gtheta,

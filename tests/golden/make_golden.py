@@ -382,6 +382,32 @@ def gen_dopri5(data):
                 sols.append(sol.reshape(len(t), 2)); nfes.append(cf.nfe)
             out[f"{name}_{fname}_sol"] = torch.stack(sols, 1)          # [T,N,2]
             out[f"{name}_{fname}_nfe"] = np.array(nfes)
+    # gradients: the reference's adjoint through dopri5 (per-row solves, rtol 1e-7 / atol 1e-9 = odeint defaults)
+    Xt = torch.from_numpy(data["X"])
+    for q in net.parameters():
+        q.grad = None
+    loss = 0
+    for r in range(x0.size(0)):
+        xode = torchdiffeq.odeint_adjoint(net, x0[r], t, rtol=1e-7, atol=1e-9, method="dopri5")
+        loss = loss + torch.sum((Xt[r] - xode) ** 2)
+    out["mlp_sqerr"] = loss.detach().clone()
+    loss = loss + 0.5 * sum([torch.sum(q ** 2) for q in net.parameters()])
+    loss.backward()
+    out["mlp_loss"] = loss.detach()
+    out["mlp_grad_adjoint"] = torch.cat([q.grad.reshape(-1) for q in net.parameters()])
+    out["X"] = Xt
+    kreg.zero_grad()
+    loss = 0
+    for r in range(x0.size(0)):
+        xode = torchdiffeq.odeint_adjoint(kreg, x0[r:r + 1], t, rtol=1e-7, atol=1e-9, method="dopri5")[:, 0]
+        loss = loss + torch.sum((Yt[r] - xode) ** 2 / (2 * torch.exp(kreg.logsn) ** 2))
+    loss = loss + torch.numel(Yt) * torch.sum(kreg.logsn) / 2
+    loss = loss + torch.sum(torch.diag(torch.mm(kreg.U.t(), torch.mm(kreg.Kzzinv, kreg.U)))) / 2
+    loss.backward()
+    out["npde_loss"] = loss.detach()
+    out["npde_gU_adjoint"] = kreg.U.grad.clone()
+    out["npde_glogsn_adjoint"] = kreg.logsn.grad.clone()
+    out["Y"] = Yt
     trev = torch.linspace(3., 0., 7)
     sols = []
     for r in range(x0.size(0)):

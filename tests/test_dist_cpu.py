@@ -76,12 +76,22 @@ def _worker(rank, world, port, ret):
     dist.destroy_process_group()
 
 
-def test_sharded_median_protocol_world2_gloo():
+def _main():
     world = 2
     mgr = mp.Manager()
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, 29641, ret), nprocs=world, join=True)
     assert len(ret) == world and ret[0] == ret[1]
+    print("GLOO_OK", ret[0])
+
+
+def test_sharded_median_protocol_world2_gloo():
+    """Runs in its own interpreter: forking / process-group state must not leak into the pytest process (a BLAS call
+    after an in-process mp.Manager() fork was seen to deadlock)."""
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.abspath(__file__)], capture_output=True, text=True, timeout=240)
+    assert "GLOO_OK" in out.stdout, out.stdout[-1500:] + out.stderr[-1500:]
 
 
 def test_shard_range_partitions_exactly():
@@ -94,3 +104,9 @@ def test_shard_range_partitions_exactly():
             assert all(edges[i][1] == edges[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in edges]
             assert max(sizes) - min(sizes) <= 1
+
+
+if __name__ == "__main__":
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    _main()
