@@ -14,8 +14,11 @@ import torch
 
 from . import _grid, _lib
 from .fields import MLPField, NPDEField
-from . import odeint as _om
+import sys as _sys
+
 from .odeint import _grid_struct, _norm_y0, _scratch, odeint
+
+_om = _sys.modules[__package__ + ".odeint"]      # the module (the package attribute `odeint` is the function)
 
 
 class _FusedNLP(torch.autograd.Function):

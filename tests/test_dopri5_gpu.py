@@ -29,7 +29,7 @@ def test_dopri5_matches_reference(case, kw):
         sol = bode.odeint(f, x0, t, **kw)                        # method=None -> dopri5 (odeint.py:68-69)
         sol = sol if sol.dim() == 3 else sol[:, 0]
         tol = 1e-5 if case == "default" else 1e-4      # the solver itself only controls the error to rtol
-        assert relerr(sol.cpu().numpy(), g[f"{case}_{fname}_sol"]) < tol, (fname, case)
+        assert relerr(sol.detach().cpu().numpy(), g[f"{case}_{fname}_sol"]) < tol, (fname, case)
         st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
         attempted_ref = (g[f"{case}_{fname}_nfe"] - (1 if case == "firststep" else 2)) / 6.0
         assert np.all(st[:, 2] == 0)
@@ -52,7 +52,7 @@ def test_dopri5_control_flow_matches_float32_oracle():
         f32 = lambda y: fo.f(y[None, None].astype(np.float64))[0, 0]
         so, so_st = dopri5.odeint_dopri5(f32, g["x0"][r].astype(np.float32), g["t"], rtol=1e-5, atol=1e-7)
         same += int(st[r, 0] == so_st["accepted"] and st[r, 1] == so_st["rejected"])
-        assert relerr(sol[:, r].cpu().numpy(), so) < 1e-4
+        assert relerr(sol[:, r].detach().cpu().numpy(), so) < 1e-4
     assert same >= 3, st
 
 
@@ -62,7 +62,7 @@ def test_dopri5_reversed_time_and_errors():
     fn, _ = _fields(g)
     x0 = torch.from_numpy(g["x0"])
     sol = bode.odeint(fn, x0, torch.from_numpy(g["rev_t"]), rtol=1e-5, atol=1e-7)
-    assert relerr(sol.cpu().numpy(), g["rev_npde_sol"]) < 1e-4
+    assert relerr(sol.detach().cpu().numpy(), g["rev_npde_sol"]) < 1e-4
     with pytest.raises(AssertionError):                      # dopri5.py:89 max_num_steps
         bode.odeint(fn, x0, torch.from_numpy(g["t"]), method="dopri5", options=dict(max_num_steps=2))
     with pytest.warns(UserWarning):                          # misc.py:79-81
@@ -75,7 +75,7 @@ def test_dopri5_config4_sizes_run():
     g = load_golden("dopri5")
     f = bode.MLPField(512, hidden_size=64, generator=torch.Generator().manual_seed(0))
     sol = bode.odeint(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), rtol=1e-5, atol=1e-7)
-    assert sol.shape == (40, 512, 5, 2) and bool(torch.isfinite(sol).all())
+    assert sol.shape == (40, 512, 5, 2) and bool(torch.isfinite(sol.detach()).all())
     st = bode.last_dopri5_stats()
     assert int(st[..., 2].max()) == 0 and int(st[..., 0].min()) >= 5
 
@@ -91,4 +91,75 @@ def test_dopri5_zero_field_takes_the_ratio_zero_branch():
     st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
     so, so_st = dopri5.odeint_dopri5(lambda y: np.zeros_like(y), g["x0"][0].astype(np.float32), g["t"])
     assert np.all(st[:, 0] == so_st["accepted"]) and np.all(st[:, 1] == so_st["rejected"])
-    assert np.array_equal(sol[:, 0].cpu().numpy(), so)
+    assert np.array_equal(sol[:, 0].detach().cpu().numpy(), so)
+
+
+def test_dopri5_gradient_mlp_matches_reference_adjoint():
+    """bayesian_closure through dopri5 (rtol 1e-7 / atol 1e-9): loss and gradient vs the reference's odeint_adjoint(dopri5).
+    The reference's own adjoint-vs-backprop cross-check bars are 3e-4 .. 2e-3 (gradient_tests.py:114-116)."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("dopri5")
+    f = bode.MLPField(1, hidden_size=20, theta=torch.from_numpy(g["theta"])[None])
+    post = bode.MLPPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["X"]), method="dopri5", reg=0.5)
+    loss, gth, _ = post.loss_and_grad_()
+    assert relerr(loss.cpu().numpy(), g["mlp_loss"][None]) < 1e-4
+    assert relerr(post.sqerr.cpu().numpy(), g["mlp_sqerr"][None]) < 1e-4
+    assert relerr(gth.cpu().numpy()[0], g["mlp_grad_adjoint"]) < 2e-3
+
+
+def test_dopri5_gradient_npde_matches_reference_adjoint():
+    import bayesian_ode_b200 as bode
+    g = load_golden("dopri5")
+    f = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
+    post = bode.NPDEPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["Y"]), method="dopri5")
+    loss, gU, gl = post.loss_and_grad_()
+    assert relerr(loss.cpu().numpy(), g["npde_loss"][None]) < 1e-4
+    assert relerr(gU.cpu().numpy()[0], g["npde_gU_adjoint"]) < 2e-3
+    assert relerr(gl.cpu().numpy()[0], g["npde_glogsn_adjoint"]) < 1e-3
+
+
+def test_dopri5_autograd_matches_frozen_step_oracle():
+    """odeint(method='dopri5') + a torch loss + backward(): the CUDA reverse sweep vs the float64 oracle of the same
+    definition (accepted steps frozen), one trajectory row at a time."""
+    import bayesian_ode_b200 as bode
+    from oracle import dopri5, mlp
+    g = load_golden("dopri5")
+    f = bode.MLPField(1, hidden_size=20, theta=torch.from_numpy(g["theta"])[None])
+    rng = np.random.default_rng(4)
+    w = rng.standard_normal((40, 1, 5, 2))
+    x0 = torch.from_numpy(g["x0"]).cuda().float().requires_grad_(True)
+    sol = bode.odeint(f, x0, torch.from_numpy(g["t"]), rtol=1e-6, atol=1e-8, method="dopri5")
+    (sol * torch.from_numpy(w).cuda().float()).sum().backward()
+    got = torch.cat([p.grad.reshape(1, -1) for p in f.parameters()], 1)[0].cpu().numpy()
+    fm = mlp.MLPField(g["theta"][None], 20)
+
+    class F:
+        def f(self, y): return fm.f(y[None, None])[0, 0]
+        def vjp(self, y, a):
+            j, gg = fm.vjp(y[None, None], a[None, None])
+            return j[0, 0], gg[0]
+        def zero_grad(self): return np.zeros(522)
+        add_grad = staticmethod(lambda a, b: a + b)
+    want, wx0 = np.zeros(522), []
+    for r in range(5):
+        _, gy0, gth = dopri5.solve_and_grad(F(), g["x0"][r], g["t"].astype(np.float64), lambda s, r=r: w[:, 0, r], rtol=1e-6, atol=1e-8)
+        want += gth
+        wx0.append(gy0)
+    assert relerr(got, want) < 2e-3
+    assert relerr(x0.grad.cpu().numpy(), np.stack(wx0)) < 2e-3
+
+
+def test_dopri5_config4_step_runs_with_asghmc():
+    """BASELINE config 4 in miniature: 2-64-64-2 MLP chains, dopri5 fwd+grad, aSGHMC update on the flat buffer."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import aSGHMC
+    g = load_golden("dopri5")
+    f = bode.MLPField(64, hidden_size=64, generator=torch.Generator().manual_seed(0))
+    post = bode.MLPPosterior(f, torch.from_numpy(g["x0"]), torch.from_numpy(g["t"]), torch.from_numpy(g["X"]), method="dopri5",
+                             rtol=1e-5, atol=1e-7)
+    smp = aSGHMC(list(f.parameters()), lr=1e-4, mom_decay=5e-2)
+    th0 = f.theta.clone()
+    smp.sample(post, num_samples=1, burn_in=2, print_iters=False)
+    assert bool(torch.isfinite(f.theta).all()) and not torch.equal(th0, f.theta)
+    st = bode.last_dopri5_stats()
+    assert int(st[..., 2].max()) == 0
