@@ -109,9 +109,10 @@ __global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ 
 // ---------------------------------------------------------------- d2 tile = Gram on tensor cores
 constexpr int GT = 128;       // output tile per CTA: GT rows x GN columns (two CTAs per SM by shared memory)
 constexpr int GN = 64;
+constexpr int GTH = 256;      // threads per CTA: two warpgroups share operand generation and split the epilogue columns
 
 template <int KP>             // K padded to a multiple of 8 (d <= KP)
-__global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict__ Xr, long long ldr, int nr, int row_offset,
+__global__ void __launch_bounds__(GTH) gram_d2_tc_kernel(const float* __restrict__ Xr, long long ldr, int nr, int row_offset,
                                                          const float* __restrict__ Xc, long long ldc, int nc, int d,
                                                          const float* __restrict__ mu, float* __restrict__ D2,
                                                          unsigned int* __restrict__ maxbits) {
@@ -137,12 +138,11 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
   if (vec) {
     const int dch = d >> 2;
     // all loads of the CTA's operand rows are issued before the first use (fixed trip counts: KCH and KCH/2 per thread)
-    constexpr int NA = GT * KCH / 128, NB = GN * KCH / 128;
-    static_assert(GT * KCH % 128 == 0 && GN * KCH % 128 == 0, "tile chunks must divide evenly over 128 threads");
+    constexpr int NA = (GT * KCH + GTH - 1) / GTH, NB = (GN * KCH + GTH - 1) / GTH;
     float4 xa[NA], xb[NB], ma[NA], mb[NB];
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
-      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const int idx = min(tid + GTH * q, GT * KCH - 1), row = idx / KCH, kc = idx - row * KCH;
       const bool ok = kc < dch && r0 + row < nr;
       const int rr = min(r0 + row, nr - 1), kk = min(kc, dch - 1);
       xa[q] = __ldg(reinterpret_cast<const float4*>(Xr + (long long)rr * ldr) + kk);
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const int idx = min(tid + GTH * q, GN * KCH - 1), row = idx / KCH, kc = idx - row * KCH;
       const bool ok = kc < dch && c0 + row < nc;
       const int rr = min(c0 + row, nc - 1), kk = min(kc, dch - 1);
       xb[q] = __ldg(reinterpret_cast<const float4*>(Xc + (long long)rr * ldc) + kk);
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
     }
 #pragma unroll
     for (int q = 0; q < NA; ++q) {
-      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const int idx = tid + GTH * q, row = idx / KCH, kc = idx - row * KCH;
+      if (idx >= GT * KCH) break;
       float h[4], l[4];
       split_tf32(xa[q].x - ma[q].x, h[0], l[0]); split_tf32(xa[q].y - ma[q].y, h[1], l[1]);
       split_tf32(xa[q].z - ma[q].z, h[2], l[2]); split_tf32(xa[q].w - ma[q].w, h[3], l[3]);
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
     }
 #pragma unroll
     for (int q = 0; q < NB; ++q) {
-      const int idx = tid + 128 * q, row = idx / KCH, kc = idx - row * KCH;
+      const int idx = tid + GTH * q, row = idx / KCH, kc = idx - row * KCH;
+      if (idx >= GN * KCH) break;
       float h[4], l[4];
       split_tf32(xb[q].x - mb[q].x, h[0], l[0]); split_tf32(xb[q].y - mb[q].y, h[1], l[1]);
       split_tf32(xb[q].z - mb[q].z, h[2], l[2]); split_tf32(xb[q].w - mb[q].w, h[3], l[3]);
@@ -179,24 +181,20 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
       *reinterpret_cast<float4*>(sBl + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
     __syncthreads();
-    {
-      float sa = 0.f, sb = 0.f;
+    if (tid < GT + GN) {                  // threads 0..127: |xc|^2 of the A rows, 128..191: of the B rows
+      const bool isA = tid < GT;
+      const int rr = isA ? tid : tid - GT;
+      float sa = 0.f;
       for (int kc = 0; kc < KCH; ++kc) {
-        const float4 h = *reinterpret_cast<const float4*>(sAh + kmajor_off<GT>(tid, kc));
-        const float4 l = *reinterpret_cast<const float4*>(sAl + kmajor_off<GT>(tid, kc));
+        const uint32_t off = isA ? kmajor_off<GT>(rr, kc) : kmajor_off<GN>(rr, kc);
+        const float4 h = *reinterpret_cast<const float4*>((isA ? sAh : sBh) + off);
+        const float4 l = *reinterpret_cast<const float4*>((isA ? sAl : sBl) + off);
         const float a0 = h.x + l.x, a1 = h.y + l.y, a2 = h.z + l.z, a3 = h.w + l.w;
         sa = fmaf(a0, a0, sa); sa = fmaf(a1, a1, sa); sa = fmaf(a2, a2, sa); sa = fmaf(a3, a3, sa);
-        if (tid < GN) {
-          const float4 hb = *reinterpret_cast<const float4*>(sBh + kmajor_off<GN>(tid, kc));
-          const float4 lb = *reinterpret_cast<const float4*>(sBl + kmajor_off<GN>(tid, kc));
-          const float b0 = hb.x + lb.x, b1 = hb.y + lb.y, b2 = hb.z + lb.z, b3 = hb.w + lb.w;
-          sb = fmaf(b0, b0, sb); sb = fmaf(b1, b1, sb); sb = fmaf(b2, b2, sb); sb = fmaf(b3, b3, sb);
-        }
       }
-      ni[tid] = sa;
-      if (tid < GN) nj[tid] = sb;
+      if (isA) ni[rr] = sa; else nj[rr] = sa;
     }
-  } else {
+  } else if (tid < GT) {
     // general path: thread t owns row t of both tiles
     float sa = 0.f, sb = 0.f;
     const bool va = r0 + tid < nr, vb = tid < GN && c0 + tid < nc;
@@ -253,13 +251,15 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
   // epilogue: TMEM lane (row) = 32*warp + lane -> d2 values -> shared staging (operand tiles are dead) -> coalesced rows
   float* stage = reinterpret_cast<float*>(smraw);                  // [GT][GN+4]
   constexpr int SP = GN + 4;
-  const int row = r0 + tid;
-  const float nrow = ni[tid];
+  const int rl = 32 * (warp & 3) + lane;                           // TMEM lane = tile row; warps 4..7 take the upper column half
+  const int row = r0 + rl;
+  const float nrow = ni[rl];
   float mx = 0.f;
+  const int cbeg = (warp >> 2) * (GN / 2);
 #pragma unroll 1
-  for (int cb = 0; cb < GN; cb += 8) {
+  for (int cb = cbeg; cb < cbeg + GN / 2; cb += 8) {
     float s[8];
-    tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + cb, s);
+    tmem_ld8(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cb, s);
     float o[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
@@ -269,18 +269,18 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
       o[q] = v;
       if (row < nr && col < nc) mx = fmaxf(mx, v);
     }
-    *reinterpret_cast<float4*>(stage + tid * SP + cb) = make_float4(o[0], o[1], o[2], o[3]);
-    *reinterpret_cast<float4*>(stage + tid * SP + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    *reinterpret_cast<float4*>(stage + rl * SP + cb) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(stage + rl * SP + cb + 4) = make_float4(o[4], o[5], o[6], o[7]);
   }
   __syncthreads();
   if ((nc & 3) == 0 && c0 + GN <= nc) {
-    for (int idx = tid; idx < GT * (GN / 4); idx += 128) {
+    for (int idx = tid; idx < GT * (GN / 4); idx += GTH) {
       const int rr = idx / (GN / 4), c4 = idx - rr * (GN / 4);
       if (r0 + rr < nr)
         *reinterpret_cast<float4*>(D2 + (long long)(r0 + rr) * nc + c0 + 4 * c4) = *reinterpret_cast<const float4*>(stage + rr * SP + 4 * c4);
     }
   } else {
-    for (int idx = tid; idx < GT * GN; idx += 128) {
+    for (int idx = tid; idx < GT * GN; idx += GTH) {
       const int rr = idx / GN, cc = idx - rr * GN;
       if (r0 + rr < nr && c0 + cc < nc) D2[(long long)(r0 + rr) * nc + c0 + cc] = stage[rr * SP + cc];
     }
@@ -296,9 +296,10 @@ __global__ void __launch_bounds__(128) gram_d2_tc_kernel(const float* __restrict
 // ---------------------------------------------------------------- phi partials on tensor cores
 constexpr int PT = 128;       // rows per CTA
 constexpr int PK = 32;        // j per stage (4 MMA k-steps)
+constexpr int PTH = 256;      // threads per CTA (two warpgroups: each builds half of the K tile, half of the epilogue columns)
 
 template <int NF>             // padded feature count, multiple of 16, >= 2d+1
-__global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D2, int nr, int nc, const float* __restrict__ Xc,
+__global__ void __launch_bounds__(PTH) phi_tc_kernel(const float* __restrict__ D2, int nr, int nc, const float* __restrict__ Xc,
                                                      long long ldx, const float* __restrict__ Gc, long long ldg, int d,
                                                      const float* __restrict__ mu, const float* __restrict__ gam, float gsign,
                                                      int jsplit, float* __restrict__ part) {
@@ -327,16 +328,17 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
   constexpr uint32_t A_LBO = PT * 16, A_SBO = 128;                   // [kchunk][row/8][row%8][16B]
   constexpr uint32_t B_LBO = NF * 16, B_SBO = 128;
   uint32_t phase = 0, acc = 0;
-  const int row = r0 + tid;
+  const int rl = tid & (PT - 1), half = tid >> 7;                    // tile row and which half of the stage's columns
+  const int row = r0 + rl;
   constexpr int NV = NF * (PK / 4);                                  // 16-byte chunks of V^T per stage
-  constexpr int NQ = (NV + 127) / 128;
+  constexpr int NQ = (NV + PTH - 1) / PTH;
   const float* vsrc[NQ];
   long long vld[NQ];
   float vscale[NQ], vadd[NQ];
   int vjc[NQ], voff[NQ];
 #pragma unroll
   for (int q = 0; q < NQ; ++q) {
-    const int slot = tid + 128 * q;
+    const int slot = tid + PTH * q;
     const int jc = slot / NF, f = slot - jc * NF;
     vjc[q] = jc;
     voff[q] = slot < NV ? (int)kmajor_off<NF>(f, jc) : -1;
@@ -350,18 +352,20 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
   const bool avec = (nc & 3) == 0;
   for (int j0 = jbeg; j0 < jend; j0 += PK) {
     // ---- A: K[row][j0..j0+31] = 2^(-g d2), split hi/lo
-    float4 dv[PK / 4];
+    constexpr int KCH2 = PK / 8;                                      // chunks of 4 columns built by each half
+    float4 dv[KCH2];
 #pragma unroll
-    for (int kc = 0; kc < PK / 4; ++kc) {
+    for (int kq = 0; kq < KCH2; ++kq) {
+      const int kc = half * KCH2 + kq;
       const int j = j0 + 4 * kc;
       if (avec && j + 4 <= jend) {
-        dv[kc] = __ldg(reinterpret_cast<const float4*>(D2 + (long long)min(row, nr - 1) * nc + j));
-        if (row >= nr) dv[kc] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
+        dv[kq] = __ldg(reinterpret_cast<const float4*>(D2 + (long long)min(row, nr - 1) * nc + j));
+        if (row >= nr) dv[kq] = make_float4(INFINITY, INFINITY, INFINITY, INFINITY);
       } else {
         float t[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) t[q] = (row < nr && j + q < jend) ? __ldg(D2 + (long long)row * nc + j + q) : INFINITY;
-        dv[kc] = make_float4(t[0], t[1], t[2], t[3]);
+        dv[kq] = make_float4(t[0], t[1], t[2], t[3]);
       }
     }
     // ---- B: V^T[f][j] = [gsign*G | X - mu | 1 | 0]^T, K-major like A (thread <-> (feature f, 4 consecutive j)); the
@@ -385,12 +389,13 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
       tc_fence_after();
     }
 #pragma unroll
-    for (int kc = 0; kc < PK / 4; ++kc) {
-      const float k4[4] = {ex2(ngamma * dv[kc].x), ex2(ngamma * dv[kc].y), ex2(ngamma * dv[kc].z), ex2(ngamma * dv[kc].w)};
+    for (int kq = 0; kq < KCH2; ++kq) {
+      const int kc = half * KCH2 + kq;
+      const float k4[4] = {ex2(ngamma * dv[kq].x), ex2(ngamma * dv[kq].y), ex2(ngamma * dv[kq].z), ex2(ngamma * dv[kq].w)};
       float h[4], l[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q) split_tf32(k4[q], h[q], l[q]);
-      const uint32_t off = kmajor_off<PT>(tid, kc);
+      const uint32_t off = kmajor_off<PT>(rl, kc);
       *reinterpret_cast<float4*>(sAh + off) = make_float4(h[0], h[1], h[2], h[3]);
       *reinterpret_cast<float4*>(sAl + off) = make_float4(l[0], l[1], l[2], l[3]);
     }
@@ -427,10 +432,11 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
   }
   // ---- epilogue: one TMEM lane per thread = one output row
   if (jbeg < jend) {
+    const int cbeg = half * (NF / 2);                              // warps 4..7 read the upper half of the feature columns
 #pragma unroll 1
-    for (int cb = 0; cb < NF; cb += 8) {
+    for (int cb = cbeg; cb < cbeg + NF / 2; cb += 8) {
       float s[8];
-      tmem_ld8(tmem + ((uint32_t)(32 * warp) << 16) + cb, s);
+      tmem_ld8(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cb, s);
       if (row < nr) {
         float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
 #pragma unroll
@@ -438,7 +444,7 @@ __global__ void __launch_bounds__(128) phi_tc_kernel(const float* __restrict__ D
           if (cb + q <= 2 * d) dst[cb + q] = s[q];
       }
     }
-  } else if (row < nr) {
+  } else if (row < nr && half == 0) {
     float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
     for (int f = 0; f <= 2 * d; ++f) dst[f] = 0.f;
   }
@@ -481,7 +487,7 @@ int svgd_tc_gram(const float* Xr, long long ldr, int nr, int row_offset, const f
   const size_t smem = 2 * (size_t)(GT + GN) * KP * 4 + (GT + GN) * 4 + 64;
   BODE_CUDA(cudaFuncSetAttribute(gram_d2_tc_kernel<KP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((nc + GN - 1) / GN, (nr + GT - 1) / GT);
-  gram_d2_tc_kernel<KP><<<grid, 128, smem, st>>>(Xr, ldr, nr, row_offset, Xc, ldc, nc, d, mu, D2, maxbits);
+  gram_d2_tc_kernel<KP><<<grid, GTH, smem, st>>>(Xr, ldr, nr, row_offset, Xc, ldc, nc, d, mu, D2, maxbits);
   return check_cuda(cudaGetLastError(), "gram tc launch");
 }
 
@@ -491,7 +497,7 @@ int svgd_tc_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx,
   const size_t smem = 2 * (size_t)PT * PK * 4 + 2 * (size_t)PK * NF * 4 + 64;
   BODE_CUDA(cudaFuncSetAttribute(phi_tc_kernel<NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((nr + PT - 1) / PT, jsplit);
-  phi_tc_kernel<NF><<<grid, 128, smem, st>>>(D2, nr, nc, Xc, ldx, Gc, ldg, d, mu, gam, gsign, jsplit, part);
+  phi_tc_kernel<NF><<<grid, PTH, smem, st>>>(D2, nr, nc, Xc, ldx, Gc, ldg, d, mu, gam, gsign, jsplit, part);
   return check_cuda(cudaGetLastError(), "phi tc launch");
 }
 
