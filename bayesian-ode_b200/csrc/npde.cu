@@ -9,6 +9,8 @@ namespace bode {
 #define BODE_DECL_SEP(M)                                                                               \
   int launch_sep_fwd_##M(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
   int launch_sep_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_pair_fwd_##M(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
+  int launch_pair_grad_##M(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
   int launch_sep_dopri5_##M(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem, cudaStream_t st); \
   int launch_sep_dopri5_grad_##M(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid, dim3 block, \
                                  size_t smem, cudaStream_t st);
@@ -82,6 +84,70 @@ static int plan(NpdeKParams& prm, int G, int max_threads, dim3* grid, dim3* bloc
   return BODE_OK;
 }
 
+// Component-split kernels (npde_pair.cuh): ppc particles x N trajectories x 2 lanes per CTA.  ppc is sized so that the
+// grid is about one CTA per SM (persistent-style sizing, every SM gets the same number of warps) and capped by the
+// 320-thread launch bound and the per-particle shared-memory footprint.
+static size_t stage_floats(const NpdeKParams& prm);
+static const int PAIR_MAX_THREADS = 320;
+static bool use_pair(const bode_npde_field* f, int N) { return use_sep(f) && 2 * N <= PAIR_MAX_THREADS; }
+
+static int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  return sms;
+}
+
+static int plan_pair(NpdeKParams& prm, bool grad, dim3* grid, dim3* block, size_t* smem) {
+  const int per_particle = 2 * prm.N;
+  int ppc = (prm.P + sm_count() - 1) / sm_count();
+  const int cap = PAIR_MAX_THREADS / per_particle;
+  if (ppc > cap) ppc = cap;
+  if (ppc < 1) ppc = 1;
+  size_t floats = 0;
+  for (;; --ppc) {
+    prm.ppc = ppc;
+    if (grad) {
+      prm.stage_off = (int)(((size_t)ppc * 2 * prm.m * (2 + prm.N) + (size_t)ppc * prm.N * 2 + 3) & ~(size_t)3);
+      floats = (size_t)prm.stage_off + stage_floats(prm);
+    } else {
+      floats = (size_t)ppc * 2 * prm.m * 2;
+    }
+    if (floats * sizeof(float) <= 160 * 1024 || ppc == 1) break;
+  }
+  BODE_REQUIRE(floats * sizeof(float) <= 200 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
+  *smem = floats * sizeof(float);
+  *block = dim3(((ppc * per_particle + 31) / 32) * 32);
+  *grid = dim3((prm.P + ppc - 1) / ppc);
+  return BODE_OK;
+}
+
+static int dispatch_pair_fwd(const NpdeKParams& prm, int M, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  switch (M) {
+    case 3: return launch_pair_fwd_3(prm, method, grid, block, smem, st);
+    case 4: return launch_pair_fwd_4(prm, method, grid, block, smem, st);
+    case 5: return launch_pair_fwd_5(prm, method, grid, block, smem, st);
+    case 6: return launch_pair_fwd_6(prm, method, grid, block, smem, st);
+  }
+  set_error("no separable kernel for M=%d", M);
+  return BODE_ERR_UNSUPPORTED;
+}
+
+static int dispatch_pair_grad(const NpdeKParams& prm, int M, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st) {
+  switch (M) {
+    case 3: return launch_pair_grad_3(prm, method, inj, adj, grid, block, smem, st);
+    case 4: return launch_pair_grad_4(prm, method, inj, adj, grid, block, smem, st);
+    case 5: return launch_pair_grad_5(prm, method, inj, adj, grid, block, smem, st);
+    case 6: return launch_pair_grad_6(prm, method, inj, adj, grid, block, smem, st);
+  }
+  set_error("no separable kernel for M=%d", M);
+  return BODE_ERR_UNSUPPORTED;
+}
+
 static int dispatch_fwd(const NpdeKParams& prm, int M, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   switch (M) {
     case 3: return launch_sep_fwd_3(prm, method, grid, block, smem, st);
@@ -124,6 +190,14 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
   prm.ck = reinterpret_cast<float2*>(scratch);
   prm.npairs = (long long)f->P * N;
   dim3 grid, block;
+  if (use_pair(f, N)) {
+    int st_ = fill_sep(prm, f);
+    if (st_ != BODE_OK) return st_;
+    size_t smem = 0;
+    st_ = plan_pair(prm, true, &grid, &block, &smem);
+    if (st_ != BODE_OK) return st_;
+    return dispatch_pair_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
+  }
   if (use_sep(f)) {
     int st_ = fill_sep(prm, f);
     if (st_ != BODE_OK) return st_;
@@ -165,6 +239,14 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
   BODE_REQUIRE(sol, "null sol");
   prm.sol = sol;
   dim3 grid, block;
+  if (use_pair(f, N)) {
+    st = fill_sep(prm, f);
+    if (st != BODE_OK) return st;
+    size_t smem = 0;
+    st = plan_pair(prm, false, &grid, &block, &smem);
+    if (st != BODE_OK) return st;
+    return dispatch_pair_fwd(prm, f->grid_mx, method, grid, block, smem, (cudaStream_t)stream);
+  }
   if (use_sep(f)) {
     st = fill_sep(prm, f);
     if (st != BODE_OK) return st;

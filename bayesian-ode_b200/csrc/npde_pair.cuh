@@ -1,0 +1,374 @@
+// Component-split separable npde kernels: TWO lanes per (particle, trajectory) pair.
+//
+// The tensor-grid kernel factorises, k_ab(x) = kx_a(x0) ky_b(x1), and the 2-D state splits the same way:
+// lane d of a pair owns state component y_d, adjoint component a_d, the d-th column of W = A U_p and of the
+// gradient accumulator (M*M floats each, stored [own axis][partner axis]), and evaluates only the M kernel
+// factors of ITS axis; the partner's factors arrive with M warp shuffles.  Compared with one thread per pair
+// (npde_sep.cuh) this doubles the number of resident warps at a fixed particle count (the 4096-particle
+// configuration only has 20 480 pairs for 148 SMs), halves the per-thread register footprint, and keeps the
+// SFU work identical (2M ex2 per RHS evaluation per pair).
+//
+// The reverse sweep recomputes the Jacobian row of the lane's own output component,
+//   df_d/dx_d   = -k_d  sum_i (k_i delta_i) T_i ,   T_i  = sum_j W_ij k'_j
+//   df_d/dx_d'  = -k_d' sum_i  k_i          T'_i ,  T'_i = sum_j W_ij (k'_j delta'_j)
+// (k, delta: own-axis factors / scaled offsets, primes: the partner axis), none of which depends on the incoming
+// adjoint, so only two multiplies per stage sit on the serial adjoint chain; J^T a is completed with one shuffle.
+// Reference semantics are those of npde_sep.cuh / npde_solve.cuh: gp.py:69-71 (field), solvers.py:79-99 +
+// rk_common.py:72-78 (fixed-grid RK), gp.py:342-353 (closure), adjoint.py:23-102 (continuous adjoint).
+#pragma once
+#include "npde_solve.cuh"
+
+namespace bode {
+
+constexpr unsigned FULL_MASK = 0xffffffffu;
+
+template <int M>
+struct PairField {
+  static constexpr int G = 2;
+  static constexpr int MAX_THREADS = 320;
+  float W[M][M];    // W[i][j]: i indexes the lane's own axis, j the partner's
+  float gW[M][M];
+  float gm[M], gt[M];   // scaled grid coordinates c_d * g_d[i] of the own / partner axis
+  float cm, ct;         // coordinate scales
+  float nkm, nkt;       // -k_own, -k_partner  (d kappa / dx = -k delta kappa)
+
+  __device__ __forceinline__ void load(const NpdeKParams& prm, const float* Wp, int d) {
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      gm[i] = d ? prm.gys[i] : prm.gxs[i];
+      gt[i] = d ? prm.gxs[i] : prm.gys[i];
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        W[i][j] = d ? Wp[2 * (j * M + i) + 1] : Wp[2 * (i * M + j)];
+        gW[i][j] = 0.f;
+      }
+    }
+    cm = d ? prm.c1 : prm.c0;
+    ct = d ? prm.c0 : prm.c1;
+    nkm = d ? -prm.k1 : -prm.k0;
+    nkt = d ? -prm.k0 : -prm.k1;
+  }
+  // npde_epilogue's contract: write this lane's share of gW[m][2]
+  __device__ __forceinline__ void store_gW(const NpdeKParams&, float* gp, int d) const {
+#pragma unroll
+    for (int i = 0; i < M; ++i)
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        if (d) gp[2 * (j * M + i) + 1] = gW[i][j];
+        else gp[2 * (i * M + j)] = gW[i][j];
+      }
+  }
+
+  // f_d(x), x_d = ym (the partner lane holds x_d')
+  __device__ __forceinline__ float eval(float ym) const {
+    const float u = cm * ym;
+    float km[M], kt[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const float dl = u - gm[i];
+      km[i] = ex2(-dl * dl);
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) kt[j] = __shfl_xor_sync(FULL_MASK, km[j], 1);
+    float f = 0.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < M; ++j) t = fmaf(kt[j], W[i][j], t);
+      f = fmaf(km[i], t, f);
+    }
+    return f;
+  }
+
+  // Component d of J(x)^T a, given this lane's a_d; accumulates gW += wg a_d kappa(x).  WITH_F: also f_d(x).
+  template <bool WITH_F>
+  __device__ __forceinline__ float vjp(float ym, float yt, float a, float wg, float* fout) {
+    const float um = cm * ym, ut = ct * yt;
+    float km[M], kdm[M], kt[M], kdt[M];
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const float dl = um - gm[i];
+      km[i] = ex2(-dl * dl);
+      kdm[i] = km[i] * dl;
+    }
+#pragma unroll
+    for (int j = 0; j < M; ++j) {
+      kt[j] = __shfl_xor_sync(FULL_MASK, km[j], 1);
+      kdt[j] = kt[j] * (ut - gt[j]);
+    }
+    const float aw = a * wg;
+    float sm = 0.f, st = 0.f, f = 0.f;
+#pragma unroll
+    for (int i = 0; i < M; ++i) {
+      const float kaw = km[i] * aw;
+      float t = 0.f, tp = 0.f;
+#pragma unroll
+      for (int j = 0; j < M; ++j) {
+        t = fmaf(W[i][j], kt[j], t);
+        tp = fmaf(W[i][j], kdt[j], tp);
+        gW[i][j] = fmaf(kaw, kt[j], gW[i][j]);
+      }
+      sm = fmaf(kdm[i], t, sm);
+      st = fmaf(km[i], tp, st);
+      if (WITH_F) f = fmaf(km[i], t, f);
+    }
+    if (WITH_F) *fout = f;
+    const float recv = __shfl_xor_sync(FULL_MASK, (nkt * a) * st, 1);
+    return fmaf(nkm * a, sm, recv);
+  }
+};
+
+// ------------------------------------------------------------------ one forward step on the lane's component
+template <int METHOD, bool STORE, int M>
+__device__ __forceinline__ float pair_step_fwd(const NpdeKParams& prm, const PairField<M>& fld, float y, float dt, float* ckp,
+                                               long long stride, bool act) {
+  // `act` only predicates the checkpoint stores: every lane of the warp must reach the shuffles in eval() together
+  const float sg = prm.sign;
+  if (METHOD == BODE_EULER) {
+    if (STORE && act) ckp[0] = y;
+    return fmaf(dt, sg * fld.eval(y), y);
+  } else if (METHOD == BODE_MIDPOINT) {
+    if (STORE && act) ckp[0] = y;
+    const float k1 = sg * fld.eval(y);
+    const float y2 = fmaf(0.5f * dt, k1, y);
+    if (STORE && act) ckp[stride] = y2;
+    return fmaf(dt, sg * fld.eval(y2), y);
+  } else {  // 3/8 rule, rk_common.py:72-78
+    if (STORE && act) ckp[0] = y;
+    const float k1 = sg * fld.eval(y);
+    const float dt3 = dt * (1.f / 3.f);
+    const float y2 = fmaf(dt3, k1, y);
+    if (STORE && act) ckp[stride] = y2;
+    const float k2 = sg * fld.eval(y2);
+    const float y3 = fmaf(dt, k2, fmaf(-dt3, k1, y));
+    if (STORE && act) ckp[2 * stride] = y3;
+    const float k3 = sg * fld.eval(y3);
+    const float y4 = fmaf(dt, (k1 - k2) + k3, y);
+    if (STORE && act) ckp[3 * stride] = y4;
+    const float k4 = sg * fld.eval(y4);
+    return fmaf(dt * 0.125f, (k1 + k4) + 3.f * (k2 + k3), y);
+  }
+}
+
+// stage points of one step as (own, partner) components
+template <int METHOD>
+__device__ __forceinline__ void pair_load_stage_points(float2 (&ys)[Stages<METHOD>::value], const float2* ckp, long long stride, int d) {
+#pragma unroll
+  for (int i = 0; i < Stages<METHOD>::value; ++i) {
+    const float2 v = ckp[(long long)i * stride];
+    ys[i] = d ? f2(v.y, v.x) : v;
+  }
+}
+
+// ------------------------------------------------------------------ discrete adjoint of one step
+template <int METHOD, int M>
+__device__ __forceinline__ float pair_step_bwd(const NpdeKParams& prm, PairField<M>& fld, float a, float dt,
+                                               const float2 (&ys)[Stages<METHOD>::value], float* y_start) {
+  const float sg = prm.sign;
+  *y_start = ys[0].x;
+  if (METHOD == BODE_EULER) {
+    return a + fld.template vjp<false>(ys[0].x, ys[0].y, (sg * dt) * a, 1.f, nullptr);
+  } else if (METHOD == BODE_MIDPOINT) {
+    const float v2 = fld.template vjp<false>(ys[1].x, ys[1].y, (sg * dt) * a, 1.f, nullptr);
+    const float v1 = fld.template vjp<false>(ys[0].x, ys[0].y, (sg * 0.5f * dt) * v2, 1.f, nullptr);
+    return (a + v2) + v1;
+  } else {
+    constexpr int I2 = METHOD == BODE_RK4 ? 2 : 0, I3 = METHOD == BODE_RK4 ? 3 : 0;
+    const float dt3 = dt * (1.f / 3.f);
+    float kb1 = (dt * 0.125f) * a, kb2 = (dt * 0.375f) * a, kb3 = kb2;
+    float yb = a;
+    const float v4 = fld.template vjp<false>(ys[I3].x, ys[I3].y, sg * kb1, 1.f, nullptr);  // kb4 == initial kb1
+    yb += v4;
+    kb1 = fmaf(dt, v4, kb1);
+    kb2 = fmaf(-dt, v4, kb2);
+    kb3 = fmaf(dt, v4, kb3);
+    const float v3 = fld.template vjp<false>(ys[I2].x, ys[I2].y, sg * kb3, 1.f, nullptr);
+    yb += v3;
+    kb1 = fmaf(-dt3, v3, kb1);
+    kb2 = fmaf(dt, v3, kb2);
+    const float v2 = fld.template vjp<false>(ys[1].x, ys[1].y, sg * kb2, 1.f, nullptr);
+    yb += v2;
+    kb1 = fmaf(dt3, v2, kb1);
+    const float v1 = fld.template vjp<false>(ys[0].x, ys[0].y, sg * kb1, 1.f, nullptr);
+    return yb + v1;
+  }
+}
+
+// ------------------------------------------------------------------ one step of the augmented reverse solve (adjoint.py:32-55)
+template <int METHOD, int M>
+__device__ __forceinline__ void pair_step_aug(PairField<M>& fld, float& y, float& a, float dt, float s_in) {
+  float f1, f2_, f3, f4;
+  auto partner = [](float v) { return __shfl_xor_sync(FULL_MASK, v, 1); };
+  if (METHOD == BODE_EULER) {
+    const float j1 = fld.template vjp<true>(y, partner(y), a, -s_in * dt, &f1);
+    y = fmaf(s_in * dt, f1, y);
+    a = fmaf(-s_in * dt, j1, a);
+  } else if (METHOD == BODE_MIDPOINT) {
+    const float j1 = fld.template vjp<true>(y, partner(y), a, 0.f, &f1);
+    const float h = 0.5f * dt * s_in;
+    const float y2 = fmaf(h, f1, y), a2 = fmaf(-h, j1, a);
+    const float j2 = fld.template vjp<true>(y2, partner(y2), a2, -s_in * dt, &f2_);
+    y = fmaf(s_in * dt, f2_, y);
+    a = fmaf(-s_in * dt, j2, a);
+  } else {
+    const float h = s_in * dt, h3 = h * (1.f / 3.f);
+    const float j1 = fld.template vjp<true>(y, partner(y), a, -h * 0.125f, &f1);
+    const float y2 = fmaf(h3, f1, y), a2 = fmaf(-h3, j1, a);
+    const float j2 = fld.template vjp<true>(y2, partner(y2), a2, -h * 0.375f, &f2_);
+    const float y3 = fmaf(h, f2_, fmaf(-h3, f1, y)), a3 = fmaf(-h, j2, fmaf(h3, j1, a));
+    const float j3 = fld.template vjp<true>(y3, partner(y3), a3, -h * 0.375f, &f3);
+    const float y4 = fmaf(h, (f1 - f2_) + f3, y), a4 = fmaf(-h, (j1 - j2) + j3, a);
+    const float j4 = fld.template vjp<true>(y4, partner(y4), a4, -h * 0.125f, &f4);
+    y = fmaf(h * 0.125f, (f1 + f4) + 3.f * (f2_ + f3), y);
+    a = fmaf(-h * 0.125f, (j1 + j4) + 3.f * (j2 + j3), a);
+  }
+}
+
+// Thread -> (particle slot, trajectory, component).  Padding threads (past the CTA's pairs or past P) shadow a valid
+// pair so that every warp-wide shuffle is executed by all 32 lanes; they never write.
+struct PairIds {
+  int pl, n, d, p;
+  bool active;
+  long long pair;
+};
+__device__ __forceinline__ PairIds pair_ids(const NpdeKParams& prm) {
+  PairIds id;
+  const int tid = threadIdx.x;
+  id.d = tid & 1;
+  int pairl = tid >> 1;
+  const int npl = prm.ppc * prm.N;
+  bool ok = pairl < npl;
+  if (!ok) pairl = npl - 1;
+  id.pl = pairl / prm.N;
+  id.n = pairl - id.pl * prm.N;
+  id.p = blockIdx.x * prm.ppc + id.pl;
+  if (id.p >= prm.P) {
+    ok = false;
+    id.p = prm.P - 1;
+    id.pl = id.p - blockIdx.x * prm.ppc;   // >= 0: the CTA's first particle always exists
+  }
+  id.active = ok;
+  id.pair = (long long)id.p * prm.N + id.n;
+  return id;
+}
+
+// ------------------------------------------------------------------ forward-only kernel: sol[T,P,N,2]
+template <int M, int METHOD>
+__global__ void __launch_bounds__(PairField<M>::MAX_THREADS) npde_pair_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
+  extern __shared__ __align__(16) float smem[];
+  project_W(prm, smem, smem + prm.ppc * 2 * prm.m);
+  const PairIds id = pair_ids(prm);
+  PairField<M> fld;
+  fld.load(prm, smem + (prm.ppc + id.pl) * 2 * prm.m, id.d);
+  const long long PN2 = 2ll * prm.P * prm.N;
+  float y = __ldg(prm.y0 + (prm.y0_stride ? 2ll * id.p * prm.N : 0) + 2 * id.n + id.d);
+  float* sol = prm.sol + 2 * id.pair + id.d;
+  if (id.active) sol[0] = y;
+  for (int s = 0; s < prm.S; ++s) {
+    y = pair_step_fwd<METHOD, false>(prm, fld, y, __ldg(prm.dt + s), nullptr, 0, false);
+    const int j1 = __ldg(prm.obs_ptr + s + 1);
+    for (int j = __ldg(prm.obs_ptr + s); j < j1; ++j)
+      if (id.active) sol[(long long)j * PN2] = y;
+  }
+}
+
+// ------------------------------------------------------------------ fused forward + closure + gradient kernel
+template <int M, int METHOD, int INJ, int ADJ>
+__global__ void __launch_bounds__(PairField<M>::MAX_THREADS) npde_pair_grad_kernel(const __grid_constant__ NpdeKParams prm) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int STG = Stages<METHOD>::value;
+  const int N = prm.N;
+  // solver grid and observations staged once per CTA
+  float* sdt = smem + prm.stage_off;
+  int* sptr = reinterpret_cast<int*>(sdt + prm.S);
+  float* sY = sdt + ((2 * prm.S + 2) & ~1);
+  for (int i = threadIdx.x; i < prm.S; i += blockDim.x) sdt[i] = __ldg(prm.dt + i);
+  for (int i = threadIdx.x; i <= prm.S; i += blockDim.x) sptr[i] = prm.S > 0 ? __ldg(prm.obs_ptr + i) : 1;
+  if (INJ == INJ_LIK)
+    for (int i = threadIdx.x; i < 2 * N * prm.T; i += blockDim.x) sY[i] = __ldg(prm.Y + i);
+  project_W(prm, smem, smem + prm.ppc * 2 * prm.m);
+
+  const PairIds id = pair_ids(prm);
+  const int d = id.d;
+  const bool active = id.active;
+  PairField<M> fld;
+  fld.load(prm, smem + (prm.ppc + id.pl) * 2 * prm.m, d);
+  const long long PN2 = 2ll * prm.P * N;
+  const float* Yd = sY + 2 * id.n * prm.T + d;                    // Y[n][j][d] at Yd[2 j]
+  const float* go = prm.gout + 2 * id.pair + d;                   // gout[j][pair][d]
+  float e2inv = 0.f;                                              // dL/dx_d = -e2inv (Y_d - x_d)
+  if (INJ == INJ_LIK) e2inv = expf(-2.f * __ldg(prm.logsn + (long long)id.p * prm.logsn_stride + d));
+  const long long stride = prm.npairs;                            // checkpoint slot stride in float2
+  float* ckf = reinterpret_cast<float*>(prm.ck) + 2 * id.pair + d;
+  const float2* ck2 = prm.ck + id.pair;
+  float r2 = 0.f;
+
+  // ---------------- forward
+  float y = __ldg(prm.y0 + (prm.y0_stride ? 2ll * id.p * N : 0) + 2 * id.n + d);
+  if (INJ == INJ_LIK) {
+    const float r = Yd[0] - y;
+    r2 = r * r;
+  }
+  if (ADJ == BODE_GRAD_ADJOINT && active) ckf[0] = y;
+  for (int s = 0; s < prm.S; ++s) {
+    if (ADJ == BODE_GRAD_DISCRETE) {
+      y = pair_step_fwd<METHOD, true>(prm, fld, y, sdt[s], ckf + 2ll * s * STG * stride, 2 * stride, active);
+    } else {
+      y = pair_step_fwd<METHOD, false>(prm, fld, y, sdt[s], nullptr, 0, false);
+    }
+    const int j1 = sptr[s + 1];
+    for (int j = sptr[s]; j < j1; ++j) {
+      if (INJ == INJ_LIK) {
+        const float r = Yd[2 * j] - y;
+        r2 = fmaf(r, r, r2);
+      }
+      if (ADJ == BODE_GRAD_ADJOINT && active) ckf[2ll * j * stride] = y;
+    }
+  }
+
+  // ---------------- backward
+  __syncwarp();   // the partner lane's checkpoint stores are read below
+  float a = 0.f;
+  if (ADJ == BODE_GRAD_DISCRETE) {
+    float yend = y;
+    float2 ys[STG], yn[STG];
+    if (prm.S > 0) pair_load_stage_points<METHOD>(ys, ck2 + (long long)(prm.S - 1) * STG * stride, stride, d);
+    for (int s = prm.S - 1; s >= 0; --s) {
+      // software prefetch: the stage points of step s-1 travel from L2 while step s is differentiated
+      if (s > 0) pair_load_stage_points<METHOD>(yn, ck2 + (long long)(s - 1) * STG * stride, stride, d);
+      const int j0 = sptr[s];
+      for (int j = sptr[s + 1] - 1; j >= j0; --j) {
+        if (INJ == INJ_LIK) a = fmaf(yend - Yd[2 * j], e2inv, a);
+        else a += __ldg(go + (long long)j * PN2);
+      }
+      a = pair_step_bwd<METHOD>(prm, fld, a, sdt[s], ys, &yend);
+#pragma unroll
+      for (int i = 0; i < STG; ++i) ys[i] = yn[i];
+    }
+    if (INJ == INJ_LIK) a = fmaf(yend - Yd[0], e2inv, a);
+    else a += __ldg(go);
+  } else {
+    // continuous adjoint, adjoint.py:57-95: restart from the stored forward value at every t[i]
+    const float s_in = -prm.sign;
+    {
+      const float yT = ckf[2ll * (prm.T - 1) * stride];
+      if (INJ == INJ_LIK) a = (yT - Yd[2 * (prm.T - 1)]) * e2inv;
+      else a = __ldg(go + (long long)(prm.T - 1) * PN2);
+    }
+    for (int i = prm.T - 1; i >= 1; --i) {
+      float yy = ckf[2ll * i * stride];
+      const int q1 = __ldg(prm.adj_ptr + i);
+      for (int q = __ldg(prm.adj_ptr + i - 1); q < q1; ++q) pair_step_aug<METHOD>(fld, yy, a, __ldg(prm.adj_dt + q), s_in);
+      const float yp = ckf[2ll * (i - 1) * stride];
+      if (INJ == INJ_LIK) a = fmaf(yp - Yd[2 * (i - 1)], e2inv, a);
+      else a += __ldg(go + (long long)(i - 1) * PN2);
+    }
+  }
+  if (prm.gy0 != nullptr && active) prm.gy0[2 * id.pair + d] = prm.scale * a;
+
+  const float r2o = __shfl_xor_sync(FULL_MASK, r2, 1);
+  npde_epilogue<INJ>(prm, smem, fld, active, id.pl, id.n, id.pl * N + id.n, d, r2, r2o);
+}
+
+}  // namespace bode
