@@ -22,27 +22,52 @@ namespace bode {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// Packed FP32 pairs: sm_100a's FFMA2 (PTX fma.rn.f32x2) retires two FMAs per issue slot; ptxas folds a (x, x) pair
+// into a scalar-broadcast operand, so a broadcast costs no extra instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2x(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float hsum(f32x2 v) {
+  float lo, hi;
+  upk(v, lo, hi);
+  return lo + hi;
+}
+
 template <int M>
 struct PairField {
   static constexpr int G = 2;
   static constexpr int MAX_THREADS = 320;
-  float W[M][M];    // W[i][j]: i indexes the lane's own axis, j the partner's
-  float gW[M][M];
+  static constexpr int MP = (M + 1) / 2;
+  // i indexes the lane's own axis, j the partner's.  W is held as pairs over j (zero padded when M is odd), the
+  // gradient accumulator as pairs over i, so that every contraction below is an FFMA2 with one broadcast operand.
+  f32x2 Wp[M][MP];    // (W[i][2jp], W[i][2jp+1])
+  f32x2 gWp[MP][M];   // (gW[2ip][j], gW[2ip+1][j])
   float gm[M], gt[M];   // scaled grid coordinates c_d * g_d[i] of the own / partner axis
   float cm, ct;         // coordinate scales
   float nkm, nkt;       // -k_own, -k_partner  (d kappa / dx = -k delta kappa)
 
-  __device__ __forceinline__ void load(const NpdeKParams& prm, const float* Wp, int d) {
+  __device__ __forceinline__ void load(const NpdeKParams& prm, const float* Wp_, int d) {
+    auto w = [&](int i, int j) { return j < M ? (d ? Wp_[2 * (j * M + i) + 1] : Wp_[2 * (i * M + j)]) : 0.f; };
 #pragma unroll
     for (int i = 0; i < M; ++i) {
       gm[i] = d ? prm.gys[i] : prm.gxs[i];
       gt[i] = d ? prm.gxs[i] : prm.gys[i];
 #pragma unroll
-      for (int j = 0; j < M; ++j) {
-        W[i][j] = d ? Wp[2 * (j * M + i) + 1] : Wp[2 * (i * M + j)];
-        gW[i][j] = 0.f;
-      }
+      for (int jp = 0; jp < MP; ++jp) Wp[i][jp] = pk(w(i, 2 * jp), w(i, 2 * jp + 1));
     }
+#pragma unroll
+    for (int ip = 0; ip < MP; ++ip)
+#pragma unroll
+      for (int j = 0; j < M; ++j) gWp[ip][j] = pk(0.f, 0.f);
     cm = d ? prm.c1 : prm.c0;
     ct = d ? prm.c0 : prm.c1;
     nkm = d ? -prm.k1 : -prm.k0;
@@ -51,67 +76,86 @@ struct PairField {
   // npde_epilogue's contract: write this lane's share of gW[m][2]
   __device__ __forceinline__ void store_gW(const NpdeKParams&, float* gp, int d) const {
 #pragma unroll
-    for (int i = 0; i < M; ++i)
+    for (int ip = 0; ip < MP; ++ip)
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        if (d) gp[2 * (j * M + i) + 1] = gW[i][j];
-        else gp[2 * (i * M + j)] = gW[i][j];
+        float g[2];
+        upk(gWp[ip][j], g[0], g[1]);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = 2 * ip + h;
+          if (i < M) {
+            if (d) gp[2 * (j * M + i) + 1] = g[h];
+            else gp[2 * (i * M + j)] = g[h];
+          }
+        }
       }
   }
 
   // f_d(x), x_d = ym (the partner lane holds x_d')
   __device__ __forceinline__ float eval(float ym) const {
-    const float u = cm * ym;
-    float km[M], kt[M];
+    float km[M], kt[2 * MP];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      const float dl = u - gm[i];
+      const float dl = fmaf(cm, ym, -gm[i]);
       km[i] = ex2(-dl * dl);
     }
 #pragma unroll
     for (int j = 0; j < M; ++j) kt[j] = __shfl_xor_sync(FULL_MASK, km[j], 1);
-    float f = 0.f;
+    if (M & 1) kt[M] = 0.f;
+    f32x2 ktp[MP];
+#pragma unroll
+    for (int jp = 0; jp < MP; ++jp) ktp[jp] = pk(kt[2 * jp], kt[2 * jp + 1]);
+    f32x2 facc = pk(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      float t = 0.f;
+      f32x2 acc = pk(0.f, 0.f);
 #pragma unroll
-      for (int j = 0; j < M; ++j) t = fmaf(kt[j], W[i][j], t);
-      f = fmaf(km[i], t, f);
+      for (int jp = 0; jp < MP; ++jp) acc = fma2x(Wp[i][jp], ktp[jp], acc);
+      facc = fma2x(acc, pk(km[i], km[i]), facc);
     }
-    return f;
+    return hsum(facc);
   }
 
   // Component d of J(x)^T a, given this lane's a_d; accumulates gW += wg a_d kappa(x).  WITH_F: also f_d(x).
   template <bool WITH_F>
   __device__ __forceinline__ float vjp(float ym, float yt, float a, float wg, float* fout) {
-    const float um = cm * ym, ut = ct * yt;
-    float km[M], kdm[M], kt[M], kdt[M];
+    float km[2 * MP], kdm[M], kt[M], kdt[M];
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      const float dl = um - gm[i];
+      const float dl = fmaf(cm, ym, -gm[i]);
       km[i] = ex2(-dl * dl);
       kdm[i] = km[i] * dl;
     }
+    if (M & 1) km[M] = 0.f;
 #pragma unroll
     for (int j = 0; j < M; ++j) {
       kt[j] = __shfl_xor_sync(FULL_MASK, km[j], 1);
-      kdt[j] = kt[j] * (ut - gt[j]);
+      kdt[j] = kt[j] * fmaf(ct, yt, -gt[j]);
     }
     const float aw = a * wg;
     float sm = 0.f, st = 0.f, f = 0.f;
 #pragma unroll
     for (int i = 0; i < M; ++i) {
-      const float kaw = km[i] * aw;
-      float t = 0.f, tp = 0.f;
+      f32x2 tt = pk(0.f, 0.f);   // (T_i, T'_i)
 #pragma unroll
       for (int j = 0; j < M; ++j) {
-        t = fmaf(W[i][j], kt[j], t);
-        tp = fmaf(W[i][j], kdt[j], tp);
-        gW[i][j] = fmaf(kaw, kt[j], gW[i][j]);
+        float wlo, whi;
+        upk(Wp[i][j >> 1], wlo, whi);
+        const float w = (j & 1) ? whi : wlo;
+        tt = fma2x(pk(kt[j], kdt[j]), pk(w, w), tt);
       }
+      float t, tp;
+      upk(tt, t, tp);
       sm = fmaf(kdm[i], t, sm);
       st = fmaf(km[i], tp, st);
       if (WITH_F) f = fmaf(km[i], t, f);
+    }
+#pragma unroll
+    for (int ip = 0; ip < MP; ++ip) {
+      const f32x2 kaw = pk(km[2 * ip] * aw, km[2 * ip + 1] * aw);
+#pragma unroll
+      for (int j = 0; j < M; ++j) gWp[ip][j] = fma2x(kaw, pk(kt[j], kt[j]), gWp[ip][j]);
     }
     if (WITH_F) *fout = f;
     const float recv = __shfl_xor_sync(FULL_MASK, (nkt * a) * st, 1);

@@ -12,6 +12,7 @@
 // integer histograms only); with several ranks the per-pass histograms are summed by the caller (one small
 // all-reduce per pass) before bode_svgd_select_digit runs, so every rank selects the same element.
 #include "common.cuh"
+#include "svgd_state.cuh"
 
 namespace bode {
 
@@ -24,6 +25,15 @@ int svgd_tc_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx,
                 const float* gam, float gsign, int jsplit, float* part, cudaStream_t st);
 int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* Xr, long long ldr, const float* mu, const float* gam,
                     float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t st);
+// pipelined tensor-core path with resident A tiles, bulk-copied operands and the median window (svgd_tc2.cu)
+int svgd_tc2_supported(int d, int nc);
+size_t svgd_tc2_carved_bytes(int nr, int nc);
+int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
+                  void* ops_base, float* D2, SelState* st, int sms, cudaStream_t stream);
+int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream);
+unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
+int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
+                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, cudaStream_t stream);
 static int g_tensor_cores = 1;
 
 // ---------------------------------------------------------------- squared distances (difference form, fp32)
@@ -73,13 +83,11 @@ __global__ void __launch_bounds__(256) sqdist_kernel(const float* __restrict__ X
 }
 
 // ---------------------------------------------------------------- exact median by radix select
-// state[0..1] = prefix bits of order statistics A, B ; state[2..3] (as 64-bit pairs) = remaining ranks
-struct SelState { unsigned int prefix[2]; unsigned int maxbits; unsigned int pad; unsigned long long rank[2]; };
-
 __global__ void select_init_kernel(SelState* st, unsigned long long* hist, unsigned long long total) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
     st->prefix[0] = st->prefix[1] = 0u;
     st->maxbits = 0u;
+    st->hit = 0u;
     st->rank[0] = (total - 1) / 2;             // lower middle (0-based, ascending)
     st->rank[1] = total / 2;                   // upper middle; equal to rank[0] when total is odd
   }
@@ -95,6 +103,7 @@ __global__ void __launch_bounds__(512) hist0_kernel(const float* __restrict__ D2
                                                     unsigned long long* __restrict__ hist) {
   __shared__ unsigned int hot[HOTB][32];
   __shared__ unsigned int cold[2048];
+  if (st->hit) return;                              // the window already resolved the median (svgd_state.cuh)
   for (int i = threadIdx.x; i < HOTB * 32; i += blockDim.x) (&hot[0][0])[i] = 0u;
   for (int i = threadIdx.x; i < 2048; i += blockDim.x) cold[i] = 0u;
   __syncthreads();
@@ -132,6 +141,7 @@ __global__ void __launch_bounds__(512) hist0_kernel(const float* __restrict__ D2
 __global__ void __launch_bounds__(512) hist_kernel(const float* __restrict__ D2, long long n, const SelState* __restrict__ st,
                                                    int shift, int nbits, unsigned int himask, unsigned long long* __restrict__ hist) {
   __shared__ unsigned int sh[2][2048];
+  if (st->hit) return;
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) (&sh[0][0])[i] = 0u;
   __syncthreads();
   const unsigned int pa = st->prefix[0], pb = st->prefix[1];
@@ -168,6 +178,7 @@ __global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsign
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned int newp[2];
   __shared__ unsigned long long newr[2];
+  if (st->hit) return;
   const int nb = 1 << nbits;
   const bool two = st->prefix[0] != st->prefix[1];
   const unsigned long long rank0 = st->rank[0], rank1 = st->rank[1];
@@ -209,8 +220,13 @@ __global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsign
 }
 
 // out[0] = median, out[1] = gamma   (stein.py:25-31)
-__global__ void gamma_kernel(const SelState* st, int n, float sigma_fixed, float* out) {
+__global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_window, float* out) {
   const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
+  // arm the window of the next call around the lower middle element just selected (svgd_state.cuh)
+  if (arm_window) {
+    st->win_lo = st->prefix[0] > WIN_HALF ? st->prefix[0] - WIN_HALF : 0u;
+    st->win_valid = 1u;
+  }
   const float med = 0.5f * (a + b);
   double s2;
   if (sigma_fixed > 0.f) s2 = (double)sigma_fixed * (double)sigma_fixed;
@@ -329,12 +345,13 @@ extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int3
   b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials (last column: row sums)
   b += 2 * 2048 * sizeof(unsigned long long) + 256;             // histograms + select state
   b += 256;                                                     // column means (tensor-core path)
+  b += svgd_tc2_carved_bytes(n_rows, n_cols);                   // pre-split operands + median window table
   return b + 1024;
 }
 
 namespace {
 struct Ws {
-  float* d2; float* part; unsigned long long* hist; SelState* st; float* mu;
+  float* d2; float* part; unsigned long long* hist; SelState* st; float* mu; void* ops;
 };
 Ws carve(void* ws, int nr, int nc, int d) {
   Ws w;
@@ -343,7 +360,8 @@ Ws carve(void* ws, int nr, int nc, int d) {
   w.part = (float*)p; p += ((MAXSPLIT * (size_t)nr * (2 * d + 1) * sizeof(float)) + 255) / 256 * 256;
   w.hist = (unsigned long long*)p; p += 2 * 2048 * sizeof(unsigned long long);
   w.st = (SelState*)p; p += 256;
-  w.mu = (float*)p;
+  w.mu = (float*)p; p += 256;
+  w.ops = p;
   return w;
 }
 }  // namespace
@@ -369,6 +387,14 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
     // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles
     int e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, st);
     if (e != BODE_OK) return e;
+    if (svgd_tc2_supported(d, n_cols)) {
+      const int sms = bode_device_sm_count();
+      if (sms < 0) return BODE_ERR_CUDA;
+      e = svgd_tc2_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.ops, w.d2, w.st, sms, st);
+      if (e != BODE_OK) return e;
+      if (hist_out) *hist_out = w.hist;
+      return BODE_OK;
+    }
     e = svgd_tc_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.d2, &w.st->maxbits, st);
     if (e != BODE_OK) return e;
   } else {
@@ -377,6 +403,33 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   }
   if (hist_out) *hist_out = w.hist;
   return BODE_OK;
+}
+
+/* Zero the persistent selection state (median window disarmed, table cleared).  Call once after allocating a workspace. */
+extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, size_t workspace_bytes, bode_stream_t stream) {
+  BODE_REQUIRE(workspace && n_rows > 0 && n_cols > 0 && d > 0, "bad args");
+  BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  BODE_CUDA(cudaMemsetAsync(w.st, 0, 256, (cudaStream_t)stream));
+  BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long), (cudaStream_t)stream));
+  return BODE_OK;
+}
+
+/* Median window (svgd_state.cuh): *table_out = device address of WIN_TABLE+1 uint64 counters filled by bode_svgd_sqdist
+ * (multi-rank callers all-reduce them); bode_svgd_window_select then reads the median off the table when both middle
+ * ranks fall inside the window, which turns the following bode_svgd_hist_pass / bode_svgd_select_digit calls into no-ops. */
+extern "C" int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, void** table_out, size_t* count_out) {
+  BODE_REQUIRE(workspace && table_out && count_out, "null pointer");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  *table_out = svgd_tc2_table(w.ops, n_rows, n_cols);
+  *count_out = (size_t)WIN_TABLE + 1;
+  return BODE_OK;
+}
+
+extern "C" int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+  BODE_REQUIRE(workspace, "null workspace");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  return svgd_tc2_window_select(w.st, w.ops, n_rows, n_cols, (cudaStream_t)stream);
 }
 
 /* 1 (default): Gram and K@[S|X|1] on tcgen05 tensor cores (3xTF32) when d <= 56; 0: FP32-pipe kernels */
@@ -423,7 +476,8 @@ extern "C" int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int
                                float* med_gamma, bode_stream_t stream) {
   BODE_REQUIRE(workspace && med_gamma && n_total > 0, "bad args");
   Ws w = carve(workspace, n_rows, n_cols, d);
-  gamma_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(w.st, n_total, sigma, med_gamma);
+  const int arm = (sigma <= 0.f && g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
+  gamma_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(w.st, n_total, sigma, arm, med_gamma);
   return check_cuda(cudaGetLastError(), "gamma launch");
 }
 
@@ -446,6 +500,13 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
   if (jsplit > (n_cols + PJ - 1) / PJ) jsplit = (n_cols + PJ - 1) / PJ;
   if (jsplit < 1) jsplit = 1;
   if (g_tensor_cores && svgd_tc_supported(d)) {
+    if (svgd_tc2_supported(d, n_cols)) {
+      int js2 = 1;
+      int e2 = svgd_tc2_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, w.ops, &js2, w.part, sms, st);
+      if (e2 != BODE_OK) return e2;
+      return svgd_tc_combine(w.part, js2, n_rows, d, Xrows, ld_rows, w.mu, med_gamma, 1.f / (float)n_total, phi, ld_phi, theta, ld_theta,
+                             step, st);
+    }
     int js = (2 * sms) / ((n_rows + 127) / 128);        // ~2 CTAs per SM, one wave
     if (js > MAXSPLIT) js = MAXSPLIT;
     if (js > (n_cols + 31) / 32) js = (n_cols + 31) / 32;

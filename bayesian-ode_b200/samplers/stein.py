@@ -73,6 +73,12 @@ class _Workspace:
         self.med_gamma = torch.zeros(2, dtype=torch.float32, device=device)
         self.hist_ptr = C.c_void_p()
         self._hist = None
+        self._dims = (nr, nc, d)
+        _lib.check(lib.bode_svgd_workspace_init(nr, nc, d, C.c_void_p(self.base.data_ptr()), nbytes, _lib.stream_ptr()))
+        tp, tn = C.c_void_p(), C.c_size_t()
+        _lib.check(lib.bode_svgd_window_table(nr, nc, d, C.c_void_p(self.base.data_ptr()), C.byref(tp), C.byref(tn)))
+        off = tp.value - self.base.data_ptr()
+        self._wtable = self.base[off:off + tn.value * 8].view(torch.int64)      # median window counters (summed over ranks)
 
     def sqdist(self, Xr, nr, Xc, nc, d, total, row_offset=-1):
         lib = _lib.load()
@@ -88,6 +94,10 @@ class _Workspace:
         lib = _lib.load()
         w = C.c_void_p(self.base.data_ptr())
         if sigma is None:
+            # fast path: the window around the previous call's median usually holds both middle ranks (one all-reduce)
+            if group is not None:
+                torch.distributed.all_reduce(self._wtable, group=group if group is not True else None)
+            _lib.check(lib.bode_svgd_window_select(nr, nc, d, w, _lib.stream_ptr()))
             radix_select_protocol(
                 lambda ps: _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr())),
                 None if group is None else (lambda: torch.distributed.all_reduce(self._hist, group=group if group is not True else None)),

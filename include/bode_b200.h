@@ -273,6 +273,18 @@ int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const 
  * bode_svgd_set_tensor_cores(1) (default) runs the two contractions as 3xTF32 tcgen05.mma (d <= 56); 0 selects the FP32-pipe
  * kernels.  Returns the previous setting. */
 int bode_svgd_set_tensor_cores(int32_t on);
+/* Persistent selection state (svgd_state.cuh).  Consecutive SVGD steps move the median of d2 by far less than 0.2 %, so
+ * bode_svgd_sqdist also counts, in its Gram epilogue, the entries below a window of +-16384 ulps around the previous
+ * call's median and histograms the raw fp32 bit patterns inside it (one counter per representable float: still an exact
+ * order-statistic selection, np.median semantics of stein.py:25-26).  bode_svgd_window_select reads the median off that
+ * table when both middle ranks fall inside the window; the three radix passes below then return immediately.  A miss
+ * (first call, large step) falls back to them transparently.  Multi-rank callers all-reduce (sum) the table returned by
+ * bode_svgd_window_table between bode_svgd_sqdist and bode_svgd_window_select.  bode_svgd_workspace_init zeroes the state
+ * once after the workspace is allocated.  Call order per step:
+ *   bode_svgd_sqdist -> [all-reduce table] -> bode_svgd_window_select -> radix passes (no-ops on a hit) -> bode_svgd_gamma -> bode_svgd_phi */
+int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, size_t workspace_bytes, bode_stream_t stream);
+int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, void** table_out, size_t* count_out);
+int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
