@@ -13,12 +13,13 @@
 // all-reduce per pass) before bode_svgd_select_digit runs, so every rank selects the same element.
 #include "common.cuh"
 #include "svgd_state.cuh"
+#include <cooperative_groups.h>
 
 namespace bode {
 
 // tensor-core path (svgd_tc.cu)
 int svgd_tc_supported(int d);
-int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, cudaStream_t st);
+int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, SelState* sel, unsigned long long total, cudaStream_t st);
 int svgd_tc_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
                  float* D2, unsigned int* maxbits, cudaStream_t st);
 int svgd_tc_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
@@ -219,6 +220,102 @@ __global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsign
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
 }
 
+// Single-rank fallback in ONE cooperative launch: when the median window missed (first call, large step) the three radix
+// passes run back to back with grid-wide barriers; when it hit, every CTA returns at once, so a captured CUDA graph pays one
+// near-empty launch instead of seven.  1024 threads per CTA (the select scan needs them), grid = co-resident CTAs.
+__device__ __forceinline__ void hist_pass_dev(const float* __restrict__ D2, long long n, unsigned int pa, unsigned int pb, int shift, int nbits,
+                                              unsigned int himask, unsigned int* sh /*[2][2048]*/, unsigned long long* __restrict__ hist) {
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) sh[i] = 0u;
+  __syncthreads();
+  const bool two = pa != pb;
+  const unsigned int dmask = (1u << nbits) - 1u;
+  const long long n4 = n >> 2;
+  const uint4* D4 = reinterpret_cast<const uint4*>(D2);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 q = __ldg(D4 + i);
+    const unsigned int v[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const unsigned int hi = v[u] & himask, dig = (v[u] >> shift) & dmask;
+      if (hi == pa) atomicAdd(&sh[dig], 1u);
+      else if (two && hi == pb) atomicAdd(&sh[2048 + dig], 1u);
+    }
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (int)(n - (n4 << 2))) {          // scalar tail
+    const unsigned int v = __float_as_uint(__ldg(D2 + (n4 << 2) + threadIdx.x));
+    const unsigned int hi = v & himask, dig = (v >> shift) & dmask;
+    if (hi == pa) atomicAdd(&sh[dig], 1u);
+    else if (two && hi == pb) atomicAdd(&sh[2048 + dig], 1u);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
+    const unsigned int c = sh[i];
+    if (c) atomicAdd(hist + i, (unsigned long long)c);
+  }
+}
+
+__device__ __forceinline__ void select_digit_dev(SelState* st, unsigned long long* hist, int shift, int nbits, unsigned long long* wsum /*[32]*/,
+                                                 unsigned int* newp /*[2]*/, unsigned long long* newr /*[2]*/) {
+  const int nb = 1 << nbits;
+  const bool two = st->prefix[0] != st->prefix[1];
+  const unsigned long long rank0 = st->rank[0], rank1 = st->rank[1];
+  const unsigned int pre0 = st->prefix[0], pre1 = st->prefix[1];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int which = 0; which < 2; ++which) {
+    const unsigned long long* h = hist + ((which == 1 && two) ? 2048 : 0);
+    const unsigned long long r = which ? rank1 : rank0;
+    const int i0 = 2 * threadIdx.x;
+    const unsigned long long c0 = i0 < nb ? h[i0] : 0ull, c1 = i0 + 1 < nb ? h[i0 + 1] : 0ull;
+    unsigned long long incl = c0 + c1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    if (lane == 31) wsum[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      unsigned long long w = wsum[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += t;
+      }
+      wsum[lane] = w;
+    }
+    __syncthreads();
+    const unsigned long long excl = incl - (c0 + c1) + (wid ? wsum[wid - 1] : 0ull);
+    if (r >= excl && r < excl + c0) { newp[which] = (which ? pre1 : pre0) | ((unsigned)i0 << shift); newr[which] = r - excl; }
+    else if (r >= excl + c0 && r < excl + c0 + c1) { newp[which] = (which ? pre1 : pre0) | ((unsigned)(i0 + 1) << shift); newr[which] = r - excl - c0; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    st->prefix[0] = newp[0]; st->prefix[1] = newp[1];
+    st->rank[0] = newr[0]; st->rank[1] = newr[1];
+  }
+  for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
+}
+
+__global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __restrict__ D2, long long n, SelState* st, unsigned long long* hist) {
+  __shared__ unsigned int sh[2 * 2048];
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned int newp[2];
+  __shared__ unsigned long long newr[2];
+  if (st->hit) return;                               // uniform over the grid: written before this launch
+  cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+  const int sh_[3] = {20, 9, 0}, nb_[3] = {11, 11, 9};
+  for (int pass = 0; pass < 3; ++pass) {
+    const unsigned int himask = pass == 0 ? 0u : (0xffffffffu << (sh_[pass] + nb_[pass]));
+    // pass 0: himask = 0 and both prefixes are 0, so every element lands in sh[0][digit]
+    hist_pass_dev(D2, n, st->prefix[0], st->prefix[1], sh_[pass], nb_[pass], himask, sh, hist);
+    __threadfence();
+    grid.sync();
+    if (blockIdx.x == 0) select_digit_dev(st, hist, sh_[pass], nb_[pass], wsum, newp, newr);
+    __threadfence();
+    grid.sync();
+  }
+}
+
 // out[0] = median, out[1] = gamma   (stein.py:25-31)
 __global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_window, float* out) {
   const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
@@ -381,11 +478,10 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   const size_t smem = 2 * (size_t)TS * (d | 1) * sizeof(float);
   if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n_cols + TS - 1) / TS, (n_rows + TS - 1) / TS);
-  select_init_kernel<<<4, 1024, 0, st>>>(w.st, w.hist, total_entries);
-  BODE_CUDA(cudaGetLastError());
   if (g_tensor_cores && svgd_tc_supported(d)) {
-    // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles
-    int e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, st);
+    // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles.
+    // The column-mean kernel also resets the selection state (the histograms are left zeroed by every select pass).
+    int e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, w.st, total_entries, st);
     if (e != BODE_OK) return e;
     if (svgd_tc2_supported(d, n_cols)) {
       const int sms = bode_device_sm_count();
@@ -398,6 +494,8 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
     e = svgd_tc_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.d2, &w.st->maxbits, st);
     if (e != BODE_OK) return e;
   } else {
+    select_init_kernel<<<4, 1024, 0, st>>>(w.st, w.hist, total_entries);
+    BODE_CUDA(cudaGetLastError());
     sqdist_kernel<<<grid, 256, smem, st>>>(Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, w.d2, &w.st->maxbits);
     BODE_CUDA(cudaGetLastError());
   }
@@ -410,6 +508,7 @@ extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t 
   BODE_REQUIRE(workspace && n_rows > 0 && n_cols > 0 && d > 0, "bad args");
   BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
   Ws w = carve(workspace, n_rows, n_cols, d);
+  BODE_CUDA(cudaMemsetAsync(w.hist, 0, 2 * 2048 * sizeof(unsigned long long), (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(w.st, 0, 256, (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long), (cudaStream_t)stream));
   return BODE_OK;
@@ -469,6 +568,29 @@ extern "C" int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_co
   window(pass, &shift, &nbits, &himask);
   select_digit_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(w.st, w.hist, shift, nbits);
   return check_cuda(cudaGetLastError(), "select launch");
+}
+
+/* Single-rank fallback of the exact median: the three radix passes in one cooperative launch (returns immediately when
+ * bode_svgd_window_select resolved the median).  Multi-rank callers keep the per-pass calls with their all-reduces. */
+extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+  BODE_REQUIRE(workspace, "null workspace");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  static int grid_blocks = 0;
+  if (grid_blocks == 0) {
+    int per_sm = 0;
+    BODE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, radix_fallback_kernel, 1024, 0));
+    const int sms = bode_device_sm_count();
+    if (sms < 0) return BODE_ERR_CUDA;
+    BODE_REQUIRE(per_sm >= 1, "radix_fallback_kernel does not fit an SM");
+    grid_blocks = sms * per_sm;
+  }
+  const float* d2 = w.d2;
+  long long n = (long long)n_rows * n_cols;
+  SelState* stp = w.st;
+  unsigned long long* hist = w.hist;
+  void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist};
+  BODE_CUDA(cudaLaunchCooperativeKernel((const void*)radix_fallback_kernel, dim3(grid_blocks), dim3(1024), args, 0, (cudaStream_t)stream));
+  return BODE_OK;
 }
 
 /* med_gamma[0] = median(d2), med_gamma[1] = gamma; sigma > 0 fixes the bandwidth (RBFKernel(sigma), stein.py:13-16,28) */

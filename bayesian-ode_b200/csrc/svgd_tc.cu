@@ -10,13 +10,22 @@
 // accumulators with tcgen05.ld (one TMEM lane = one output row per thread).  No TMA: the A operand of the second
 // contraction (exp of a distance tile) does not exist in memory, and the first one needs the centred/split transform.
 #include "tc_ptx.cuh"
+#include "svgd_state.cuh"
 
 namespace bode {
 
 // ---------------------------------------------------------------- column means (deterministic tree per column)
-__global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ X, long long ld, int n, int d, float* __restrict__ mu) {
+__global__ void __launch_bounds__(256) colmean_kernel(const float* __restrict__ X, long long ld, int n, int d, float* __restrict__ mu,
+                                                      SelState* st, unsigned long long total) {
   __shared__ float red[256];
   const int c = blockIdx.x;
+  if (c == 0 && threadIdx.x == 0 && st) {        // start of a selection: same reset as select_init_kernel (svgd.cu)
+    st->prefix[0] = st->prefix[1] = 0u;
+    st->maxbits = 0u;
+    st->hit = 0u;
+    st->rank[0] = (total - 1) / 2;
+    st->rank[1] = total / 2;
+  }
   float acc = 0.f;
   for (int r = threadIdx.x; r < n; r += 256) acc += X[(long long)r * ld + c];
   red[threadIdx.x] = acc;
@@ -398,8 +407,8 @@ __global__ void phi_combine_tc_kernel(const float* __restrict__ part, int jsplit
 // ---------------------------------------------------------------- host launchers (called from svgd.cu)
 int svgd_tc_supported(int d) { return d >= 1 && d <= 56; }
 
-int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, cudaStream_t st) {
-  colmean_kernel<<<d, 256, 0, st>>>(X, ld, n, d, mu);
+int svgd_tc_colmean(const float* X, long long ld, int n, int d, float* mu, SelState* sel, unsigned long long total, cudaStream_t st) {
+  colmean_kernel<<<d, 256, 0, st>>>(X, ld, n, d, mu, sel, total);
   return check_cuda(cudaGetLastError(), "colmean launch");
 }
 

@@ -14,6 +14,7 @@
 // operand generation.
 #include "tc_ptx.cuh"
 #include "svgd_state.cuh"
+#include <cuda.h>
 
 namespace bode {
 
@@ -29,36 +30,40 @@ constexpr int NWARP = NWORK / 32;
 constexpr int NTHR = NWORK + 32;
 
 // ---------------------------------------------------------------- operand preparation
-// XH/XL[blk][kc][r/8][r%8][4] : K-major core matrices of the centred rows, zero padded to n_pad rows (multiple of 128)
+// XH/XL[blk][kc][r/8][r%8][4] : K-major core matrices of the centred rows, zero padded to a multiple of 128 rows.
+// One CTA per 128-row block; norms[r] = |xc_r|^2 summed chunk by chunk in a fixed order.
 __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ X, long long ld, int n, int d, const float* __restrict__ mu,
-                                                     int n_pad, float* __restrict__ XH, float* __restrict__ XL, float* __restrict__ norms) {
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long tot = (long long)n_pad * KCH2;
-  if (idx < tot) {
-    const int r = (int)(idx % BLK);
-    const long long q = idx / BLK;
-    const int kc = (int)(q % KCH2);
-    const long long blk = q / KCH2;
-    const long long row = blk * BLK + r;
-    float h[4], l[4];
+                                                     float* __restrict__ XH, float* __restrict__ XL, float* __restrict__ norms,
+                                                     unsigned int* __restrict__ maxbits) {
+  __shared__ float part[KCH2][BLK + 1];
+  const int blk = blockIdx.x;
+  for (int idx = threadIdx.x; idx < BLK * KCH2; idx += 256) {
+    const int r = idx % BLK, kc = idx / BLK;
+    const long long row = (long long)blk * BLK + r;
+    float h[4], l[4], s = 0.f;
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * kc + e;
       const float v = (row < n && k < d) ? __ldg(X + row * ld + k) - __ldg(mu + k) : 0.f;
+      s = fmaf(v, v, s);
       split_tf32(v, h[e], l[e]);
     }
-    const long long off = blk * (BLK_BYTES / 4) + (long long)(kc * (BLK / 8) + (r >> 3)) * 32 + (r & 7) * 4;
+    part[kc][r] = s;
+    const long long off = (long long)blk * (BLK_BYTES / 4) + (long long)(kc * (BLK / 8) + (r >> 3)) * 32 + (r & 7) * 4;
     *reinterpret_cast<float4*>(XH + off) = make_float4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<float4*>(XL + off) = make_float4(l[0], l[1], l[2], l[3]);
   }
-  if (idx < n_pad) {                       // |xc|^2, summed in feature order
+  __syncthreads();
+  if (threadIdx.x < BLK) {
     float s = 0.f;
-    if (idx < n)
-      for (int k = 0; k < d; ++k) {
-        const float v = __ldg(X + idx * ld + k) - __ldg(mu + k);
-        s = fmaf(v, v, s);
-      }
-    norms[idx] = s;
+#pragma unroll
+    for (int kc = 0; kc < KCH2; ++kc) s += part[kc][threadIdx.x];
+    norms[(long long)blk * BLK + threadIdx.x] = s;
+    // d2_ij <= (|xc_i| + |xc_j|)^2 <= 4 max |xc|^2: positions the hot buckets of the radix fallback's first pass (svgd.cu)
+    float m = 4.f * s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && maxbits) atomicMax(maxbits, __float_as_uint(m));
   }
 }
 
@@ -87,6 +92,47 @@ __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X
 }
 
 // ---------------------------------------------------------------- Gram tiles + window count
+// One 32 x 32 chunk of a Gram tile: d2 values, window count, staged coalesced store.  FULL: the tile lies inside the matrix
+// (no bounds checks); DIAG: the tile intersects the diagonal (cdist(x, x) = 0 is forced there).
+template <bool FULL, bool DIAG>
+__device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* ncs, float* stage, float nrow, int lane, int dcol, int row, int nr,
+                                            int colbase, int nc, int grow0, unsigned int wlo, unsigned int wspan,
+                                            unsigned long long* table, unsigned int& below, float* __restrict__ D2) {
+#pragma unroll
+  for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const float4 nj = *reinterpret_cast<const float4*>(ncs + 16 * hf + 4 * k4);
+      const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = 16 * hf + 4 * k4 + e;
+        float v = fmaxf(fmaf(-2.f, s[c], nrow + njv[e]), 0.f);
+        if (DIAG && c == dcol) v = 0.f;                          // cdist(x, x) = 0 on the diagonal
+        o[e] = v;
+        unsigned int off = __float_as_uint(v) - wlo;             // wraps (sign bit set) for entries below the window
+        if (!FULL && !(row < nr && colbase + c < nc)) off = 0x7fffffffu;      // outside the matrix: neither below nor inside
+        below += off >> 31;
+        // predicated reduction, no branch: the address is only dereferenced when the entry lies inside the window
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p red.global.add.u64 [%0], 1;\n\t}" ::"l"(table + off), "r"(off), "r"(wspan)
+                     : "memory");
+      }
+      *reinterpret_cast<float4*>(stage + lane * 20 + 4 * k4) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncwarp();
+    // coalesced rows: 4 lanes cover the 64 bytes of one row of the 16-column half
+#pragma unroll
+    for (int rr = 0; rr < 32; rr += 8) {
+      const int r2 = rr + (lane >> 2), c4 = lane & 3;
+      const int grow = grow0 + r2, gcol = colbase + 16 * hf + 4 * c4;
+      if (FULL || (grow < nr && gcol < nc))
+        *reinterpret_cast<float4*>(D2 + (long long)grow * nc + gcol) = *reinterpret_cast<const float4*>(stage + r2 * 20 + 4 * c4);
+    }
+    __syncwarp();
+  }
+}
+
 struct Gram2Smem {
   static constexpr uint32_t A = 0;                                  // hi | lo
   static constexpr uint32_t B = 2 * BLK_BYTES;                      // 2 slots x (hi | lo)
@@ -141,20 +187,22 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
         bulk_g2s(dst, XcH + src, BLK_BYTES, barB + slot);
         bulk_g2s(dst + BLK_BYTES, XcL + src, BLK_BYTES, barB + slot);
       };
+      // descriptors are built once: a K step only adds (2 LBO) >> 4 to the 14-bit start-address field
+      const uint64_t dAh = smem_desc(smem_u32(sm + Gram2Smem::A), LBO, SBO), dAl = smem_desc(smem_u32(sm + Gram2Smem::A) + BLK_BYTES, LBO, SBO);
+      const uint64_t dB0h = smem_desc(smem_u32(sm + Gram2Smem::B), LBO, SBO), dB0l = smem_desc(smem_u32(sm + Gram2Smem::B) + BLK_BYTES, LBO, SBO);
+      const uint64_t dB1h = smem_desc(smem_u32(sm + Gram2Smem::B) + 2 * BLK_BYTES, LBO, SBO),
+                     dB1l = smem_desc(smem_u32(sm + Gram2Smem::B) + 3 * BLK_BYTES, LBO, SBO);
+      constexpr uint64_t KSTEP = (2 * LBO) >> 4;
       auto issue = [&](int t) {
         const int slot = t & 1;
-        const uint32_t ah = smem_u32(sm + Gram2Smem::A), al = ah + BLK_BYTES;
-        const uint32_t bh = smem_u32(sm + Gram2Smem::B + slot * 2 * BLK_BYTES), bl = bh + BLK_BYTES;
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = pass == 2 ? al : ah, b0 = pass == 1 ? bl : bh;
-#pragma unroll 1
-          for (int ks = 0; ks < KP2 / 8; ++ks) {
-            umma_tf32(tmem + slot * BLK, smem_desc(a0 + ks * 2 * LBO, LBO, SBO), smem_desc(b0 + ks * 2 * LBO, LBO, SBO), idesc, acc);
-            acc = 1;
-          }
-        }
+        const uint64_t bh = slot ? dB1h : dB0h, bl = slot ? dB1l : dB0l;
+        const uint32_t dst = tmem + slot * BLK;
+#pragma unroll
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAh + ks * KSTEP, bh + ks * KSTEP, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAh + ks * KSTEP, bl + ks * KSTEP, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAl + ks * KSTEP, bh + ks * KSTEP, idesc, 1u);
         umma_commit(barS + slot);
       };
     if (lane == 0) {
@@ -193,67 +241,37 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
     float* stage = reinterpret_cast<float*>(sm + Gram2Smem::STAGE) + warp * 32 * 20;
     float* ncs = reinterpret_cast<float*>(sm + Gram2Smem::NCS) + warp * 32;
     const bool win = st->win_valid != 0;
-    const unsigned int wlo = win ? st->win_lo : 0xffffffffu;     // disarmed: nothing is below, nothing is inside
+    // disarmed: wlo = 0x80000000 makes every offset wrap to >= 0x80000000 - 0x7f800000 > 0 with the sign bit clear only for
+    // bit patterns >= 0x80000000 (none: d2 >= 0), i.e. nothing falls inside; the "below" count is simply not published
+    const unsigned int wlo = win ? st->win_lo : 0x80000000u;
     const unsigned int wspan = win ? WIN_SPAN : 0u;
     unsigned int below = 0;
-    float mx = 0.f;
     const int cb = 32 * cq;                                        // first tile column of this warp
+    float nreg = __ldg(nrm_c + ct0 * BLK + cb + lane);
     for (int t = 0; t < nt; ++t) {
       const int c0 = (ct0 + t) * BLK;
-      ncs[lane] = __ldg(nrm_c + c0 + cb + lane);                   // in flight while the MMAs of this tile finish
+      ncs[lane] = nreg;
+      if (t + 1 < nt) nreg = __ldg(nrm_c + c0 + BLK + cb + lane);  // next tile's column norms travel during this tile
       mbar_wait(barS + (t & 1), (t >> 1) & 1);
       tc_fence_after();
       float s[32];
       tmem_ld32(tmem + (t & 1) * BLK + cb + ((uint32_t)(32 * q) << 16), s);
       __syncwarp();
       const bool full = rb * BLK + BLK <= nr && c0 + BLK <= nc;
-      const int dcol = row + row_offset - (c0 + cb);               // tile-local column of the diagonal entry (if 0..31)
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll
-        for (int k4 = 0; k4 < 4; ++k4) {
-          const float4 nj = *reinterpret_cast<const float4*>(ncs + 16 * hf + 4 * k4);
-          const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = 16 * hf + 4 * k4 + e;
-            float v = fmaxf(fmaf(-2.f, s[c], nrow + njv[e]), 0.f);
-            if (c == dcol) v = 0.f;                                // cdist(x, x) = 0 on the diagonal
-            o[e] = v;
-            if (full || (row < nr && c0 + cb + c < nc)) {
-              mx = fmaxf(mx, v);
-              const unsigned int off = __float_as_uint(v) - wlo;   // wraps for entries below the window
-              below += (int)off < 0;
-              if (off <= wspan) atomicAdd(table + off, 1ull);
-            }
-          }
-          *reinterpret_cast<float4*>(stage + lane * 20 + 4 * k4) = make_float4(o[0], o[1], o[2], o[3]);
-        }
-        __syncwarp();
-        // coalesced rows: 4 lanes cover the 64 bytes of one row of the 16-column half
-#pragma unroll
-        for (int rr = 0; rr < 32; rr += 8) {
-          const int r2 = rr + (lane >> 2), c4 = lane & 3;
-          const int grow = rb * BLK + 32 * q + r2, gcol = c0 + cb + 16 * hf + 4 * c4;
-          if (full || (grow < nr && gcol < nc))
-            *reinterpret_cast<float4*>(D2 + (long long)grow * nc + gcol) = *reinterpret_cast<const float4*>(stage + r2 * 20 + 4 * c4);
-        }
-        __syncwarp();
-      }
+      const int dcol = row + row_offset - (c0 + cb);               // chunk-local column of the diagonal entry (if 0..31)
+      const int dtile = rb * BLK + 32 * q + row_offset - (c0 + cb);  // warp-uniform: diagonal crosses this chunk iff -31 <= dtile <= 31
+      const bool diag = dtile > -32 && dtile < 32;
+      const int grow0 = rb * BLK + 32 * q, colbase = c0 + cb;
+      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
+      else if (full) gram2_chunk<true, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
+      else gram2_chunk<false, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
       tc_fence_before();
       __syncthreads();
       tc_fence_after();
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      below += __shfl_xor_sync(0xffffffffu, below, o);
-    }
-    if (lane == 0) {
-      atomicMax(&st->maxbits, __float_as_uint(mx));
-      if (win && below) atomicAdd(table + WIN_TABLE, (unsigned long long)below);
-    }
+    for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (lane == 0 && win && below) atomicAdd(table + WIN_TABLE, (unsigned long long)below);
   }
   tc_fence_before();
   __syncthreads();
@@ -261,48 +279,69 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- median from the window table (one CTA)
+// 32 warps, each owning a contiguous segment of 33 x 32 bins: coalesced segment sums, a scan over the 32 segment totals, then
+// only the (one or two) warps whose segment holds a middle rank walk their segment again.
 __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table) {
-  __shared__ unsigned long long wsum[32];
+  constexpr int SEG_IT = (WIN_TABLE + 1023) / 1024;                   // 33
+  constexpr int SEG = SEG_IT * 32;
+  __shared__ unsigned long long wtot[32], wexcl[32];
   __shared__ unsigned int found[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  constexpr int PER = (WIN_TABLE + 1023) / 1024;             // bins per thread (contiguous)
   const bool armed = st->win_valid != 0;
   unsigned long long sum = 0;
-  for (int i = 0; i < PER; ++i) {
-    const int b = tid * PER + i;
-    if (armed && b < (int)WIN_TABLE) sum += table[b];
+  if (armed) {
+#pragma unroll 11
+    for (int i = 0; i < SEG_IT; ++i) {
+      const int b = wid * SEG + i * 32 + lane;
+      if (b < (int)WIN_TABLE) sum += table[b];
+    }
   }
-  unsigned long long incl = sum;
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-    if (lane >= o) incl += t;
-  }
-  if (lane == 31) wsum[wid] = incl;
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if (lane == 0) wtot[wid] = sum;
   if (tid < 2) found[tid] = 0xffffffffu;
   __syncthreads();
   if (wid == 0) {
-    unsigned long long w = wsum[lane];
+    const unsigned long long mine = wtot[lane];
+    unsigned long long incl = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
-      if (lane >= o) w += t;
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
     }
-    wsum[lane] = w;
+    wexcl[lane] = incl - mine + (armed ? table[WIN_TABLE] : 0ull);    // entries strictly below this warp's segment
   }
   __syncthreads();
-  const unsigned long long below = armed ? table[WIN_TABLE] : 0ull;
-  unsigned long long excl = below + incl - sum + (wid ? wsum[wid - 1] : 0ull);     // entries strictly below this thread's first bin
   const unsigned long long r0 = st->rank[0], r1 = st->rank[1];
-  if (sum) {
-    for (int i = 0; i < PER; ++i) {
-      const int b = tid * PER + i;
-      const unsigned long long c = b < (int)WIN_TABLE ? table[b] : 0ull;
+  const unsigned long long lo = wexcl[wid], hi = lo + wtot[wid];
+  if (armed && ((r0 >= lo && r0 < hi) || (r1 >= lo && r1 < hi))) {     // warp-uniform
+    unsigned long long run = lo;
+    unsigned long long cv[11];
+    for (int i = 0; i < SEG_IT; ++i) {
+      if (i % 11 == 0) {                                               // 11 independent loads in flight per batch
+#pragma unroll
+        for (int u = 0; u < 11; ++u) {
+          const int bb = wid * SEG + (i + u) * 32 + lane;
+          cv[u] = (i + u < SEG_IT && bb < (int)WIN_TABLE) ? table[bb] : 0ull;
+        }
+      }
+      const int b = wid * SEG + i * 32 + lane;
+      unsigned long long c = 0ull;
+#pragma unroll
+      for (int u = 0; u < 11; ++u)
+        if (u == i % 11) c = cv[u];
+      unsigned long long incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned long long excl = run + incl - c;
       if (c) {
         if (r0 >= excl && r0 < excl + c) found[0] = b;
         if (r1 >= excl && r1 < excl + c) found[1] = b;
       }
-      excl += c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
     }
   }
   __syncthreads();
@@ -319,23 +358,37 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
 
 // ---------------------------------------------------------------- phi partials
 struct Phi2Smem {
-  static constexpr uint32_t RAW = 0;                                   // 3 slots x [128][36] floats (d2 tile, row-major)
-  static constexpr uint32_t RAW_SLOT = BLK * 36 * 4;
+  static constexpr uint32_t RAW = 0;                                   // 3 slots x [128][32] floats, TMA tile with 128-byte swizzle
+  static constexpr uint32_t RAW_SLOT = BLK * PK2 * 4;                  // 16384 (1024-byte aligned)
   static constexpr uint32_t K = RAW + 3 * RAW_SLOT;                    // 2 slots x (hi | lo) x [8 kc][16][8][4]
   static constexpr uint32_t K_HALF = BLK * PK2 * 4;
   static constexpr uint32_t V = K + 4 * K_HALF;                        // 3 slots x (hi | lo)
-  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[2], barV[3]
-  static constexpr uint32_t TSLOT = BARS + 5 * 8;
-  static constexpr uint32_t TOTAL = TSLOT + 16;
+  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[2], barV[3], barR[3], barK[2]
+  static constexpr uint32_t TSLOT = BARS + 10 * 8;
+  static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;                 // + slack to align the dynamic base to 1024 bytes
 };
 
-__global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const float* __restrict__ D2, int nr, int nc, const float* __restrict__ VH,
+// 2-D tiled TMA load (SASS UTMALDG): box {32 columns, 128 rows} of the row-major d2 matrix, 128-byte swizzle
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
                                                        float* __restrict__ part) {
-  extern __shared__ __align__(128) unsigned char sm[];
+  extern __shared__ unsigned char sm_raw[];
+  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Phi2Smem::BARS);
-  uint64_t* barM = bars;
-  uint64_t* barV = bars + 2;
+  uint64_t* barM = bars;          // MMAs of a stage complete (K slot / V slot free)
+  uint64_t* barV = bars + 2;      // V^T tile landed
+  uint64_t* barR = bars + 5;      // d2 tile landed
+  uint64_t* barK = bars + 8;      // K tile written by all worker warps (count NWARP)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + Phi2Smem::TSLOT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * BLK;
@@ -346,11 +399,10 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const float* __restrict__
 
   if (warp == 0) tmem_alloc(tslot, 128);
   if (tid == 0) {
-    mbar_init(barM + 0, 1);
-    mbar_init(barM + 1, 1);
-    mbar_init(barV + 0, 1);
-    mbar_init(barV + 1, 1);
-    mbar_init(barV + 2, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(barM + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(barV + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(barR + i, 1);
+    for (int i = 0; i < 2; ++i) mbar_init(barK + i, NWARP);
   }
   tc_fence_before();
   __syncthreads();
@@ -359,100 +411,91 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const float* __restrict__
   constexpr uint32_t idesc = idesc_tf32(BLK, NF2, 0, 0);
   constexpr uint32_t A_LBO = BLK * 16, B_LBO = NF2 * 16, SBO = 128;
 
+  // No CTA-wide barrier inside the stage loop: the warps only meet through mbarriers, so a slow warp delays nobody but the MMA
+  // that needs its rows.
   if (warp == NWARP) {
-    auto load_v = [&](int t) {
-      const int slot = t % 3;
-      unsigned char* dst = sm + Phi2Smem::V + slot * 2 * VST_BYTES;
-      const long long src = (long long)(s0 + t) * (VST_BYTES / 4);
-      mbar_expect_tx(barV + slot, 2 * VST_BYTES);
-      bulk_g2s(dst, VH + src, VST_BYTES, barV + slot);
-      bulk_g2s(dst + VST_BYTES, VL + src, VST_BYTES, barV + slot);
-    };
     if (lane == 0 && nst > 0) {
+      auto load_v = [&](int t) {
+        const int slot = t % 3;
+        unsigned char* dst = sm + Phi2Smem::V + slot * 2 * VST_BYTES;
+        const long long src = (long long)(s0 + t) * (VST_BYTES / 4);
+        mbar_expect_tx(barV + slot, 2 * VST_BYTES);
+        bulk_g2s(dst, VH + src, VST_BYTES, barV + slot);
+        bulk_g2s(dst + VST_BYTES, VL + src, VST_BYTES, barV + slot);
+      };
+      auto load_raw = [&](int t) {
+        if (t < nst) {
+          const int slot = t % 3;
+          mbar_expect_tx(barR + slot, Phi2Smem::RAW_SLOT);             // out-of-range box elements are zero-filled and counted
+          tma_load_2d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, (s0 + t) * PK2, r0, barR + slot);
+        }
+      };
+      load_raw(0);
+      load_raw(1);
+      load_raw(2);
       load_v(0);
       if (nst > 1) load_v(1);
-    }
-    __syncwarp();
-    for (int t = 0; t < nst; ++t) {
-      tc_fence_before();
-      __syncthreads();                                                 // K(t) is in shared memory
-      tc_fence_after();
-      if (lane == 0) {
+      // descriptors are built once: slots and K steps only add to the 14-bit start-address field (shared memory < 256 KB)
+      const uint64_t dK = smem_desc(smem_u32(sm + Phi2Smem::K), A_LBO, SBO), dV = smem_desc(smem_u32(sm + Phi2Smem::V), B_LBO, SBO);
+      constexpr uint64_t AK = (2 * A_LBO) >> 4, BK = (2 * B_LBO) >> 4;
+      for (int t = 0; t < nst; ++t) {
+        mbar_wait(barK + (t & 1), (t >> 1) & 1);                       // K(t) written and fenced by every worker warp; raw(t) consumed
+        tc_fence_after();
         mbar_wait(barV + (t % 3), (t / 3) & 1);
-        const int ks_ = t & 1;
-        const uint32_t ah = smem_u32(sm + Phi2Smem::K + ks_ * 2 * Phi2Smem::K_HALF), al = ah + Phi2Smem::K_HALF;
-        const uint32_t bh = smem_u32(sm + Phi2Smem::V + (t % 3) * 2 * VST_BYTES), bl = bh + VST_BYTES;
-#pragma unroll 1
-        for (int pass = 0; pass < 3; ++pass) {
-          const uint32_t a0 = pass == 2 ? al : ah, b0 = pass == 1 ? bl : bh;
+        const uint64_t ah = dK + (uint64_t)((t & 1) * ((2 * Phi2Smem::K_HALF) >> 4)), al = ah + (Phi2Smem::K_HALF >> 4);
+        const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
 #pragma unroll
-          for (int ks = 0; ks < PK2 / 8; ++ks)
-            umma_tf32(tmem, smem_desc(a0 + ks * 2 * A_LBO, A_LBO, SBO), smem_desc(b0 + ks * 2 * B_LBO, B_LBO, SBO), idesc,
-                      (t > 0 || pass > 0 || ks > 0) ? 1u : 0u);
-        }
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, ah + ks * AK, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, ah + ks * AK, bl + ks * BK, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, al + ks * AK, bh + ks * BK, idesc, 1u);
         umma_commit(barM + (t & 1));
-        // V(t+2) reuses the slot of V(t-1): wait for stage t-1's MMAs
-        if (t + 2 < nst) {
+        load_raw(t + 3);                                               // reuses the slot of raw(t)
+        if (t + 2 < nst) {                                             // V(t+2) reuses the slot of V(t-1): wait for stage t-1's MMAs
           if (t >= 1) mbar_wait(barM + ((t - 1) & 1), ((t - 1) >> 1) & 1);
           load_v(t + 2);
         }
       }
-      __syncwarp();
     }
   } else {
     const float ngamma = -gam[1] * 1.4426950408889634f;
     const int rl = tid & (BLK - 1), qd = tid >> 7;                     // tile row, which 8 of the stage's 32 columns
     const int row = r0 + rl;
     const bool rows_full = r0 + BLK <= nr;
-    auto load_raw = [&](int t) {                                       // 128 x 32 floats of d2, 2 x 16 B per thread, coalesced
-      if (t < nst) {
-        float* dst = reinterpret_cast<float*>(sm + Phi2Smem::RAW + (t % 3) * Phi2Smem::RAW_SLOT);
-        const int j0 = (s0 + t) * PK2;
-#pragma unroll
-        for (int qq = 0; qq < 2; ++qq) {
-          const int idx = tid + NWORK * qq, rr = idx >> 3, c4 = idx & 7;
-          const int gr = min(r0 + rr, nr - 1), gc = min(j0 + 4 * c4, nc - 4);
-          cp_async16(dst + rr * 36 + 4 * c4, D2 + (long long)gr * nc + gc);
-        }
-      }
-      cp_async_commit();
-    };
-    load_raw(0);
-    load_raw(1);
+    const uint32_t koff0 = kmajor_off<BLK>(rl, 2 * qd), koff1 = kmajor_off<BLK>(rl, 2 * qd + 1);
+    // 128-byte swizzle of the TMA tile: 16-byte chunk c of row r sits at chunk c ^ (r % 8)
+    const uint32_t roff0 = rl * 128 + (((2 * qd) ^ (rl & 7)) << 4), roff1 = rl * 128 + (((2 * qd + 1) ^ (rl & 7)) << 4);
     for (int t = 0; t < nst; ++t) {
-      load_raw(t + 2);
-      cp_async_wait<2>();
-      named_bar_sync(1, NWORK);                                        // raw(t) complete for every worker
+      mbar_wait(barR + (t % 3), (t / 3) & 1);                          // d2 tile of this stage has landed
+      const unsigned char* raw = sm + Phi2Smem::RAW + (t % 3) * Phi2Smem::RAW_SLOT;
+      const float4 dv0 = *reinterpret_cast<const float4*>(raw + roff0), dv1 = *reinterpret_cast<const float4*>(raw + roff1);
+      float kv[8] = {ex2(ngamma * dv0.x), ex2(ngamma * dv0.y), ex2(ngamma * dv0.z), ex2(ngamma * dv0.w),
+                     ex2(ngamma * dv1.x), ex2(ngamma * dv1.y), ex2(ngamma * dv1.z), ex2(ngamma * dv1.w)};
+      if (!(rows_full && (s0 + t) * PK2 + PK2 <= nc)) {                // ragged edge: zero the entries outside the matrix
+        const int j0 = (s0 + t) * PK2 + 8 * qd;
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (!(row < nr && j0 + e < nc)) kv[e] = 0.f;
+      }
+      float h[8], l[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) split_tf32(kv[e], h[e], l[e]);
       if (t >= 2) {                                                    // K slot t&1 was read by stage t-2's MMAs
         mbar_wait(barM + (t & 1), ((t - 2) >> 1) & 1);
         tc_fence_after();
       }
-      const float* raw = reinterpret_cast<const float*>(sm + Phi2Smem::RAW + (t % 3) * Phi2Smem::RAW_SLOT) + rl * 36 + 8 * qd;
       unsigned char* kh = sm + Phi2Smem::K + (t & 1) * 2 * Phi2Smem::K_HALF;
       unsigned char* kl = kh + Phi2Smem::K_HALF;
-      const int j0 = (s0 + t) * PK2 + 8 * qd;
-      const bool full = rows_full && (s0 + t) * PK2 + PK2 <= nc;
-#pragma unroll
-      for (int kq = 0; kq < 2; ++kq) {
-        const float4 dv = *reinterpret_cast<const float4*>(raw + 4 * kq);
-        const float dd[4] = {dv.x, dv.y, dv.z, dv.w};
-        float h[4], l[4];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          float kv = ex2(ngamma * dd[e]);
-          if (!full && !(row < nr && j0 + 4 * kq + e < nc)) kv = 0.f;
-          split_tf32(kv, h[e], l[e]);
-        }
-        const uint32_t off = kmajor_off<BLK>(rl, 2 * qd + kq);
-        *reinterpret_cast<float4*>(kh + off) = make_float4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<float4*>(kl + off) = make_float4(l[0], l[1], l[2], l[3]);
-      }
+      *reinterpret_cast<float4*>(kh + koff0) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4*>(kl + koff0) = make_float4(l[0], l[1], l[2], l[3]);
+      *reinterpret_cast<float4*>(kh + koff1) = make_float4(h[4], h[5], h[6], h[7]);
+      *reinterpret_cast<float4*>(kl + koff1) = make_float4(l[4], l[5], l[6], l[7]);
       fence_async_smem();
       tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barK + (t & 1));
     }
-    cp_async_wait<0>();
     // ---------------- epilogue: one TMEM lane per thread = one output row; warps 4..7 take the upper feature half
     const int half = qd;
     if (nst > 0 && warp < 8) {
@@ -526,16 +569,29 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
                   void* ops_base, float* D2, SelState* st, int sms, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int nrp = (nr + BLK - 1) / BLK * BLK, ncp = (nc + BLK - 1) / BLK * BLK;
-  prep_x_kernel<<<(int)(((long long)nrp * KCH2 + 255) / 256), 256, 0, stream>>>(Xr, ldr, nr, d, mu, nrp, o.XrH, o.XrL, o.nrm_r);
-  prep_x_kernel<<<(int)(((long long)ncp * KCH2 + 255) / 256), 256, 0, stream>>>(Xc, ldc, nc, d, mu, ncp, o.XcH, o.XcL, o.nrm_c);
+  prep_x_kernel<<<ncp / BLK, 256, 0, stream>>>(Xc, ldc, nc, d, mu, o.XcH, o.XcL, o.nrm_c, &st->maxbits);
+  const float *rH = o.XrH, *rL = o.XrL, *rN = o.nrm_r;
+  // the local rows usually ARE a 128-aligned block of the gathered columns: reuse the column operands
+  const bool alias = row_offset >= 0 && (row_offset % BLK) == 0 && ldr == ldc && Xr == Xc + (long long)row_offset * ldc &&
+                     (row_offset + nrp <= ncp) && (nr % BLK == 0 || row_offset + nr == nc);
+  if (alias) {
+    rH = o.XcH + (long long)(row_offset / BLK) * (BLK_BYTES / 4);
+    rL = o.XcL + (long long)(row_offset / BLK) * (BLK_BYTES / 4);
+    rN = o.nrm_c + row_offset;
+  } else {
+    prep_x_kernel<<<nrp / BLK, 256, 0, stream>>>(Xr, ldr, nr, d, mu, o.XrH, o.XrL, o.nrm_r, nullptr);
+  }
   BODE_CUDA(cudaGetLastError());
-  BODE_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gram2Smem::TOTAL));
+  static bool attr_set = false;
+  if (!attr_set) {
+    BODE_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gram2Smem::TOTAL));
+    attr_set = true;
+  }
   const int nrb = nrp / BLK, nct = ncp / BLK;
   const int js = split_for(nrb, nct, sms);
   const int tiles_per = (nct + js - 1) / js;
   dim3 grid((nct + tiles_per - 1) / tiles_per, nrb);
-  gram2_kernel<<<grid, NTHR, Gram2Smem::TOTAL, stream>>>(o.XrH, o.XrL, o.nrm_r, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st,
-                                                         o.table);
+  gram2_kernel<<<grid, NTHR, Gram2Smem::TOTAL, stream>>>(rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st, o.table);
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
@@ -547,18 +603,46 @@ int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStr
 
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc) { return svgd_tc2_carve(ops_base, nr, nc).table; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int ncp = (nc + BLK - 1) / BLK * BLK;
   prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VL);
   BODE_CUDA(cudaGetLastError());
-  BODE_CUDA(cudaFuncSetAttribute(phi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Phi2Smem::TOTAL));
+  static bool attr_set = false;
+  if (!attr_set) {
+    BODE_CUDA(cudaFuncSetAttribute(phi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Phi2Smem::TOTAL));
+    attr_set = true;
+  }
+  // TMA descriptor of the row-major d2[nr][nc] matrix: box = 32 columns x 128 rows, 128-byte swizzle, zero fill outside
+  EncodeTiledFn enc = encode_tiled_fn();
+  BODE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tm;
+  const cuuint64_t gdim[2] = {(cuuint64_t)nc, (cuuint64_t)nr};
+  const cuuint64_t gstr[1] = {(cuuint64_t)nc * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)PK2, (cuuint32_t)BLK};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
   const int nrb = (nr + BLK - 1) / BLK, nst = (nc + PK2 - 1) / PK2;
   const int js = split_for(nrb, nst, sms);
   *jsplit_out = js;
   dim3 grid(nrb, js);
-  phi2_kernel<<<grid, NTHR, Phi2Smem::TOTAL, stream>>>(D2, nr, nc, o.VH, o.VL, d, gam, js, part);
+  phi2_kernel<<<grid, NTHR, Phi2Smem::TOTAL, stream>>>(tm, nr, nc, o.VH, o.VL, d, gam, js, part);
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 

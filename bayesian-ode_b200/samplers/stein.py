@@ -98,10 +98,14 @@ class _Workspace:
             if group is not None:
                 torch.distributed.all_reduce(self._wtable, group=group if group is not True else None)
             _lib.check(lib.bode_svgd_window_select(nr, nc, d, w, _lib.stream_ptr()))
-            radix_select_protocol(
-                lambda ps: _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr())),
-                None if group is None else (lambda: torch.distributed.all_reduce(self._hist, group=group if group is not True else None)),
-                lambda ps: _lib.check(lib.bode_svgd_select_digit(ps, nr, nc, d, w, _lib.stream_ptr())))
+            if group is None:
+                # single rank: the radix passes are one cooperative launch that returns at once after a window hit
+                _lib.check(lib.bode_svgd_radix_fallback(nr, nc, d, w, _lib.stream_ptr()))
+            else:
+                radix_select_protocol(
+                    lambda ps: _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr())),
+                    lambda: torch.distributed.all_reduce(self._hist, group=group if group is not True else None),
+                    lambda ps: _lib.check(lib.bode_svgd_select_digit(ps, nr, nc, d, w, _lib.stream_ptr())))
         _lib.check(lib.bode_svgd_gamma(n_total, float(sigma or 0.0), nr, nc, d, w, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
 
     def d2(self, nr, nc):

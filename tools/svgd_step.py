@@ -30,6 +30,27 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+if a.graph:
+    # per-segment timing: each C-ABI call sequence captured in its own graph and replayed back to back (warm L2, like a real step)
+    segs = {"sqdist (colmean+prep+gram)": lambda: ws.sqdist(X, n, X, n, d, n * n, row_offset=0),
+            "median (window+fallback+gamma)": lambda: ws.median(n, n, d, n),
+            "phi (prep_v+phi+combine)": lambda: bode._lib.check(lib.bode_svgd_phi(xr, xs, n, xr, xs, gr, gs, -1.0, n, d, n, bode._lib.ptr(ws.med_gamma),
+                                        C.c_void_p(ws.base.data_ptr()), bode._lib.ptr(phi), d, None, 0, 0.0, bode._lib.stream_ptr()))}
+    graphs = {}
+    for k, f in segs.items():
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            f()
+        graphs[k] = g
+    tot = {k: [] for k in segs}
+    for it in range(a.iters):
+        for k, g in graphs.items():
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); e1.synchronize()
+            tot[k].append(e0.elapsed_time(e1) * 1e3)
+    for k, v in tot.items():
+        v.sort()
+        print("  %-34s median %.1f us" % (k, v[len(v) // 2]))
 run = step
 if a.graph:
     g = torch.cuda.CUDAGraph()
