@@ -279,69 +279,52 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
 }
 
 // ---------------------------------------------------------------- median from the window table (one CTA)
-// 32 warps, each owning a contiguous segment of 33 x 32 bins: coalesced segment sums, a scan over the 32 segment totals, then
-// only the (one or two) warps whose segment holds a middle rank walk their segment again.
+// Thread t owns the 33 consecutive bins [33 t, 33 t + 33): local sums, one block-wide scan, then the (at most two) threads whose
+// range holds a middle rank walk their own bins.
 __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table) {
-  constexpr int SEG_IT = (WIN_TABLE + 1023) / 1024;                   // 33
-  constexpr int SEG = SEG_IT * 32;
-  __shared__ unsigned long long wtot[32], wexcl[32];
+  constexpr int PER = (WIN_TABLE + 1023) / 1024;                      // 33
+  __shared__ unsigned long long wsum[32];
   __shared__ unsigned int found[2];
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const bool armed = st->win_valid != 0;
+  const unsigned long long* mine = table + tid * PER;
   unsigned long long sum = 0;
   if (armed) {
-#pragma unroll 11
-    for (int i = 0; i < SEG_IT; ++i) {
-      const int b = wid * SEG + i * 32 + lane;
-      if (b < (int)WIN_TABLE) sum += table[b];
-    }
-  }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  if (lane == 0) wtot[wid] = sum;
+    for (int i = 0; i < PER; ++i)
+      if (tid * PER + i < (int)WIN_TABLE) sum += mine[i];
+  }
+  unsigned long long incl = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[wid] = incl;
   if (tid < 2) found[tid] = 0xffffffffu;
   __syncthreads();
   if (wid == 0) {
-    const unsigned long long mine = wtot[lane];
-    unsigned long long incl = mine;
+    unsigned long long w = wsum[lane];
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
+      const unsigned long long t = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += t;
     }
-    wexcl[lane] = incl - mine + (armed ? table[WIN_TABLE] : 0ull);    // entries strictly below this warp's segment
+    wsum[lane] = w;
   }
   __syncthreads();
+  const unsigned long long below = armed ? table[WIN_TABLE] : 0ull;
+  unsigned long long excl = below + incl - sum + (wid ? wsum[wid - 1] : 0ull);     // entries strictly below this thread's first bin
   const unsigned long long r0 = st->rank[0], r1 = st->rank[1];
-  const unsigned long long lo = wexcl[wid], hi = lo + wtot[wid];
-  if (armed && ((r0 >= lo && r0 < hi) || (r1 >= lo && r1 < hi))) {     // warp-uniform
-    unsigned long long run = lo;
-    unsigned long long cv[11];
-    for (int i = 0; i < SEG_IT; ++i) {
-      if (i % 11 == 0) {                                               // 11 independent loads in flight per batch
-#pragma unroll
-        for (int u = 0; u < 11; ++u) {
-          const int bb = wid * SEG + (i + u) * 32 + lane;
-          cv[u] = (i + u < SEG_IT && bb < (int)WIN_TABLE) ? table[bb] : 0ull;
-        }
-      }
-      const int b = wid * SEG + i * 32 + lane;
-      unsigned long long c = 0ull;
-#pragma unroll
-      for (int u = 0; u < 11; ++u)
-        if (u == i % 11) c = cv[u];
-      unsigned long long incl = c;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const unsigned long long excl = run + incl - c;
+  if (sum && ((r0 >= excl && r0 < excl + sum) || (r1 >= excl && r1 < excl + sum))) {
+    for (int i = 0; i < PER; ++i) {
+      const int b = tid * PER + i;
+      const unsigned long long c = b < (int)WIN_TABLE ? mine[i] : 0ull;
       if (c) {
         if (r0 >= excl && r0 < excl + c) found[0] = b;
         if (r1 >= excl && r1 < excl + c) found[1] = b;
       }
-      run += __shfl_sync(0xffffffffu, incl, 31);
+      excl += c;
     }
   }
   __syncthreads();
@@ -383,7 +366,8 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
                                                        float* __restrict__ part) {
   extern __shared__ unsigned char sm_raw[];
-  unsigned char* sm = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sm_raw) + 1023) & ~(uintptr_t)1023);
+  // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
+  unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Phi2Smem::BARS);
   uint64_t* barM = bars;          // MMAs of a stage complete (K slot / V slot free)
   uint64_t* barV = bars + 2;      // V^T tile landed

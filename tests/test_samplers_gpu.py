@@ -204,6 +204,35 @@ def test_median_selection_is_bit_exact_at_full_size():
     assert relerr(phi[rows], ref) < 1e-4
 
 
+def test_median_window_path_is_bit_exact_and_falls_back():
+    """The warm-workspace path (window table filled by the Gram epilogue, svgd_state.cuh) must return the same order
+    statistics, bit for bit, as np.median of the kernel's own d2 -- when the median drifts a little (window hit), when it
+    jumps (window miss -> radix fallback), for an odd and an even entry count, and for ragged tile edges (n % 128 != 0)."""
+    from bayesian_ode_b200.samplers.stein import _Workspace
+    rng = np.random.default_rng(11)
+    for n in (300, 1024):                                         # n*n even; 300 % 128 != 0 exercises the ragged tiles
+        d = 52
+        X0 = torch.from_numpy((rng.standard_normal((n, d)) * 0.3 + 1.5).astype(np.float32)).cuda()
+        ws = _Workspace(n, n, d, X0.device)
+        scales = [1.0, 1.0 + 2e-5, 1.0 - 3e-5, 1.7, 1.7 + 1e-5, 0.2]    # small drifts hit the window, 1.7x / 0.2x jumps miss it
+        for it, sc in enumerate(scales):
+            X = (X0 * sc).contiguous()
+            ws.sqdist(X, n, X, n, d, n * n, row_offset=0)
+            ws.median(n, n, d, n)
+            d2 = ws.d2(n, n).cpu().numpy()
+            assert np.float32(float(ws.med_gamma[0])) == np.median(d2), (n, it)
+    # rectangular block (rows are a prefix of the columns, as on rank 0 of a sharded job)
+    n = 255
+    X0 = torch.from_numpy((rng.standard_normal((n, 52)) * 0.3 + 1.5).astype(np.float32)).cuda()
+    Xp = torch.zeros(256, 52, device="cuda"); Xp[:n] = X0        # rows padded so the column count stays a multiple of 4
+    ws = _Workspace(n, 256, 52, X0.device)
+    for sc in (1.0, 1.0 + 1e-5):
+        X = (Xp * sc).contiguous()
+        ws.sqdist(X[:n], n, X, 256, 52, n * 256, row_offset=0)
+        ws.median(n, 256, 52, 256)
+        assert np.float32(float(ws.med_gamma[0])) == np.median(ws.d2(n, 256).cpu().numpy())
+
+
 def test_sample_loop_fused_and_protocol_paths_agree():
     """SGLD.sample() drives NPDEPosterior through the fused path; the autograd closure protocol gives the same chain
     when the same noise stream is used (in-kernel Philox is a pure function of (seed, step, element))."""
