@@ -89,7 +89,15 @@ static int plan(NpdeKParams& prm, int G, int max_threads, dim3* grid, dim3* bloc
 // 320-thread launch bound and the per-particle shared-memory footprint.
 static size_t stage_floats(const NpdeKParams& prm);
 static const int PAIR_MAX_THREADS = 320;
-static bool use_pair(const bode_npde_field* f, int N) { return use_sep(f) && 2 * N <= PAIR_MAX_THREADS; }
+static int sm_count();
+static int g_lanes_per_pair = 0;   // 0 = automatic, 1 = one thread per pair (npde_sep.cuh), 2 = component-split lanes (npde_pair.cuh)
+static bool use_pair(const bode_npde_field* f, int N) {
+  if (!(use_sep(f) && 2 * N <= PAIR_MAX_THREADS)) return false;
+  if (g_lanes_per_pair != 0) return g_lanes_per_pair == 2;
+  // automatic: two lanes per pair while the pairs alone cannot fill the machine (measured on B200, 5x5 grid, rk4: 98 vs 108 us
+  // at P = 4096, 0.68 vs 0.50 ms at P = 32768); beyond ~2 resident CTAs of pairs per SM the one-thread-per-pair kernel wins
+  return (long long)f->P * N <= (long long)sm_count() * PAIR_MAX_THREADS;
+}
 
 static int sm_count() {
   static int sms = 0;
@@ -112,10 +120,11 @@ static int plan_pair(NpdeKParams& prm, bool grad, dim3* grid, dim3* block, size_
     prm.ppc = ppc;
     if (grad) {
       prm.stage_off = (int)(((size_t)ppc * 2 * prm.m * (2 + prm.N) + (size_t)ppc * prm.N * 2 + 3) & ~(size_t)3);
-      floats = (size_t)prm.stage_off + stage_floats(prm);
+      prm.a_off = (int)(((size_t)prm.stage_off + stage_floats(prm) + 3) & ~(size_t)3);
     } else {
-      floats = (size_t)ppc * 2 * prm.m * 2;
+      prm.a_off = ppc * 2 * prm.m * 2;
     }
+    floats = (size_t)prm.a_off + 2 * (size_t)prm.m * prm.m;       // + A | Ksym
     if (floats * sizeof(float) <= 160 * 1024 || ppc == 1) break;
   }
   BODE_REQUIRE(floats * sizeof(float) <= 200 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
@@ -226,6 +235,13 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
 }  // namespace bode
 
 using namespace bode;
+
+/* Kernel choice for square 3x3..6x6 grids: 0 automatic, 1 one thread per (particle, trajectory) pair, 2 two lanes per pair. */
+extern "C" int bode_npde_set_lanes_per_pair(int32_t lanes) {
+  const int old = g_lanes_per_pair;
+  g_lanes_per_pair = (lanes == 1 || lanes == 2) ? lanes : 0;
+  return old;
+}
 
 extern "C" size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode) {
   return scratch_floats(P, N, S, T, method, grad_mode);

@@ -22,26 +22,6 @@ namespace bode {
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
-// Packed FP32 pairs: sm_100a's FFMA2 (PTX fma.rn.f32x2) retires two FMAs per issue slot; ptxas folds a (x, x) pair
-// into a scalar-broadcast operand, so a broadcast costs no extra instruction.
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pk(float lo, float hi) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ f32x2 fma2x(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-__device__ __forceinline__ float hsum(f32x2 v) {
-  float lo, hi;
-  upk(v, lo, hi);
-  return lo + hi;
-}
-
 template <int M>
 struct PairField {
   static constexpr int G = 2;
@@ -269,6 +249,105 @@ __device__ __forceinline__ void pair_step_aug(PairField<M>& fld, float& y, float
   }
 }
 
+// ------------------------------------------------------------------ CTA prologue / epilogue of the pair kernels
+// Same maths as project_W / npde_epilogue (npde_solve.cuh), but A = sf^2 Kzz^-1 L and Ksym are staged in shared memory first, so
+// the projection W = A U, the back-projection gU = A^T gW and the prior read shared memory instead of chains of dependent
+// global loads; every global load of the prologue is issued before the first barrier (one memory latency in total).
+__device__ __forceinline__ void pair_stage_and_project(const NpdeKParams& prm, float* smem, bool with_prior) {
+  const int m = prm.m, m2 = 2 * m, nout = prm.ppc * m2, mm = m * m;
+  float* Us = smem;
+  float* Ws = smem + nout;
+  float* As = smem + prm.a_off;
+  float* Ks = As + mm;
+  const int p0 = blockIdx.x * prm.ppc;
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2;
+    Us[idx] = (p0 + q < prm.P) ? __ldg(prm.U + (long long)(p0 + q) * prm.U_stride + r) : 0.f;
+  }
+  for (int i = threadIdx.x; i < mm; i += blockDim.x) As[i] = __ldg(prm.A + i);
+  if (with_prior)
+    for (int i = threadIdx.x; i < mm; i += blockDim.x) Ks[i] = __ldg(prm.Ksym + i);
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2, j = r >> 1, d = r & 1;
+    const float* Uq = Us + q * m2 + d;
+    const float* Aj = As + j * m;
+    float acc = 0.f;
+    for (int k = 0; k < m; ++k) acc = fmaf(Aj[k], Uq[2 * k], acc);
+    Ws[idx] = acc;
+  }
+  __syncthreads();
+}
+
+template <int INJ, int M>
+__device__ __forceinline__ void pair_epilogue(const NpdeKParams& prm, float* smem, const PairField<M>& fld, bool active, int pl, int n,
+                                              int d, float r2x, float r2y) {
+  const int tid = threadIdx.x;
+  const int m = prm.m, m2 = 2 * m, mm = m * m;
+  const int N = prm.N, ppc = prm.ppc;
+  float* Us = smem;                      // [ppc][m2]   U of this CTA's particles
+  float* Ws = Us + ppc * m2;             // [ppc][m2]   W = A U, later sum_n gW
+  float* gWs = Ws + ppc * m2;            // [N][ppc][m2]
+  float* red = gWs + N * ppc * m2;       // [ppc*N][2]  sum of squared residuals per pair
+  const float* As = smem + prm.a_off;
+  const float* Ks = As + mm;
+  __syncthreads();   // everyone is done reading Ws
+  if (active) {
+    fld.store_gW(prm, gWs + (n * ppc + pl) * m2, d);
+    if (d == 0) {
+      red[(pl * N + n) * 2 + 0] = r2x;
+      red[(pl * N + n) * 2 + 1] = r2y;
+    }
+  }
+  __syncthreads();
+  const int nout = ppc * m2;
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    float acc = 0.f;
+    for (int nn = 0; nn < N; ++nn) acc += gWs[nn * nout + idx];
+    Ws[idx] = acc;
+  }
+  __syncthreads();
+  float* pri = gWs;                      // reuse: prior partials [ppc][m2]
+  for (int idx = tid; idx < nout; idx += blockDim.x) {
+    const int q = idx / m2, r = idx - q * m2, k = r >> 1, dd = r & 1;
+    const int pp = blockIdx.x * ppc + q;
+    if (pp >= prm.P) { pri[idx] = 0.f; continue; }
+    float acc = 0.f;
+    const float* Wq = Ws + q * m2 + dd;
+    for (int j = 0; j < m; ++j) acc = fmaf(As[j * m + k], Wq[2 * j], acc);
+    float pr = 0.f;
+    if (prm.add_prior) {
+      const float* Uq = Us + q * m2 + dd;
+      for (int j = 0; j < m; ++j) pr = fmaf(Ks[k * m + j], Uq[2 * j], pr);
+      acc += pr;
+      pr *= 0.5f * Us[idx];
+    }
+    pri[idx] = pr;
+    prm.gU[(long long)pp * prm.gU_stride + r] = prm.scale * acc;
+  }
+  if (INJ == INJ_LIK) {
+    __syncthreads();
+    if (tid < ppc) {
+      const int pp = blockIdx.x * ppc + tid;
+      if (pp < prm.P) {
+        float sx = 0.f, sy = 0.f, pr = 0.f;
+        for (int nn = 0; nn < N; ++nn) {
+          sx += red[(tid * N + nn) * 2 + 0];
+          sy += red[(tid * N + nn) * 2 + 1];
+        }
+        for (int j = 0; j < m2; ++j) pr += pri[tid * m2 + j];
+        const float2 ls = *reinterpret_cast<const float2*>(prm.logsn + (long long)pp * prm.logsn_stride);
+        const float ex = expf(-2.f * ls.x), ey = expf(-2.f * ls.y);
+        const float nt = (float)N * (float)prm.T;
+        prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
+        prm.sqerr[pp] = sx + sy;
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = prm.scale * (nt - sx * ex);
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = prm.scale * (nt - sy * ey);
+      }
+    }
+  }
+}
+
 // Thread -> (particle slot, trajectory, component).  Padding threads (past the CTA's pairs or past P) shadow a valid
 // pair so that every warp-wide shuffle is executed by all 32 lanes; they never write.
 struct PairIds {
@@ -301,7 +380,7 @@ __device__ __forceinline__ PairIds pair_ids(const NpdeKParams& prm) {
 template <int M, int METHOD>
 __global__ void __launch_bounds__(PairField<M>::MAX_THREADS) npde_pair_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
   extern __shared__ __align__(16) float smem[];
-  project_W(prm, smem, smem + prm.ppc * 2 * prm.m);
+  pair_stage_and_project(prm, smem, false);
   const PairIds id = pair_ids(prm);
   PairField<M> fld;
   fld.load(prm, smem + (prm.ppc + id.pl) * 2 * prm.m, id.d);
@@ -331,7 +410,7 @@ __global__ void __launch_bounds__(PairField<M>::MAX_THREADS) npde_pair_grad_kern
   for (int i = threadIdx.x; i <= prm.S; i += blockDim.x) sptr[i] = prm.S > 0 ? __ldg(prm.obs_ptr + i) : 1;
   if (INJ == INJ_LIK)
     for (int i = threadIdx.x; i < 2 * N * prm.T; i += blockDim.x) sY[i] = __ldg(prm.Y + i);
-  project_W(prm, smem, smem + prm.ppc * 2 * prm.m);
+  pair_stage_and_project(prm, smem, prm.add_prior != 0);
 
   const PairIds id = pair_ids(prm);
   const int d = id.d;
@@ -412,7 +491,7 @@ __global__ void __launch_bounds__(PairField<M>::MAX_THREADS) npde_pair_grad_kern
   if (prm.gy0 != nullptr && active) prm.gy0[2 * id.pair + d] = prm.scale * a;
 
   const float r2o = __shfl_xor_sync(FULL_MASK, r2, 1);
-  npde_epilogue<INJ>(prm, smem, fld, active, id.pl, id.n, id.pl * N + id.n, d, r2, r2o);
+  pair_epilogue<INJ>(prm, smem, fld, active, id.pl, id.n, d, r2, r2o);
 }
 
 }  // namespace bode

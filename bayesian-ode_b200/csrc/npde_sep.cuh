@@ -26,6 +26,7 @@ struct NpdeKParams {
   long long npairs;
   long long U_stride, logsn_stride, gU_stride, glogsn_stride;
   int stage_off;      // float offset in dynamic shared memory of the staged dt[S] | obs_ptr[S+1] | Y[N,T,2]
+  int a_off;          // pair kernels: float offset of the staged A[m,m] | Ksym[m,m]
   float reg, lik_w;   // MLP closure: lik_w * sum (X - x)^2 + reg * sum theta^2
   float *sol, *loss, *sqerr, *gU, *glogsn, *gy0;
 };
@@ -38,12 +39,32 @@ __device__ __forceinline__ float2 operator-(float2 a, float2 b) { return f2(a.x 
 __device__ __forceinline__ float2 operator*(float s, float2 a) { return f2(s * a.x, s * a.y); }
 __device__ __forceinline__ float2 fma2(float s, float2 a, float2 b) { return f2(fmaf(s, a.x, b.x), fmaf(s, a.y, b.y)); }
 
+// Packed FP32 pairs: sm_100a's FFMA2 (PTX fma.rn.f32x2) retires two FMAs per issue slot; ptxas folds a (x, x) pair
+// into a scalar-broadcast operand, so a broadcast costs no extra instruction.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void upk(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 fma2x(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ float hsum(f32x2 v) {
+  float lo, hi;
+  upk(v, lo, hi);
+  return lo + hi;
+}
+
 template <int MX, int MY>
 struct SepField {
   static constexpr int G = 1;              // lanes cooperating on one (particle, trajectory) pair
   static constexpr int MAX_THREADS = 256;
-  float2 W[MX][MY];
-  float2 gW[MX][MY];
+  f32x2 W[MX][MY];      // (W_ab0, W_ab1): both output components of one inducing point in one FFMA2 operand
+  f32x2 gW[MX][MY];
 
   static __device__ __forceinline__ void prologue(const NpdeKParams& prm, float* smem);
   static __device__ __forceinline__ float2 lik_weight(const NpdeKParams& prm, int p) {
@@ -60,86 +81,81 @@ struct SepField {
 #pragma unroll
     for (int a = 0; a < MX; ++a)
 #pragma unroll
-      for (int b = 0; b < MY; ++b) W[a][b] = f2(Wp[2 * (a * MY + b)], Wp[2 * (a * MY + b) + 1]);
+      for (int b = 0; b < MY; ++b) W[a][b] = pk(Wp[2 * (a * MY + b)], Wp[2 * (a * MY + b) + 1]);
   }
   __device__ __forceinline__ void store_gW(const NpdeKParams&, float* gp, int) const {
 #pragma unroll
     for (int a = 0; a < MX; ++a)
 #pragma unroll
-      for (int b = 0; b < MY; ++b) {
-        gp[2 * (a * MY + b)] = gW[a][b].x;
-        gp[2 * (a * MY + b) + 1] = gW[a][b].y;
-      }
+      for (int b = 0; b < MY; ++b) upk(gW[a][b], gp[2 * (a * MY + b)], gp[2 * (a * MY + b) + 1]);
   }
 
   __device__ __forceinline__ void zero_grad() {
 #pragma unroll
     for (int a = 0; a < MX; ++a)
 #pragma unroll
-      for (int b = 0; b < MY; ++b) gW[a][b] = f2(0.f, 0.f);
+      for (int b = 0; b < MY; ++b) gW[a][b] = pk(0.f, 0.f);
   }
 
   // f(x) = sum_ab kx_a ky_b W_ab
   __device__ __forceinline__ float2 eval(const NpdeKParams& prm, float2 x) const {
-    const float u0 = prm.c0 * x.x, u1 = prm.c1 * x.y;
     float ky[MY];
 #pragma unroll
     for (int b = 0; b < MY; ++b) {
-      const float d = u1 - prm.gys[b];
+      const float d = fmaf(prm.c1, x.y, -prm.gys[b]);
       ky[b] = ex2(-d * d);
     }
-    float2 f = f2(0.f, 0.f);
+    f32x2 f = pk(0.f, 0.f);
 #pragma unroll
     for (int a = 0; a < MX; ++a) {
-      const float d = u0 - prm.gxs[a];
+      const float d = fmaf(prm.c0, x.x, -prm.gxs[a]);
       const float kx = ex2(-d * d);
-      float2 t = f2(0.f, 0.f);
+      f32x2 t = pk(0.f, 0.f);
 #pragma unroll
-      for (int b = 0; b < MY; ++b) t = fma2(ky[b], W[a][b], t);
-      f = fma2(kx, t, f);
+      for (int b = 0; b < MY; ++b) t = fma2x(W[a][b], pk(ky[b], ky[b]), t);
+      f = fma2x(t, pk(kx, kx), f);
     }
-    return f;
+    float2 r;
+    upk(f, r.x, r.y);
+    return r;
   }
 
   // Returns J(x)^T a and accumulates gW += wg * kappa(x) (x) a.   If WITH_F also returns f(x).
+  // The two Jacobian columns  df/dx0 = -k0 sum_a (kx_a dx_a) T_a,  df/dx1 = -k1 sum_a kx_a T'_a  with
+  // T_a = sum_b ky_b W_ab,  T'_a = sum_b (ky_b dy_b) W_ab  do not depend on the adjoint: only four FMAs sit on the serial chain.
   template <bool WITH_F>
   __device__ __forceinline__ float2 vjp(const NpdeKParams& prm, float2 x, float2 a, float wg, float2* fout) {
-    const float u0 = prm.c0 * x.x, u1 = prm.c1 * x.y;
-    float ky[MY], dy[MY], ub[MY];
+    float ky[MY], kdy[MY];
 #pragma unroll
     for (int b = 0; b < MY; ++b) {
-      dy[b] = u1 - prm.gys[b];
-      ky[b] = ex2(-dy[b] * dy[b]);
-      ub[b] = 0.f;
+      const float d = fmaf(prm.c1, x.y, -prm.gys[b]);
+      ky[b] = ex2(-d * d);
+      kdy[b] = ky[b] * d;
     }
-    const float aw0 = a.x * wg, aw1 = a.y * wg;
-    float sx = 0.f;
-    float2 f = f2(0.f, 0.f);
+    const f32x2 aw = pk(a.x * wg, a.y * wg);
+    f32x2 jx = pk(0.f, 0.f), jy = pk(0.f, 0.f), f = pk(0.f, 0.f);
 #pragma unroll
     for (int ia = 0; ia < MX; ++ia) {
-      const float dx = u0 - prm.gxs[ia];
+      const float dx = fmaf(prm.c0, x.x, -prm.gxs[ia]);
       const float kx = ex2(-dx * dx);
-      const float ka0 = kx * aw0, ka1 = kx * aw1;
-      float s = 0.f;
-      float2 t = f2(0.f, 0.f);
+      const float kdx = kx * dx;
+      const f32x2 kaw = fma2x(aw, pk(kx, kx), pk(0.f, 0.f));
+      f32x2 t = pk(0.f, 0.f), tp = pk(0.f, 0.f);
 #pragma unroll
       for (int b = 0; b < MY; ++b) {
-        const float2 w = W[ia][b];
-        const float c = fmaf(a.y, w.y, a.x * w.x);
-        s = fmaf(c, ky[b], s);
-        ub[b] = fmaf(c, kx, ub[b]);
-        gW[ia][b].x = fmaf(ka0, ky[b], gW[ia][b].x);
-        gW[ia][b].y = fmaf(ka1, ky[b], gW[ia][b].y);
-        if (WITH_F) t = fma2(ky[b], w, t);
+        t = fma2x(W[ia][b], pk(ky[b], ky[b]), t);
+        tp = fma2x(W[ia][b], pk(kdy[b], kdy[b]), tp);
+        gW[ia][b] = fma2x(kaw, pk(ky[b], ky[b]), gW[ia][b]);
       }
-      sx = fmaf(kx * dx, s, sx);
-      if (WITH_F) f = fma2(kx, t, f);
+      jx = fma2x(t, pk(kdx, kdx), jx);
+      jy = fma2x(tp, pk(kx, kx), jy);
+      if (WITH_F) f = fma2x(t, pk(kx, kx), f);
     }
-    float sy = 0.f;
-#pragma unroll
-    for (int b = 0; b < MY; ++b) sy = fmaf(ky[b] * dy[b], ub[b], sy);
-    if (WITH_F) *fout = f;
-    return f2(-prm.k0 * sx, -prm.k1 * sy);
+    if (WITH_F) upk(f, fout->x, fout->y);
+    float jx0, jx1, jy0, jy1;
+    upk(jx, jx0, jx1);
+    upk(jy, jy0, jy1);
+    return f2(-prm.k0 * fmaf(a.y, jx1, a.x * jx0), -prm.k1 * fmaf(a.y, jy1, a.x * jy0));
   }
 };
 

@@ -129,6 +129,9 @@ int bode_npde_dopri5_nlp_grad(const bode_npde_field* f, const bode_dopri5_opts* 
                               bode_stream_t stream);
 
 /* scratch floats needed by the gradient entry points for (P particles, N trajectories) */
+/* Kernel choice for square 3x3..6x6 inducing grids (fixed-step solvers): 0 = automatic, 1 = one thread per (particle,
+ * trajectory) pair, 2 = two component-split lanes per pair.  Returns the previous setting. */
+int bode_npde_set_lanes_per_pair(int32_t lanes);
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
 
 /* odeint(func=KernelRegression, y0, t, method in {euler,midpoint,rk4}) forward

@@ -21,7 +21,9 @@ def main():
     ap.add_argument("--method", default="rk4")
     ap.add_argument("--mode", default="discrete")
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--lanes", type=int, default=0)
     args = ap.parse_args()
+    bode._lib.load().bode_npde_set_lanes_per_pair(args.lanes)
     data = npde.make_vdp_data(seed=0, T=args.T)
     Z = npde.inducing_grid(data["Y"], args.M)
     U0 = npde.gradient_matching_init(data["Y"], data["t"].astype(np.float64), Z, 1.0, 0.75)
