@@ -510,7 +510,7 @@ extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t 
   Ws w = carve(workspace, n_rows, n_cols, d);
   BODE_CUDA(cudaMemsetAsync(w.hist, 0, 2 * 2048 * sizeof(unsigned long long), (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(w.st, 0, 256, (cudaStream_t)stream));
-  BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long), (cudaStream_t)stream));
+  BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, 2 * (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long) + 512, (cudaStream_t)stream));
   return BODE_OK;
 }
 

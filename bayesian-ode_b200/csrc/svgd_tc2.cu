@@ -278,30 +278,22 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
   if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
-// ---------------------------------------------------------------- median from the window table (one CTA)
-// Thread t owns the 33 consecutive bins [33 t, 33 t + 33): local sums, one block-wide scan, then the (at most two) threads whose
-// range holds a middle rank walk their own bins.
-__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table) {
-  constexpr int PER = (WIN_TABLE + 1023) / 1024;                      // 33
-  __shared__ unsigned long long wsum[32];
-  __shared__ unsigned int found[2];
-  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const bool armed = st->win_valid != 0;
-  const unsigned long long* mine = table + tid * PER;
-  unsigned long long sum = 0;
-  if (armed) {
-#pragma unroll
-    for (int i = 0; i < PER; ++i)
-      if (tid * PER + i < (int)WIN_TABLE) sum += mine[i];
-  }
-  unsigned long long incl = sum;
+// ---------------------------------------------------------------- median from the window table
+// 33 CTAs x 1024 threads, one bin per thread (a single CTA pulling the 262 KB table through one SM took 20 us): every CTA moves
+// its bins to a scratch copy, clears them for the next call and publishes its segment total; the last CTA to finish (ticket)
+// scans the 33 totals and then only the one or two segments that hold a middle rank.
+constexpr int WSEL_CTAS = (WIN_TABLE + 1 + 1023) / 1024;               // bins + the "below" counter
+
+__device__ __forceinline__ unsigned long long block_incl_scan_u64(unsigned long long v, unsigned long long* wsum, unsigned long long* total) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  unsigned long long incl = v;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
     const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
     if (lane >= o) incl += t;
   }
+  __syncthreads();                       // wsum may still be read from a previous call
   if (lane == 31) wsum[wid] = incl;
-  if (tid < 2) found[tid] = 0xffffffffu;
   __syncthreads();
   if (wid == 0) {
     unsigned long long w = wsum[lane];
@@ -313,19 +305,59 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
     wsum[lane] = w;
   }
   __syncthreads();
-  const unsigned long long below = armed ? table[WIN_TABLE] : 0ull;
-  unsigned long long excl = below + incl - sum + (wid ? wsum[wid - 1] : 0ull);     // entries strictly below this thread's first bin
-  const unsigned long long r0 = st->rank[0], r1 = st->rank[1];
-  if (sum && ((r0 >= excl && r0 < excl + sum) || (r1 >= excl && r1 < excl + sum))) {
-    for (int i = 0; i < PER; ++i) {
-      const int b = tid * PER + i;
-      const unsigned long long c = b < (int)WIN_TABLE ? mine[i] : 0ull;
-      if (c) {
-        if (r0 >= excl && r0 < excl + c) found[0] = b;
-        if (r1 >= excl && r1 < excl + c) found[1] = b;
-      }
-      excl += c;
+  if (total) *total = wsum[31];
+  return incl + (wid ? wsum[wid - 1] : 0ull);
+}
+
+__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table, unsigned long long* scratch) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long segex[WSEL_CTAS + 1];
+  __shared__ unsigned int found[2];
+  __shared__ int is_last;
+  unsigned long long* segtot = scratch + WIN_TABLE + 1;                // [WSEL_CTAS]
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(segtot + WSEL_CTAS);
+  const int tid = threadIdx.x, c = blockIdx.x;
+  const int b = c * 1024 + tid;
+  const bool armed = st->win_valid != 0;
+  unsigned long long v = 0;
+  if (b <= (int)WIN_TABLE) {
+    const unsigned long long raw = table[b];
+    scratch[b] = raw;
+    table[b] = 0ull;                                                   // ready for the next call
+    if (armed && b < (int)WIN_TABLE) v = raw;
+  }
+  unsigned long long tot;
+  block_incl_scan_u64(v, wsum, &tot);
+  if (tid == 0) {
+    segtot[c] = tot;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  if (tid == 0) {
+    *ticket = 0u;
+    unsigned long long run = armed ? scratch[WIN_TABLE] : 0ull;       // entries below the window
+    for (int i = 0; i < WSEL_CTAS; ++i) {
+      segex[i] = run;
+      run += segtot[i];
     }
+    segex[WSEL_CTAS] = run;
+    found[0] = found[1] = 0xffffffffu;
+  }
+  __syncthreads();
+  const unsigned long long r[2] = {st->rank[0], st->rank[1]};
+  for (int which = 0; which < 2; ++which) {
+    int seg = -1;
+    for (int i = 0; i < WSEL_CTAS; ++i)
+      if (r[which] >= segex[i] && r[which] < segex[i + 1]) seg = i;   // uniform over the CTA
+    if (!armed || seg < 0) continue;
+    const int bb = seg * 1024 + tid;
+    const unsigned long long cnt = bb < (int)WIN_TABLE ? scratch[bb] : 0ull;
+    const unsigned long long incl = block_incl_scan_u64(cnt, wsum, nullptr);
+    const unsigned long long excl = segex[seg] + incl - cnt;
+    if (cnt && r[which] >= excl && r[which] < excl + cnt) found[which] = bb;
   }
   __syncthreads();
   if (tid == 0) {
@@ -336,7 +368,6 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
     }
     st->hit = hit ? 1u : 0u;
   }
-  for (int b = tid; b <= (int)WIN_TABLE; b += 1024) table[b] = 0ull;      // ready for the next call
 }
 
 // ---------------------------------------------------------------- phi partials
@@ -514,7 +545,7 @@ size_t svgd_tc2_operand_bytes(int nr, int nc) {
   b += 2 * nrp * KP2 * 4 + nrp * 4;             // row operands hi/lo + norms
   b += 2 * ncp * KP2 * 4 + ncp * 4;             // column operands hi/lo + norms
   b += 2 * ncp * NF2 * 4;                       // V^T hi/lo
-  b += (size_t)(WIN_TABLE + 1) * 8;             // window table + below counter
+  b += 2 * (size_t)(WIN_TABLE + 1) * 8 + 512;   // window table + below counter, scratch copy + segment totals + ticket
   return b + 1024;
 }
 
@@ -530,13 +561,13 @@ Tc2Ops svgd_tc2_carve(void* base, int nr, int nc) {
   o.XrH = (float*)take(nrp * KP2 * 4); o.XrL = (float*)take(nrp * KP2 * 4); o.nrm_r = (float*)take(nrp * 4);
   o.XcH = (float*)take(ncp * KP2 * 4); o.XcL = (float*)take(ncp * KP2 * 4); o.nrm_c = (float*)take(ncp * 4);
   o.VH = (float*)take(ncp * NF2 * 4); o.VL = (float*)take(ncp * NF2 * 4);
-  o.table = (unsigned long long*)take((size_t)(WIN_TABLE + 1) * 8);
+  o.table = (unsigned long long*)take(2 * (size_t)(WIN_TABLE + 1) * 8 + 512);
   return o;
 }
 size_t svgd_tc2_carved_bytes(int nr, int nc) {
   const size_t nrp = (size_t)(nr + BLK - 1) / BLK * BLK, ncp = (size_t)(nc + BLK - 1) / BLK * BLK;
   auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-  return 2 * al(nrp * KP2 * 4) + al(nrp * 4) + 2 * al(ncp * KP2 * 4) + al(ncp * 4) + 2 * al(ncp * NF2 * 4) + al((size_t)(WIN_TABLE + 1) * 8);
+  return 2 * al(nrp * KP2 * 4) + al(nrp * 4) + 2 * al(ncp * KP2 * 4) + al(ncp * 4) + 2 * al(ncp * NF2 * 4) + al(2 * (size_t)(WIN_TABLE + 1) * 8 + 512);
 }
 
 int svgd_tc2_supported(int d, int nc) { return d >= 1 && d <= 55 && (nc & 3) == 0 && nc >= 4; }
@@ -581,7 +612,7 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
 
 int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
-  window_select_kernel<<<1, 1024, 0, stream>>>(st, o.table);
+  window_select_kernel<<<WSEL_CTAS, 1024, 0, stream>>>(st, o.table, o.table + WIN_TABLE + 1);
   return check_cuda(cudaGetLastError(), "window select launch");
 }
 
