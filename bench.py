@@ -364,7 +364,17 @@ def run_b200(args, wl):
             k["peak"] = hbm_peak
         k["frac"] = k["achieved"] / k["peak"]
     dom = max(kernels, key=lambda k: k["ms"])
-    roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"], traffic=None,
+    # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+    # `ncu --set full` capture (profiles/traffic_r01_final.json, written by tools/ncu_summary.py); not measurable from here
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic_r01_final.json")
+    if os.path.exists(tpath):
+        tb = json.load(open(tpath)).get("bytes_per_launch", {})
+        key = "npde_pair_grad_kernel" if dom["bound"] == "fp32" else ("gram2_kernel" if "sqdist" in dom["name"] else "phi2_kernel")
+        for name, val in tb.items():
+            if name.startswith(key):
+                traffic = {"bytes_per_launch": val, "source": "profiles/traffic_r01_final.json (ncu --set full, P=4096 c3 launch)"}
+    roofline = dict(bound=dom["bound"], achieved=dom["achieved"], peak=dom["peak"], unit=dom["unit"], frac=dom["frac"], traffic=traffic,
                     kernel=dom["name"], kernel_ms=dom["ms"],
                     peak_source=("fp32 FMA-chain microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 figure)"
                                  if dom["bound"] == "fp32" else ("half of MEASURED_PEAKS.json bf16_tflops (tf32 dense rate); algorithmic flops, "
