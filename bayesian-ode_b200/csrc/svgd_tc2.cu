@@ -28,6 +28,7 @@ constexpr uint32_t VST_BYTES = PK2 * NF2 * 4; // 14336: one hi (or lo) V^T stage
 constexpr int NWORK = 512;                    // worker threads (16 warps: 4 per SM sub-partition); warp 16 is the control warp
 constexpr int NWARP = NWORK / 32;
 constexpr int NTHR = NWORK + 32;
+constexpr int NTHR_PHI = NWORK + 64;            // phi2: warp 16 issues the MMAs, warp 17 the TMA / bulk loads
 
 // ---------------------------------------------------------------- operand preparation
 // XH/XL[blk][kc][r/8][r%8][4] : K-major core matrices of the centred rows, zero padded to a multiple of 128 rows.
@@ -374,9 +375,7 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
 struct Phi2Smem {
   static constexpr uint32_t RAW = 0;                                   // 3 slots x [128][32] floats, TMA tile with 128-byte swizzle
   static constexpr uint32_t RAW_SLOT = BLK * PK2 * 4;                  // 16384 (1024-byte aligned)
-  static constexpr uint32_t K = RAW + 3 * RAW_SLOT;                    // 2 slots x (hi | lo) x [8 kc][16][8][4]
-  static constexpr uint32_t K_HALF = BLK * PK2 * 4;
-  static constexpr uint32_t V = K + 4 * K_HALF;                        // 3 slots x (hi | lo)
+  static constexpr uint32_t V = RAW + 3 * RAW_SLOT;                    // 3 slots x (hi | lo); the K tile (A operand) lives in TMEM
   static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[2], barV[3], barR[3], barK[2]
   static constexpr uint32_t TSLOT = BARS + 10 * 8;
   static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;                 // + slack to align the dynamic base to 1024 bytes
@@ -389,11 +388,27 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
                "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
                : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (one row per TMEM lane, K 32-bit columns) never touches shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(__float_as_uint(v[0])),
+               "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+               "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+               : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
+__global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
                                                        float* __restrict__ part) {
   extern __shared__ unsigned char sm_raw[];
@@ -412,7 +427,8 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
   const int s0 = blockIdx.y * per;
   const int nst = min(per, nst_all - s0);                              // stages of this CTA (may be <= 0)
 
-  if (warp == 0) tmem_alloc(tslot, 128);
+  // TMEM columns: [0,112) accumulator, [128 + 64 s, +32) K_hi and [+32, +64) K_lo of slot s
+  if (warp == 0) tmem_alloc(tslot, 256);
   if (tid == 0) {
     for (int i = 0; i < 2; ++i) mbar_init(barM + i, 1);
     for (int i = 0; i < 3; ++i) mbar_init(barV + i, 1);
@@ -424,11 +440,14 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
   tc_fence_after();
   const uint32_t tmem = *tslot;
   constexpr uint32_t idesc = idesc_tf32(BLK, NF2, 0, 0);
-  constexpr uint32_t A_LBO = BLK * 16, B_LBO = NF2 * 16, SBO = 128;
+  constexpr uint32_t B_LBO = NF2 * 16, SBO = 128;
 
   // No CTA-wide barrier inside the stage loop: the warps only meet through mbarriers, so a slow warp delays nobody but the MMA
   // that needs its rows.
-  if (warp == NWARP) {
+  if (warp == NWARP + 1) {
+    // ---------------- loader warp (lane 0): d2 tiles by 2-D TMA three stages ahead, V^T tiles by bulk copy two stages ahead.
+    // It only waits for slots to drain (barK: the workers consumed raw(t); barM: the MMAs that read V(t-1) retired), so the
+    // MMA-issuing thread never spends time on copies.
     if (lane == 0 && nst > 0) {
       auto load_v = [&](int t) {
         const int slot = t % 3;
@@ -450,27 +469,35 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
       load_raw(2);
       load_v(0);
       if (nst > 1) load_v(1);
-      // descriptors are built once: slots and K steps only add to the 14-bit start-address field (shared memory < 256 KB)
-      const uint64_t dK = smem_desc(smem_u32(sm + Phi2Smem::K), A_LBO, SBO), dV = smem_desc(smem_u32(sm + Phi2Smem::V), B_LBO, SBO);
-      constexpr uint64_t AK = (2 * A_LBO) >> 4, BK = (2 * B_LBO) >> 4;
       for (int t = 0; t < nst; ++t) {
-        mbar_wait(barK + (t & 1), (t >> 1) & 1);                       // K(t) written and fenced by every worker warp; raw(t) consumed
-        tc_fence_after();
-        mbar_wait(barV + (t % 3), (t / 3) & 1);
-        const uint64_t ah = dK + (uint64_t)((t & 1) * ((2 * Phi2Smem::K_HALF) >> 4)), al = ah + (Phi2Smem::K_HALF >> 4);
-        const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
-#pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, ah + ks * AK, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, ah + ks * AK, bl + ks * BK, idesc, 1u);
-#pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32(tmem, al + ks * AK, bh + ks * BK, idesc, 1u);
-        umma_commit(barM + (t & 1));
-        load_raw(t + 3);                                               // reuses the slot of raw(t)
-        if (t + 2 < nst) {                                             // V(t+2) reuses the slot of V(t-1): wait for stage t-1's MMAs
-          if (t >= 1) mbar_wait(barM + ((t - 1) & 1), ((t - 1) >> 1) & 1);
+        if (t + 3 < nst) {
+          mbar_wait(barK + (t & 1), (t >> 1) & 1);                     // raw(t) consumed by every worker warp
+          load_raw(t + 3);
+        }
+        if (t + 2 < nst) {
+          if (t >= 1) mbar_wait(barM + ((t - 1) & 1), ((t - 1) >> 1) & 1);   // V(t+2) reuses the slot of V(t-1)
           load_v(t + 2);
         }
+      }
+    }
+  } else if (warp == NWARP) {
+    // ---------------- MMA warp (lane 0): issue is back-pressured by the tensor core, so this loop runs at MMA speed
+    if (lane == 0 && nst > 0) {
+      const uint64_t dV = smem_desc(smem_u32(sm + Phi2Smem::V), B_LBO, SBO);
+      constexpr uint64_t BK = (2 * B_LBO) >> 4;
+      for (int t = 0; t < nst; ++t) {
+        mbar_wait(barK + (t & 1), (t >> 1) & 1);                       // K(t) written (TMEM) and fenced by every worker warp
+        tc_fence_after();
+        mbar_wait(barV + (t % 3), (t / 3) & 1);
+        const uint32_t ah = tmem + 128 + (t & 1) * 64, al = ah + 32;         // K_hi / K_lo of this stage in TMEM
+        const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
+#pragma unroll
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+#pragma unroll
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bl + ks * BK, idesc, 1u);
+#pragma unroll
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, al + ks * 8, bh + ks * BK, idesc, 1u);
+        umma_commit(barM + (t & 1));
       }
     }
   } else {
@@ -478,7 +505,7 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
     const int rl = tid & (BLK - 1), qd = tid >> 7;                     // tile row, which 8 of the stage's 32 columns
     const int row = r0 + rl;
     const bool rows_full = r0 + BLK <= nr;
-    const uint32_t koff0 = kmajor_off<BLK>(rl, 2 * qd), koff1 = kmajor_off<BLK>(rl, 2 * qd + 1);
+    const uint32_t klane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 128 + 8 * qd;   // this thread's row (TMEM lane), its 8 K columns
     // 128-byte swizzle of the TMA tile: 16-byte chunk c of row r sits at chunk c ^ (r % 8)
     const uint32_t roff0 = rl * 128 + (((2 * qd) ^ (rl & 7)) << 4), roff1 = rl * 128 + (((2 * qd + 1) ^ (rl & 7)) << 4);
     for (int t = 0; t < nst; ++t) {
@@ -500,13 +527,9 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
         mbar_wait(barM + (t & 1), ((t - 2) >> 1) & 1);
         tc_fence_after();
       }
-      unsigned char* kh = sm + Phi2Smem::K + (t & 1) * 2 * Phi2Smem::K_HALF;
-      unsigned char* kl = kh + Phi2Smem::K_HALF;
-      *reinterpret_cast<float4*>(kh + koff0) = make_float4(h[0], h[1], h[2], h[3]);
-      *reinterpret_cast<float4*>(kl + koff0) = make_float4(l[0], l[1], l[2], l[3]);
-      *reinterpret_cast<float4*>(kh + koff1) = make_float4(h[4], h[5], h[6], h[7]);
-      *reinterpret_cast<float4*>(kl + koff1) = make_float4(l[4], l[5], l[6], l[7]);
-      fence_async_smem();
+      tmem_st8(klane + (t & 1) * 64, h);
+      tmem_st8(klane + (t & 1) * 64 + 32, l);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(barK + (t & 1));
@@ -535,7 +558,7 @@ __global__ void __launch_bounds__(NTHR, 1) phi2_kernel(const __grid_constant__ C
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 128);
+  if (warp == 0) tmem_dealloc(tmem, 256);
 }
 
 // ---------------------------------------------------------------- host launchers (called from svgd.cu)
@@ -657,7 +680,7 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   const int js = split_for(nrb, nst, sms);
   *jsplit_out = js;
   dim3 grid(nrb, js);
-  phi2_kernel<<<grid, NTHR, Phi2Smem::TOTAL, stream>>>(tm, nr, nc, o.VH, o.VL, d, gam, js, part);
+  phi2_kernel<<<grid, NTHR_PHI, Phi2Smem::TOTAL, stream>>>(tm, nr, nc, o.VH, o.VL, d, gam, js, part);
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 
