@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(1024) select_digit_kernel(SelState* st, unsign
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
 }
 
+__device__ __forceinline__ void gamma_dev(SelState* st, int n, float sigma_fixed, int arm_window, float* out);
+
 // Single-rank fallback in ONE cooperative launch: when the median window missed (first call, large step) the three radix
 // passes run back to back with grid-wide barriers; when it hit, every CTA returns at once, so a captured CUDA graph pays one
 // near-empty launch instead of seven.  1024 threads per CTA (the select scan needs them), grid = co-resident CTAs.
@@ -296,12 +298,16 @@ __device__ __forceinline__ void select_digit_dev(SelState* st, unsigned long lon
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
 }
 
-__global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __restrict__ D2, long long n, SelState* st, unsigned long long* hist) {
+__global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __restrict__ D2, long long n, SelState* st, unsigned long long* hist,
+                                                              int n_total, int arm_window, float* med_gamma) {
   __shared__ unsigned int sh[2 * 2048];
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned int newp[2];
   __shared__ unsigned long long newr[2];
-  if (st->hit) return;                               // uniform over the grid: written before this launch
+  if (st->hit) {                                     // uniform over the grid: written before this launch
+    if (med_gamma && blockIdx.x == 0 && threadIdx.x == 0) gamma_dev(st, n_total, 0.f, arm_window, med_gamma);
+    return;
+  }
   cooperative_groups::grid_group grid = cooperative_groups::this_grid();
   const int sh_[3] = {20, 9, 0}, nb_[3] = {11, 11, 9};
   for (int pass = 0; pass < 3; ++pass) {
@@ -314,10 +320,11 @@ __global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __res
     __threadfence();
     grid.sync();
   }
+  if (med_gamma && blockIdx.x == 0 && threadIdx.x == 0) gamma_dev(st, n_total, 0.f, arm_window, med_gamma);
 }
 
 // out[0] = median, out[1] = gamma   (stein.py:25-31)
-__global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_window, float* out) {
+__device__ __forceinline__ void gamma_dev(SelState* st, int n, float sigma_fixed, int arm_window, float* out) {
   const float a = __uint_as_float(st->prefix[0]), b = __uint_as_float(st->prefix[1]);
   // arm the window of the next call around the lower middle element just selected (svgd_state.cuh)
   if (arm_window) {
@@ -331,6 +338,7 @@ __global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_win
   out[0] = med;
   out[1] = (float)(1.0 / (1e-8 + 2.0 * s2));
 }
+__global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_window, float* out) { gamma_dev(st, n, sigma_fixed, arm_window, out); }
 
 // ---------------------------------------------------------------- phi partials: K[rows, jslice] @ [S | X | 1]
 // CTA = 64 rows x F features (F = 16*FT >= 2d+1; the trailing ones column yields the row sums), 128 threads, each an
@@ -571,8 +579,10 @@ extern "C" int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_co
 }
 
 /* Single-rank fallback of the exact median: the three radix passes in one cooperative launch (returns immediately when
- * bode_svgd_window_select resolved the median).  Multi-rank callers keep the per-pass calls with their all-reduces. */
-extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+ * bode_svgd_window_select resolved the median).  With med_gamma != NULL the launch also does bode_svgd_gamma's work for the
+ * median heuristic (median -> gamma, next window armed).  Multi-rank callers keep the per-pass calls with their all-reduces. */
+extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, int32_t n_total, float* med_gamma,
+                                        bode_stream_t stream) {
   BODE_REQUIRE(workspace, "null workspace");
   Ws w = carve(workspace, n_rows, n_cols, d);
   static int grid_blocks = 0;
@@ -588,7 +598,10 @@ extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t 
   long long n = (long long)n_rows * n_cols;
   SelState* stp = w.st;
   unsigned long long* hist = w.hist;
-  void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist};
+  int ntot = n_total;
+  int arm = (g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
+  float* mg = med_gamma;
+  void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist, (void*)&ntot, (void*)&arm, (void*)&mg};
   BODE_CUDA(cudaLaunchCooperativeKernel((const void*)radix_fallback_kernel, dim3(grid_blocks), dim3(1024), args, 0, (cudaStream_t)stream));
   return BODE_OK;
 }

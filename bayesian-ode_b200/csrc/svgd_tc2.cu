@@ -10,8 +10,8 @@
 //   phi2_kernel                     part[i,:] = sum_j 2^(-g d2_ij) [ -grad_j | xc_j | 1 ]   (stein.py:75-86).  d2 tiles arrive
 //                                   by cp.async three stages ahead, V^T tiles by bulk copy, the exp/split of stage t runs
 //                                   under the MMAs of stage t-1.
-// A seventeenth "control" warp issues every bulk copy and MMA; warps 0-15 (four per SM sub-partition) own the TMEM lanes /
-// operand generation.
+// Warp 16 issues the MMAs (its issue loop is back-pressured by the tensor core), warp 17 the bulk / TMA copies; warps 0-15 (four per
+// SM sub-partition) own the TMEM lanes / operand generation.  Inside the tile loops the warps meet only through mbarriers.
 #include "tc_ptx.cuh"
 #include "svgd_state.cuh"
 #include <cuda.h>
@@ -27,8 +27,11 @@ constexpr int PK2 = 32;                       // j per phi stage
 constexpr uint32_t VST_BYTES = PK2 * NF2 * 4; // 14336: one hi (or lo) V^T stage
 constexpr int NWORK = 512;                    // worker threads (16 warps: 4 per SM sub-partition); warp 16 is the control warp
 constexpr int NWARP = NWORK / 32;
-constexpr int NTHR = NWORK + 32;
-constexpr int NTHR_PHI = NWORK + 64;            // phi2: warp 16 issues the MMAs, warp 17 the TMA / bulk loads
+constexpr int NTHR_PHI = NWORK + 64;            // warp 16 issues the MMAs, warp 17 the TMA / bulk loads
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
 // ---------------------------------------------------------------- operand preparation
 // XH/XL[blk][kc][r/8][r%8][4] : K-major core matrices of the centred rows, zero padded to a multiple of 128 rows.
@@ -139,12 +142,12 @@ struct Gram2Smem {
   static constexpr uint32_t B = 2 * BLK_BYTES;                      // 2 slots x (hi | lo)
   static constexpr uint32_t STAGE = B + 4 * BLK_BYTES;              // per warp [32][20] floats (16 columns at a time)
   static constexpr uint32_t NCS = STAGE + NWARP * 32 * 20 * 4;      // per warp 32 column norms
-  static constexpr uint32_t BARS = NCS + NWARP * 32 * 4;            // barA, barB[2], barS[2]
-  static constexpr uint32_t TSLOT = BARS + 5 * 8;
+  static constexpr uint32_t BARS = NCS + NWARP * 32 * 4;            // barA, barB[2], barS[2], barE[2]
+  static constexpr uint32_t TSLOT = BARS + 7 * 8;
   static constexpr uint32_t TOTAL = TSLOT + 16;
 };
 
-__global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict__ XrH, const float* __restrict__ XrL,
+__global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restrict__ XrH, const float* __restrict__ XrL,
                                                         const float* __restrict__ nrm_r, int nr, int row_offset,
                                                         const float* __restrict__ XcH, const float* __restrict__ XcL,
                                                         const float* __restrict__ nrm_c, int nc, int tiles_per_cta,
@@ -154,7 +157,8 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Gram2Smem::BARS);
   uint64_t* barA = bars;
   uint64_t* barB = bars + 1;
-  uint64_t* barS = bars + 3;
+  uint64_t* barS = bars + 3;      // MMAs of a tile retired: accumulator readable, B slot free
+  uint64_t* barE = bars + 5;      // all 16 worker warps have pulled the accumulator of a tile into registers (count NWARP)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + Gram2Smem::TSLOT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rb = blockIdx.y;
@@ -170,6 +174,8 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
     mbar_init(barB + 1, 1);
     mbar_init(barS + 0, 1);
     mbar_init(barS + 1, 1);
+    mbar_init(barE + 0, NWARP);
+    mbar_init(barE + 1, NWARP);
   }
   tc_fence_before();
   __syncthreads();
@@ -178,9 +184,11 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
   constexpr uint32_t idesc = idesc_tf32(BLK, BLK, 0, 0);
   constexpr uint32_t LBO = BLK * 16, SBO = 128;
 
-  if (warp == NWARP) {
-    // ---------------- control warp: bulk copies + MMA issue (lane 0)
-    auto load_b = [&](int t) {
+  // No CTA-wide barrier in the tile loop: the MMA thread, the loader thread and the 16 epilogue warps meet only through mbarriers.
+  if (warp == NWARP + 1) {
+    // ---------------- loader warp (lane 0): A once, B tiles two ahead; a B slot is free when the MMAs that read it retired
+    if (lane == 0) {
+      auto load_b = [&](int t) {
         const int slot = t & 1;
         unsigned char* dst = sm + Gram2Smem::B + slot * 2 * BLK_BYTES;
         const long long src = (long long)(ct0 + t) * (BLK_BYTES / 4);
@@ -188,14 +196,30 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
         bulk_g2s(dst, XcH + src, BLK_BYTES, barB + slot);
         bulk_g2s(dst + BLK_BYTES, XcL + src, BLK_BYTES, barB + slot);
       };
-      // descriptors are built once: a K step only adds (2 LBO) >> 4 to the 14-bit start-address field
+      mbar_expect_tx(barA, 2 * BLK_BYTES);
+      bulk_g2s(sm + Gram2Smem::A, XrH + (long long)rb * (BLK_BYTES / 4), BLK_BYTES, barA);
+      bulk_g2s(sm + Gram2Smem::A + BLK_BYTES, XrL + (long long)rb * (BLK_BYTES / 4), BLK_BYTES, barA);
+      load_b(0);
+      if (nt > 1) load_b(1);
+      for (int t = 0; t + 2 < nt; ++t) {
+        mbar_wait(barS + (t & 1), (t >> 1) & 1);
+        load_b(t + 2);
+      }
+    }
+  } else if (warp == NWARP) {
+    // ---------------- MMA warp (lane 0): 21 MMAs per tile into accumulator t & 1, free once every worker warp has read tile t-2
+    if (lane == 0) {
       const uint64_t dAh = smem_desc(smem_u32(sm + Gram2Smem::A), LBO, SBO), dAl = smem_desc(smem_u32(sm + Gram2Smem::A) + BLK_BYTES, LBO, SBO);
       const uint64_t dB0h = smem_desc(smem_u32(sm + Gram2Smem::B), LBO, SBO), dB0l = smem_desc(smem_u32(sm + Gram2Smem::B) + BLK_BYTES, LBO, SBO);
       const uint64_t dB1h = smem_desc(smem_u32(sm + Gram2Smem::B) + 2 * BLK_BYTES, LBO, SBO),
                      dB1l = smem_desc(smem_u32(sm + Gram2Smem::B) + 3 * BLK_BYTES, LBO, SBO);
-      constexpr uint64_t KSTEP = (2 * LBO) >> 4;
-      auto issue = [&](int t) {
+      constexpr uint64_t KSTEP = (2 * LBO) >> 4;       // a K step only adds to the 14-bit start-address field
+      mbar_wait(barA, 0);
+      for (int t = 0; t < nt; ++t) {
         const int slot = t & 1;
+        mbar_wait(barB + slot, (t >> 1) & 1);
+        if (t >= 2) mbar_wait(barE + slot, ((t - 2) >> 1) & 1);
+        tc_fence_after();
         const uint64_t bh = slot ? dB1h : dB0h, bl = slot ? dB1l : dB0l;
         const uint32_t dst = tmem + slot * BLK;
 #pragma unroll
@@ -205,33 +229,7 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
 #pragma unroll
         for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAl + ks * KSTEP, bh + ks * KSTEP, idesc, 1u);
         umma_commit(barS + slot);
-      };
-    if (lane == 0) {
-      mbar_expect_tx(barA, 2 * BLK_BYTES);
-      bulk_g2s(sm + Gram2Smem::A, XrH + (long long)rb * (BLK_BYTES / 4), BLK_BYTES, barA);
-      bulk_g2s(sm + Gram2Smem::A + BLK_BYTES, XrL + (long long)rb * (BLK_BYTES / 4), BLK_BYTES, barA);
-      load_b(0);
-      if (nt > 1) load_b(1);
-      mbar_wait(barA, 0);
-      mbar_wait(barB + 0, 0);
-      tc_fence_after();
-      issue(0);
-    }
-    __syncwarp();
-    for (int t = 0; t < nt; ++t) {
-      if (lane == 0) {
-        if (t + 1 < nt) {                       // S[(t+1)&1] was released by the barrier that ended iteration t-1
-          mbar_wait(barB + ((t + 1) & 1), ((t + 1) >> 1) & 1);
-          tc_fence_after();
-          issue(t + 1);
-        }
-        mbar_wait(barS + (t & 1), (t >> 1) & 1);            // tile t's MMAs are done: its B slot is free
-        if (t + 2 < nt) load_b(t + 2);
       }
-      __syncwarp();
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
     }
   } else {
     // ---------------- worker warps: epilogue.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (tile rows), columns 32 (w / 4) .. +31
@@ -257,7 +255,9 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
       tc_fence_after();
       float s[32];
       tmem_ld32(tmem + (t & 1) * BLK + cb + ((uint32_t)(32 * q) << 16), s);
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive(barE + (t & 1));                  // this warp's part of the accumulator is in registers
       const bool full = rb * BLK + BLK <= nr && c0 + BLK <= nc;
       const int dcol = row + row_offset - (c0 + cb);               // chunk-local column of the diagonal entry (if 0..31)
       const int dtile = rb * BLK + 32 * q + row_offset - (c0 + cb);  // warp-uniform: diagonal crosses this chunk iff -31 <= dtile <= 31
@@ -266,9 +266,6 @@ __global__ void __launch_bounds__(NTHR, 1) gram2_kernel(const float* __restrict_
       if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
       else if (full) gram2_chunk<true, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
       else gram2_chunk<false, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
-      tc_fence_before();
-      __syncthreads();
-      tc_fence_after();
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
@@ -403,9 +400,6 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
                "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
                : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
@@ -629,7 +623,7 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
   const int js = split_for(nrb, nct, sms);
   const int tiles_per = (nct + js - 1) / js;
   dim3 grid((nct + tiles_per - 1) / tiles_per, nrb);
-  gram2_kernel<<<grid, NTHR, Gram2Smem::TOTAL, stream>>>(rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st, o.table);
+  gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st, o.table);
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 

@@ -100,7 +100,8 @@ class _Workspace:
             _lib.check(lib.bode_svgd_window_select(nr, nc, d, w, _lib.stream_ptr()))
             if group is None:
                 # single rank: the radix passes are one cooperative launch that returns at once after a window hit
-                _lib.check(lib.bode_svgd_radix_fallback(nr, nc, d, w, _lib.stream_ptr()))
+                _lib.check(lib.bode_svgd_radix_fallback(nr, nc, d, w, n_total, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
+                return                                   # gamma and the next window were written by the same launch
             else:
                 radix_select_protocol(
                     lambda ps: _lib.check(lib.bode_svgd_hist_pass(ps, nr, nc, d, w, _lib.stream_ptr())),

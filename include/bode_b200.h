@@ -288,8 +288,11 @@ int bode_svgd_set_tensor_cores(int32_t on);
 int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, size_t workspace_bytes, bode_stream_t stream);
 int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, void** table_out, size_t* count_out);
 int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
-/* single-rank: the three radix passes fused into one cooperative launch (a no-op after a window hit) */
-int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
+/* single-rank: the three radix passes fused into one cooperative launch (a no-op after a window hit); with med_gamma != NULL it
+ * also writes med_gamma[0] = median, med_gamma[1] = gamma (median heuristic, n = n_total) and arms the next window, i.e. it
+ * replaces the bode_svgd_gamma call */
+int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, int32_t n_total, float* med_gamma,
+                             bode_stream_t stream);
 int bode_svgd_hist_pass(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
