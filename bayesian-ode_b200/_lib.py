@@ -89,6 +89,8 @@ SYMBOLS = {
     "bode_sampler_schedule": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _P]),
     "bode_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint32, _P]),
     "bode_npde_set_lanes_per_pair": (C.c_int, [C.c_int32]),
+    "bode_mala_accept": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_float,
+                                   C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "bode_svgd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     "bode_svgd_set_tensor_cores": (C.c_int, [C.c_int32]),
     "bode_svgd_sqdist": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, _P, C.c_size_t,

@@ -205,6 +205,54 @@ static int check_ptrs(const void* p, const void* g, long long n) {
   return BODE_OK;
 }
 
+
+// ---------------------------------------------------------------- MALA accept / reject (samplers/langevin.py:57-95)
+// One warp per chain: the two proposal terms are length-d sums (warp-shuffle reduction, fixed order), the decision is
+// accepted = isfinite(log_alpha) && log(u) < log_alpha (:88).  theta_prev == NULL reproduces the reference as it runs:
+// its saved state aliases the parameter it then updates in place (:45, :60), so both terms see theta_prev == theta_new and
+// a rejection restores nothing.  With theta_prev the textbook ratio is used and rejected chains are restored in place.
+__global__ void __launch_bounds__(256) mala_accept_kernel(const float* __restrict__ theta_prev, long long ld_prev, float* __restrict__ theta,
+                                                          long long ld_theta, const float* __restrict__ g_prev, long long ld_gp,
+                                                          const float* __restrict__ g_new, long long ld_gn,
+                                                          const float* __restrict__ loss_prev, const float* __restrict__ loss_new,
+                                                          const float* __restrict__ log_u, int P, int d, float lr, int restore,
+                                                          uint64_t seed, uint32_t step, float* __restrict__ log_alpha_out,
+                                                          int* __restrict__ accepted_out) {
+  const int chain = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+  if (chain >= P) return;
+  const float* tp = theta_prev ? theta_prev + (long long)chain * ld_prev : nullptr;
+  float* tn = theta + (long long)chain * ld_theta;
+  const float* gp = g_prev + (long long)chain * ld_gp;
+  const float* gn = g_new + (long long)chain * ld_gn;
+  float rev = 0.f, fwd = 0.f;
+  for (int k = lane; k < d; k += 32) {
+    const float dth = tp ? tp[k] - tn[k] : 0.f;         // theta_prev - theta_new
+    const float r = fmaf(lr, gn[k], dth), f = fmaf(lr, gp[k], -dth);
+    rev = fmaf(r, r, rev);
+    fwd = fmaf(f, f, fwd);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rev += __shfl_xor_sync(0xffffffffu, rev, o);
+    fwd += __shfl_xor_sync(0xffffffffu, fwd, o);
+  }
+  const float c = -1.f / (4.f * lr);
+  const float la = (loss_prev[chain] - loss_new[chain]) + c * rev - c * fwd;
+  float lu;
+  if (log_u) lu = log_u[chain];
+  else {
+    const Philox rng(seed);
+    lu = __logf(u01(rng((uint32_t)chain, step, 0x3a1au, 0x5eedu).x));
+  }
+  const bool acc = (fabsf(la) <= 3.4028234e38f) && (lu < la);
+  if (lane == 0) {
+    if (log_alpha_out) log_alpha_out[chain] = la;
+    accepted_out[chain] = acc ? 1 : 0;
+  }
+  if (!acc && restore && tp)
+    for (int k = lane; k < d; k += 32) tn[k] = tp[k];
+}
+
 }  // namespace bode
 
 using namespace bode;
@@ -256,6 +304,20 @@ extern "C" int bode_asghmc_step(float* p, const float* g, float* tau, float* gba
   if (st != BODE_OK) return st;
   sampler_kernel<K_ASGHMC><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   return check_cuda(cudaGetLastError(), "asghmc launch");
+}
+
+extern "C" int bode_mala_accept(const float* theta_prev, int64_t ld_prev, float* theta, int64_t ld_theta, const float* grad_prev,
+                                int64_t ld_gprev, const float* grad_new, int64_t ld_gnew, const float* loss_prev, const float* loss_new,
+                                const float* log_u, int32_t P, int32_t d, float lr, int32_t restore, uint64_t seed, uint32_t step,
+                                float* log_alpha, int32_t* accepted, bode_stream_t stream) {
+  BODE_REQUIRE(theta && grad_prev && grad_new && loss_prev && loss_new && accepted, "null pointer");
+  BODE_REQUIRE(P > 0 && d > 0 && lr > 0.f, "P, d, lr must be positive");
+  BODE_REQUIRE(ld_theta >= d && ld_gprev >= d && ld_gnew >= d && (!theta_prev || ld_prev >= d), "row strides must be >= d");
+  const long long threads = (long long)P * 32;
+  mala_accept_kernel<<<(int)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(theta_prev, ld_prev, theta, ld_theta, grad_prev, ld_gprev,
+                                                                                    grad_new, ld_gnew, loss_prev, loss_new, log_u, P, d, lr,
+                                                                                    restore, seed, step, log_alpha, accepted);
+  return check_cuda(cudaGetLastError(), "mala_accept launch");
 }
 
 extern "C" int bode_axpy(float* p, const float* x, float alpha, int64_t n, int32_t* status, const bode_sampler_ctl* ctl,

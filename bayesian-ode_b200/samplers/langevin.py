@@ -1,6 +1,6 @@
 """Langevin-family samplers (reference samplers/langevin.py) as fused CUDA updates over particle-batched chains.
 
-SGLD   langevin.py:151-258      pSGLD  langevin.py:422-567
+SGLD   langevin.py:151-258      pSGLD  langevin.py:422-567      MALA  langevin.py:13-149
 Constructor kwargs, ``step`` / ``get_lr`` / ``sample`` signatures and the lr schedule follow the reference; the extra
 ``noise=`` argument of ``step`` injects standard-normal draws (one tensor per parameter, param_groups order, or one
 flat [P, d] tensor) for bit-parity runs.
@@ -101,6 +101,102 @@ class SGLD(_LangevinBase):
                                           int(bool(group["add_noise"])), self.seed + k, self._step_index,
                                           _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
+
+
+class MALA(Sampler):
+    """langevin.py:13-149.  MALA(params, lr=, add_noise=True): Langevin proposal (the SGLD update, :27-54) followed by
+    ``accept_or_reject(closure)`` (:57-95), batched over the chain axis: every chain gets its own log-ratio and uniform draw.
+
+    ``exact=False`` (default) reproduces the reference as it runs: its saved state ``self.state[p]['data'] = p.data`` (:45) is a
+    view of the parameter the proposal then updates in place, so both proposal terms of the ratio see theta_prev == theta_new
+    and a rejection restores nothing (the accept flags are still recorded in the chain).  ``exact=True`` keeps a copy of the
+    state before the proposal, uses the textbook ratio and restores rejected chains.
+    ``step(noise=)`` / ``accept_or_reject(closure, log_u=)`` inject the draws for bit-parity runs.
+    """
+
+    def __init__(self, params, exact=False, **kwargs):
+        defaults = kwargs
+        if "add_noise" not in defaults:
+            defaults["add_noise"] = True
+        super().__init__(params, defaults)
+        if self._flat is None:
+            raise _lib.BodeError("MALA needs parameters laid out as column blocks of one theta[P, d] buffer")
+        self.exact = bool(exact)
+        self.logp = None
+        self.loss = None
+        P, d = self._flat.shape
+        dev = self._flat.device
+        self._prev = torch.empty_like(self._flat) if self.exact else None
+        self._gprev = torch.empty_like(self._flat)
+        self.log_alpha = torch.zeros(P, dtype=torch.float32, device=dev)
+        self.accepted = torch.ones(P, dtype=torch.int32, device=dev)
+
+    def step(self, noise=None):
+        """Proposal step (langevin.py:27-54): theta <- theta - lr (g + xi / sqrt(lr / 2)); remembers state and gradient."""
+        lib = _lib.load()
+        group = self.param_groups[0]
+        (p, g), = self._tensors_for_launch()
+        self._gprev.copy_(g)                                   # state['grad'] (:46)
+        if self.exact:
+            self._prev.copy_(p)
+        xi = _flat_noise(noise, self, 0, p)
+        _lib.check(lib.bode_sgld_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(xi), p.numel(), float(group["lr"]),
+                                      int(bool(group["add_noise"])), self.seed, self._step_index, _lib.ptr(self._status), None,
+                                      _lib.stream_ptr()))
+        self._after_step()
+
+    def accept_or_reject(self, closure, log_u=None):
+        """langevin.py:57-95.  Re-evaluates loss and gradient at the proposal, then one fused accept / reject launch.
+        Returns ``(params, accepted)`` like the reference, ``accepted`` being the per-chain int32 flags (device tensor)."""
+        lib = _lib.load()
+        group = self.param_groups[0]
+        if group["add_noise"]:
+            if hasattr(closure, "loss_and_grad_"):
+                new_loss = closure.loss_and_grad_()[0]
+            else:
+                self.zero_grad()
+                new_loss = closure()
+                self._backward(new_loss)
+            (p, g), = self._tensors_for_launch()
+            P, d = p.shape
+            lp = self.loss.detach().to(torch.float32).reshape(-1).expand(P).contiguous()
+            ln = new_loss.detach().to(torch.float32).reshape(-1).expand(P).contiguous()
+            lu = None if log_u is None else log_u.to(device=p.device, dtype=torch.float32).reshape(-1).expand(P).contiguous()
+            prev = self._prev if self.exact else None
+            _lib.check(lib.bode_mala_accept(_lib.ptr(prev), p.stride(0), _lib.ptr(p), p.stride(0), _lib.ptr(self._gprev),
+                                            self._gprev.stride(0), _lib.ptr(g), g.stride(0), _lib.ptr(lp), _lib.ptr(ln), _lib.ptr(lu),
+                                            P, d, float(group["lr"]), int(self.exact), self.seed + 0x9E37, self._step_index,
+                                            _lib.ptr(self.log_alpha), _lib.ptr(self.accepted), _lib.stream_ptr()))
+        else:
+            self.accepted.fill_(1)
+        params = [[q.detach().clone() for q in g_["params"]] for g_ in self.param_groups]
+        return params, self.accepted
+
+    def sample(self, closure, num_samples=1000, burn_in=100, print_loss=False, print_iters=False, arr_closure=None):
+        """langevin.py:98-149: loss + backward, proposal, accept / reject, record ``[params, accepted]``."""
+        chain = self.samples
+        fused = hasattr(closure, "loss_and_grad_")
+        if fused and self._grad_flat() is None and hasattr(closure.field, "bind_flat_grads"):
+            closure.field.bind_flat_grads()
+        for i in range(burn_in + num_samples):
+            if fused:
+                self.loss = closure.loss_and_grad_()[0].clone()
+            else:
+                self.zero_grad()
+                self.loss = closure()
+                self._backward(self.loss)
+            self.step()
+            params, acc = self.accept_or_reject(closure)
+            if i >= burn_in:
+                chain.append((params, acc.clone()))
+            if arr_closure is not None or (print_iters and print_loss):
+                sq_err_loss = closure(add_prior=False)
+                if arr_closure is not None:
+                    arr_closure(self.loss, sq_err_loss)
+            if print_iters:
+                print(("Burn-in iter {:04d} | accepted={}" if i < burn_in else "Sample iter {:04d} | accepted={}").format(
+                    i + 1 if i < burn_in else i - burn_in + 1, int(acc.sum())))
+        return chain
 
 
 class pSGLD(_LangevinBase):

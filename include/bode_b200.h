@@ -253,6 +253,18 @@ int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* hist_theta, fl
                      int32_t add_params, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
                      bode_stream_t stream);
 
+/* MALA.accept_or_reject, samplers/langevin.py:57-95, for P chains of d parameters (rows of theta).  The proposal itself is
+ * bode_sgld_step (langevin.py:27-54 is the SGLD update).  Per chain:
+ *   log_alpha = loss_prev - loss_new - |theta_prev - theta + lr grad_new|^2 / (4 lr) + |theta - theta_prev + lr grad_prev|^2 / (4 lr)
+ *   accepted  = isfinite(log_alpha) && log_u < log_alpha           (log_u = log of a U(0,1) draw; NULL: Philox (seed, step))
+ * theta_prev == NULL reproduces the reference as it runs: its saved state is a view of the parameter that the proposal then
+ * updates in place (:45, :60), so both proposal terms see theta_prev == theta and a rejection restores nothing.  With
+ * theta_prev != NULL the textbook ratio is used and, if restore != 0, rejected chains are copied back into theta. */
+int bode_mala_accept(const float* theta_prev, int64_t ld_prev, float* theta, int64_t ld_theta, const float* grad_prev,
+                     int64_t ld_gprev, const float* grad_new, int64_t ld_gnew, const float* loss_prev, const float* loss_new,
+                     const float* log_u, int32_t P, int32_t d, float lr, int32_t restore, uint64_t seed, uint32_t step,
+                     float* log_alpha, int32_t* accepted, bode_stream_t stream);
+
 /* p <- p + alpha x   (the SVGD particle update: the optimiser wrapped by stein.py:37-106 descends -phi) */
 int bode_axpy(float* p, const float* x, float alpha, int64_t n, int32_t* status, const bode_sampler_ctl* ctl,
               bode_stream_t stream);

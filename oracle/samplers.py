@@ -4,6 +4,7 @@
   psgld_step    samplers/langevin.py:457-500
   asghmc_step   samplers/hamiltonian.py:38-99
   get_lr        samplers/langevin.py:205-210
+  mala_*        samplers/langevin.py:27-95   (proposal = sgld_step; acceptance ratio incl. the aliased-state quirk)
   rbf_kernel    samplers/stein.py:18-34  (cdist^2, median heuristic over all n*n entries)
   svgd_phi      samplers/stein.py:75-86  (closed form of the autograd expression)
 ``xi`` arguments are standard-normal draws (the reference's Normal(0, std).sample() == std * randn bit for bit).
@@ -49,6 +50,23 @@ def asghmc_step(p, grad, st, lr, mom_decay, lambda_, burn_in, resample_mom_every
         mom = mom + xi * sigma
     st.update(tau=tau, g=g, v_hat=v_hat, momentum=mom)
     return p + mom, st
+
+
+def mala_log_alpha(theta_prev, theta_new, g_prev, g_new, loss_prev, loss_new, lr, aliased=True):
+    """samplers/langevin.py:57-86: log acceptance ratio of the Langevin proposal, one value per chain (leading axis).
+    ``aliased=True`` reproduces the reference as it actually runs: ``self.state[p]['data'] = p.data`` (:45) keeps a VIEW of
+    the parameter, which ``p.data.add_`` (:60) then updates in place, so both proposal terms see theta_prev == theta_new;
+    ``aliased=False`` is the textbook MALA ratio."""
+    tp = theta_new if aliased else theta_prev
+    P = theta_new.shape[0]
+    rev = ((tp - theta_new + lr * g_new) ** 2).reshape(P, -1).sum(1)
+    fwd = ((theta_new - tp + lr * g_prev) ** 2).reshape(P, -1).sum(1)
+    return loss_prev - loss_new + (-1.0 / (4 * lr)) * rev - (-1.0 / (4 * lr)) * fwd
+
+
+def mala_accept(log_alpha, log_u):
+    """langevin.py:88: accepted iff log_alpha is finite and log(u) < log_alpha."""
+    return np.isfinite(log_alpha) & (log_u < log_alpha)
 
 
 def sq_dists(X, Y):

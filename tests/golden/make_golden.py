@@ -469,7 +469,64 @@ def gen_hamcmc():
     save("hamcmc", **out)
 
 
+def gen_mala():
+    """MALA (langevin.py:13-149) on a quadratic negative log posterior over two parameter tensors: per step the state before,
+    the gradients, the replayed noise and log(u), the proposal, and the reference's own accept flag.  The generator also pins
+    the aliased-state quirk: the reference's decisions equal the oracle's ``aliased=True`` ratio and the parameters are never
+    restored after a rejection."""
+    from samplers.langevin import MALA
+    from oracle import samplers as osamp
+    gen = torch.Generator().manual_seed(77)
+    cA = 0.5 + 4.0 * torch.rand(6, 2, generator=gen)
+    cB = 0.5 + 4.0 * torch.rand(3, generator=gen)
+    A = torch.nn.Parameter(torch.randn(6, 2, generator=gen))
+    B = torch.nn.Parameter(torch.randn(3, generator=gen))
+    lr = 0.15
+
+    def closure(add_prior=True):
+        return 0.5 * (cA * A * A).sum() + 0.5 * (cB * B * B).sum() + 0.1 * (A.sum() * B.sum())
+
+    smp = MALA([A, B], lr=lr)
+    rec = {k: [] for k in ("A", "B", "gA", "gB", "xiA", "xiB", "logu", "A_new", "B_new", "gA_new", "gB_new", "loss", "loss_new", "accepted",
+                           "A_after", "B_after")}
+    n_rej = 0
+    for i in range(12):
+        smp.zero_grad()
+        smp.loss = closure()
+        smp.loss.backward()
+        rec["A"].append(A.data.clone()); rec["B"].append(B.data.clone())
+        rec["gA"].append(A.grad.clone()); rec["gB"].append(B.grad.clone())
+        rec["loss"].append(smp.loss.detach().clone())
+        torch.manual_seed(500 + i)
+        smp.step()
+        rec["A_new"].append(A.data.clone()); rec["B_new"].append(B.data.clone())
+        params, acc = smp.accept_or_reject(closure)
+        rec["accepted"].append(torch.tensor(int(acc)))
+        rec["A_after"].append(A.data.clone()); rec["B_after"].append(B.data.clone())
+        rec["gA_new"].append(A.grad.clone()); rec["gB_new"].append(B.grad.clone())
+        rec["loss_new"].append(closure().detach().clone())
+        torch.manual_seed(500 + i)
+        xa, xb = torch.randn(6, 2), torch.randn(3)
+        u = torch.rand(1)
+        rec["xiA"].append(xa); rec["xiB"].append(xb); rec["logu"].append(torch.log(u)[0])
+        # pin: proposal == SGLD update with the replayed noise; nothing restored; decision == aliased ratio
+        assert np.abs(osamp.sgld_step(rec["A"][-1].numpy(), rec["gA"][-1].numpy(), lr, xa.numpy()) - rec["A_new"][-1].numpy()).max() < 1e-13
+        assert torch.equal(rec["A_after"][-1], rec["A_new"][-1]) and torch.equal(rec["B_after"][-1], rec["B_new"][-1])
+        th0 = np.concatenate([rec["A"][-1].numpy().ravel(), rec["B"][-1].numpy().ravel()])[None]
+        th1 = np.concatenate([rec["A_new"][-1].numpy().ravel(), rec["B_new"][-1].numpy().ravel()])[None]
+        g0 = np.concatenate([rec["gA"][-1].numpy().ravel(), rec["gB"][-1].numpy().ravel()])[None]
+        g1 = np.concatenate([rec["gA_new"][-1].numpy().ravel(), rec["gB_new"][-1].numpy().ravel()])[None]
+        la = osamp.mala_log_alpha(th0, th1, g0, g1, np.array([float(rec["loss"][-1])]), np.array([float(rec["loss_new"][-1])]), lr, aliased=True)
+        assert bool(osamp.mala_accept(la, np.array([float(rec["logu"][-1])]))[0]) == bool(acc), ("aliased-state ratio does not explain the reference", i)
+        n_rej += int(not acc)
+    assert 0 < n_rej < 12, "want both accepted and rejected steps in the fixture (got %d rejections)" % n_rej
+    save("mala_steps", lr=lr, cA=cA, cB=cB, **{k: torch.stack(v) for k, v in rec.items()})
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "mala":
+        gen_mala()
+        sys.exit(0)
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
     gen_npde(data, 5, 4, "npde_m5")
@@ -480,3 +537,4 @@ if __name__ == "__main__":
     gen_mlp(data)
     gen_dopri5(data)
     gen_hamcmc()
+    gen_mala()

@@ -71,3 +71,23 @@ def test_hamcmc_oracle_matches_reference_run():
             new = orc.step(g["grad"][i], float(g["lr"][i]), g["xi"][i])
         assert relerr(new, g["theta"][i + 1]) < 1e-10, i
     assert len(orc.s) == int(g["n_pairs"])
+
+
+def test_mala_oracle_explains_reference_decisions():
+    """langevin.py:57-95: the oracle's aliased-state ratio reproduces every accept/reject decision of the reference run in the
+    fixture; the textbook ratio (aliased=False) does not (that is the quirk the fixture pins)."""
+    g = load_golden("mala_steps")
+    lr = float(g["lr"])
+    flat = lambda a, b, i: np.concatenate([g[a][i].ravel(), g[b][i].ravel()])[None]
+    agree_aliased, agree_exact = 0, 0
+    for i in range(len(g["accepted"])):
+        args = (flat("A", "B", i), flat("A_new", "B_new", i), flat("gA", "gB", i), flat("gA_new", "gB_new", i),
+                np.array([g["loss"][i]]), np.array([g["loss_new"][i]]), lr)
+        lu = np.array([g["logu"][i]])
+        agree_aliased += bool(osamp.mala_accept(osamp.mala_log_alpha(*args, aliased=True), lu)[0]) == bool(g["accepted"][i])
+        agree_exact += bool(osamp.mala_accept(osamp.mala_log_alpha(*args, aliased=False), lu)[0]) == bool(g["accepted"][i])
+        # the proposal is the SGLD update with the replayed noise, and a rejection restores nothing
+        assert np.abs(osamp.sgld_step(g["A"][i], g["gA"][i], lr, g["xiA"][i]) - g["A_new"][i]).max() < 1e-13
+        assert np.array_equal(g["A_after"][i], g["A_new"][i]) and np.array_equal(g["B_after"][i], g["B_new"][i])
+    assert agree_aliased == len(g["accepted"])
+    assert agree_exact < len(g["accepted"])

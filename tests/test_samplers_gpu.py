@@ -292,3 +292,106 @@ def test_hamcmc_batched_chains_on_npde():
     assert len(chain) == 3 and len(logp) == 111
     assert bool(torch.isfinite(f.theta).all())
     assert smp._hs["meta"][:, 0].tolist() == [5, 5, 5, 5]
+
+
+def test_mala_matches_reference_run():
+    """samplers/langevin.py:13-149 against the fixture recorded from the reference: the batched MALA class replays the
+    reference chain (proposal noise and log u injected) and must reproduce every accept flag (selection logic: bit exact) and
+    the proposals (fp32 of an fp64 reference); the kernel's log-ratio matches the float64 oracle in both modes."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200.samplers import MALA
+    from oracle import samplers as osamp
+    g = load_golden("mala_steps")
+    lr = float(g["lr"])
+    cA, cB = torch.from_numpy(g["cA"]).float().cuda(), torch.from_numpy(g["cB"]).float().cuda()
+    P = 3                                                    # three identical chains: the batch axis must not mix them
+    theta = torch.zeros(P, 15, device="cuda")
+    A = torch.nn.Parameter(theta[:, :12].view(P, 6, 2))
+    B = torch.nn.Parameter(theta[:, 12:].view(P, 3))
+
+    def closure(add_prior=True):
+        return 0.5 * (cA * A * A).sum((1, 2)) + 0.5 * (cB * B * B).sum(1) + 0.1 * (A.sum((1, 2)) * B.sum(1))
+
+    smp = MALA([A, B], lr=lr)
+    for i in range(len(g["accepted"])):
+        with torch.no_grad():                                # every step starts from the reference's own state
+            A.copy_(torch.from_numpy(g["A"][i]).float().cuda().expand(P, 6, 2))
+            B.copy_(torch.from_numpy(g["B"][i]).float().cuda().expand(P, 3))
+        smp.zero_grad()
+        smp.loss = closure()
+        smp._backward(smp.loss)
+        assert relerr(A.grad[1].cpu().numpy(), g["gA"][i]) < 1e-5
+        xi = torch.from_numpy(np.concatenate([g["xiA"][i].ravel(), g["xiB"][i].ravel()])).float().cuda().expand(P, 15).contiguous()
+        smp.step(noise=xi)
+        assert relerr(A.detach()[2].cpu().numpy(), g["A_new"][i]) < 2e-6 and relerr(B.detach()[0].cpu().numpy(), g["B_new"][i]) < 2e-6
+        params, acc = smp.accept_or_reject(closure, log_u=torch.full((P,), float(g["logu"][i])))
+        assert acc.cpu().tolist() == [int(g["accepted"][i])] * P, i
+        assert relerr(A.detach()[0].cpu().numpy(), g["A_after"][i]) < 2e-6             # nothing restored (reference quirk)
+        flat = lambda a, b: np.concatenate([g[a][i].ravel(), g[b][i].ravel()])[None]
+        la = osamp.mala_log_alpha(flat("A", "B"), flat("A_new", "B_new"), flat("gA", "gB"), flat("gA_new", "gB_new"),
+                                  np.array([g["loss"][i]]), np.array([g["loss_new"][i]]), lr, aliased=True)
+        assert abs(float(smp.log_alpha[0]) - float(la[0])) < 2e-4 * max(1.0, abs(float(la[0])))
+
+    # textbook mode: ratio vs the oracle (aliased=False), rejected chains restored, accepted ones kept
+    lib = bode._lib.load()
+    rng = np.random.default_rng(3)
+    P, d = 257, 52
+    th0, th1 = rng.standard_normal((P, d)), None
+    g0, g1 = rng.standard_normal((P, d)), rng.standard_normal((P, d))
+    th1 = th0 - 0.05 * g0 + np.sqrt(0.1) * rng.standard_normal((P, d))
+    l0, l1 = rng.standard_normal(P) * 3, rng.standard_normal(P) * 3
+    lu = np.log(rng.uniform(size=P))
+    lu[:3] = [-np.inf, 0.0, -1e-30]
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).float().cuda()
+    t0, t1, G0, G1, L0, L1, LU = dev(th0), dev(th1), dev(g0), dev(g1), dev(l0), dev(l1), dev(lu)
+    la_out = torch.empty(P, device="cuda"); acc = torch.empty(P, dtype=torch.int32, device="cuda")
+    t1_in = t1.clone()
+    bode._lib.check(lib.bode_mala_accept(bode._lib.ptr(t0), d, bode._lib.ptr(t1), d, bode._lib.ptr(G0), d, bode._lib.ptr(G1), d,
+                                         bode._lib.ptr(L0), bode._lib.ptr(L1), bode._lib.ptr(LU), P, d, 0.05, 1, 0, 0,
+                                         bode._lib.ptr(la_out), bode._lib.ptr(acc), bode._lib.stream_ptr()))
+    f32 = lambda a: a.astype(np.float32).astype(np.float64)
+    la = osamp.mala_log_alpha(f32(th0), f32(th1), f32(g0), f32(g1), f32(l0), f32(l1), float(np.float32(0.05)), aliased=False)
+    assert np.abs(la_out.cpu().numpy() - la).max() < 1e-4 * np.abs(la).max()
+    want = osamp.mala_accept(la, f32(lu))
+    clear = np.abs(la - f32(lu)) > 1e-3 * np.maximum(1.0, np.abs(la))               # away from fp32 ties the decisions are identical
+    assert np.array_equal(acc.cpu().numpy().astype(bool)[clear], want[clear]) and clear.sum() > 200
+    a = acc.cpu().numpy().astype(bool)
+    assert torch.equal(t1[torch.from_numpy(a).cuda()], t1_in[torch.from_numpy(a).cuda()])
+    assert torch.equal(t1[torch.from_numpy(~a).cuda()], t0[torch.from_numpy(~a).cuda()])
+    assert 20 < a.sum() < P - 20
+
+
+def test_mala_sample_loop_on_npde_posterior():
+    """MALA.sample with the fused NPDEPosterior closure (langevin.py:98-149 protocol): chain entries are [params, accepted],
+    exact=True restores rejected chains (theta of a rejected chain equals its value before the proposal)."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200 import problems
+    from bayesian_ode_b200.samplers import MALA
+    data = problems.make_dataset(seed=0)
+    Z = problems.inducing_grid(data["Y"], 5)
+    U0 = problems.gradient_matching_init(data["Y"], data["t"], Z, 1.0, 0.75)
+    P = 16
+    U = U0[None] + 0.05 * torch.randn(P, 25, 2, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+    f = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
+    post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
+    f.bind_flat_grads()
+    smp = MALA([f.U, f.logsn], lr=2e-5, exact=True, seed=3)
+    chain = smp.sample(post, num_samples=6, burn_in=2)
+    assert len(chain) == 6
+    params, acc = chain[-1]
+    assert params[0][0].shape == (P, 25, 2) and acc.shape == (P,) and acc.dtype == torch.int32
+    assert bool(torch.isfinite(f.theta).all())
+    # one more step by hand: rejected chains are restored exactly, accepted ones keep the proposal
+    smp.loss = post.loss_and_grad_()[0].clone()
+    before = f.theta.clone()
+    smp.step()
+    proposal = f.theta.clone()
+    _, acc = smp.accept_or_reject(post, log_u=torch.full((P,), -float("inf")))     # every finite ratio accepts: theta stays the proposal
+    assert bool(acc.bool().all()) and torch.equal(f.theta, proposal)
+    la = smp.log_alpha.clone()
+    sign = torch.tensor([1.0, -1.0], device="cuda").repeat(P // 2)                 # even chains: log u above the ratio -> rejected
+    _, acc = smp.accept_or_reject(post, log_u=la + sign * (1.0 + 0.01 * la.abs()))
+    a = acc.bool()
+    assert a.tolist() == [False, True] * (P // 2)
+    assert torch.equal(f.theta[a], proposal[a]) and torch.equal(f.theta[~a], before[~a])
+    assert bool(a.any()) and bool((~a).any())
