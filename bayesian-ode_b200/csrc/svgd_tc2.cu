@@ -373,8 +373,8 @@ struct Phi2Smem {
   static constexpr uint32_t RAW = 0;                                   // 3 slots x [128][32] floats, TMA tile with 128-byte swizzle
   static constexpr uint32_t RAW_SLOT = BLK * PK2 * 4;                  // 16384 (1024-byte aligned)
   static constexpr uint32_t V = RAW + 3 * RAW_SLOT;                    // 3 slots x (hi | lo); the K tile (A operand) lives in TMEM
-  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[2], barV[3], barR[3], barK[2]
-  static constexpr uint32_t TSLOT = BARS + 10 * 8;
+  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[3], barR[3], barKV[6]
+  static constexpr uint32_t TSLOT = BARS + 12 * 8;
   static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;                 // + slack to align the dynamic base to 1024 bytes
 };
 
@@ -409,10 +409,11 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Phi2Smem::BARS);
-  uint64_t* barM = bars;          // MMAs of a stage complete (K slot / V slot free)
-  uint64_t* barV = bars + 2;      // V^T tile landed
-  uint64_t* barR = bars + 5;      // d2 tile landed
-  uint64_t* barK = bars + 8;      // K tile written by all worker warps (count NWARP)
+  // An mbarrier wait costs ~250 cycles on this part even when the phase is already complete (clock64 trace of one CTA), so the
+  // MMA thread gets ONE barrier per stage: barKV completes when all 16 worker warps have written K(t) AND V(t) has landed.
+  uint64_t* barM = bars;          // [3] MMAs of stage t retired: K slot t % 3 and V slot t % 3 are free
+  uint64_t* barR = bars + 3;      // [3] d2 tile landed
+  uint64_t* barKV = bars + 6;     // [6] stage t ready for the tensor core (count NWARP + 1 arrivals, + the V bytes)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + Phi2Smem::TSLOT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * BLK;
@@ -421,13 +422,12 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   const int s0 = blockIdx.y * per;
   const int nst = min(per, nst_all - s0);                              // stages of this CTA (may be <= 0)
 
-  // TMEM columns: [0,112) accumulator, [128 + 64 s, +32) K_hi and [+32, +64) K_lo of slot s
-  if (warp == 0) tmem_alloc(tslot, 256);
+  // TMEM columns: [0,112) accumulator, [128 + 64 s, +32) K_hi and [+32, +64) K_lo of slot s = 0..2
+  if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) mbar_init(barM + i, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(barV + i, 1);
+    for (int i = 0; i < 3; ++i) mbar_init(barM + i, 1);
     for (int i = 0; i < 3; ++i) mbar_init(barR + i, 1);
-    for (int i = 0; i < 2; ++i) mbar_init(barK + i, NWARP);
+    for (int i = 0; i < 6; ++i) mbar_init(barKV + i, NWARP + 1);
   }
   tc_fence_before();
   __syncthreads();
@@ -440,16 +440,16 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   // that needs its rows.
   if (warp == NWARP + 1) {
     // ---------------- loader warp (lane 0): d2 tiles by 2-D TMA three stages ahead, V^T tiles by bulk copy two stages ahead.
-    // It only waits for slots to drain (barK: the workers consumed raw(t); barM: the MMAs that read V(t-1) retired), so the
+    // It only waits for slots to drain (barKV: the workers consumed raw(t); barM: the MMAs that read V(t-1) retired), so the
     // MMA-issuing thread never spends time on copies.
     if (lane == 0 && nst > 0) {
       auto load_v = [&](int t) {
         const int slot = t % 3;
         unsigned char* dst = sm + Phi2Smem::V + slot * 2 * VST_BYTES;
         const long long src = (long long)(s0 + t) * (VST_BYTES / 4);
-        mbar_expect_tx(barV + slot, 2 * VST_BYTES);
-        bulk_g2s(dst, VH + src, VST_BYTES, barV + slot);
-        bulk_g2s(dst + VST_BYTES, VL + src, VST_BYTES, barV + slot);
+        mbar_expect_tx(barKV + t % 6, 2 * VST_BYTES);
+        bulk_g2s(dst, VH + src, VST_BYTES, barKV + t % 6);
+        bulk_g2s(dst + VST_BYTES, VL + src, VST_BYTES, barKV + t % 6);
       };
       auto load_raw = [&](int t) {
         if (t < nst) {
@@ -464,13 +464,13 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       load_v(0);
       if (nst > 1) load_v(1);
       for (int t = 0; t < nst; ++t) {
-        if (t + 3 < nst) {
-          mbar_wait(barK + (t & 1), (t >> 1) & 1);                     // raw(t) consumed by every worker warp
-          load_raw(t + 3);
-        }
         if (t + 2 < nst) {
-          if (t >= 1) mbar_wait(barM + ((t - 1) & 1), ((t - 1) >> 1) & 1);   // V(t+2) reuses the slot of V(t-1)
+          if (t >= 1) mbar_wait(barM + (t - 1) % 3, ((t - 1) / 3) & 1);      // V(t+2) reuses the slot of V(t-1)
           load_v(t + 2);
+        }
+        if (t + 3 < nst) {
+          mbar_wait(barKV + t % 6, (t / 6) & 1);                       // raw(t) consumed by every worker warp
+          load_raw(t + 3);
         }
       }
     }
@@ -479,19 +479,20 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
     if (lane == 0 && nst > 0) {
       const uint64_t dV = smem_desc(smem_u32(sm + Phi2Smem::V), B_LBO, SBO);
       constexpr uint64_t BK = (2 * B_LBO) >> 4;
+      mbar_wait(barKV + 0, 0);
       for (int t = 0; t < nst; ++t) {
-        mbar_wait(barK + (t & 1), (t >> 1) & 1);                       // K(t) written (TMEM) and fenced by every worker warp
         tc_fence_after();
-        mbar_wait(barV + (t % 3), (t / 3) & 1);
-        const uint32_t ah = tmem + 128 + (t & 1) * 64, al = ah + 32;         // K_hi / K_lo of this stage in TMEM
+        const uint32_t ah = tmem + 128 + (t % 3) * 64, al = ah + 32;         // K_hi / K_lo of this stage in TMEM
         const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
         for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bl + ks * BK, idesc, 1u);
+        // the wait for the NEXT stage is taken while eight MMAs of this one are queued on the tensor core
+        if (t + 1 < nst) mbar_wait(barKV + (t + 1) % 6, ((t + 1) / 6) & 1);
 #pragma unroll
         for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, al + ks * 8, bh + ks * BK, idesc, 1u);
-        umma_commit(barM + (t & 1));
+        umma_commit(barM + t % 3);
       }
     }
   } else {
@@ -499,7 +500,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
     const int rl = tid & (BLK - 1), qd = tid >> 7;                     // tile row, which 8 of the stage's 32 columns
     const int row = r0 + rl;
     const bool rows_full = r0 + BLK <= nr;
-    const uint32_t klane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 128 + 8 * qd;   // this thread's row (TMEM lane), its 8 K columns
+    const uint32_t klane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 128 + 8 * qd;   // this thread's row (TMEM lane), its 8 K columns of slot 0
     // 128-byte swizzle of the TMA tile: 16-byte chunk c of row r sits at chunk c ^ (r % 8)
     const uint32_t roff0 = rl * 128 + (((2 * qd) ^ (rl & 7)) << 4), roff1 = rl * 128 + (((2 * qd + 1) ^ (rl & 7)) << 4);
     for (int t = 0; t < nst; ++t) {
@@ -517,21 +518,21 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       float h[8], l[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_tf32(kv[e], h[e], l[e]);
-      if (t >= 2) {                                                    // K slot t&1 was read by stage t-2's MMAs
-        mbar_wait(barM + (t & 1), ((t - 2) >> 1) & 1);
+      if (t >= 3) {                                                    // K slot t % 3 was read by stage t-3's MMAs
+        mbar_wait(barM + t % 3, ((t - 3) / 3) & 1);
         tc_fence_after();
       }
-      tmem_st8(klane + (t & 1) * 64, h);
-      tmem_st8(klane + (t & 1) * 64 + 32, l);
+      tmem_st8(klane + (t % 3) * 64, h);
+      tmem_st8(klane + (t % 3) * 64 + 32, l);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(barK + (t & 1));
+      if (lane == 0) mbar_arrive(barKV + t % 6);
     }
     // ---------------- epilogue: one TMEM lane per thread = one output row; warps 4..7 take the upper feature half
     const int half = qd;
     if (nst > 0 && warp < 8) {
-      mbar_wait(barM + ((nst - 1) & 1), ((nst - 1) >> 1) & 1);
+      mbar_wait(barM + (nst - 1) % 3, ((nst - 1) / 3) & 1);
       tc_fence_after();
       const int cbeg = half * (NF2 / 2);
 #pragma unroll 1
@@ -552,7 +553,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------- host launchers (called from svgd.cu)

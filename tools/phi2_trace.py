@@ -20,9 +20,10 @@ lib.bode_svgd_debug_trace(C.c_void_p(tr.data_ptr()))
 step(); torch.cuda.synchronize()
 t = tr.cpu().numpy().reshape(64, 8)[:32]
 t0 = t[0, 0]
-print("stage  barR  comp  barM  sttm  arrive | ctl:barK  issued  done   (cycles since stage-0 barR; deltas per stage)")
+print("stage  barR_done  comp  barM_done  sttm  loop_top | mma:barK_done  barV_done  committed")
 for i in range(32):
     print(i, *(int(x - t0) for x in t[i]))
-print("per-stage period (worker arrive):", np.diff(t[:, 4]).astype(int))
-print("ctl issue time:", (t[:, 6] - t[:, 5]).astype(int))
+print("per-stage period (worker sttm):", np.diff(t[:, 3]).astype(int))
+print("mma issue time:", (t[:, 7] - t[:, 6]).astype(int), " mma wait barK (from prev commit):", (t[1:, 5] - t[:-1, 7]).astype(int), " barV wait:", (t[:, 6] - t[:, 5]).astype(int))
+print("worker barR wait:", (t[:, 0] - t[:, 4]).astype(int))
 print("worker: barR->comp", (t[:, 1] - t[:, 0]).astype(int), " barM wait", (t[:, 2] - t[:, 1]).astype(int), " sttm", (t[:, 3] - t[:, 2]).astype(int))
