@@ -207,8 +207,9 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restr
       }
     }
   } else if (warp == NWARP) {
-    // ---------------- MMA warp (lane 0): 21 MMAs per tile into accumulator t & 1, free once every worker warp has read tile t-2
-    if (lane == 0) {
+    // ---------------- MMA warp (all lanes, one elected issuer): 21 MMAs per tile into accumulator t & 1, free once every worker
+    // warp has read tile t-2
+    {
       const uint64_t dAh = smem_desc(smem_u32(sm + Gram2Smem::A), LBO, SBO), dAl = smem_desc(smem_u32(sm + Gram2Smem::A) + BLK_BYTES, LBO, SBO);
       const uint64_t dB0h = smem_desc(smem_u32(sm + Gram2Smem::B), LBO, SBO), dB0l = smem_desc(smem_u32(sm + Gram2Smem::B) + BLK_BYTES, LBO, SBO);
       const uint64_t dB1h = smem_desc(smem_u32(sm + Gram2Smem::B) + 2 * BLK_BYTES, LBO, SBO),
@@ -223,12 +224,12 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restr
         const uint64_t bh = slot ? dB1h : dB0h, bl = slot ? dB1l : dB0l;
         const uint32_t dst = tmem + slot * BLK;
 #pragma unroll
-        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAh + ks * KSTEP, bh + ks * KSTEP, idesc, ks > 0 ? 1u : 0u);
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32_w(dst, dAh + ks * KSTEP, bh + ks * KSTEP, idesc, ks > 0 ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAh + ks * KSTEP, bl + ks * KSTEP, idesc, 1u);
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32_w(dst, dAh + ks * KSTEP, bl + ks * KSTEP, idesc, 1u);
 #pragma unroll
-        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32(dst, dAl + ks * KSTEP, bh + ks * KSTEP, idesc, 1u);
-        umma_commit(barS + slot);
+        for (int ks = 0; ks < KP2 / 8; ++ks) umma_tf32_w(dst, dAl + ks * KSTEP, bh + ks * KSTEP, idesc, 1u);
+        umma_commit_w(barS + slot);
       }
     }
   } else {
@@ -475,8 +476,8 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       }
     }
   } else if (warp == NWARP) {
-    // ---------------- MMA warp (lane 0): issue is back-pressured by the tensor core, so this loop runs at MMA speed
-    if (lane == 0 && nst > 0) {
+    // ---------------- MMA warp: all 32 lanes run the loop, one elected lane issues (see umma_tf32_ts_w)
+    if (nst > 0) {
       const uint64_t dV = smem_desc(smem_u32(sm + Phi2Smem::V), B_LBO, SBO);
       constexpr uint64_t BK = (2 * B_LBO) >> 4;
       mbar_wait(barKV + 0, 0);
@@ -485,14 +486,14 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
         const uint32_t ah = tmem + 128 + (t % 3) * 64, al = ah + 32;         // K_hi / K_lo of this stage in TMEM
         const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
 #pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
 #pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, ah + ks * 8, bl + ks * BK, idesc, 1u);
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, ah + ks * 8, bl + ks * BK, idesc, 1u);
         // the wait for the NEXT stage is taken while eight MMAs of this one are queued on the tensor core
         if (t + 1 < nst) mbar_wait(barKV + (t + 1) % 6, ((t + 1) / 6) & 1);
 #pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts(tmem, al + ks * 8, bh + ks * BK, idesc, 1u);
-        umma_commit(barM + t % 3);
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, al + ks * 8, bh + ks * BK, idesc, 1u);
+        umma_commit_w(barM + t % 3);
       }
     }
   } else {
