@@ -104,7 +104,13 @@ SYMBOLS = {
     "bode_svgd_gamma": (C.c_int, [C.c_int32, C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P]),
     "bode_svgd_phi": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                  _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
+    "bode_svgd_staged_supported": (C.c_int, [C.c_int32, C.c_int32]),
+    "bode_svgd_sqdist_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
+                                           _P, C.c_size_t, C.POINTER(C.c_void_p), _P]),
+    "bode_svgd_phi_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32,
+                                        C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
 }
+SVGD_PREPARE, SVGD_COMPUTE = 1, 2
 
 
 def load():

@@ -30,11 +30,11 @@ int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* X
 int svgd_tc2_supported(int d, int nc);
 size_t svgd_tc2_carved_bytes(int nr, int nc);
 int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
-                  void* ops_base, float* D2, SelState* st, int sms, cudaStream_t stream);
+                  void* ops_base, float* D2, SelState* st, int sms, int stages, cudaStream_t stream);
 int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream);
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
-                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, cudaStream_t stream);
+                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, cudaStream_t stream);
 static int g_tensor_cores = 1;
 
 // ---------------------------------------------------------------- squared distances (difference form, fp32)
@@ -474,10 +474,21 @@ Ws carve(void* ws, int nr, int nc, int d) {
 /* d2[rows, cols] for the local rows, and reset of the select state; total = number of entries the median runs over
  * (n*n for the whole job).  hist_out receives the device address of the 2x2048 uint64 histogram block so a multi-rank
  * caller can all-reduce it between bode_svgd_hist_pass and bode_svgd_select_digit. */
-extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
-                                int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
-                                size_t workspace_bytes, void** hist_out, bode_stream_t stream) {
+extern "C" int bode_svgd_staged_supported(int32_t n_cols, int32_t d) {
+  return (g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
+}
+
+/* stages: BODE_SVGD_PREPARE (column means, selection-state reset, pre-split operands: needs only the positions) and / or
+ * BODE_SVGD_COMPUTE (the Gram kernel).  On shapes bode_svgd_staged_supported rejects, PREPARE is empty and COMPUTE does it all. */
+extern "C" int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols,
+                                       int64_t ld_cols, int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries,
+                                       void* workspace, size_t workspace_bytes, void** hist_out, bode_stream_t stream) {
   BODE_REQUIRE(Xrows && Xcols && workspace, "null pointer");
+  BODE_REQUIRE((stages & ~3) == 0 && stages != 0, "stages must be a combination of BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE");
+  if (!bode_svgd_staged_supported(n_cols, d)) {
+    if (!(stages & BODE_SVGD_COMPUTE)) return BODE_OK;
+    stages = BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE;
+  }
   BODE_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && d <= 512, "bad sizes");
   BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
   BODE_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
@@ -489,12 +500,13 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   if (g_tensor_cores && svgd_tc_supported(d)) {
     // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles.
     // The column-mean kernel also resets the selection state (the histograms are left zeroed by every select pass).
-    int e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, w.st, total_entries, st);
+    int e = BODE_OK;
+    if (stages & BODE_SVGD_PREPARE) e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, w.st, total_entries, st);
     if (e != BODE_OK) return e;
     if (svgd_tc2_supported(d, n_cols)) {
       const int sms = bode_device_sm_count();
       if (sms < 0) return BODE_ERR_CUDA;
-      e = svgd_tc2_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.ops, w.d2, w.st, sms, st);
+      e = svgd_tc2_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.ops, w.d2, w.st, sms, stages, st);
       if (e != BODE_OK) return e;
       if (hist_out) *hist_out = w.hist;
       return BODE_OK;
@@ -509,6 +521,13 @@ extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_r
   }
   if (hist_out) *hist_out = w.hist;
   return BODE_OK;
+}
+
+extern "C" int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
+                                int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
+                                size_t workspace_bytes, void** hist_out, bode_stream_t stream) {
+  return bode_svgd_sqdist_staged(BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE, Xrows, ld_rows, n_rows, Xcols, ld_cols, n_cols, d, row_offset,
+                                 total_entries, workspace, workspace_bytes, hist_out, stream);
 }
 
 /* Zero the persistent selection state (median window disarmed, table cleared).  Call once after allocating a workspace. */
@@ -619,11 +638,16 @@ extern "C" int bode_svgd_gamma(int32_t n_total, float sigma, int32_t n_rows, int
 /* phi for the local rows (uses d2 left in the workspace by bode_svgd_sqdist).  Scols holds score_sign * score, so the
  * gradient of the negative log posterior can be passed as is with score_sign = -1 (score = -grad loss).  phi may be NULL; when theta != NULL the
  * update theta_i += step * phi_i is fused (the wrapped optimiser of stein.py descends -phi with lr = step). */
-extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
-                             const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
-                             const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
-                             int64_t ld_theta, float step, bode_stream_t stream) {
+extern "C" int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
+                                    const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
+                                    const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
+                                    int64_t ld_theta, float step, bode_stream_t stream) {
   BODE_REQUIRE(Xrows && Xcols && Scols && med_gamma && workspace, "null pointer");
+  BODE_REQUIRE((stages & ~3) == 0 && stages != 0, "stages must be a combination of BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE");
+  if (!bode_svgd_staged_supported(n_cols, d)) {
+    if (!(stages & BODE_SVGD_COMPUTE)) return BODE_OK;
+    stages = BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE;
+  }
   BODE_REQUIRE(d > 0 && 2 * d + 1 <= 256, "svgd phi kernel supports d <= 127 (got %d)", d);
   Ws w = carve(workspace, n_rows, n_cols, d);
   cudaStream_t st = (cudaStream_t)stream;
@@ -637,8 +661,8 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
   if (g_tensor_cores && svgd_tc_supported(d)) {
     if (svgd_tc2_supported(d, n_cols)) {
       int js2 = 1;
-      int e2 = svgd_tc2_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, w.ops, &js2, w.part, sms, st);
-      if (e2 != BODE_OK) return e2;
+      int e2 = svgd_tc2_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, w.ops, &js2, w.part, sms, stages, st);
+      if (e2 != BODE_OK || !(stages & BODE_SVGD_COMPUTE)) return e2;
       return svgd_tc_combine(w.part, js2, n_rows, d, Xrows, ld_rows, w.mu, med_gamma, 1.f / (float)n_total, phi, ld_phi, theta, ld_theta,
                              step, st);
     }
@@ -669,4 +693,12 @@ extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows
   phi_combine_kernel<<<(int)((tot + 255) / 256), 256, 0, st>>>(w.part, jsplit, n_rows, d, Xrows, ld_rows, med_gamma,
                                                                1.f / (float)n_total, phi, ld_phi, theta, ld_theta, step);
   return check_cuda(cudaGetLastError(), "phi combine launch");
+}
+
+extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
+                             const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
+                             const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
+                             int64_t ld_theta, float step, bode_stream_t stream) {
+  return bode_svgd_phi_staged(BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE, Xrows, ld_rows, n_rows, Xcols, ld_xc, Scols, ld_sc, score_sign, n_cols,
+                              d, n_total, med_gamma, workspace, phi, ld_phi, theta, ld_theta, step, stream);
 }

@@ -599,11 +599,11 @@ static int split_for(int blocks_y, int units, int sms) {
   return js;
 }
 
+// stages: bit 0 = operand preparation (pre-split, centred column operands; needs only the positions), bit 1 = the Gram kernel
 int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
-                  void* ops_base, float* D2, SelState* st, int sms, cudaStream_t stream) {
+                  void* ops_base, float* D2, SelState* st, int sms, int stages, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int nrp = (nr + BLK - 1) / BLK * BLK, ncp = (nc + BLK - 1) / BLK * BLK;
-  prep_x_kernel<<<ncp / BLK, 256, 0, stream>>>(Xc, ldc, nc, d, mu, o.XcH, o.XcL, o.nrm_c, &st->maxbits);
   const float *rH = o.XrH, *rL = o.XrL, *rN = o.nrm_r;
   // the local rows usually ARE a 128-aligned block of the gathered columns: reuse the column operands
   const bool alias = row_offset >= 0 && (row_offset % BLK) == 0 && ldr == ldc && Xr == Xc + (long long)row_offset * ldc &&
@@ -612,10 +612,13 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
     rH = o.XcH + (long long)(row_offset / BLK) * (BLK_BYTES / 4);
     rL = o.XcL + (long long)(row_offset / BLK) * (BLK_BYTES / 4);
     rN = o.nrm_c + row_offset;
-  } else {
-    prep_x_kernel<<<nrp / BLK, 256, 0, stream>>>(Xr, ldr, nr, d, mu, o.XrH, o.XrL, o.nrm_r, nullptr);
   }
-  BODE_CUDA(cudaGetLastError());
+  if (stages & 1) {
+    prep_x_kernel<<<ncp / BLK, 256, 0, stream>>>(Xc, ldc, nc, d, mu, o.XcH, o.XcL, o.nrm_c, &st->maxbits);
+    if (!alias) prep_x_kernel<<<nrp / BLK, 256, 0, stream>>>(Xr, ldr, nr, d, mu, o.XrH, o.XrL, o.nrm_r, nullptr);
+    BODE_CUDA(cudaGetLastError());
+  }
+  if (!(stages & 2)) return BODE_OK;
   static bool attr_set = false;
   if (!attr_set) {
     BODE_CUDA(cudaFuncSetAttribute(gram2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Gram2Smem::TOTAL));
@@ -651,11 +654,17 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
-                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, cudaStream_t stream) {
+                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int ncp = (nc + BLK - 1) / BLK * BLK;
-  prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VL);
-  BODE_CUDA(cudaGetLastError());
+  const int nrb = (nr + BLK - 1) / BLK, nst = (nc + PK2 - 1) / PK2;
+  const int js = split_for(nrb, nst, sms);
+  *jsplit_out = js;
+  if (stages & 1) {   // V^T = [-G | X - mu | 1] operand tiles: needs positions and scores, not d2 or gamma
+    prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VL);
+    BODE_CUDA(cudaGetLastError());
+  }
+  if (!(stages & 2)) return BODE_OK;
   static bool attr_set = false;
   if (!attr_set) {
     BODE_CUDA(cudaFuncSetAttribute(phi2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Phi2Smem::TOTAL));
@@ -672,9 +681,6 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
-  const int nrb = (nr + BLK - 1) / BLK, nst = (nc + PK2 - 1) / PK2;
-  const int js = split_for(nrb, nst, sms);
-  *jsplit_out = js;
   dim3 grid(nrb, js);
   phi2_kernel<<<grid, NTHR_PHI, Phi2Smem::TOTAL, stream>>>(tm, nr, nc, o.VH, o.VL, d, gam, js, part);
   return check_cuda(cudaGetLastError(), "phi2 launch");

@@ -2,7 +2,7 @@
 import torch
 
 from .. import _lib
-from .langevin import _flat_noise
+from .langevin import _CyclicalSchedule, _flat_noise
 from .sampler import Sampler
 
 
@@ -28,21 +28,22 @@ class aSGHMC(Sampler):
             self._st[key] = st
         return st
 
-    def step(self, lr, burn_in=False, resample_mom_every=50, noise=None, noise_resample=None, use_ctl=False):
+    def step(self, lr, burn_in=False, resample_mom_every=50, noise=None, noise_resample=None, use_ctl=False, _add_noise=None):
         lib = _lib.load()
         group = self.param_groups[0]
+        add_noise = bool(group["add_noise"]) if _add_noise is None else bool(_add_noise)
         for k, (p, g) in enumerate(self._tensors_for_launch()):
             st = self._state_for(p)
             st["iteration"] += 1
             # hamiltonian.py:81-83 -- integer selection logic stays on the host, bit-exact
             resample = (not burn_in) and resample_mom_every is not None and st["iteration"] % resample_mom_every == 0
-            xi = _flat_noise(noise, self, k, p)
+            xi = _flat_noise(noise, self, k, p) if add_noise else None
             xr = _flat_noise(noise_resample, self, k, p) if resample else None
             ctl = self.ctl() if use_ctl else None
             _lib.check(lib.bode_asghmc_step(
                 _lib.ptr(p), _lib.ptr(g), _lib.ptr(st["tau"]), _lib.ptr(st["g"]), _lib.ptr(st["v_hat"]), _lib.ptr(st["momentum"]),
                 _lib.ptr(xi), _lib.ptr(xr), p.numel(), float(lr), float(group["mom_decay"]), float(group["lambda_"]),
-                int(bool(burn_in)), int(bool(resample)), int(bool(group["add_noise"])), self.seed + k, self._step_index,
+                int(bool(burn_in)), int(bool(resample)), int(add_noise), self.seed + k, self._step_index,
                 _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
 
@@ -83,3 +84,30 @@ class aSGHMC(Sampler):
                                                                  i + 1 if i < burn_in else i - burn_in + 1,
                                                                  float(sq_err_loss.sum())))
         return chain
+
+
+class acSGHMC(_CyclicalSchedule, aSGHMC):
+    """hamiltonian.py:167-326: adaptive SGHMC on the cosine cycle schedule.  acSGHMC(params, lr0=0.01, M=5, beta=0.25,
+    mom_decay=5e-2, lambda_=1e-5, add_noise=True): the aSGHMC update (same fused launch, stale ``tau_inv`` included) with
+    the momentum noise switched by ``r(iter_num) > beta and add_noise`` (hamiltonian.py:250-254)."""
+
+    def __init__(self, params, **kwargs):
+        kwargs.setdefault("lr0", 0.01)
+        kwargs.setdefault("M", 5)
+        kwargs.setdefault("beta", 0.25)
+        super().__init__(params, **kwargs)
+        self.param_groups[0].pop("lr", None)            # the reference's acSGHMC has no fixed ``lr`` default
+
+    def step(self, lr, iter_num, burn_in=False, resample_mom_every=50, noise=None, noise_resample=None):
+        noisy = self._sampling_phase(iter_num) and bool(self.param_groups[0]["add_noise"])
+        aSGHMC.step(self, lr, burn_in=burn_in, resample_mom_every=resample_mom_every, noise=noise,
+                    noise_resample=noise_resample, _add_noise=noisy)
+
+    def get_lr(self, t):
+        return _CyclicalSchedule.get_lr(self, t)
+
+    def sample(self, closure, num_samples=1000, burn_in=100, print_iters=True, print_loss=False, resample_mom_every=None,
+               arr_closure=None):
+        return self._cyclical_sample(closure, num_samples, burn_in, print_iters, print_loss, arr_closure,
+                                     lambda i: self.step(lr=self.get_lr(i), iter_num=i, burn_in=i < burn_in,
+                                                         resample_mom_every=resample_mom_every))

@@ -1,6 +1,6 @@
 """Langevin-family samplers (reference samplers/langevin.py) as fused CUDA updates over particle-batched chains.
 
-SGLD   langevin.py:151-258      pSGLD  langevin.py:422-567      MALA  langevin.py:13-149
+SGLD   langevin.py:151-258      pSGLD  langevin.py:422-567      MALA  langevin.py:13-149      cSGLD  langevin.py:1600-1724
 Constructor kwargs, ``step`` / ``get_lr`` / ``sample`` signatures and the lr schedule follow the reference; the extra
 ``noise=`` argument of ``step`` injects standard-normal draws (one tensor per parameter, param_groups order, or one
 flat [P, d] tensor) for bit-parity runs.
@@ -101,6 +101,93 @@ class SGLD(_LangevinBase):
                                           int(bool(group["add_noise"])), self.seed + k, self._step_index,
                                           _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
+
+
+class _CyclicalSchedule:
+    """Cosine step-size cycles shared by cSGLD (langevin.py:1659-1667) and acSGHMC (hamiltonian.py:259-267):
+    ``r(t) = ((t - 1) mod L) / L`` with ``L = (num_iters + M) // M``, ``lr(t) = lr0 / 2 (cos(pi r) + 1)``; noise is
+    injected only in the sampling part of a cycle, ``r > beta``.  ``num_iters`` is set by ``sample()``; the modulo is
+    Python's (t = 0 gives r = (L - 1) / L), integer selection logic kept on the host."""
+
+    def _r(self, t):
+        M = self.param_groups[0]["M"]
+        L = (self.num_iters + M) // M
+        return ((t - 1) % L) / L
+
+    def get_lr(self, t):
+        return self.param_groups[0]["lr0"] / 2.0 * (np.cos(np.pi * self._r(t)) + 1)
+
+    def _sampling_phase(self, t):
+        return self._r(t) > self.param_groups[0]["beta"]
+
+    def _cyclical_sample(self, closure, num_samples, burn_in, print_iters, print_loss, arr_closure, step_fn):
+        """The reference's loop (langevin.py:1669-1724 / hamiltonian.py:269-326): every sampling iteration appends an
+        entry; outside the sampling part of a cycle the entry is ``([[None, ...]], True)``."""
+        chain = self.samples
+        self.num_iters = num_samples + burn_in
+        fused = hasattr(closure, "loss_and_grad_") and self._flat is not None
+        if fused:
+            if self._grad_flat() is None and hasattr(closure.field, "bind_flat_grads"):
+                closure.field.bind_flat_grads()
+            keep = sum(1 for i in range(burn_in, self.num_iters) if self._sampling_phase(i))
+            chain.reserve(max(keep, 1), self._flat, self._plist)
+        log = arr_closure is not None or (print_iters and print_loss)
+        for i in range(self.num_iters):
+            if fused:
+                self.loss = closure.loss_and_grad_()[0]
+            else:
+                self.zero_grad()
+                self.loss = closure()
+                self._backward(self.loss)
+            step_fn(i)
+            if i >= burn_in:
+                if self._sampling_phase(i):
+                    self._record(chain)
+                else:
+                    chain.push_none(len(self._plist))
+            if log:
+                sq_err_loss = closure(add_prior=False)
+                if arr_closure is not None:
+                    arr_closure(self.loss, sq_err_loss)
+            if print_iters:
+                tag, k = ("Burn-in", i + 1) if i < burn_in else ("Sample", i - burn_in + 1)
+                if print_loss:
+                    print("{} iter {:04d} | loss {:.06f}".format(tag, k, float(sq_err_loss.sum())))
+                else:
+                    print("{} iter {:04d}".format(tag, k))
+        return chain
+
+
+class cSGLD(_CyclicalSchedule, Sampler):
+    """langevin.py:1600-1724: cyclical SGLD.  cSGLD(params, lr0=0.01, M=5, beta=0.25, add_noise=True); the update is the
+    fused SGLD launch with the noise term switched by ``r(iter_num) > beta`` (the reference ignores ``add_noise`` here,
+    langevin.py:1648-1649, and so does this class)."""
+
+    def __init__(self, params, **kwargs):
+        defaults = kwargs
+        defaults.setdefault("add_noise", True)
+        defaults.setdefault("lr0", 0.01)
+        defaults.setdefault("M", 5)
+        defaults.setdefault("beta", 0.25)
+        super().__init__(params, defaults)
+        self.logp = None
+
+    def step(self, iter_num, lr=None, noise=None):
+        lib = _lib.load()
+        for group in self.param_groups:
+            if lr:
+                group["lr"] = lr
+        group = self.param_groups[0]
+        noisy = self._sampling_phase(iter_num)
+        for k, (p, g) in enumerate(self._tensors_for_launch()):
+            xi = _flat_noise(noise, self, k, p) if noisy else None
+            _lib.check(lib.bode_sgld_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(xi), p.numel(), float(group["lr"]), int(noisy),
+                                          self.seed + k, self._step_index, _lib.ptr(self._status), None, _lib.stream_ptr()))
+        self._after_step()
+
+    def sample(self, closure, num_samples=1000, burn_in=100, print_iters=False, print_loss=False, arr_closure=None):
+        return self._cyclical_sample(closure, num_samples, burn_in, print_iters, print_loss, arr_closure,
+                                     lambda i: self.step(lr=self.get_lr(i), iter_num=i))
 
 
 class MALA(Sampler):

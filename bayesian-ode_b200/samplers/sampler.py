@@ -45,17 +45,21 @@ def _flat_base(tensors):
 
 class ChainStore:
     """List-like view of an on-device chain [num_samples, P, d]; entries materialise lazily in the reference's
-    format ``([[param arrays ...]], True)`` (langevin.py:243-245) so no per-sample D2H copy or sync happens."""
+    format ``([[param arrays ...]], True)`` (langevin.py:243-245) so no per-sample D2H copy or sync happens.
+    Entries keep their order of arrival whether they were appended the reference way (host), pushed from the flat
+    device buffer, or recorded as the cyclical samplers' ``[[None, ...]]`` placeholders (langevin.py:1703-1706)."""
 
     def __init__(self):
-        self._host = []           # entries appended the slow (reference) way
+        self._host = []
         self._dev = None
         self._count = 0
         self._split = None
+        self._order = []          # ("h", index into _host) | ("d", device slot) | ("n", number of parameters)
 
     def reserve(self, n, flat, params):
         self._dev = torch.empty((n,) + tuple(flat.shape), dtype=flat.dtype, device=flat.device)
         self._count = 0
+        self._order = [e for e in self._order if e[0] != "d"]
         offs, pos = [], 0
         for p in params:
             inner = p[0].numel()
@@ -65,21 +69,29 @@ class ChainStore:
 
     def push_flat(self, flat):
         self._dev[self._count].copy_(flat, non_blocking=True)
+        self._order.append(("d", self._count))
         self._count += 1
 
+    def push_none(self, nparams):
+        self._order.append(("n", nparams))
+
     def append(self, item):
+        self._order.append(("h", len(self._host)))
         self._host.append(item)
 
     def device_tensor(self):
         return None if self._dev is None else self._dev[:self._count]
 
     def __len__(self):
-        return len(self._host) + self._count
+        return len(self._order)
 
     def _entry(self, i):
-        if i < len(self._host):
-            return self._host[i]
-        row = self._dev[i - len(self._host)].cpu().numpy()
+        kind, k = self._order[i]
+        if kind == "h":
+            return self._host[k]
+        if kind == "n":
+            return ([[None] * k], True)
+        row = self._dev[k].cpu().numpy()
         return ([[row[:, o:o + n].reshape(shape) for (o, n, shape) in self._split]], True)
 
     def __getitem__(self, i):

@@ -80,12 +80,12 @@ class _Workspace:
         off = tp.value - self.base.data_ptr()
         self._wtable = self.base[off:off + tn.value * 8].view(torch.int64)      # median window counters (summed over ranks)
 
-    def sqdist(self, Xr, nr, Xc, nc, d, total, row_offset=-1):
+    def sqdist(self, Xr, nr, Xc, nc, d, total, row_offset=-1, stages=_lib.SVGD_PREPARE | _lib.SVGD_COMPUTE):
         lib = _lib.load()
         rp, rs = _lib.rows(Xr, d)
         cp, cs = _lib.rows(Xc, d)
-        _lib.check(lib.bode_svgd_sqdist(rp, rs, nr, cp, cs, nc, d, int(row_offset), int(total), C.c_void_p(self.base.data_ptr()), self.nbytes,
-                                        C.byref(self.hist_ptr), _lib.stream_ptr()))
+        _lib.check(lib.bode_svgd_sqdist_staged(int(stages), rp, rs, nr, cp, cs, nc, d, int(row_offset), int(total),
+                                               C.c_void_p(self.base.data_ptr()), self.nbytes, C.byref(self.hist_ptr), _lib.stream_ptr()))
         if self._hist is None:
             off = self.hist_ptr.value - self.base.data_ptr()
             self._hist = self.base[off:off + 2 * 2048 * 8].view(torch.int64)
@@ -118,9 +118,16 @@ class SVGD(Sampler):
 
     ``step(lr=None)`` consumes the gradients of the per-particle negative log posterior left in ``p.grad`` (score =
     -grad), all-gathers [theta | score] across ranks if torch.distributed is initialised, and applies theta += lr*phi.
+
+    Stream overlap (``overlap=True``, the default): the interaction has two pieces that do not depend on the scores or on
+    the bandwidth -- the centred, pre-split Gram operands (positions only) and the ``[-G | X - mu | 1]`` operand (no d2, no
+    gamma).  ``prefetch()`` forks the first onto a side stream so it runs beside the ODE solve that produces the scores
+    (``sample()`` calls it before the closure; call it yourself before ``closure.loss_and_grad_()`` in a hand-written loop);
+    ``phi()`` forks the second beside the Gram kernel and the median selection.  Both rejoin the calling stream, so the
+    sequence is capturable in one CUDA graph.  Nothing may write the particles between ``prefetch()`` and ``phi()``.
     """
 
-    def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, **kwargs):
+    def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, overlap=True, **kwargs):
         defaults = kwargs
         if "lr" not in defaults:
             defaults["lr"] = 1e-4                        # stein.py:40-41
@@ -139,6 +146,29 @@ class SVGD(Sampler):
         self.phi_buf = torch.empty_like(self._flat)
         if self.world > 1:
             self._gath = torch.empty(2, self.n_total, self.d, dtype=torch.float32, device=dev)
+        self.overlap = bool(overlap) and bool(_lib.load().bode_svgd_staged_supported(self.n_total, self.d))
+        self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        self._prefetched = False
+
+    def _gather_positions(self, X):
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(self._gath[0], X)
+            return self._gath[0]
+        return X
+
+    def prefetch(self):
+        """Fork the position-only part of the interaction (all-gather of the positions, column means, pre-split Gram
+        operands) onto the side stream; the next ``phi()`` joins it.  A no-op with ``overlap=False``."""
+        if not self.overlap or self._prefetched:
+            return
+        cur = torch.cuda.current_stream()
+        self._side.wait_stream(cur)
+        with torch.cuda.stream(self._side):
+            Xall = self._gather_positions(self._flat)
+            nt = self.n_total
+            self._ws.sqdist(self._flat, self.P_local, Xall, nt, self.d, nt * nt, row_offset=self.rank * self.P_local,
+                            stages=_lib.SVGD_PREPARE)
+        self._prefetched = True
 
     def phi(self, X=None, grad=None, update_lr=None):
         """stein.py:75-86 for the local rows.  Returns phi [P_local, d]; with ``update_lr`` the update is fused."""
@@ -148,23 +178,43 @@ class SVGD(Sampler):
         if G is None:
             raise _lib.BodeError("SVGD.phi: gradients missing (call closure + backward, or pass grad=)")
         d, nl, nt = self.d, self.P_local, self.n_total
-        if self.world > 1:
-            # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
-            torch.distributed.all_gather_into_tensor(self._gath[0], X)
-            torch.distributed.all_gather_into_tensor(self._gath[1], G)
-            Xall, Gall = self._gath[0], self._gath[1]
-        else:
-            Xall, Gall = X, G
         ws = self._ws
-        ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl)
-        ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
+        cur = torch.cuda.current_stream()
+        prefetched = self._prefetched and X is self._flat
+        if self._prefetched:
+            cur.wait_stream(self._side)                     # join: operands (and the gathered positions) are ready
+            self._prefetched = False
+        # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
+        Xall = (self._gath[0] if self.world > 1 else X) if prefetched else self._gather_positions(X)
+        if self.world > 1:
+            torch.distributed.all_gather_into_tensor(self._gath[1], G)
+            Gall = self._gath[1]
+        else:
+            Gall = G
         xr, xrs = _lib.rows(X, d)
         xc, xcs = _lib.rows(Xall, d)
         sc, scs = _lib.rows(Gall, d)
         th = (xr, xrs) if update_lr is not None else (None, 0)
-        _lib.check(lib.bode_svgd_phi(xr, xrs, nl, xc, xcs, sc, scs, -1.0, nt, d, nt, _lib.ptr(ws.med_gamma),
-                                     C.c_void_p(ws.base.data_ptr()), _lib.ptr(self.phi_buf), d, th[0], th[1],
-                                     float(update_lr or 0.0), _lib.stream_ptr()))
+
+        def phi_stage(stages):
+            _lib.check(lib.bode_svgd_phi_staged(int(stages), xr, xrs, nl, xc, xcs, sc, scs, -1.0, nt, d, nt, _lib.ptr(ws.med_gamma),
+                                                C.c_void_p(ws.base.data_ptr()), _lib.ptr(self.phi_buf), d, th[0], th[1],
+                                                float(update_lr or 0.0), _lib.stream_ptr()))
+        both = _lib.SVGD_PREPARE | _lib.SVGD_COMPUTE
+        if self.overlap:
+            if not prefetched:
+                ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
+            self._side.wait_stream(cur)                     # fork: the V operand beside the Gram kernel + median selection
+            with torch.cuda.stream(self._side):
+                phi_stage(_lib.SVGD_PREPARE)
+            ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
+            ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
+            cur.wait_stream(self._side)
+            phi_stage(_lib.SVGD_COMPUTE)
+        else:
+            ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=both)
+            ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
+            phi_stage(both)
         return self.phi_buf
 
     def step(self, lr=None, closure=None):
@@ -189,6 +239,7 @@ class SVGD(Sampler):
             closure.field.bind_flat_grads()
         chain.reserve((num_samples + thinning - 1) // thinning, self._flat, self._plist)
         for i in range(burn_in + num_samples):
+            self.prefetch()                                  # position-only operands beside the solve
             if fused:
                 self.loss = closure.loss_and_grad_()[0]
             else:

@@ -242,6 +242,8 @@ def run_b200(args, wl):
     smp.check_finite = "deferred"
 
     def step():
+        if wl["sampler"] == "svgd":
+            smp.prefetch()                  # position-only SVGD operands on a side stream, beside the ODE kernel
         post.loss_and_grad_()
         if wl["sampler"] == "svgd":
             smp.phi(update_lr=smp.param_groups[0]["lr"])

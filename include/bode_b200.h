@@ -315,6 +315,26 @@ int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const flo
                   const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                   int64_t ld_theta, float step, bode_stream_t stream);
 
+/* Split forms of bode_svgd_sqdist / bode_svgd_phi for callers that overlap the operand preparation with other work on a second
+ * stream (the reference computes everything serially inside RBFKernel.forward / SVGD.phi, stein.py:18-34, 75-86):
+ *   bode_svgd_sqdist_staged(BODE_SVGD_PREPARE)  column means, selection-state reset, pre-split centred operands -- needs only the
+ *                                               particle positions, so it can run beside the ODE solve that produces the scores;
+ *   bode_svgd_phi_staged(BODE_SVGD_PREPARE)     the V = [-G | X - mu | 1] operand -- needs positions and scores but neither d2 nor
+ *                                               gamma, so it can run beside the Gram kernel and the median selection;
+ *   ..._staged(BODE_SVGD_COMPUTE)               the rest.  PREPARE | COMPUTE equals the plain call.  Where
+ * bode_svgd_staged_supported(n_cols, d) returns 0 (shapes outside the pipelined tensor-core kernels) PREPARE alone does nothing
+ * and COMPUTE alone does all the work, so callers need no second code path. */
+#define BODE_SVGD_PREPARE 1
+#define BODE_SVGD_COMPUTE 2
+int bode_svgd_staged_supported(int32_t n_cols, int32_t d);
+int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
+                            int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
+                            size_t workspace_bytes, void** hist_out, bode_stream_t stream);
+int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
+                         const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
+                         const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
+                         int64_t ld_theta, float step, bode_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

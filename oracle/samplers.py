@@ -4,6 +4,9 @@
   psgld_step    samplers/langevin.py:457-500
   asghmc_step   samplers/hamiltonian.py:38-99
   get_lr        samplers/langevin.py:205-210
+  cyclical_r / cyclical_lr   samplers/langevin.py:1659-1667 == hamiltonian.py:259-267 (cSGLD / acSGHMC cosine schedule;
+                the update rules are sgld_step / asghmc_step with the noise gated by r > beta, langevin.py:1648-1658,
+                hamiltonian.py:250-254)
   mala_*        samplers/langevin.py:27-95   (proposal = sgld_step; acceptance ratio incl. the aliased-state quirk)
   rbf_kernel    samplers/stein.py:18-34  (cdist^2, median heuristic over all n*n entries)
   svgd_phi      samplers/stein.py:75-86  (closed form of the autograd expression)
@@ -14,6 +17,16 @@ import numpy as np
 
 def get_lr(t, lr0, lr_gamma, lr_t0, lr_alpha):
     return lr0 / np.power(lr_t0 + lr_alpha * t, lr_gamma)
+
+
+def cyclical_r(t, num_iters, M):
+    """Position inside the current cycle, in [0, 1): Python's floor-mod semantics matter at t = 0 (r = (L-1)/L)."""
+    L = (num_iters + M) // M
+    return ((t - 1) % L) / L
+
+
+def cyclical_lr(t, lr0, num_iters, M):
+    return lr0 / 2.0 * (np.cos(np.pi * cyclical_r(t, num_iters, M)) + 1)
 
 
 def sgld_step(p, g, lr, xi=None):

@@ -523,9 +523,100 @@ def gen_mala():
     save("mala_steps", lr=lr, cA=cA, cB=cB, **{k: torch.stack(v) for k, v in rec.items()})
 
 
+def gen_cyclical(data):
+    """cSGLD (langevin.py:1600-1724) and acSGHMC (hamiltonian.py:167-326): cosine step-size cycles with the noise gated by
+    r > beta.  Step sequences from the reference with seeded synthetic gradients and replayed noise, as in gen_sampler_steps."""
+    from samplers.langevin import cSGLD
+    from samplers.hamiltonian import acSGHMC
+    from oracle import samplers as osamp
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    gg = torch.Generator().manual_seed(777)
+    out = {}
+    num_iters, M, beta = 12, 3, 0.25            # cycle length (12 + 3) // 3 = 5: r in {0.8, 0, 0.2, 0.4, 0.6, ...}
+    out.update(num_iters=num_iters, M=M, beta=beta)
+
+    def run(name, smp, kreg, step_fn, draws_fn):
+        rec = {k: [] for k in ("U", "logsn", "gU", "glogsn", "U_new", "logsn_new", "lr", "r")}
+        noises = []
+        for i in range(num_iters):
+            kreg.U.grad = 50.0 * torch.randn(25, 2, generator=gg)
+            kreg.logsn.grad = 5.0 * torch.randn(2, generator=gg)
+            rec["U"].append(kreg.U.data.clone()); rec["logsn"].append(kreg.logsn.data.clone())
+            rec["gU"].append(kreg.U.grad.clone()); rec["glogsn"].append(kreg.logsn.grad.clone())
+            torch.manual_seed(2000 + i)
+            lr = smp.get_lr(i)
+            step_fn(i, lr)
+            rec["lr"].append(torch.tensor(float(lr))); rec["r"].append(torch.tensor(float(smp._r(i))))
+            rec["U_new"].append(kreg.U.data.clone()); rec["logsn_new"].append(kreg.logsn.data.clone())
+            noises.append(_replay_noise(2000 + i, draws_fn(i, float(smp._r(i)))))
+        for k, v in rec.items():
+            out[f"{name}_{k}"] = torch.stack(v)
+        return noises
+
+    # ---- cSGLD
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    smp = cSGLD([kreg.U, kreg.logsn], lr0=2e-4, M=M, beta=beta)
+    smp.num_iters = num_iters                                  # set by sample() (langevin.py:1671)
+    noises = run("csgld", smp, kreg, lambda i, lr: smp.step(iter_num=i, lr=lr),
+                 lambda i, r: [(25, 2), (2,)] if r > beta else [])
+    out["csgld_xiU"] = torch.stack([n[0] if n else torch.zeros(25, 2) for n in noises])
+    out["csgld_xilogsn"] = torch.stack([n[1] if n else torch.zeros(2) for n in noises])
+    gated = 0
+    for i in range(num_iters):
+        r = osamp.cyclical_r(i, num_iters, M)
+        assert r == float(out["csgld_r"][i]) and osamp.cyclical_lr(i, 2e-4, num_iters, M) == float(out["csgld_lr"][i])
+        gated += int(not r > beta)
+        for nm, k in (("U", 0), ("logsn", 1)):
+            xi = noises[i][k].numpy() if r > beta else None
+            mine = osamp.sgld_step(out[f"csgld_{nm}"][i].numpy(), out[f"csgld_g{nm}"][i].numpy(), float(out["csgld_lr"][i]), xi)
+            assert np.abs(out[f"csgld_{nm}_new"][i].numpy() - mine).max() < 1e-13, ("noise replay mismatch (csgld)", i)
+    assert 0 < gated < num_iters
+
+    # ---- acSGHMC: 4 burn-in iterations, then sampling with momentum resampling every 3rd iteration
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    smp2 = acSGHMC([kreg.U, kreg.logsn], lr0=1e-2, M=M, beta=beta, mom_decay=5e-2, lambda_=1e-5)
+    smp2.num_iters = num_iters
+    burn, k_res = 4, 3
+    out.update(acsghmc_burn=burn, acsghmc_resample_every=k_res)
+
+    def draws(i, r):
+        res = (i >= burn) and ((i + 1) % k_res == 0)
+        per = (1 if res else 0) + (1 if r > beta else 0)
+        return [(25, 2)] * per + [(2,)] * per
+    noises = run("acsghmc", smp2, kreg,
+                 lambda i, lr: smp2.step(lr=lr, iter_num=i, burn_in=i < burn, resample_mom_every=k_res), draws)
+    xiU, xiL, xrU, xrL = [], [], [], []
+    for i, n in enumerate(noises):
+        r = float(out["acsghmc_r"][i])
+        res = (i >= burn) and ((i + 1) % k_res == 0)
+        per = len(n) // 2
+        nU, nL = list(n[:per]), list(n[per:])
+        xrU.append(nU.pop(0) if res else torch.zeros(25, 2)); xrL.append(nL.pop(0) if res else torch.zeros(2))
+        xiU.append(nU.pop(0) if r > beta else torch.zeros(25, 2)); xiL.append(nL.pop(0) if r > beta else torch.zeros(2))
+    out.update(acsghmc_xiU=torch.stack(xiU), acsghmc_xilogsn=torch.stack(xiL), acsghmc_xrU=torch.stack(xrU),
+               acsghmc_xrlogsn=torch.stack(xrL))
+    for nm, pt in (("U", kreg.U), ("logsn", kreg.logsn)):
+        for k in ("tau", "g", "v_hat", "momentum"):
+            out[f"acsghmc_{k}_{nm}_final"] = smp2.state[pt][k].clone()
+    st = {"U": osamp.asghmc_init(np.zeros((25, 2))), "logsn": osamp.asghmc_init(np.zeros(2))}
+    for i in range(num_iters):
+        r = float(out["acsghmc_r"][i])
+        for nm in ("U", "logsn"):
+            xi = out[f"acsghmc_xi{nm}"][i].numpy() if r > beta else None
+            mine, st[nm] = osamp.asghmc_step(out[f"acsghmc_{nm}"][i].numpy(), out[f"acsghmc_g{nm}"][i].numpy(), st[nm],
+                                             float(out["acsghmc_lr"][i]), 5e-2, 1e-5, i < burn, k_res, xi,
+                                             out[f"acsghmc_xr{nm}"][i].numpy())
+            assert np.abs(out[f"acsghmc_{nm}_new"][i].numpy() - mine).max() < 1e-12, ("noise replay mismatch (acsghmc)", i, nm)
+    save("cyclical_steps", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "mala":
         gen_mala()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "cyclical":
+        gen_cyclical(make_data())
         sys.exit(0)
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
@@ -538,3 +629,4 @@ if __name__ == "__main__":
     gen_dopri5(data)
     gen_hamcmc()
     gen_mala()
+    gen_cyclical(data)

@@ -44,6 +44,29 @@ def test_asghmc_steps_incl_resample_and_stale_tau_inv():
         assert relerr(st["U"][key], g[f"asghmc_{key}_U_final"]) < 1e-12
 
 
+def test_cyclical_schedule_and_gated_steps():
+    """cSGLD / acSGHMC (langevin.py:1600-1724, hamiltonian.py:167-326): schedule bit-exact, updates to 1e-12."""
+    g = load_golden("cyclical_steps")
+    n_it, M, beta = int(g["num_iters"]), int(g["M"]), float(g["beta"])
+    burn, k = int(g["acsghmc_burn"]), int(g["acsghmc_resample_every"])
+    st = {"U": osamp.asghmc_init(np.zeros((25, 2))), "logsn": osamp.asghmc_init(np.zeros(2))}
+    for i in range(n_it):
+        r = osamp.cyclical_r(i, n_it, M)
+        assert r == float(g["csgld_r"][i]) == float(g["acsghmc_r"][i])
+        assert osamp.cyclical_lr(i, 2e-4, n_it, M) == float(g["csgld_lr"][i])
+        assert osamp.cyclical_lr(i, 1e-2, n_it, M) == float(g["acsghmc_lr"][i])
+        for nm in ("U", "logsn"):
+            xi = g[f"csgld_xi{nm}"][i] if r > beta else None
+            out = osamp.sgld_step(g[f"csgld_{nm}"][i], g[f"csgld_g{nm}"][i], float(g["csgld_lr"][i]), xi)
+            assert relerr(out, g[f"csgld_{nm}_new"][i]) < 1e-13
+            xi = g[f"acsghmc_xi{nm}"][i] if r > beta else None
+            out, st[nm] = osamp.asghmc_step(g[f"acsghmc_{nm}"][i], g[f"acsghmc_g{nm}"][i], st[nm], float(g["acsghmc_lr"][i]), 5e-2,
+                                            1e-5, i < burn, k, xi, g[f"acsghmc_xr{nm}"][i])
+            assert relerr(out, g[f"acsghmc_{nm}_new"][i]) < 1e-12
+    for key in ("tau", "g", "v_hat", "momentum"):
+        assert relerr(st["U"][key], g[f"acsghmc_{key}_U_final"]) < 1e-12
+
+
 def test_rbf_kernel_and_phi():
     g = load_golden("svgd")
     for n in (64, 257):

@@ -79,6 +79,70 @@ def test_asghmc_matches_reference_steps():
         assert relerr(st[key].cpu().numpy()[0][:50].reshape(25, 2), g[f"asghmc_{key}_U_final"]) < 1e-5, key
 
 
+def test_csgld_matches_reference_steps_incl_noise_gating():
+    """langevin.py:1600-1724: cosine schedule (host float64, bit-exact) and noise only where r > beta."""
+    from bayesian_ode_b200.samplers import cSGLD
+    g = load_golden("cyclical_steps")
+    n_it, M, beta = int(g["num_iters"]), int(g["M"]), float(g["beta"])
+    f = _single_chain_field()
+    smp = cSGLD([f.U, f.logsn], lr0=2e-4, M=M, beta=beta)
+    smp.num_iters = n_it
+    _set(f, g["csgld_U"][0], g["csgld_logsn"][0])
+    for i in range(n_it):
+        _setgrad(f, g["csgld_gU"][i], g["csgld_glogsn"][i])
+        assert smp._r(i) == float(g["csgld_r"][i]) and smp.get_lr(i) == float(g["csgld_lr"][i])
+        # the injected draws are ignored outside the sampling part of a cycle, exactly like the reference draws none
+        smp.step(iter_num=i, lr=smp.get_lr(i), noise=[torch.ones(1, 25, 2), torch.ones(1, 2)] if not smp._sampling_phase(i)
+                 else _noise(g, "csgld_xi", i))
+        assert relerr(f.U.data.cpu().numpy()[0], g["csgld_U_new"][i]) < TOL, i
+        assert relerr(f.logsn.data.cpu().numpy()[0], g["csgld_logsn_new"][i]) < TOL, i
+
+
+def test_acsghmc_matches_reference_steps():
+    """hamiltonian.py:167-326: aSGHMC update on the cosine schedule, momentum noise gated by r > beta, resampling."""
+    from bayesian_ode_b200.samplers import acSGHMC
+    g = load_golden("cyclical_steps")
+    n_it, M, beta = int(g["num_iters"]), int(g["M"]), float(g["beta"])
+    burn, k = int(g["acsghmc_burn"]), int(g["acsghmc_resample_every"])
+    f = _single_chain_field()
+    smp = acSGHMC([f.U, f.logsn], lr0=1e-2, M=M, beta=beta, mom_decay=5e-2, lambda_=1e-5)
+    smp.num_iters = n_it
+    _set(f, g["acsghmc_U"][0], g["acsghmc_logsn"][0])
+    for i in range(n_it):
+        _setgrad(f, g["acsghmc_gU"][i], g["acsghmc_glogsn"][i])
+        lr = smp.get_lr(i)
+        assert lr == float(g["acsghmc_lr"][i])
+        smp.step(lr=lr, iter_num=i, burn_in=i < burn, resample_mom_every=k, noise=_noise(g, "acsghmc_xi", i),
+                 noise_resample=_noise(g, "acsghmc_xr", i))
+        assert relerr(f.U.data.cpu().numpy()[0], g["acsghmc_U_new"][i]) < 1e-5, i
+        assert relerr(f.logsn.data.cpu().numpy()[0], g["acsghmc_logsn_new"][i]) < 1e-5, i
+    st = list(smp._st.values())[0]
+    for key in ("tau", "g", "v_hat", "momentum"):
+        assert relerr(st[key].cpu().numpy()[0][:50].reshape(25, 2), g[f"acsghmc_{key}_U_final"]) < 1e-5, key
+
+
+def test_cyclical_sample_loop_records_none_outside_sampling_phase():
+    """langevin.py:1697-1706: every sampling iteration appends an entry; params are None where r <= beta."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200 import problems
+    from bayesian_ode_b200.samplers import cSGLD
+    data = problems.make_dataset(seed=0)
+    Z = problems.inducing_grid(data["Y"], 5)
+    U0 = problems.gradient_matching_init(data["Y"], data["t"], Z, 1.0, 0.75)
+    f = bode.NPDEField(U0[None].repeat(8, 1, 1), Z, 1.0, 0.75, 0.1)
+    post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
+    smp = cSGLD([f.U, f.logsn], lr0=1e-6, M=3, beta=0.25)
+    chain = smp.sample(post, num_samples=9, burn_in=3)
+    assert len(chain) == 9
+    for i in range(9):
+        params, acc = chain[i]
+        if smp._sampling_phase(i + 3):
+            assert params[0][0].shape == (8, 25, 2) and params[0][1].shape == (8, 2) and np.isfinite(params[0][0]).all()
+        else:
+            assert params == [[None, None]]
+        assert acc is True
+
+
 def test_non_flat_tensors_and_scalar_tail():
     """Parameters that are NOT column blocks of one buffer take one launch per tensor; logsn (2 elements) exercises
     the scalar tail of the vectorised kernel."""
@@ -231,6 +295,46 @@ def test_median_window_path_is_bit_exact_and_falls_back():
         ws.sqdist(X[:n], n, X, 256, 52, n * 256, row_offset=0)
         ws.median(n, 256, 52, 256)
         assert np.float32(float(ws.med_gamma[0])) == np.median(ws.d2(n, 256).cpu().numpy())
+
+
+def test_svgd_stream_overlap_is_bit_identical_and_graph_capturable():
+    """prefetch()/phi() fork the position-only operands and the V operand onto a side stream (same kernels, same inputs):
+    the particles must come out bit-identical to the serial order, eagerly and when the step is replayed from one CUDA graph."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200 import problems
+    from bayesian_ode_b200.samplers import SVGD
+    data = problems.make_dataset(seed=0)
+    Z = problems.inducing_grid(data["Y"], 5)
+    U0 = problems.gradient_matching_init(data["Y"], data["t"], Z, 1.0, 0.75)
+    U = U0[None] + 0.1 * torch.randn(384, 25, 2, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
+
+    def run(overlap, graph):
+        f = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
+        post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
+        f.bind_flat_grads()
+        smp = SVGD([f.U, f.logsn], lr=1e-4, overlap=overlap)
+        assert smp.overlap == overlap
+
+        def step():
+            smp.prefetch()
+            post.loss_and_grad_()
+            smp.phi(update_lr=1e-4)
+        step()
+        torch.cuda.synchronize()
+        if graph:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            step = g.replay
+        for _ in range(3):
+            step()
+        torch.cuda.synchronize()
+        return f.theta.clone(), smp._ws.med_gamma.clone()
+
+    th0, mg0 = run(False, False)
+    for overlap, graph in ((True, False), (True, True)):
+        th, mg = run(overlap, graph)
+        assert torch.equal(th, th0) and torch.equal(mg, mg0), (overlap, graph)
 
 
 def test_sample_loop_fused_and_protocol_paths_agree():
