@@ -5,6 +5,7 @@ Public surface mirrors the reference:
   NPDEField / KernelRegression    (scripts/vanderpol/gp.py:56-71)
   NPDEPosterior                   (loss_closure, gp.py:342-353)
   samplers.*                      (samplers/{langevin,hamiltonian,stein}.py)
+  posterior_predictive            (ensemble re-integration of a chain, gp.py:440-464)
 All compute runs in hand-written CUDA behind the C ABI of include/bode_b200.h; there is no CPU path.
 """
 from . import _lib
@@ -12,5 +13,6 @@ from .fields import KernelRegression, MLPField, NPDEField, rbf_kernel
 from .odeint import last_dopri5_stats, odeint, odeint_adjoint
 from .posterior import MLPPosterior, NPDEPosterior
 from . import samplers
+from .predictive import ensemble_trajectories, posterior_predictive
 
-__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "MLPField", "MLPPosterior", "rbf_kernel", "samplers", "_lib"]
+__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "MLPField", "MLPPosterior", "rbf_kernel", "samplers", "ensemble_trajectories", "posterior_predictive", "_lib"]

@@ -29,8 +29,8 @@ int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* X
 // pipelined tensor-core path with resident A tiles, bulk-copied operands and the median window (svgd_tc2.cu)
 int svgd_tc2_supported(int d, int nc);
 size_t svgd_tc2_carved_bytes(int nr, int nc);
-int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
-                  void* ops_base, float* D2, SelState* st, int sms, int stages, cudaStream_t stream);
+int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, float* mu,
+                  void* ops_base, float* D2, SelState* st, unsigned long long total, int sms, int stages, cudaStream_t stream);
 int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream);
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
@@ -337,6 +337,7 @@ __device__ __forceinline__ void gamma_dev(SelState* st, int n, float sigma_fixed
   else s2 = (double)med / (2.0 * log((double)n + 1.0));
   out[0] = med;
   out[1] = (float)(1.0 / (1e-8 + 2.0 * s2));
+  st->maxbits = 0u;   // end of this selection: the next operand pass raises it again (pipelined path has no separate reset launch)
 }
 __global__ void gamma_kernel(SelState* st, int n, float sigma_fixed, int arm_window, float* out) { gamma_dev(st, n, sigma_fixed, arm_window, out); }
 
@@ -498,19 +499,20 @@ extern "C" int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64
   if (smem > 48 * 1024) BODE_CUDA(cudaFuncSetAttribute(sqdist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid((n_cols + TS - 1) / TS, (n_rows + TS - 1) / TS);
   if (g_tensor_cores && svgd_tc_supported(d)) {
-    // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on the mean of ALL particles.
-    // The column-mean kernel also resets the selection state (the histograms are left zeroed by every select pass).
+    // 3xTF32 Gram on tcgen05: d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j with xc centred on a reference point inside the cloud.
     int e = BODE_OK;
-    if (stages & BODE_SVGD_PREPARE) e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, w.st, total_entries, st);
-    if (e != BODE_OK) return e;
     if (svgd_tc2_supported(d, n_cols)) {
+      // pipelined path: the operand kernel forms the centre itself and starts the selection (no column-mean launch)
       const int sms = bode_device_sm_count();
       if (sms < 0) return BODE_ERR_CUDA;
-      e = svgd_tc2_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.ops, w.d2, w.st, sms, stages, st);
+      e = svgd_tc2_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.ops, w.d2, w.st, total_entries, sms, stages, st);
       if (e != BODE_OK) return e;
       if (hist_out) *hist_out = w.hist;
       return BODE_OK;
     }
+    // centred on the mean of ALL particles; the column-mean kernel also resets the selection state
+    e = svgd_tc_colmean(Xcols, ld_cols, n_cols, d, w.mu, w.st, total_entries, st);
+    if (e != BODE_OK) return e;
     e = svgd_tc_gram(Xrows, ld_rows, n_rows, row_offset, Xcols, ld_cols, n_cols, d, w.mu, w.d2, &w.st->maxbits, st);
     if (e != BODE_OK) return e;
   } else {

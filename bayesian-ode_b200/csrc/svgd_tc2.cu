@@ -36,11 +36,43 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 // ---------------------------------------------------------------- operand preparation
 // XH/XL[blk][kc][r/8][r%8][4] : K-major core matrices of the centred rows, zero padded to a multiple of 128 rows.
 // One CTA per 128-row block; norms[r] = |xc_r|^2 summed chunk by chunk in a fixed order.
-__global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ X, long long ld, int n, int d, const float* __restrict__ mu,
-                                                     float* __restrict__ XH, float* __restrict__ XL, float* __restrict__ norms,
-                                                     unsigned int* __restrict__ maxbits) {
+// Centre: d2 is translation invariant, the centre only keeps |xc|^2 small against the cancellation in |xi|^2 + |xj|^2 - 2 xi.xj.
+// Every CTA therefore forms the SAME reference point itself -- the mean of the first min(n_ref, 128) rows of the (gathered)
+// column set, summed in a fixed order, 26 KB of L2 reads -- instead of waiting for a separate column-mean launch over all
+// particles.  CTA 0 of the column launch publishes it as mu (read by prep_v / the combine kernel, which need a point that is
+// consistent, not a particular one: phi is invariant to it as well) and starts the order-statistic selection (ranks of the two
+// middle elements, stein.py:25-26); `sel` is null for the row-operand launch.
+constexpr int CREF = 128;
+__global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ X, long long ld, int n, int d, const float* __restrict__ Xref,
+                                                     long long ldref, int n_ref, float* __restrict__ mu, float* __restrict__ XH,
+                                                     float* __restrict__ XL, float* __restrict__ norms, SelState* sel,
+                                                     unsigned long long total) {
   __shared__ float part[KCH2][BLK + 1];
+  __shared__ float cpart[4][64];
+  __shared__ float ctr[64];
   const int blk = blockIdx.x;
+  {
+    const int k = threadIdx.x & 63, g = threadIdx.x >> 6;
+    const int nr = n_ref < CREF ? n_ref : CREF;
+    float acc = 0.f;
+    if (k < d)
+      for (int r = g * (CREF / 4); r < (g + 1) * (CREF / 4) && r < nr; ++r) acc += __ldg(Xref + (long long)r * ldref + k);
+    cpart[g][k] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64) {
+      const float c = (k < d) ? ((cpart[0][k] + cpart[1][k]) + (cpart[2][k] + cpart[3][k])) / (float)nr : 0.f;
+      ctr[k] = c;
+      if (blk == 0 && sel && k < d) mu[k] = c;
+    }
+    if (blk == 0 && threadIdx.x == 0 && sel) {       // start of a selection: same reset as select_init_kernel (svgd.cu); maxbits is
+      sel->prefix[0] = sel->prefix[1] = 0u;          // re-armed by gamma_kernel / workspace_init (other CTAs are raising it now)
+      sel->hit = 0u;
+      sel->rank[0] = (total - 1) / 2;
+      sel->rank[1] = total / 2;
+    }
+    __syncthreads();
+  }
+  unsigned int* maxbits = sel ? &sel->maxbits : nullptr;
   for (int idx = threadIdx.x; idx < BLK * KCH2; idx += 256) {
     const int r = idx % BLK, kc = idx / BLK;
     const long long row = (long long)blk * BLK + r;
@@ -48,7 +80,7 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ X
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int k = 4 * kc + e;
-      const float v = (row < n && k < d) ? __ldg(X + row * ld + k) - __ldg(mu + k) : 0.f;
+      const float v = (row < n && k < d) ? __ldg(X + row * ld + k) - ctr[k] : 0.f;
       s = fmaf(v, v, s);
       split_tf32(v, h[e], l[e]);
     }
@@ -600,8 +632,8 @@ static int split_for(int blocks_y, int units, int sms) {
 }
 
 // stages: bit 0 = operand preparation (pre-split, centred column operands; needs only the positions), bit 1 = the Gram kernel
-int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, const float* mu,
-                  void* ops_base, float* D2, SelState* st, int sms, int stages, cudaStream_t stream) {
+int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, float* mu,
+                  void* ops_base, float* D2, SelState* st, unsigned long long total, int sms, int stages, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int nrp = (nr + BLK - 1) / BLK * BLK, ncp = (nc + BLK - 1) / BLK * BLK;
   const float *rH = o.XrH, *rL = o.XrL, *rN = o.nrm_r;
@@ -614,8 +646,8 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
     rN = o.nrm_c + row_offset;
   }
   if (stages & 1) {
-    prep_x_kernel<<<ncp / BLK, 256, 0, stream>>>(Xc, ldc, nc, d, mu, o.XcH, o.XcL, o.nrm_c, &st->maxbits);
-    if (!alias) prep_x_kernel<<<nrp / BLK, 256, 0, stream>>>(Xr, ldr, nr, d, mu, o.XrH, o.XrL, o.nrm_r, nullptr);
+    prep_x_kernel<<<ncp / BLK, 256, 0, stream>>>(Xc, ldc, nc, d, Xc, ldc, nc, mu, o.XcH, o.XcL, o.nrm_c, st, total);
+    if (!alias) prep_x_kernel<<<nrp / BLK, 256, 0, stream>>>(Xr, ldr, nr, d, Xc, ldc, nc, mu, o.XrH, o.XrL, o.nrm_r, nullptr, 0ull);
     BODE_CUDA(cudaGetLastError());
   }
   if (!(stages & 2)) return BODE_OK;

@@ -63,6 +63,7 @@ class NPDEField(torch.nn.Module):
         device = torch.device(device if device is not None else "cuda")
         U0 = torch.as_tensor(U0)
         self.batched = U0.dim() == 3
+        self._stable = bool(stable_solve)
         if U0.dim() not in (2, 3) or U0.shape[-1] != 2:
             raise ValueError("U0 must be [m, 2] or [P, m, 2]")
         U0 = U0 if self.batched else U0[None]

@@ -251,7 +251,7 @@ def run_b200(args, wl):
             smp.schedule_(**sched)
             smp.step(use_ctl=True)
 
-    launches_per_step = 9 if wl["sampler"] == "svgd" else 3
+    launches_per_step = 8 if wl["sampler"] == "svgd" else 3
     peaks = measure_peaks(torch, bode)
 
     # eager warm-up (allocates every buffer), then capture one step in a CUDA graph (single-GPU path)
@@ -346,7 +346,7 @@ def run_b200(args, wl):
         if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
             tpeak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))).get("bf16_tflops")
         tpeak = (tpeak or 1590.0) / 2.0          # tf32 dense = half the bf16 rate; no measured tf32 figure exists
-        kernels.append(dict(name="svgd sqdist: colmean + prep_x + gram2 (3xTF32 tcgen05, d2 store + median window count)" if tc else "svgd sqdist_kernel",
+        kernels.append(dict(name="svgd sqdist: prep_x + gram2 (3xTF32 tcgen05, d2 store + median window count)" if tc else "svgd sqdist_kernel",
                             ms=sq_ms, bound="tensor" if tc else "fp32", achieved=2.0 * nl * nt * d / (sq_ms * 1e-3) / 1e12,
                             peak=tpeak if tc else peaks["fp32_fma_tflops"], unit="TFLOP/s"))
         kernels.append(dict(name="svgd exact median: window_select + radix fallback (no-op after a window hit) + gamma", ms=med_ms, bound="hbm",

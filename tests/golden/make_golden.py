@@ -611,7 +611,38 @@ def gen_cyclical(data):
     save("cyclical_steps", **out)
 
 
+def gen_predictive(data):
+    """Posterior-predictive ensemble exactly as gp.py:440-464 computes it: every chain entry re-integrated with
+    ``odeint_adjoint(kreg, x0_, t_)`` (default dopri5), then np.mean / np.std over the chain."""
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    gen = torch.Generator().manual_seed(99)
+    chain = [([[(U0 + 0.05 * torch.randn(25, 2, generator=gen)).numpy(), np.log(0.1) * np.ones(2)]], True) for _ in range(6)]
+    rs = np.random.RandomState(5)
+    x0_ = torch.from_numpy(2 * 3 * rs.uniform(size=[4, 2]) - 3)
+    t_ = torch.linspace(0., 14., 30)
+    out = dict(U=np.stack([c[0][0][0] for c in chain]), x0=x0_, t=t_)
+    for name, kw in (("dopri5", {}), ("rk4", dict(method="rk4"))):
+        xode_gp = []
+        for i in range(len(chain)):
+            kreg.U.data = torch.from_numpy(chain[i][0][0][0])
+            with torch.no_grad():
+                xode_gp.append(np.transpose(gp.odeint(kreg, x0_, t_, **kw).detach().numpy(), [1, 0, 2]))
+        out[f"{name}_traj"] = np.stack(xode_gp)                        # [S, N, T, 2]
+        mean, std = np.zeros_like(xode_gp[0]), np.zeros_like(xode_gp[0])
+        for i in range(mean.shape[0]):                                  # gp.py:460-464
+            for c in range(2):
+                mean[i, :, c] = np.mean([xode_gp[j][i, :, c] for j in range(len(xode_gp))], axis=0)
+                std[i, :, c] = np.std([xode_gp[j][i, :, c] for j in range(len(xode_gp))], axis=0)
+        out[f"{name}_mean"], out[f"{name}_std"] = mean, std
+    save("predictive", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "predictive":
+        gen_predictive(make_data())
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "mala":
         gen_mala()
         sys.exit(0)
@@ -630,3 +661,4 @@ if __name__ == "__main__":
     gen_hamcmc()
     gen_mala()
     gen_cyclical(data)
+    gen_predictive(data)

@@ -36,7 +36,9 @@ def _worker():
         smp = SVGD([f.U, f.logsn], lr=1e-4)
         if not distributed:
             smp.world, smp.rank, smp.n_total = 1, 0, smp.P_local
-        for _ in range(3):
+        for it in range(3):
+            if it != 1:
+                smp.prefetch()            # positions gathered + Gram operands built on the side stream, beside the solve
             post.loss_and_grad_()
             smp.phi(update_lr=1e-4)
         return f.theta.clone(), smp._ws.med_gamma.clone()
