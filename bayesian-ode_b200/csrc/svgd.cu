@@ -34,7 +34,8 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
 int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream);
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
-                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, cudaStream_t stream);
+                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
+                 long long ldr, float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t stream);
 static int g_tensor_cores = 1;
 
 // ---------------------------------------------------------------- squared distances (difference form, fp32)
@@ -663,10 +664,9 @@ extern "C" int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t 
   if (g_tensor_cores && svgd_tc_supported(d)) {
     if (svgd_tc2_supported(d, n_cols)) {
       int js2 = 1;
-      int e2 = svgd_tc2_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, w.ops, &js2, w.part, sms, stages, st);
-      if (e2 != BODE_OK || !(stages & BODE_SVGD_COMPUTE)) return e2;
-      return svgd_tc_combine(w.part, js2, n_rows, d, Xrows, ld_rows, w.mu, med_gamma, 1.f / (float)n_total, phi, ld_phi, theta, ld_theta,
-                             step, st);
+      // the split-K combine and the update theta += step * phi run in the tail of the phi kernel (last CTA of each row block)
+      return svgd_tc2_phi(w.d2, n_rows, n_cols, Xcols, ld_xc, Scols, ld_sc, d, w.mu, med_gamma, score_sign, w.ops, &js2, w.part, sms, stages,
+                          Xrows, ld_rows, 1.f / (float)n_total, phi, ld_phi, theta, ld_theta, step, st);
     }
     int js = (2 * sms) / ((n_rows + 127) / 128);        // ~2 CTAs per SM, one wave
     if (js > MAXSPLIT) js = MAXSPLIT;

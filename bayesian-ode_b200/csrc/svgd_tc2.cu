@@ -15,6 +15,7 @@
 #include "tc_ptx.cuh"
 #include "svgd_state.cuh"
 #include <cuda.h>
+#include <cooperative_groups.h>
 
 namespace bode {
 
@@ -310,10 +311,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restr
 }
 
 // ---------------------------------------------------------------- median from the window table
-// 33 CTAs x 1024 threads, one bin per thread (a single CTA pulling the 262 KB table through one SM took 20 us): every CTA moves
-// its bins to a scratch copy, clears them for the next call and publishes its segment total; the last CTA to finish (ticket)
-// scans the 33 totals and then only the one or two segments that hold a middle rank.
-constexpr int WSEL_CTAS = (WIN_TABLE + 1 + 1023) / 1024;               // bins + the "below" counter
+// (the cluster kernel follows the block-scan helper)
 
 __device__ __forceinline__ unsigned long long block_incl_scan_u64(unsigned long long v, unsigned long long* wsum, unsigned long long* total) {
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -340,58 +338,64 @@ __device__ __forceinline__ unsigned long long block_incl_scan_u64(unsigned long 
   return incl + (wid ? wsum[wid - 1] : 0ull);
 }
 
-__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table, unsigned long long* scratch) {
+// One thread-block cluster of 16 CTAs x 1024 threads, two adjacent bins per thread (16 x 2048 = 32768 bins; bin 32768 and the
+// "below" counter are handled by CTA 0): ONE global round trip for the table, segment totals exchanged through distributed
+// shared memory, two cluster barriers.  The 33-CTA ticket version this replaces needed ~8 dependent global round trips
+// (table -> totals -> ticket -> totals -> segment -> segment) and took 10.9 us for 262 KB.
+constexpr int WSEL_CLUSTER = 16;
+static_assert(WSEL_CLUSTER * 2048 == (int)WIN_SPAN, "two bins per thread must tile the window");
+
+__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
   __shared__ unsigned long long wsum[32];
-  __shared__ unsigned long long segex[WSEL_CTAS + 1];
-  __shared__ unsigned int found[2];
-  __shared__ int is_last;
-  unsigned long long* segtot = scratch + WIN_TABLE + 1;                // [WSEL_CTAS]
-  unsigned int* ticket = reinterpret_cast<unsigned int*>(segtot + WSEL_CTAS);
-  const int tid = threadIdx.x, c = blockIdx.x;
-  const int b = c * 1024 + tid;
+  __shared__ unsigned long long segtot[WSEL_CLUSTER];
+  __shared__ unsigned long long mytot;
+  __shared__ unsigned int found[2];                                   // meaningful in CTA 0
+  const int tid = threadIdx.x, c = (int)cl.block_rank();
   const bool armed = st->win_valid != 0;
-  unsigned long long v = 0;
-  if (b <= (int)WIN_TABLE) {
-    const unsigned long long raw = table[b];
-    scratch[b] = raw;
-    table[b] = 0ull;                                                   // ready for the next call
-    if (armed && b < (int)WIN_TABLE) v = raw;
+  const unsigned long long r0 = st->rank[0], r1 = st->rank[1];
+  ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table) + c * 1024 + tid;
+  ulonglong2 v = *t2;
+  *t2 = make_ulonglong2(0ull, 0ull);                                  // ready for the next call
+  unsigned long long last = 0ull, below = 0ull;
+  if (tid == 0) {                                                     // every CTA needs `below`; CTA 0 clears it after the barrier
+    last = table[WIN_SPAN];
+    below = table[WIN_TABLE];
+    if (c == 0) found[0] = found[1] = 0xffffffffu;
   }
-  unsigned long long tot;
-  block_incl_scan_u64(v, wsum, &tot);
-  if (tid == 0) {
-    segtot[c] = tot;
-    __threadfence();
-    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  }
+  if (!armed) v = make_ulonglong2(0ull, 0ull);
+  const unsigned long long mine = v.x + v.y;
+  const unsigned long long incl = block_incl_scan_u64(mine, wsum, &mytot);
   __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  if (tid < WSEL_CLUSTER) cl.map_shared_rank(segtot, tid)[c] = mytot;
+  __shared__ unsigned long long below_s, last_s;
   if (tid == 0) {
-    *ticket = 0u;
-    unsigned long long run = armed ? scratch[WIN_TABLE] : 0ull;       // entries below the window
-    for (int i = 0; i < WSEL_CTAS; ++i) {
-      segex[i] = run;
-      run += segtot[i];
-    }
-    segex[WSEL_CTAS] = run;
-    found[0] = found[1] = 0xffffffffu;
+    below_s = armed ? below : 0ull;
+    last_s = armed ? last : 0ull;
   }
-  __syncthreads();
-  const unsigned long long r[2] = {st->rank[0], st->rank[1]};
+  cl.sync();
+  if (c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
+  unsigned long long run = below_s;
+  for (int i = 0; i < c; ++i) run += segtot[i];
+  const unsigned long long e0 = run + incl - mine, e1 = e0 + v.x;
+  const unsigned int b0 = (unsigned int)(c * 2048 + 2 * tid);
+  unsigned int* f0 = cl.map_shared_rank(found, 0);
+  const unsigned long long rr[2] = {r0, r1};
+#pragma unroll
   for (int which = 0; which < 2; ++which) {
-    int seg = -1;
-    for (int i = 0; i < WSEL_CTAS; ++i)
-      if (r[which] >= segex[i] && r[which] < segex[i + 1]) seg = i;   // uniform over the CTA
-    if (!armed || seg < 0) continue;
-    const int bb = seg * 1024 + tid;
-    const unsigned long long cnt = bb < (int)WIN_TABLE ? scratch[bb] : 0ull;
-    const unsigned long long incl = block_incl_scan_u64(cnt, wsum, nullptr);
-    const unsigned long long excl = segex[seg] + incl - cnt;
-    if (cnt && r[which] >= excl && r[which] < excl + cnt) found[which] = bb;
+    if (v.x && rr[which] >= e0 && rr[which] < e1) f0[which] = b0;
+    else if (v.y && rr[which] >= e1 && rr[which] < e1 + v.y) f0[which] = b0 + 1;
   }
-  __syncthreads();
-  if (tid == 0) {
+  if (c == WSEL_CLUSTER - 1 && tid == 0 && last_s) {                  // the closing bin of the window
+    unsigned long long tot = below_s;
+    for (int i = 0; i < WSEL_CLUSTER; ++i) tot += segtot[i];
+#pragma unroll
+    for (int which = 0; which < 2; ++which)
+      if (rr[which] >= tot && rr[which] < tot + last_s) f0[which] = WIN_SPAN;
+  }
+  cl.sync();
+  if (c == 0 && tid == 0) {
     const bool hit = armed && found[0] != 0xffffffffu && found[1] != 0xffffffffu;
     if (hit) {
       st->prefix[0] = st->win_lo + found[0];
@@ -435,9 +439,23 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                : "memory");
 }
 
+// Arguments of the fused combine.
+constexpr int ACC_PITCH = NF2 + 1;   // odd pitch: a warp's 32 rows hit 32 banks
+struct Phi2Combine {
+  const float* Xr;            // local rows (positions)
+  long long ldr;
+  const float* mu;
+  float inv_n;
+  float* phi;
+  long long ldp;
+  float* theta;
+  long long ldt;
+  float step;
+};
+
 __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
-                                                       float* __restrict__ part) {
+                                                       float* __restrict__ part, const Phi2Combine cmb) {
   extern __shared__ unsigned char sm_raw[];
   // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
@@ -562,8 +580,10 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(barKV + t % 6);
     }
-    // ---------------- epilogue: one TMEM lane per thread = one output row; warps 4..7 take the upper feature half
+    // ---------------- epilogue: one TMEM lane per thread = one output row; warps 4..7 take the upper feature half.  The partial
+    // tile goes to shared memory (the drained d2 / V pipeline buffers) for the cluster-wide split-K reduction below.
     const int half = qd;
+    float* acc_s = reinterpret_cast<float*>(sm);                       // [BLK][ACC_PITCH]
     if (nst > 0 && warp < 8) {
       mbar_wait(barM + (nst - 1) % 3, ((nst - 1) / 3) & 1);
       tc_fence_after();
@@ -572,21 +592,53 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       for (int cb = cbeg; cb < cbeg + NF2 / 2; cb += 8) {
         float s[8];
         tmem_ld8(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cb, s);
-        if (row < nr) {
-          float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
 #pragma unroll
-          for (int qq = 0; qq < 8; ++qq)
-            if (cb + qq <= 2 * d) dst[cb + qq] = s[qq];
-        }
+        for (int qq = 0; qq < 8; ++qq)
+          if (cb + qq <= 2 * d) acc_s[rl * ACC_PITCH + cb + qq] = s[qq];
       }
-    } else if (nst <= 0 && row < nr && half == 0) {
-      float* dst = part + ((long long)blockIdx.y * nr + row) * (2 * d + 1);
-      for (int f = 0; f <= 2 * d; ++f) dst[f] = 0.f;
+    } else if (nst <= 0 && half == 0) {
+      for (int f = 0; f <= 2 * d; ++f) acc_s[rl * ACC_PITCH + f] = 0.f;
     }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 512);
+  // ---------------- fused combine (stein.py:84-86).  The jsplit CTAs of a row block form one thread-block cluster; after the
+  // cluster barrier CTA y sums rows [y BLK / jsplit, (y + 1) BLK / jsplit) of all jsplit partial tiles through distributed shared
+  // memory in a fixed order, forms phi = (KS + 2 gamma (rowsum (x_i - mu) - K(X - mu))) / n and applies theta += step phi.
+  // No partials in global memory, no second launch.
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  cl.sync();
+  {
+    const float* acc_s = reinterpret_cast<const float*>(sm);
+    const int y = blockIdx.y;
+    const int rbeg = (y * BLK) / jsplit, rend = ((y + 1) * BLK) / jsplit;
+    const float g2 = 2.f * gam[1];
+    const float* rem[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) rem[q] = cl.map_shared_rank(acc_s, q < jsplit ? q : 0);
+    const int tot = (rend - rbeg) * d;
+    for (int idx = tid; idx < tot; idx += blockDim.x) {
+      const int rl = rbeg + idx / d, c = idx % d;
+      const long long r = r0 + rl;
+      if (r >= nr) break;
+      float ks = 0.f, kx = 0.f, rs = 0.f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        if (q < jsplit) {
+          const float* p = rem[q] + rl * ACC_PITCH;
+          ks += p[c];
+          kx += p[d + c];
+          rs += p[2 * d];
+        }
+      const float x = cmb.Xr[r * cmb.ldr + c];
+      const float ph = (ks + g2 * (rs * (x - cmb.mu[c]) - kx)) * cmb.inv_n;
+      if (cmb.phi) cmb.phi[r * cmb.ldp + c] = ph;
+      if (cmb.theta) cmb.theta[r * cmb.ldt + c] = fmaf(cmb.step, ph, cmb.theta[r * cmb.ldt + c]);
+    }
+  }
+  cl.sync();                                                           // nobody leaves while its tile is still being read
 }
 
 // ---------------------------------------------------------------- host launchers (called from svgd.cu)
@@ -666,8 +718,25 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
 
 int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
-  window_select_kernel<<<WSEL_CTAS, 1024, 0, stream>>>(st, o.table, o.table + WIN_TABLE + 1);
-  return check_cuda(cudaGetLastError(), "window select launch");
+  static bool attr_set = false;
+  if (!attr_set) {
+    BODE_CUDA(cudaFuncSetAttribute(window_select_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(WSEL_CLUSTER);
+  cfg.blockDim = dim3(1024);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = WSEL_CLUSTER;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, window_select_kernel, st, o.table));
+  return BODE_OK;
 }
 
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc) { return svgd_tc2_carve(ops_base, nr, nc).table; }
@@ -686,11 +755,13 @@ static EncodeTiledFn encode_tiled_fn() {
 }
 
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
-                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, cudaStream_t stream) {
+                 const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
+                 long long ldr, float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   const int ncp = (nc + BLK - 1) / BLK * BLK;
   const int nrb = (nr + BLK - 1) / BLK, nst = (nc + PK2 - 1) / PK2;
-  const int js = split_for(nrb, nst, sms);
+  int js = split_for(nrb, nst, sms);
+  if (js > 8) js = 8;                                                  // portable cluster size
   *jsplit_out = js;
   if (stages & 1) {   // V^T = [-G | X - mu | 1] operand tiles: needs positions and scores, not d2 or gamma
     prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VL);
@@ -714,7 +785,22 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
   dim3 grid(nrb, js);
-  phi2_kernel<<<grid, NTHR_PHI, Phi2Smem::TOTAL, stream>>>(tm, nr, nc, o.VH, o.VL, d, gam, js, part);
+  Phi2Combine cmb;
+  cmb.Xr = Xr; cmb.ldr = ldr; cmb.mu = mu; cmb.inv_n = inv_n; cmb.phi = phi; cmb.ldp = ldp; cmb.theta = theta; cmb.ldt = ldt; cmb.step = step;
+  static_assert((size_t)BLK * ACC_PITCH * 4 <= Phi2Smem::BARS, "the partial tile must fit the drained pipeline buffers");
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(NTHR_PHI);
+  cfg.dynamicSmemBytes = Phi2Smem::TOTAL;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;                      // the split-K CTAs of a row block share one cluster
+  at[0].val.clusterDim.x = 1;
+  at[0].val.clusterDim.y = js;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb));
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 

@@ -251,7 +251,7 @@ def run_b200(args, wl):
             smp.schedule_(**sched)
             smp.step(use_ctl=True)
 
-    launches_per_step = 8 if wl["sampler"] == "svgd" else 3
+    launches_per_step = 7 if wl["sampler"] == "svgd" else 3
     peaks = measure_peaks(torch, bode)
 
     # eager warm-up (allocates every buffer), then capture one step in a CUDA graph (single-GPU path)
