@@ -89,6 +89,7 @@ SYMBOLS = {
     "bode_sampler_schedule": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _P]),
     "bode_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint32, _P]),
     "bode_npde_set_lanes_per_pair": (C.c_int, [C.c_int32]),
+    "bode_npde_set_cta_limit": (C.c_int, [C.c_int32]),
     "bode_mala_accept": (C.c_int, [_P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, C.c_int64, _P, _P, _P, C.c_int32, C.c_int32, C.c_float,
                                    C.c_int32, C.c_uint64, C.c_uint32, _P, _P, _P]),
     "bode_svgd_workspace_bytes": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
@@ -105,6 +106,7 @@ SYMBOLS = {
     "bode_svgd_phi": (C.c_int, [_P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32, C.c_int32, _P, _P,
                                  _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
     "bode_svgd_staged_supported": (C.c_int, [C.c_int32, C.c_int32]),
+    "bode_svgd_set_gram_split": (C.c_int, [C.c_int32]),
     "bode_svgd_sqdist_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                            _P, C.c_size_t, C.POINTER(C.c_void_p), _P]),
     "bode_svgd_phi_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32,

@@ -88,7 +88,9 @@ static int plan(NpdeKParams& prm, int G, int max_threads, dim3* grid, dim3* bloc
 // grid is about one CTA per SM (persistent-style sizing, every SM gets the same number of warps) and capped by the
 // 320-thread launch bound and the per-particle shared-memory footprint.
 static size_t stage_floats(const NpdeKParams& prm);
-static const int PAIR_MAX_THREADS = 320;
+static const int PAIR_MAX_THREADS = 320;   // kernel choice threshold; a CTA may hold pair_max_threads(M) threads
+static int pair_max_threads(int grid_m) { return grid_m <= 5 ? 384 : 320; }   // == PairField<M>::MAX_THREADS
+static int g_cta_limit = 0;                // 0 = every SM; > 0: at most this many CTAs for the fused pair kernels
 static int sm_count();
 static int g_lanes_per_pair = 0;   // 0 = automatic, 1 = one thread per pair (npde_sep.cuh), 2 = component-split lanes (npde_pair.cuh)
 static bool use_pair(const bode_npde_field* f, int N) {
@@ -109,10 +111,11 @@ static int sm_count() {
   return sms;
 }
 
-static int plan_pair(NpdeKParams& prm, bool grad, dim3* grid, dim3* block, size_t* smem) {
+static int plan_pair(NpdeKParams& prm, int grid_m, bool grad, dim3* grid, dim3* block, size_t* smem) {
   const int per_particle = 2 * prm.N;
-  int ppc = (prm.P + sm_count() - 1) / sm_count();
-  const int cap = PAIR_MAX_THREADS / per_particle;
+  const int sms = (g_cta_limit > 0 && g_cta_limit < sm_count()) ? g_cta_limit : sm_count();
+  int ppc = (prm.P + sms - 1) / sms;
+  const int cap = pair_max_threads(grid_m) / per_particle;
   if (ppc > cap) ppc = cap;
   if (ppc < 1) ppc = 1;
   size_t floats = 0;
@@ -203,7 +206,7 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
     int st_ = fill_sep(prm, f);
     if (st_ != BODE_OK) return st_;
     size_t smem = 0;
-    st_ = plan_pair(prm, true, &grid, &block, &smem);
+    st_ = plan_pair(prm, f->grid_mx, true, &grid, &block, &smem);
     if (st_ != BODE_OK) return st_;
     return dispatch_pair_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
   }
@@ -243,6 +246,14 @@ extern "C" int bode_npde_set_lanes_per_pair(int32_t lanes) {
   return old;
 }
 
+/* Leave SMs free for kernels that run beside the fused solve on another stream (the SVGD Gram pass): the pair kernels then use
+ * at most max_ctas CTAs (one per SM), packing up to 12 warps into each.  0 restores one CTA per SM.  Returns the old value. */
+extern "C" int bode_npde_set_cta_limit(int32_t max_ctas) {
+  const int old = g_cta_limit;
+  g_cta_limit = max_ctas > 0 ? max_ctas : 0;
+  return old;
+}
+
 extern "C" size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode) {
   return scratch_floats(P, N, S, T, method, grad_mode);
 }
@@ -259,7 +270,7 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
     st = fill_sep(prm, f);
     if (st != BODE_OK) return st;
     size_t smem = 0;
-    st = plan_pair(prm, false, &grid, &block, &smem);
+    st = plan_pair(prm, f->grid_mx, false, &grid, &block, &smem);
     if (st != BODE_OK) return st;
     return dispatch_pair_fwd(prm, f->grid_mx, method, grid, block, smem, (cudaStream_t)stream);
   }

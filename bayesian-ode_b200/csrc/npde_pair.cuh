@@ -25,7 +25,7 @@ constexpr unsigned FULL_MASK = 0xffffffffu;
 template <int M>
 struct PairField {
   static constexpr int G = 2;
-  static constexpr int MAX_THREADS = 320;
+  static constexpr int MAX_THREADS = M <= 5 ? 384 : 320;   // 12 warps (three per scheduler) where the registers allow it
   static constexpr int MP = (M + 1) / 2;
   // i indexes the lane's own axis, j the partner's.  W is held as pairs over j (zero padded when M is odd), the
   // gradient accumulator as pairs over i, so that every contraction below is an FFMA2 with one broadcast operand.

@@ -36,6 +36,7 @@ unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
                  long long ldr, float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t stream);
+int svgd_tc2_set_gram_split(int js);
 static int g_tensor_cores = 1;
 
 // ---------------------------------------------------------------- squared distances (difference form, fp32)
@@ -476,6 +477,8 @@ Ws carve(void* ws, int nr, int nc, int d) {
 /* d2[rows, cols] for the local rows, and reset of the select state; total = number of entries the median runs over
  * (n*n for the whole job).  hist_out receives the device address of the 2x2048 uint64 histogram block so a multi-rank
  * caller can all-reduce it between bode_svgd_hist_pass and bode_svgd_select_digit. */
+extern "C" int bode_svgd_set_gram_split(int32_t column_splits) { return svgd_tc2_set_gram_split(column_splits); }
+
 extern "C" int bode_svgd_staged_supported(int32_t n_cols, int32_t d) {
   return (g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
 }

@@ -675,6 +675,13 @@ size_t svgd_tc2_carved_bytes(int nr, int nc) {
 
 int svgd_tc2_supported(int d, int nc) { return d >= 1 && d <= 55 && (nc & 3) == 0 && nc >= 4; }
 
+static int g_gram_split = 0;   // 0 = one wave over all SMs; > 0: column splits per row block (finer CTAs when the Gram pass shares the GPU)
+int svgd_tc2_set_gram_split(int js) {
+  const int old = g_gram_split;
+  g_gram_split = js > 0 ? js : 0;
+  return old;
+}
+
 static int split_for(int blocks_y, int units, int sms) {
   int js = sms / (blocks_y > 0 ? blocks_y : 1);
   if (js < 1) js = 1;
@@ -709,7 +716,8 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
     attr_set = true;
   }
   const int nrb = nrp / BLK, nct = ncp / BLK;
-  const int js = split_for(nrb, nct, sms);
+  int js = g_gram_split > 0 ? g_gram_split : split_for(nrb, nct, sms);
+  if (js > nct) js = nct;
   const int tiles_per = (nct + js - 1) / js;
   dim3 grid((nct + tiles_per - 1) / tiles_per, nrb);
   gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st, o.table);

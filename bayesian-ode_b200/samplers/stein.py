@@ -119,15 +119,23 @@ class SVGD(Sampler):
     ``step(lr=None)`` consumes the gradients of the per-particle negative log posterior left in ``p.grad`` (score =
     -grad), all-gathers [theta | score] across ranks if torch.distributed is initialised, and applies theta += lr*phi.
 
-    Stream overlap (``overlap=True``, the default): the interaction has two pieces that do not depend on the scores or on
-    the bandwidth -- the centred, pre-split Gram operands (positions only) and the ``[-G | X - mu | 1]`` operand (no d2, no
-    gamma).  ``prefetch()`` forks the first onto a side stream so it runs beside the ODE solve that produces the scores
-    (``sample()`` calls it before the closure; call it yourself before ``closure.loss_and_grad_()`` in a hand-written loop);
-    ``phi()`` forks the second beside the Gram kernel and the median selection.  Both rejoin the calling stream, so the
-    sequence is capturable in one CUDA graph.  Nothing may write the particles between ``prefetch()`` and ``phi()``.
+    Stream overlap.  Half of the interaction depends only on the particle POSITIONS, not on the scores: the centred,
+    pre-split Gram operands, the Gram kernel (d2) and the exact median / bandwidth.  ``prefetch()`` forks that half onto a
+    side stream so it runs beside the ODE solve that produces the scores (``sample()`` calls it before the closure; call
+    it yourself before ``closure.loss_and_grad_()`` in a hand-written loop) and ``phi()`` joins it:
+      ``overlap="gram"`` (default)  operands + Gram + median on the side stream.  The Gram CTAs cannot share an SM with the
+                                    solver's, so ``side_sms`` SMs (default 40) are kept free of the fused solve while it is
+                                    prefetched (``bode_npde_set_cta_limit``); the solve is latency-bound at three warps per
+                                    scheduler either way;
+      ``overlap="operands"``        only the operand preparation (forking the small ``[-G | X - mu | 1]`` operand kernel
+                                    beside the Gram kernel as well was measured and bought nothing);
+      ``overlap=False``             everything in call order on one stream.
+    Every fork rejoins the calling stream, so the sequence is capturable in one CUDA graph, and all three orders produce
+    bit-identical particles.  Nothing may write the particles between ``prefetch()`` and ``phi()``.
     """
 
-    def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, overlap=True, **kwargs):
+    def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, overlap="gram", side_sms=40,
+                 **kwargs):
         defaults = kwargs
         if "lr" not in defaults:
             defaults["lr"] = 1e-4                        # stein.py:40-41
@@ -146,9 +154,15 @@ class SVGD(Sampler):
         self.phi_buf = torch.empty_like(self._flat)
         if self.world > 1:
             self._gath = torch.empty(2, self.n_total, self.d, dtype=torch.float32, device=dev)
-        self.overlap = bool(overlap) and bool(_lib.load().bode_svgd_staged_supported(self.n_total, self.d))
+        if overlap is True:
+            overlap = "operands"
+        if overlap not in (False, None, "operands", "gram"):
+            raise ValueError("overlap must be False, 'operands' or 'gram'")
+        self.overlap = overlap if (overlap and _lib.load().bode_svgd_staged_supported(self.n_total, self.d)) else False
+        self.side_sms = int(side_sms)
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
         self._prefetched = False
+        self._saved_cta_limit = None
 
     def _gather_positions(self, X):
         if self.world > 1:
@@ -157,18 +171,30 @@ class SVGD(Sampler):
         return X
 
     def prefetch(self):
-        """Fork the position-only part of the interaction (all-gather of the positions, column means, pre-split Gram
-        operands) onto the side stream; the next ``phi()`` joins it.  A no-op with ``overlap=False``."""
+        """Fork the position-only part of the interaction (all-gather of the positions, pre-split Gram operands and, with
+        ``overlap="gram"``, the Gram kernel and the median selection) onto the side stream; the next ``phi()`` joins it.
+        A no-op with ``overlap=False``."""
         if not self.overlap or self._prefetched:
             return
+        lib = _lib.load()
         cur = torch.cuda.current_stream()
         self._side.wait_stream(cur)
+        nl, nt, d = self.P_local, self.n_total, self.d
         with torch.cuda.stream(self._side):
             Xall = self._gather_positions(self._flat)
-            nt = self.n_total
-            self._ws.sqdist(self._flat, self.P_local, Xall, nt, self.d, nt * nt, row_offset=self.rank * self.P_local,
-                            stages=_lib.SVGD_PREPARE)
-        self._prefetched = True
+            self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
+            if self.overlap == "gram":
+                # finer Gram CTAs (two column tiles each): the pass shares the GPU with the solve, a one-wave grid would
+                # leave a long tail on the few SMs it gets (measured on B200: 147 -> 143 us per c3 step)
+                old_split = lib.bode_svgd_set_gram_split(16)
+                self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
+                lib.bode_svgd_set_gram_split(old_split)
+                self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
+        if self.overlap == "gram" and self.side_sms > 0:
+            sms = lib.bode_device_sm_count()
+            if sms > self.side_sms:
+                self._saved_cta_limit = lib.bode_npde_set_cta_limit(sms - self.side_sms)   # until phi() restores it
+        self._prefetched = self.overlap
 
     def phi(self, X=None, grad=None, update_lr=None):
         """stein.py:75-86 for the local rows.  Returns phi [P_local, d]; with ``update_lr`` the update is fused."""
@@ -180,10 +206,15 @@ class SVGD(Sampler):
         d, nl, nt = self.d, self.P_local, self.n_total
         ws = self._ws
         cur = torch.cuda.current_stream()
-        prefetched = self._prefetched and X is self._flat
-        if self._prefetched:
+        if self._saved_cta_limit is not None:
+            lib.bode_npde_set_cta_limit(self._saved_cta_limit)
+            self._saved_cta_limit = None
+        prefetched = self._prefetched if X is self._flat else False
+        if self._prefetched and prefetched != "gram":
             cur.wait_stream(self._side)                     # join: operands (and the gathered positions) are ready
-            self._prefetched = False
+        if self._prefetched and not prefetched:
+            cur.wait_stream(self._side)                     # prefetched for other positions: drop it
+        self._prefetched = False
         # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
         Xall = (self._gath[0] if self.world > 1 else X) if prefetched else self._gather_positions(X)
         if self.world > 1:
@@ -201,16 +232,14 @@ class SVGD(Sampler):
                                                 C.c_void_p(ws.base.data_ptr()), _lib.ptr(self.phi_buf), d, th[0], th[1],
                                                 float(update_lr or 0.0), _lib.stream_ptr()))
         both = _lib.SVGD_PREPARE | _lib.SVGD_COMPUTE
-        if self.overlap:
-            if not prefetched:
-                ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
-            self._side.wait_stream(cur)                     # fork: the V operand beside the Gram kernel + median selection
-            with torch.cuda.stream(self._side):
-                phi_stage(_lib.SVGD_PREPARE)
+        if prefetched == "gram":
+            phi_stage(_lib.SVGD_PREPARE)                    # the V operand needs the scores: here, while the side stream finishes
+            cur.wait_stream(self._side)                     # join: d2, median and gamma are ready
+            phi_stage(_lib.SVGD_COMPUTE)
+        elif prefetched:
             ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
             ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
-            cur.wait_stream(self._side)
-            phi_stage(_lib.SVGD_COMPUTE)
+            phi_stage(both)
         else:
             ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=both)
             ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)

@@ -243,7 +243,7 @@ def run_b200(args, wl):
 
     def step():
         if wl["sampler"] == "svgd":
-            smp.prefetch()                  # position-only SVGD operands on a side stream, beside the ODE kernel
+            smp.prefetch()                  # position-only half of the interaction (operands, Gram, median) beside the ODE kernel
         post.loss_and_grad_()
         if wl["sampler"] == "svgd":
             smp.phi(update_lr=smp.param_groups[0]["lr"])
@@ -316,10 +316,18 @@ def run_b200(args, wl):
     # ---- per-kernel timing pass for the roofline objects: each C-ABI call sequence is captured 20x in its own CUDA graph
     # (graph_seg_ms), so the figures are device time without launch gaps; inputs stay L2-resident between repetitions.
     lib = bode._lib.load()
-    ode_ms = graph_seg_ms(torch, lambda: post.loss_and_grad_())
+    ode_all_ms = graph_seg_ms(torch, lambda: post.loss_and_grad_())              # one CTA on every SM
+    ode_ms, ode_cfg = ode_all_ms, "one CTA per SM"
+    if wl["sampler"] == "svgd" and smp.overlap == "gram" and smp.side_sms > 0:
+        # the configuration the timed step launches: packed into fewer CTAs so that the Gram pass can run beside it
+        old = lib.bode_npde_set_cta_limit(lib.bode_device_sm_count() - smp.side_sms)
+        ode_ms = graph_seg_ms(torch, lambda: post.loss_and_grad_())
+        lib.bode_npde_set_cta_limit(old)
+        ode_cfg = "as launched in the step: at most %d CTAs, timed alone" % (lib.bode_device_sm_count() - smp.side_sms)
     ode_flop = FLOP_PER_EVAL * STAGES * N * M * M * S * P_gpu
-    kernels = [dict(name="npde_pair_grad_kernel (fused rk4 solve + closure + discrete adjoint, 2 lanes per pair, FFMA2)", ms=ode_ms, bound="fp32",
-                    achieved=ode_flop / (ode_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"], unit="TFLOP/s")]
+    kernels = [dict(name="npde_pair_grad_kernel (fused rk4 solve + closure + discrete adjoint, 2 lanes per pair, FFMA2; %s)" % ode_cfg, ms=ode_ms,
+                    bound="fp32", achieved=ode_flop / (ode_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"], unit="TFLOP/s",
+                    ms_one_cta_per_sm=ode_all_ms)]
     if wl["sampler"] == "svgd" and world == 1:
         import ctypes as C
         d = field.d
@@ -422,6 +430,8 @@ def run_b200(args, wl):
         "config": {"workload": wl["desc"], "particles_per_gpu": P_gpu, "total_particles": P_total, "rk_steps": S, "trajectories": N,
                    "inducing_grid": "%dx%d" % (M, M), "sampler": wl["sampler"], "grad": "discrete adjoint (== autograd through odeint)",
                    "parallelism": "particles sharded, dp%d" % world, "cuda_graph": bool(use_graph),
+                   "streams": ("SVGD operands + Gram + exact median on a side stream beside the fused solve (solve packed into %d CTAs, %d SMs left "
+                               "to the Gram pass)" % (148 - smp.side_sms, smp.side_sms)) if wl["sampler"] == "svgd" and smp.overlap == "gram" else "single",
                    "l2": "256 MiB memset between timed steps (outside the event brackets); working set < L2"},
         "roofline": roofline, "kernels": kernels, "peaks": peaks,
         "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk,

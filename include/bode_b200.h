@@ -132,6 +132,11 @@ int bode_npde_dopri5_nlp_grad(const bode_npde_field* f, const bode_dopri5_opts* 
 /* Kernel choice for square 3x3..6x6 inducing grids (fixed-step solvers): 0 = automatic, 1 = one thread per (particle,
  * trajectory) pair, 2 = two component-split lanes per pair.  Returns the previous setting. */
 int bode_npde_set_lanes_per_pair(int32_t lanes);
+/* The component-split kernels normally spread the particles over every SM (one CTA each).  max_ctas > 0 packs them into at most
+ * that many CTAs (up to 12 warps each), leaving the other SMs to kernels that run beside the solve on a second stream -- the
+ * position-only half of the SVGD interaction (bode_svgd_sqdist_staged + median), whose CTAs cannot share an SM with the solver's.
+ * The solve is latency-bound at three warps per scheduler either way.  0 = every SM.  Returns the previous setting. */
+int bode_npde_set_cta_limit(int32_t max_ctas);
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
 
 /* odeint(func=KernelRegression, y0, t, method in {euler,midpoint,rk4}) forward
@@ -327,6 +332,9 @@ int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const flo
 #define BODE_SVGD_PREPARE 1
 #define BODE_SVGD_COMPUTE 2
 int bode_svgd_staged_supported(int32_t n_cols, int32_t d);
+/* CTA granularity of the Gram kernel: column_splits CTAs per 128-row block (0 = automatic: one wave over all SMs).  A finer
+ * split shortens the tail when the Gram pass shares the GPU with the fused solve.  Returns the previous setting. */
+int bode_svgd_set_gram_split(int32_t column_splits);
 int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
                             int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
                             size_t workspace_bytes, void** hist_out, bode_stream_t stream);

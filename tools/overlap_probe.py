@@ -30,11 +30,11 @@ def timed(fn, iters=300):
     return ts[len(ts) // 2] * 1e3
 
 
-def build(prefetch, overlap):
+def build(prefetch, overlap, side_sms=40):
     f = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
     post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]), method="rk4", grad_mode="discrete")
     f.bind_flat_grads()
-    smp = SVGD([f.U, f.logsn], lr=1e-4, overlap=overlap)
+    smp = SVGD([f.U, f.logsn], lr=1e-4, overlap=overlap, side_sms=side_sms)
 
     def step():
         if prefetch:
@@ -49,8 +49,22 @@ def build(prefetch, overlap):
         step()
     return g.replay, (f, post, smp)
 
-for name, pf, ov in (("serial", False, False), ("phi fork only", False, True), ("prefetch + phi fork", True, True)):
-    fn, keep = build(pf, ov)
-    print("%-22s %.1f us/step" % (name, timed(fn)))
-    if os.environ.get("BODE_DOT"):
-        pass
+
+lib = _lib.load()
+f0 = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
+post0 = bode.NPDEPosterior(f0, data["x0"], data["t"], torch.from_numpy(data["Y"]), method="rk4", grad_mode="discrete")
+for lim in (0, 128, 118, 108, 100):
+    lib.bode_npde_set_cta_limit(lim)
+    post0.loss_and_grad_()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        post0.loss_and_grad_()
+    print("ODE alone, cta limit %3d: %.1f us" % (lim, timed(g.replay)))
+lib.bode_npde_set_cta_limit(0)
+for js in (0, 8, 16):
+    lib.bode_svgd_set_gram_split(js)
+    for name, pf, ov, ss in (("serial", False, False, 0), ("gram side_sms=32", True, "gram", 32), ("gram side_sms=40", True, "gram", 40),
+                             ("gram side_sms=52", True, "gram", 52)):
+        fn, keep = build(pf, ov, ss)
+        print("gram split %2d  %-22s %.1f us/step" % (js, name, timed(fn)))
