@@ -189,7 +189,10 @@ class SVGD(Sampler):
                 old_split = lib.bode_svgd_set_gram_split(16)
                 self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
                 lib.bode_svgd_set_gram_split(old_split)
-                self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
+                if self.world == 1:
+                    self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=None)
+                # several ranks: the median's all-reduces are issued by phi() AFTER the all-gather of the scores -- one
+                # communicator executes collectives in issue order, and the scores are ready long before the Gram pass ends
         if self.overlap == "gram" and self.side_sms > 0:
             sms = lib.bode_device_sm_count()
             if sms > self.side_sms:
@@ -234,7 +237,9 @@ class SVGD(Sampler):
         both = _lib.SVGD_PREPARE | _lib.SVGD_COMPUTE
         if prefetched == "gram":
             phi_stage(_lib.SVGD_PREPARE)                    # the V operand needs the scores: here, while the side stream finishes
-            cur.wait_stream(self._side)                     # join: d2, median and gamma are ready
+            cur.wait_stream(self._side)                     # join: d2 (single rank: also median and gamma) are ready
+            if self.world > 1:
+                ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True)
             phi_stage(_lib.SVGD_COMPUTE)
         elif prefetched:
             ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
