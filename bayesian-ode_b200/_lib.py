@@ -107,6 +107,12 @@ SYMBOLS = {
                                  _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
     "bode_svgd_staged_supported": (C.c_int, [C.c_int32, C.c_int32]),
     "bode_svgd_set_gram_split": (C.c_int, [C.c_int32]),
+    "bode_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
+    "bode_peer_free": (C.c_int, [_P]),
+    "bode_peer_export": (C.c_int, [_P, _P]),
+    "bode_peer_import": (C.c_int, [_P, C.POINTER(C.c_void_p)]),
+    "bode_peer_release": (C.c_int, [_P]),
+    "bode_svgd_set_peers": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
     "bode_svgd_sqdist_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_uint64,
                                            _P, C.c_size_t, C.POINTER(C.c_void_p), _P]),
     "bode_svgd_phi_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32,

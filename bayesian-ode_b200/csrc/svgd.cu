@@ -13,6 +13,8 @@
 // all-reduce per pass) before bode_svgd_select_digit runs, so every rank selects the same element.
 #include "common.cuh"
 #include "svgd_state.cuh"
+#include <map>
+#include <string.h>
 #include <cooperative_groups.h>
 
 namespace bode {
@@ -31,7 +33,7 @@ int svgd_tc2_supported(int d, int nc);
 size_t svgd_tc2_carved_bytes(int nr, int nc);
 int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, float* mu,
                   void* ops_base, float* D2, SelState* st, unsigned long long total, int sms, int stages, cudaStream_t stream);
-int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream);
+int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, cudaStream_t stream);
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
@@ -300,8 +302,11 @@ __device__ __forceinline__ void select_digit_dev(SelState* st, unsigned long lon
   for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
 }
 
+// Several ranks: `hist` holds this rank's counts; after every histogram pass block 0 meets the peers at a flag barrier, sums all
+// ranks' histograms (read over NVLink) into `hsum` and selects on the sums -- every rank extends the same prefix.
 __global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __restrict__ D2, long long n, SelState* st, unsigned long long* hist,
-                                                              int n_total, int arm_window, float* med_gamma) {
+                                                              unsigned long long* hsum, int n_total, int arm_window, float* med_gamma,
+                                                              const PeerInfo peer) {
   __shared__ unsigned int sh[2 * 2048];
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned int newp[2];
@@ -318,7 +323,25 @@ __global__ void __launch_bounds__(1024) radix_fallback_kernel(const float* __res
     hist_pass_dev(D2, n, st->prefix[0], st->prefix[1], sh_[pass], nb_[pass], himask, sh, hist);
     __threadfence();
     grid.sync();
-    if (blockIdx.x == 0) select_digit_dev(st, hist, sh_[pass], nb_[pass], wsum, newp, newr);
+    if (blockIdx.x == 0) {
+      if (peer.world > 1) {
+        if (threadIdx.x == 0) peer_barrier(peer);                   // every rank's histogram of this pass is complete
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) {
+          unsigned long long acc = 0ull;
+          for (int q = 0; q < peer.world; ++q)
+            acc += peer_ld_u64(reinterpret_cast<const unsigned long long*>(peer.base[q] + peer.hist_off) + i);
+          hsum[i] = acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) peer_barrier(peer);                   // ... and has been read by everyone: clear mine
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * 2048; i += blockDim.x) hist[i] = 0ull;
+        select_digit_dev(st, hsum, sh_[pass], nb_[pass], wsum, newp, newr);
+      } else {
+        select_digit_dev(st, hist, sh_[pass], nb_[pass], wsum, newp, newr);
+      }
+    }
     __threadfence();
     grid.sync();
   }
@@ -453,13 +476,14 @@ extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int3
   b += jsplit * n_rows * (2 * (size_t)d + 1) * sizeof(float);   // phi partials (last column: row sums)
   b += 2 * 2048 * sizeof(unsigned long long) + 256;             // histograms + select state
   b += 256;                                                     // column means (tensor-core path)
+  b += 256;                                                     // peer barrier flags (svgd_state.cuh)
   b += svgd_tc2_carved_bytes(n_rows, n_cols);                   // pre-split operands + median window table
   return b + 1024;
 }
 
 namespace {
 struct Ws {
-  float* d2; float* part; unsigned long long* hist; SelState* st; float* mu; void* ops;
+  float* d2; float* part; unsigned long long* hist; SelState* st; float* mu; PeerFlags* flags; void* ops;
 };
 Ws carve(void* ws, int nr, int nc, int d) {
   Ws w;
@@ -469,14 +493,52 @@ Ws carve(void* ws, int nr, int nc, int d) {
   w.hist = (unsigned long long*)p; p += 2 * 2048 * sizeof(unsigned long long);
   w.st = (SelState*)p; p += 256;
   w.mu = (float*)p; p += 256;
+  w.flags = (PeerFlags*)p; p += 256;
   w.ops = p;
   return w;
+}
+// workspace -> peer mapping (bode_svgd_set_peers); absent = single rank
+std::map<void*, PeerInfo> g_peers;
+PeerInfo peers_of(void* workspace) {
+  auto it = g_peers.find(workspace);
+  if (it != g_peers.end()) return it->second;
+  PeerInfo p;
+  memset(&p, 0, sizeof(p));
+  return p;
 }
 }  // namespace
 
 /* d2[rows, cols] for the local rows, and reset of the select state; total = number of entries the median runs over
  * (n*n for the whole job).  hist_out receives the device address of the 2x2048 uint64 histogram block so a multi-rank
  * caller can all-reduce it between bode_svgd_hist_pass and bode_svgd_select_digit. */
+/* Peer-mapped workspaces (several ranks on one node): bases[q] = address, in THIS process, of rank q's workspace (bases[rank] ==
+ * workspace).  From then on bode_svgd_window_select and bode_svgd_radix_fallback on this workspace read the peers' window tables /
+ * histograms directly and synchronise through flag barriers, so the exact distributed median needs no collective launches.
+ * world <= 1 removes the mapping. */
+extern "C" int bode_svgd_set_peers(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, void* const* bases, int32_t rank, int32_t world) {
+  BODE_REQUIRE(workspace, "null workspace");
+  if (world <= 1) {
+    g_peers.erase(workspace);
+    return BODE_OK;
+  }
+  BODE_REQUIRE(world <= MAX_PEERS && rank >= 0 && rank < world && bases, "bad peer description (at most %d ranks)", MAX_PEERS);
+  BODE_REQUIRE(bases[rank] == workspace, "bases[rank] must be this rank's own workspace");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  PeerInfo p;
+  memset(&p, 0, sizeof(p));
+  for (int q = 0; q < world; ++q) {
+    BODE_REQUIRE(bases[q], "null peer base");
+    p.base[q] = (unsigned char*)bases[q];
+  }
+  p.rank = rank;
+  p.world = world;
+  p.hist_off = (unsigned long long)((char*)w.hist - (char*)workspace);
+  p.table_off = (unsigned long long)((char*)svgd_tc2_table(w.ops, n_rows, n_cols) - (char*)workspace);
+  p.flag_off = (unsigned long long)((char*)w.flags - (char*)workspace);
+  g_peers[workspace] = p;
+  return BODE_OK;
+}
+
 extern "C" int bode_svgd_set_gram_split(int32_t column_splits) { return svgd_tc2_set_gram_split(column_splits); }
 
 extern "C" int bode_svgd_staged_supported(int32_t n_cols, int32_t d) {
@@ -543,6 +605,7 @@ extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t 
   Ws w = carve(workspace, n_rows, n_cols, d);
   BODE_CUDA(cudaMemsetAsync(w.hist, 0, 2 * 2048 * sizeof(unsigned long long), (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(w.st, 0, 256, (cudaStream_t)stream));
+  BODE_CUDA(cudaMemsetAsync(w.flags, 0, 256, (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, 2 * (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long) + 512, (cudaStream_t)stream));
   return BODE_OK;
 }
@@ -561,7 +624,7 @@ extern "C" int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d,
 extern "C" int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
   BODE_REQUIRE(workspace, "null workspace");
   Ws w = carve(workspace, n_rows, n_cols, d);
-  return svgd_tc2_window_select(w.st, w.ops, n_rows, n_cols, (cudaStream_t)stream);
+  return svgd_tc2_window_select(w.st, w.ops, n_rows, n_cols, peers_of(workspace), (cudaStream_t)stream);
 }
 
 /* 1 (default): Gram and K@[S|X|1] on tcgen05 tensor cores (3xTF32) when d <= 56; 0: FP32-pipe kernels */
@@ -626,7 +689,10 @@ extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t 
   int ntot = n_total;
   int arm = (g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
   float* mg = med_gamma;
-  void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist, (void*)&ntot, (void*)&arm, (void*)&mg};
+  PeerInfo peer = peers_of(workspace);
+  unsigned long long* hsum = svgd_tc2_table(w.ops, n_rows, n_cols) + WIN_TABLE + 1;   // spare half of the table block
+  BODE_REQUIRE(peer.world <= 1 || arm, "peer-mapped workspaces need the pipelined tensor-core path (column count a multiple of 4, d <= 55)");
+  void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist, (void*)&hsum, (void*)&ntot, (void*)&arm, (void*)&mg, (void*)&peer};
   BODE_CUDA(cudaLaunchCooperativeKernel((const void*)radix_fallback_kernel, dim3(grid_blocks), dim3(1024), args, 0, (cudaStream_t)stream));
   return BODE_OK;
 }

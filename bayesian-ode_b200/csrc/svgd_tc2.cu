@@ -345,9 +345,16 @@ __device__ __forceinline__ unsigned long long block_incl_scan_u64(unsigned long 
 constexpr int WSEL_CLUSTER = 16;
 static_assert(WSEL_CLUSTER * 2048 == (int)WIN_SPAN, "two bins per thread must tile the window");
 
-__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table) {
+// Several ranks (peer.world > 1): the table is the SUM of every rank's table, read straight from the peers' workspaces over NVLink
+// behind a flag barrier (svgd_state.cuh) -- no all-reduce launch; every rank computes the same sums, hence the same selection.
+__global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsigned long long* table, const PeerInfo peer) {
   namespace cg = cooperative_groups;
   cg::cluster_group cl = cg::this_cluster();
+  const bool multi = peer.world > 1;
+  if (multi) {                                                        // every rank's Gram pass has filled its table
+    if (cl.block_rank() == 0 && threadIdx.x == 0) peer_barrier(peer);
+    cl.sync();
+  }
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long segtot[WSEL_CLUSTER];
   __shared__ unsigned long long mytot;
@@ -356,14 +363,28 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
   const bool armed = st->win_valid != 0;
   const unsigned long long r0 = st->rank[0], r1 = st->rank[1];
   ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table) + c * 1024 + tid;
-  ulonglong2 v = *t2;
-  *t2 = make_ulonglong2(0ull, 0ull);                                  // ready for the next call
+  ulonglong2 v;
   unsigned long long last = 0ull, below = 0ull;
-  if (tid == 0) {                                                     // every CTA needs `below`; CTA 0 clears it after the barrier
-    last = table[WIN_SPAN];
-    below = table[WIN_TABLE];
-    if (c == 0) found[0] = found[1] = 0xffffffffu;
+  if (!multi) {
+    v = *t2;
+    *t2 = make_ulonglong2(0ull, 0ull);                                // ready for the next call
+    if (tid == 0) {                                                   // every CTA needs `below`; CTA 0 clears it after the barrier
+      last = table[WIN_SPAN];
+      below = table[WIN_TABLE];
+    }
+  } else {
+    v = make_ulonglong2(0ull, 0ull);
+    for (int q = 0; q < peer.world; ++q) {
+      const unsigned long long* tq = reinterpret_cast<const unsigned long long*>(peer.base[q] + peer.table_off);
+      v.x += peer_ld_u64(tq + 2 * (c * 1024 + tid));
+      v.y += peer_ld_u64(tq + 2 * (c * 1024 + tid) + 1);
+      if (tid == 0) {
+        last += peer_ld_u64(tq + WIN_SPAN);
+        below += peer_ld_u64(tq + WIN_TABLE);
+      }
+    }
   }
+  if (tid == 0 && c == 0) found[0] = found[1] = 0xffffffffu;
   if (!armed) v = make_ulonglong2(0ull, 0ull);
   const unsigned long long mine = v.x + v.y;
   const unsigned long long incl = block_incl_scan_u64(mine, wsum, &mytot);
@@ -375,7 +396,7 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
     last_s = armed ? last : 0ull;
   }
   cl.sync();
-  if (c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
+  if (!multi && c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
   unsigned long long run = below_s;
   for (int i = 0; i < c; ++i) run += segtot[i];
   const unsigned long long e0 = run + incl - mine, e1 = e0 + v.x;
@@ -402,6 +423,12 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
       st->prefix[1] = st->win_lo + found[1];
     }
     st->hit = hit ? 1u : 0u;
+  }
+  if (multi) {                                                        // every rank has read my table: clear it for the next call
+    if (c == 0 && tid == 0) peer_barrier(peer);
+    cl.sync();
+    *t2 = make_ulonglong2(0ull, 0ull);
+    if (c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
   }
 }
 
@@ -724,7 +751,7 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
-int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStream_t stream) {
+int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
   static bool attr_set = false;
   if (!attr_set) {
@@ -743,7 +770,7 @@ int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, cudaStr
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BODE_CUDA(cudaLaunchKernelEx(&cfg, window_select_kernel, st, o.table));
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, window_select_kernel, st, o.table, peer));
   return BODE_OK;
 }
 

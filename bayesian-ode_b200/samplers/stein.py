@@ -62,13 +62,35 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+class _RawCuda:
+    """Zero-copy torch view of a raw device allocation (``torch.as_tensor`` reads ``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+
+
 class _Workspace:
-    def __init__(self, nr, nc, d, device):
+    """SVGD workspace (d2 block, operands, median state).  With ``peers=(rank, world)`` the block is a cudaMalloc allocation
+    mapped into every other rank of the node (CUDA IPC handles exchanged through torch.distributed), so that the exact
+    distributed median reads the peers' window tables / radix histograms over NVLink instead of launching collectives
+    (``bode_svgd_set_peers``); ``self.p2p`` tells whether that mapping is active on ALL ranks."""
+
+    def __init__(self, nr, nc, d, device, peers=None):
         lib = _lib.load()
         nbytes = lib.bode_svgd_workspace_bytes(nr, nc, d)
-        self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
-        off = (-self.buf.data_ptr()) % 256
-        self.base = self.buf[off:off + nbytes]
+        self._raw = None
+        self._imported = []
+        self.p2p = False
+        if peers is not None:
+            p = C.c_void_p()
+            _lib.check(lib.bode_peer_alloc(nbytes, C.byref(p)))
+            self._raw = p.value
+            self.base = torch.as_tensor(_RawCuda(self._raw, nbytes), device=device)
+            self.buf = self.base
+        else:
+            self.buf = torch.empty(nbytes + 256, dtype=torch.uint8, device=device)
+            off = (-self.buf.data_ptr()) % 256
+            self.base = self.buf[off:off + nbytes]
         self.nbytes = nbytes
         self.med_gamma = torch.zeros(2, dtype=torch.float32, device=device)
         self.hist_ptr = C.c_void_p()
@@ -79,6 +101,60 @@ class _Workspace:
         _lib.check(lib.bode_svgd_window_table(nr, nc, d, C.c_void_p(self.base.data_ptr()), C.byref(tp), C.byref(tn)))
         off = tp.value - self.base.data_ptr()
         self._wtable = self.base[off:off + tn.value * 8].view(torch.int64)      # median window counters (summed over ranks)
+        if peers is not None:
+            self._map_peers(*peers)
+
+    def _map_peers(self, rank, world):
+        """Exchange IPC handles and register the peer addresses; falls back (on every rank) to the collective protocol when
+        any rank could not map its peers."""
+        lib = _lib.load()
+        dist = torch.distributed
+        nr, nc, d = self._dims
+        ok = 1
+        bases = (C.c_void_p * world)()
+        try:
+            h = (C.c_ubyte * 64)()
+            _lib.check(lib.bode_peer_export(C.c_void_p(self._raw), h))
+            handles = [None] * world
+            dist.all_gather_object(handles, bytes(h))
+            for q in range(world):
+                if q == rank:
+                    bases[q] = self._raw
+                else:
+                    p = C.c_void_p()
+                    hq = (C.c_ubyte * 64).from_buffer_copy(handles[q])
+                    _lib.check(lib.bode_peer_import(hq, C.byref(p)))
+                    self._imported.append(p.value)
+                    bases[q] = p.value
+        except Exception:                                        # noqa: BLE001 -- any failure means "no peer access here"
+            ok = 0
+        flag = torch.tensor([ok], device=self.base.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 1:
+            _lib.check(lib.bode_svgd_set_peers(C.c_void_p(self._raw), nr, nc, d, bases, rank, world))
+            self.p2p = True
+        torch.cuda.synchronize()
+        dist.barrier()                                           # every rank's workspace is initialised and mapped
+
+    def close(self):
+        lib = _lib.load()
+        if self.p2p:
+            nr, nc, d = self._dims
+            lib.bode_svgd_set_peers(C.c_void_p(self._raw), nr, nc, d, None, 0, 1)
+            self.p2p = False
+        for p in self._imported:
+            lib.bode_peer_release(C.c_void_p(p))
+        self._imported = []
+        if self._raw is not None:
+            torch.cuda.synchronize()
+            lib.bode_peer_free(C.c_void_p(self._raw))
+            self._raw = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                                        # noqa: BLE001 -- interpreter shutdown
+            pass
 
     def sqdist(self, Xr, nr, Xc, nc, d, total, row_offset=-1, stages=_lib.SVGD_PREPARE | _lib.SVGD_COMPUTE):
         lib = _lib.load()
@@ -93,6 +169,11 @@ class _Workspace:
     def median(self, nr, nc, d, n_total, sigma=None, group=None):
         lib = _lib.load()
         w = C.c_void_p(self.base.data_ptr())
+        if sigma is None and self.p2p:
+            # peer-mapped workspaces: the single-rank call order; the kernels sum the peers' tables / histograms themselves
+            _lib.check(lib.bode_svgd_window_select(nr, nc, d, w, _lib.stream_ptr()))
+            _lib.check(lib.bode_svgd_radix_fallback(nr, nc, d, w, n_total, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
+            return
         if sigma is None:
             # fast path: the window around the previous call's median usually holds both middle ranks (one all-reduce)
             if group is not None:
@@ -135,7 +216,7 @@ class SVGD(Sampler):
     """
 
     def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, overlap="gram", side_sms=40,
-                 **kwargs):
+                 median_comm="p2p", **kwargs):
         defaults = kwargs
         if "lr" not in defaults:
             defaults["lr"] = 1e-4                        # stein.py:40-41
@@ -150,7 +231,14 @@ class SVGD(Sampler):
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.n_total = self.P_local * self.world
         dev = self._flat.device
-        self._ws = _Workspace(self.P_local, self.n_total, self.d, dev)
+        # several ranks: "p2p" maps the workspaces into each other (NVLink peer reads + flag barriers inside the median kernels);
+        # "nccl" keeps the collective protocol (one table all-reduce + three histogram all-reduces per step)
+        if median_comm not in ("p2p", "nccl"):
+            raise ValueError("median_comm must be 'p2p' or 'nccl'")
+        use_p2p = (self.world > 1 and self.world <= 8 and median_comm == "p2p" and getattr(self.kernel, "sigma", None) is None
+                   and bool(_lib.load().bode_svgd_staged_supported(self.n_total, self.d)))
+        self._ws = _Workspace(self.P_local, self.n_total, self.d, dev, peers=(self.rank, self.world) if use_p2p else None)
+        self.median_comm = "p2p" if self._ws.p2p else ("nccl" if self.world > 1 else "local")
         self.phi_buf = torch.empty_like(self._flat)
         if self.world > 1:
             self._gath = torch.empty(2, self.n_total, self.d, dtype=torch.float32, device=dev)
@@ -189,10 +277,11 @@ class SVGD(Sampler):
                 old_split = lib.bode_svgd_set_gram_split(16)
                 self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
                 lib.bode_svgd_set_gram_split(old_split)
-                if self.world == 1:
+                if self.world == 1 or self._ws.p2p:
                     self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=None)
-                # several ranks: the median's all-reduces are issued by phi() AFTER the all-gather of the scores -- one
-                # communicator executes collectives in issue order, and the scores are ready long before the Gram pass ends
+                # collective protocol (median_comm="nccl"): the median's all-reduces are issued by phi() AFTER the all-gather
+                # of the scores -- one communicator executes collectives in issue order, and the scores are ready long
+                # before the Gram pass ends
         if self.overlap == "gram" and self.side_sms > 0:
             sms = lib.bode_device_sm_count()
             if sms > self.side_sms:
@@ -238,7 +327,7 @@ class SVGD(Sampler):
         if prefetched == "gram":
             phi_stage(_lib.SVGD_PREPARE)                    # the V operand needs the scores: here, while the side stream finishes
             cur.wait_stream(self._side)                     # join: d2 (single rank: also median and gamma) are ready
-            if self.world > 1:
+            if self.world > 1 and not ws.p2p:
                 ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True)
             phi_stage(_lib.SVGD_COMPUTE)
         elif prefetched:

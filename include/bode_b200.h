@@ -343,6 +343,22 @@ int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t ld_rows, in
                          const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                          int64_t ld_theta, float step, bode_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------
+ * Peer-mapped SVGD workspaces (ranks of one NVLink / NVSwitch node).  The reference is a single-process program; this is what
+ * replaces the "tiny histogram all-reduce" of SURVEY.md 8(e): every rank allocates its workspace with bode_peer_alloc, exports
+ * it (64-byte CUDA IPC handle, exchanged by the host layer), imports the others and registers the addresses with
+ * bode_svgd_set_peers.  bode_svgd_window_select / bode_svgd_radix_fallback then read the peers' window tables and radix
+ * histograms over NVLink and meet at flag barriers inside the kernels: the exact distributed median costs no collective launch,
+ * and the call order of a rank is the single-rank one (bode_svgd_sqdist -> bode_svgd_window_select -> bode_svgd_radix_fallback
+ * -> bode_svgd_phi).  Every rank must issue the same sequence of these calls.
+ * ------------------------------------------------------------------------------------- */
+int bode_peer_alloc(size_t bytes, void** out);
+int bode_peer_free(void* ptr);
+int bode_peer_export(void* ptr, void* handle64);
+int bode_peer_import(const void* handle64, void** out);
+int bode_peer_release(void* imported);
+int bode_svgd_set_peers(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, void* const* bases, int32_t rank, int32_t world);
+
 #ifdef __cplusplus
 }
 #endif
