@@ -131,62 +131,84 @@ __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X
 // ---------------------------------------------------------------- Gram tiles + window count
 // One 32 x 32 chunk of a Gram tile: d2 values, window count, staged coalesced store.  FULL: the tile lies inside the matrix
 // (no bounds checks); DIAG: the tile intersects the diagonal (cdist(x, x) = 0 is forced there).
+// The d2 tile leaves the SM through the TMA engine: each warp stages 32 rows x 16 columns (2 KB, 64-byte rows, 64-byte swizzle so
+// that the lanes' 16-byte stores fall into distinct banks) and one lane issues a 2-D tensor store, which also clips the ragged
+// edges.  (The same data written with st.global -- 8 row segments of 64 bytes per warp instruction -- kept the LSU busy for 40 % of
+// the kernel: 158 -> 94 us at 4096 x 32768 with the stores removed.)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(smem_u32(src_smem))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 template <bool FULL, bool DIAG>
-__device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* ncs, float* stage, float nrow, int lane, int dcol, int row, int nr,
-                                            int colbase, int nc, int grow0, unsigned int wlo, unsigned int wspan,
-                                            unsigned long long* table, unsigned int& below, float* __restrict__ D2) {
+__device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* ncs, unsigned char* stage, const CUtensorMap* tmD2, float nrow,
+                                            int lane, int dcol, int row, int nr, int colbase, int nc, int grow0, unsigned int wlo,
+                                            unsigned int wspan, unsigned long long* table, unsigned int& below) {
+  const uint32_t sw = (uint32_t)(lane >> 1) & 3u;                // 64-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r / 2) % 4)
+  unsigned char* myrow = stage + lane * 64;
 #pragma unroll
   for (int hf = 0; hf < 2; ++hf) {
+    // Entries inside the window are rare (a fraction of a percent): the straight-line code only records WHICH of the lane's 16
+    // entries fell inside (one bit each); the reductions into the table are issued afterwards, off the common path.  (One
+    // predicated `red` per entry compiled to a BSSY / BRA / BSYNC region per entry: 17 instructions per entry instead of 8.)
+    unsigned int hits = 0u;
+    float o[16];
 #pragma unroll
     for (int k4 = 0; k4 < 4; ++k4) {
       const float4 nj = *reinterpret_cast<const float4*>(ncs + 16 * hf + 4 * k4);
       const float njv[4] = {nj.x, nj.y, nj.z, nj.w};
-      float o[4];
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int c = 16 * hf + 4 * k4 + e;
         float v = fmaxf(fmaf(-2.f, s[c], nrow + njv[e]), 0.f);
         if (DIAG && c == dcol) v = 0.f;                          // cdist(x, x) = 0 on the diagonal
-        o[e] = v;
+        o[4 * k4 + e] = v;
         unsigned int off = __float_as_uint(v) - wlo;             // wraps (sign bit set) for entries below the window
         if (!FULL && !(row < nr && colbase + c < nc)) off = 0x7fffffffu;      // outside the matrix: neither below nor inside
         below += off >> 31;
-        // predicated reduction, no branch: the address is only dereferenced when the entry lies inside the window
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.le.u32 p, %1, %2;\n\t@p red.global.add.u64 [%0], 1;\n\t}" ::"l"(table + off), "r"(off), "r"(wspan)
-                     : "memory");
+        hits |= (off <= wspan) ? (1u << (4 * k4 + e)) : 0u;
       }
-      *reinterpret_cast<float4*>(stage + lane * 20 + 4 * k4) = make_float4(o[0], o[1], o[2], o[3]);
     }
+    if (lane == 0) bulk_wait_read0();                            // the previous store has read the staging buffer (long ago, usually)
     __syncwarp();
-    // coalesced rows: 4 lanes cover the 64 bytes of one row of the 16-column half
 #pragma unroll
-    for (int rr = 0; rr < 32; rr += 8) {
-      const int r2 = rr + (lane >> 2), c4 = lane & 3;
-      const int grow = grow0 + r2, gcol = colbase + 16 * hf + 4 * c4;
-      if (FULL || (grow < nr && gcol < nc))
-        *reinterpret_cast<float4*>(D2 + (long long)grow * nc + gcol) = *reinterpret_cast<const float4*>(stage + r2 * 20 + 4 * c4);
-    }
+    for (int k4 = 0; k4 < 4; ++k4)
+      *reinterpret_cast<float4*>(myrow + (((uint32_t)k4 ^ sw) << 4)) = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
+    if (lane == 0) tma_store_2d(tmD2, stage, colbase + 16 * hf, grow0);
+    while (hits) {                                               // the lane's own staged row still holds the values
+      const int b = __ffs(hits) - 1;
+      hits &= hits - 1u;
+      const float v = *reinterpret_cast<const float*>(myrow + ((((uint32_t)b >> 2) ^ sw) << 4) + ((b & 3) << 2));
+      atomicAdd(table + (__float_as_uint(v) - wlo), 1ull);
+    }
   }
 }
 
 struct Gram2Smem {
   static constexpr uint32_t A = 0;                                  // hi | lo
   static constexpr uint32_t B = 2 * BLK_BYTES;                      // 2 slots x (hi | lo)
-  static constexpr uint32_t STAGE = B + 4 * BLK_BYTES;              // per warp [32][20] floats (16 columns at a time)
-  static constexpr uint32_t NCS = STAGE + NWARP * 32 * 20 * 4;      // per warp 32 column norms
+  static constexpr uint32_t STAGE = B + 4 * BLK_BYTES;              // per warp 32 rows x 64 bytes (16 columns at a time), 64-byte swizzle
+  static constexpr uint32_t STAGE_WARP = 32 * 64;
+  static constexpr uint32_t NCS = STAGE + NWARP * STAGE_WARP;       // per warp 32 column norms
   static constexpr uint32_t BARS = NCS + NWARP * 32 * 4;            // barA, barB[2], barS[2], barE[2]
   static constexpr uint32_t TSLOT = BARS + 7 * 8;
-  static constexpr uint32_t TOTAL = TSLOT + 16;
+  static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;              // + slack to align the dynamic base to 1024 bytes
 };
+static_assert(Gram2Smem::STAGE % 1024 == 0, "swizzled staging buffers need an aligned base");
 
-__global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restrict__ XrH, const float* __restrict__ XrL,
+__global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constant__ CUtensorMap tmD2, const float* __restrict__ XrH, const float* __restrict__ XrL,
                                                         const float* __restrict__ nrm_r, int nr, int row_offset,
                                                         const float* __restrict__ XcH, const float* __restrict__ XcL,
                                                         const float* __restrict__ nrm_c, int nc, int tiles_per_cta,
-                                                        float* __restrict__ D2, SelState* __restrict__ st,
-                                                        unsigned long long* __restrict__ table) {
-  extern __shared__ __align__(128) unsigned char sm[];
+                                                        SelState* __restrict__ st, unsigned long long* __restrict__ table) {
+  extern __shared__ unsigned char sm_raw_g[];
+  unsigned char* sm = sm_raw_g + ((1024u - (smem_u32(sm_raw_g) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Gram2Smem::BARS);
   uint64_t* barA = bars;
   uint64_t* barB = bars + 1;
@@ -271,7 +293,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restr
     const int rl = 32 * q + lane;
     const int row = rb * BLK + rl;
     const float nrow = __ldg(nrm_r + row);
-    float* stage = reinterpret_cast<float*>(sm + Gram2Smem::STAGE) + warp * 32 * 20;
+    unsigned char* stage = sm + Gram2Smem::STAGE + warp * Gram2Smem::STAGE_WARP;
     float* ncs = reinterpret_cast<float*>(sm + Gram2Smem::NCS) + warp * 32;
     const bool win = st->win_valid != 0;
     // disarmed: wlo = 0x80000000 makes every offset wrap to >= 0x80000000 - 0x7f800000 > 0 with the sign bit clear only for
@@ -297,10 +319,11 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const float* __restr
       const int dtile = rb * BLK + 32 * q + row_offset - (c0 + cb);  // warp-uniform: diagonal crosses this chunk iff -31 <= dtile <= 31
       const bool diag = dtile > -32 && dtile < 32;
       const int grow0 = rb * BLK + 32 * q, colbase = c0 + cb;
-      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
-      else if (full) gram2_chunk<true, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
-      else gram2_chunk<false, true>(s, ncs, stage, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, D2);
+      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
+      else if (full) gram2_chunk<true, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
+      else gram2_chunk<false, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
     }
+    if (lane == 0) bulk_wait_all0();                               // this warp's tensor stores are complete before the CTA retires
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) below += __shfl_xor_sync(0xffffffffu, below, o);
     if (lane == 0 && win && below) atomicAdd(table + WIN_TABLE, (unsigned long long)below);
@@ -702,6 +725,33 @@ size_t svgd_tc2_carved_bytes(int nr, int nc) {
 
 int svgd_tc2_supported(int d, int nc) { return d >= 1 && d <= 55 && (nc & 3) == 0 && nc >= 4; }
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+// Row-major d2[nr][nc] as a 2-D tensor: box = bx columns x by rows
+static int encode_d2_map(CUtensorMap* tm, const float* D2, int nr, int nc, int bx, int by, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  BODE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[2] = {(cuuint64_t)nc, (cuuint64_t)nr};
+  const cuuint64_t gstr[1] = {(cuuint64_t)nc * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)bx, (cuuint32_t)by};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  return BODE_OK;
+}
+
 static int g_gram_split = 0;   // 0 = one wave over all SMs; > 0: column splits per row block (finer CTAs when the Gram pass shares the GPU)
 int svgd_tc2_set_gram_split(int js) {
   const int old = g_gram_split;
@@ -715,6 +765,25 @@ static int split_for(int blocks_y, int units, int sms) {
   if (js > 16) js = 16;
   if (js > units) js = units;
   return js;
+}
+
+// Column tiles per Gram CTA (one CTA per SM is resident).  The grid is (column chunks, row blocks); its cost is
+// waves x (tiles per CTA + a fixed prologue of about one tile: TMEM allocation, A tile, pipeline fill).  One chunk count per
+// row block rarely fills the last wave (32 row blocks x 4 chunks = 128 CTAs on 148 SMs: 64 tile times for 8192 tiles, where
+// 9 chunks of 29 tiles take 2 x 29 = 58), so the choice is made by enumeration.
+static int gram_tiles_per_cta(int nrb, int nct, int sms) {
+  int best = nct;
+  long long best_cost = -1;
+  for (int tp = 1; tp <= nct; ++tp) {
+    const long long chunks = (nct + tp - 1) / tp;
+    const long long waves = (chunks * nrb + sms - 1) / sms;
+    const long long cost = waves * (tp + 1);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = tp;
+    }
+  }
+  return best;
 }
 
 // stages: bit 0 = operand preparation (pre-split, centred column operands; needs only the positions), bit 1 = the Gram kernel
@@ -743,11 +812,17 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
     attr_set = true;
   }
   const int nrb = nrp / BLK, nct = ncp / BLK;
-  int js = g_gram_split > 0 ? g_gram_split : split_for(nrb, nct, sms);
-  if (js > nct) js = nct;
-  const int tiles_per = (nct + js - 1) / js;
+  int tiles_per;
+  if (g_gram_split > 0) {
+    const int js = g_gram_split > nct ? nct : g_gram_split;
+    tiles_per = (nct + js - 1) / js;
+  } else {
+    tiles_per = gram_tiles_per_cta(nrb, nct, sms);
+  }
   dim3 grid((nct + tiles_per - 1) / tiles_per, nrb);
-  gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, D2, st, o.table);
+  CUtensorMap tm;                                                     // d2 tile stores: 16 columns x 32 rows per warp, 64-byte swizzle
+  if (int rc = encode_d2_map(&tm, D2, nr, nc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
+  gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(tm, rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, st, o.table);
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
@@ -776,19 +851,6 @@ int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const P
 
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc) { return svgd_tc2_carve(ops_base, nr, nc).table; }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
                  long long ldr, float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t stream) {
@@ -809,16 +871,8 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
     attr_set = true;
   }
   // TMA descriptor of the row-major d2[nr][nc] matrix: box = 32 columns x 128 rows, 128-byte swizzle, zero fill outside
-  EncodeTiledFn enc = encode_tiled_fn();
-  BODE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
   CUtensorMap tm;
-  const cuuint64_t gdim[2] = {(cuuint64_t)nc, (cuuint64_t)nr};
-  const cuuint64_t gstr[1] = {(cuuint64_t)nc * 4};
-  const cuuint32_t box[2] = {(cuuint32_t)PK2, (cuuint32_t)BLK};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUresult cr = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)D2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d)", (int)cr);
+  if (int rc = encode_d2_map(&tm, D2, nr, nc, PK2, BLK, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
   dim3 grid(nrb, js);
   Phi2Combine cmb;
   cmb.Xr = Xr; cmb.ldr = ldr; cmb.mu = mu; cmb.inv_n = inv_n; cmb.phi = phi; cmb.ldp = ldp; cmb.theta = theta; cmb.ldt = ldt; cmb.step = step;
