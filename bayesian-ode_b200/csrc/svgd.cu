@@ -30,6 +30,7 @@ int svgd_tc_combine(const float* part, int jsplit, int nr, int d, const float* X
                     float inv_n, float* phi, long long ldp, float* theta, long long ldt, float step, cudaStream_t st);
 // pipelined tensor-core path with resident A tiles, bulk-copied operands and the median window (svgd_tc2.cu)
 int svgd_tc2_supported(int d, int nc);
+int svgd_tc2_d2_tiled(int nr, int nc);
 size_t svgd_tc2_carved_bytes(int nr, int nc);
 int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, float* mu,
                   void* ops_base, float* D2, SelState* st, unsigned long long total, int sms, int stages, cudaStream_t stream);
@@ -543,6 +544,10 @@ extern "C" int bode_svgd_set_gram_split(int32_t column_splits) { return svgd_tc2
 
 extern "C" int bode_svgd_staged_supported(int32_t n_cols, int32_t d) {
   return (g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols)) ? 1 : 0;
+}
+
+extern "C" int bode_svgd_d2_tiled(int32_t n_rows, int32_t n_cols, int32_t d) {
+  return (bode_svgd_staged_supported(n_cols, d) && svgd_tc2_d2_tiled(n_rows, n_cols)) ? 1 : 0;
 }
 
 /* stages: BODE_SVGD_PREPARE (column means, selection-state reset, pre-split operands: needs only the positions) and / or

@@ -8,7 +8,7 @@
 //                                   double-buffered in TMEM (2 x 128 columns) so tile t+1's MMAs run under tile t's epilogue.
 //                                   The epilogue also counts the window of the exact median selection (svgd_state.cuh).
 //   phi2_kernel                     part[i,:] = sum_j 2^(-g d2_ij) [ -grad_j | xc_j | 1 ]   (stein.py:75-86).  d2 tiles arrive
-//                                   by cp.async three stages ahead, V^T tiles by bulk copy, the exp/split of stage t runs
+//                                   by 2-D TMA six stages ahead, V^T tiles by bulk copy, the exp/split of stage t runs
 //                                   under the MMAs of stage t-1.
 // Warp 16 issues the MMAs (its issue loop is back-pressured by the tensor core), warp 17 the bulk / TMA copies; warps 0-15 (four per
 // SM sub-partition) own the TMEM lanes / operand generation.  Inside the tile loops the warps meet only through mbarriers.
@@ -141,13 +141,20 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
+// the same store into the tiled d2 layout [row block][column stage][128][32] (see svgd_tc2_d2_tiled)
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c0), "r"(c1),
+               "r"(c2), "r"(c3), "r"(smem_u32(src_smem))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 template <bool FULL, bool DIAG>
 __device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* ncs, unsigned char* stage, const CUtensorMap* tmD2, float nrow,
                                             int lane, int dcol, int row, int nr, int colbase, int nc, int grow0, unsigned int wlo,
-                                            unsigned int wspan, unsigned long long* table, unsigned int& below) {
+                                            unsigned int wspan, unsigned long long* table, unsigned int& below, bool tiled) {
   const uint32_t sw = (uint32_t)(lane >> 1) & 3u;                // 64-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r / 2) % 4)
   unsigned char* myrow = stage + lane * 64;
 #pragma unroll
@@ -180,7 +187,10 @@ __device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* n
       *reinterpret_cast<float4*>(myrow + (((uint32_t)k4 ^ sw) << 4)) = make_float4(o[4 * k4], o[4 * k4 + 1], o[4 * k4 + 2], o[4 * k4 + 3]);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
-    if (lane == 0) tma_store_2d(tmD2, stage, colbase + 16 * hf, grow0);
+    if (lane == 0) {
+      if (tiled) tma_store_4d(tmD2, stage, 16 * hf, grow0 & (BLK - 1), colbase / PK2, grow0 / BLK);   // a chunk is one column stage wide
+      else tma_store_2d(tmD2, stage, colbase + 16 * hf, grow0);
+    }
     while (hits) {                                               // the lane's own staged row still holds the values
       const int b = __ffs(hits) - 1;
       hits &= hits - 1u;
@@ -206,7 +216,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constan
                                                         const float* __restrict__ nrm_r, int nr, int row_offset,
                                                         const float* __restrict__ XcH, const float* __restrict__ XcL,
                                                         const float* __restrict__ nrm_c, int nc, int tiles_per_cta,
-                                                        SelState* __restrict__ st, unsigned long long* __restrict__ table) {
+                                                        SelState* __restrict__ st, unsigned long long* __restrict__ table, int tiled) {
   extern __shared__ unsigned char sm_raw_g[];
   unsigned char* sm = sm_raw_g + ((1024u - (smem_u32(sm_raw_g) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Gram2Smem::BARS);
@@ -319,9 +329,9 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constan
       const int dtile = rb * BLK + 32 * q + row_offset - (c0 + cb);  // warp-uniform: diagonal crosses this chunk iff -31 <= dtile <= 31
       const bool diag = dtile > -32 && dtile < 32;
       const int grow0 = rb * BLK + 32 * q, colbase = c0 + cb;
-      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
-      else if (full) gram2_chunk<true, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
-      else gram2_chunk<false, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below);
+      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
+      else if (full) gram2_chunk<true, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
+      else gram2_chunk<false, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
     }
     if (lane == 0) bulk_wait_all0();                               // this warp's tensor stores are complete before the CTA retires
 #pragma unroll
@@ -457,11 +467,15 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
 
 // ---------------------------------------------------------------- phi partials
 struct Phi2Smem {
-  static constexpr uint32_t RAW = 0;                                   // 3 slots x [128][32] floats, TMA tile with 128-byte swizzle
+  // d2 ring: NRAW slots x [128][32] floats, TMA tiles with 128-byte swizzle.  Six stages (96 KB per CTA, 12 MB over the GPU) in
+  // flight: with three, the worker warps spent 37 % of their samples waiting for tiles once the d2 block no longer fits in L2
+  // (several ranks: 4096 x 32768 floats = 537 MB per rank).
+  static constexpr int NRAW = 6;
+  static constexpr uint32_t RAW = 0;
   static constexpr uint32_t RAW_SLOT = BLK * PK2 * 4;                  // 16384 (1024-byte aligned)
-  static constexpr uint32_t V = RAW + 3 * RAW_SLOT;                    // 3 slots x (hi | lo); the K tile (A operand) lives in TMEM
-  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[3], barR[3], barKV[6]
-  static constexpr uint32_t TSLOT = BARS + 12 * 8;
+  static constexpr uint32_t V = RAW + NRAW * RAW_SLOT;                 // 3 slots x (hi | lo); the K tile (A operand) lives in TMEM
+  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[3], barR[NRAW], barKV[6]
+  static constexpr uint32_t TSLOT = BARS + 16 * 8;
   static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;                 // + slack to align the dynamic base to 1024 bytes
 };
 
@@ -470,6 +484,12 @@ __device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* t
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
                    smem_u32(dst_smem)),
                "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
                : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (one row per TMEM lane, K 32-bit columns) never touches shared memory
@@ -505,7 +525,7 @@ struct Phi2Combine {
 
 __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
-                                                       float* __restrict__ part, const Phi2Combine cmb) {
+                                                       float* __restrict__ part, const Phi2Combine cmb, int tiled) {
   extern __shared__ unsigned char sm_raw[];
   // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
@@ -513,8 +533,9 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   // An mbarrier wait costs ~250 cycles on this part even when the phase is already complete (clock64 trace of one CTA), so the
   // MMA thread gets ONE barrier per stage: barKV completes when all 16 worker warps have written K(t) AND V(t) has landed.
   uint64_t* barM = bars;          // [3] MMAs of stage t retired: K slot t % 3 and V slot t % 3 are free
-  uint64_t* barR = bars + 3;      // [3] d2 tile landed
-  uint64_t* barKV = bars + 6;     // [6] stage t ready for the tensor core (count NWARP + 1 arrivals, + the V bytes)
+  constexpr int NRAW = Phi2Smem::NRAW;
+  uint64_t* barR = bars + 3;      // [NRAW] d2 tile landed
+  uint64_t* barKV = bars + 3 + NRAW;   // [6] stage t ready for the tensor core (count NWARP + 1 arrivals, + the V bytes)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + Phi2Smem::TSLOT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * BLK;
@@ -527,7 +548,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) mbar_init(barM + i, 1);
-    for (int i = 0; i < 3; ++i) mbar_init(barR + i, 1);
+    for (int i = 0; i < NRAW; ++i) mbar_init(barR + i, 1);
     for (int i = 0; i < 6; ++i) mbar_init(barKV + i, NWARP + 1);
   }
   tc_fence_before();
@@ -540,7 +561,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   // No CTA-wide barrier inside the stage loop: the warps only meet through mbarriers, so a slow warp delays nobody but the MMA
   // that needs its rows.
   if (warp == NWARP + 1) {
-    // ---------------- loader warp (lane 0): d2 tiles by 2-D TMA three stages ahead, V^T tiles by bulk copy two stages ahead.
+    // ---------------- loader warp (lane 0): d2 tiles by 2-D TMA NRAW stages ahead, V^T tiles by bulk copy two stages ahead.
     // It only waits for slots to drain (barKV: the workers consumed raw(t); barM: the MMAs that read V(t-1) retired), so the
     // MMA-issuing thread never spends time on copies.
     if (lane == 0 && nst > 0) {
@@ -554,14 +575,13 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       };
       auto load_raw = [&](int t) {
         if (t < nst) {
-          const int slot = t % 3;
+          const int slot = t % NRAW;
           mbar_expect_tx(barR + slot, Phi2Smem::RAW_SLOT);             // out-of-range box elements are zero-filled and counted
-          tma_load_2d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, (s0 + t) * PK2, r0, barR + slot);
+          if (tiled) tma_load_4d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, 0, 0, s0 + t, blockIdx.x, barR + slot);
+          else tma_load_2d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, (s0 + t) * PK2, r0, barR + slot);
         }
       };
-      load_raw(0);
-      load_raw(1);
-      load_raw(2);
+      for (int t = 0; t < NRAW; ++t) load_raw(t);
       load_v(0);
       if (nst > 1) load_v(1);
       for (int t = 0; t < nst; ++t) {
@@ -569,9 +589,9 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
           if (t >= 1) mbar_wait(barM + (t - 1) % 3, ((t - 1) / 3) & 1);      // V(t+2) reuses the slot of V(t-1)
           load_v(t + 2);
         }
-        if (t + 3 < nst) {
+        if (t + NRAW < nst) {
           mbar_wait(barKV + t % 6, (t / 6) & 1);                       // raw(t) consumed by every worker warp
-          load_raw(t + 3);
+          load_raw(t + NRAW);
         }
       }
     }
@@ -605,8 +625,8 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
     // 128-byte swizzle of the TMA tile: 16-byte chunk c of row r sits at chunk c ^ (r % 8)
     const uint32_t roff0 = rl * 128 + (((2 * qd) ^ (rl & 7)) << 4), roff1 = rl * 128 + (((2 * qd + 1) ^ (rl & 7)) << 4);
     for (int t = 0; t < nst; ++t) {
-      mbar_wait(barR + (t % 3), (t / 3) & 1);                          // d2 tile of this stage has landed
-      const unsigned char* raw = sm + Phi2Smem::RAW + (t % 3) * Phi2Smem::RAW_SLOT;
+      mbar_wait(barR + (t % NRAW), (t / NRAW) & 1);                    // d2 tile of this stage has landed
+      const unsigned char* raw = sm + Phi2Smem::RAW + (t % NRAW) * Phi2Smem::RAW_SLOT;
       const float4 dv0 = *reinterpret_cast<const float4*>(raw + roff0), dv1 = *reinterpret_cast<const float4*>(raw + roff1);
       float kv[8] = {ex2(ngamma * dv0.x), ex2(ngamma * dv0.y), ex2(ngamma * dv0.z), ex2(ngamma * dv0.w),
                      ex2(ngamma * dv1.x), ex2(ngamma * dv1.y), ex2(ngamma * dv1.z), ex2(ngamma * dv1.w)};
@@ -752,6 +772,25 @@ static int encode_d2_map(CUtensorMap* tm, const float* D2, int nr, int nc, int b
   return BODE_OK;
 }
 
+// d2 layout inside the workspace.  Row-major [nr][nc] in general; when both edges are whole tiles the block is stored as
+// [nr / 128][nc / 32][128][32], i.e. every 16 KB tile a K@V stage consumes is CONTIGUOUS.  A stage tile of the row-major matrix
+// is 128 segments of 128 bytes, one per DRAM page: once the block has left L2 (several ranks: 537 MB per rank at 8 x 4096
+// particles) those reads ran at 3.2 TB/s.  The order statistics do not care about the order of the entries.
+int svgd_tc2_d2_tiled(int nr, int nc) { return (nr % BLK == 0 && nc % PK2 == 0) ? 1 : 0; }
+static int encode_d2_map_tiled(CUtensorMap* tm, const float* D2, int nr, int nc, int bx, int by, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  BODE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t nst = (cuuint64_t)(nc / PK2);
+  const cuuint64_t gdim[4] = {(cuuint64_t)PK2, (cuuint64_t)BLK, nst, (cuuint64_t)(nr / BLK)};
+  const cuuint64_t gstr[3] = {(cuuint64_t)PK2 * 4, (cuuint64_t)BLK * PK2 * 4, (cuuint64_t)BLK * PK2 * 4 * nst};
+  const cuuint32_t box[4] = {(cuuint32_t)bx, (cuuint32_t)by, 1, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult cr = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, (void*)D2, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  BODE_REQUIRE(cr == CUDA_SUCCESS, "cuTensorMapEncodeTiled (tiled d2) failed (%d)", (int)cr);
+  return BODE_OK;
+}
+
 static int g_gram_split = 0;   // 0 = one wave over all SMs; > 0: column splits per row block (finer CTAs when the Gram pass shares the GPU)
 int svgd_tc2_set_gram_split(int js) {
   const int old = g_gram_split;
@@ -821,8 +860,12 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
   }
   dim3 grid((nct + tiles_per - 1) / tiles_per, nrb);
   CUtensorMap tm;                                                     // d2 tile stores: 16 columns x 32 rows per warp, 64-byte swizzle
-  if (int rc = encode_d2_map(&tm, D2, nr, nc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)) return rc;
-  gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(tm, rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, st, o.table);
+  const int tiled = svgd_tc2_d2_tiled(nr, nc);
+  if (int rc = tiled ? encode_d2_map_tiled(&tm, D2, nr, nc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B)
+                     : encode_d2_map(&tm, D2, nr, nc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))
+    return rc;
+  gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(tm, rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, st, o.table,
+                                                             tiled);
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
@@ -872,7 +915,10 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   }
   // TMA descriptor of the row-major d2[nr][nc] matrix: box = 32 columns x 128 rows, 128-byte swizzle, zero fill outside
   CUtensorMap tm;
-  if (int rc = encode_d2_map(&tm, D2, nr, nc, PK2, BLK, CU_TENSOR_MAP_SWIZZLE_128B)) return rc;
+  const int tiled = svgd_tc2_d2_tiled(nr, nc);
+  if (int rc = tiled ? encode_d2_map_tiled(&tm, D2, nr, nc, PK2, BLK, CU_TENSOR_MAP_SWIZZLE_128B)
+                     : encode_d2_map(&tm, D2, nr, nc, PK2, BLK, CU_TENSOR_MAP_SWIZZLE_128B))
+    return rc;
   dim3 grid(nrb, js);
   Phi2Combine cmb;
   cmb.Xr = Xr; cmb.ldr = ldr; cmb.mu = mu; cmb.inv_n = inv_n; cmb.phi = phi; cmb.ldp = ldp; cmb.theta = theta; cmb.ldt = ldt; cmb.step = step;
@@ -889,7 +935,7 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb));
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb, tiled));
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 

@@ -191,7 +191,12 @@ class _Workspace:
         _lib.check(lib.bode_svgd_gamma(n_total, float(sigma or 0.0), nr, nc, d, w, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
 
     def d2(self, nr, nc):
-        return self.base[:nr * nc * 4].view(torch.float32).view(nr, nc)
+        """The squared-distance block as a [nr, nc] matrix (a view when the workspace holds it row-major, a gathered copy when
+        it is stored as [nr/128][nc/32][128][32] tiles, ``bode_svgd_d2_tiled``)."""
+        flat = self.base[:nr * nc * 4].view(torch.float32)
+        if _lib.load().bode_svgd_d2_tiled(nr, nc, self._dims[2]):
+            return flat.view(nr // 128, nc // 32, 128, 32).permute(0, 2, 1, 3).reshape(nr, nc)
+        return flat.view(nr, nc)
 
 
 class SVGD(Sampler):

@@ -332,6 +332,12 @@ int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const flo
 #define BODE_SVGD_PREPARE 1
 #define BODE_SVGD_COMPUTE 2
 int bode_svgd_staged_supported(int32_t n_cols, int32_t d);
+/* Layout of the d2 block at the start of the workspace (internal to sqdist -> median -> phi; exposed for tests and for
+ * RBFKernel.forward, stein.py:22-32, which returns the kernel matrix).  0: row-major [n_rows][n_cols].  1: tiles
+ * [n_rows / 128][n_cols / 32][128][32] -- chosen by the pipelined tensor-core kernels when both edges are whole tiles, so that
+ * every 16 KB tile the K@V pass consumes is contiguous in HBM.  The layout must not change between a bode_svgd_sqdist and the
+ * bode_svgd_phi that consumes it (i.e. no bode_svgd_set_tensor_cores in between). */
+int bode_svgd_d2_tiled(int32_t n_rows, int32_t n_cols, int32_t d);
 /* CTA granularity of the Gram kernel: column_splits CTAs per 128-row block (0 = automatic: one wave over all SMs).  A finer
  * split shortens the tail when the Gram pass shares the GPU with the fused solve.  Returns the previous setting. */
 int bode_svgd_set_gram_split(int32_t column_splits);
