@@ -108,6 +108,8 @@ SYMBOLS = {
     "bode_svgd_staged_supported": (C.c_int, [C.c_int32, C.c_int32]),
     "bode_svgd_set_gram_split": (C.c_int, [C.c_int32]),
     "bode_svgd_d2_tiled": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    "bode_svgd_peer_gather": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.POINTER(C.c_void_p), C.c_void_p]),
     "bode_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "bode_peer_free": (C.c_int, [_P]),
     "bode_peer_export": (C.c_int, [_P, _P]),

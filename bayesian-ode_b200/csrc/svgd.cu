@@ -479,12 +479,14 @@ extern "C" size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int3
   b += 256;                                                     // column means (tensor-core path)
   b += 256;                                                     // peer barrier flags (svgd_state.cuh)
   b += svgd_tc2_carved_bytes(n_rows, n_cols);                   // pre-split operands + median window table
+  b += 2 * ((((size_t)n_cols * d * sizeof(float)) + 255) / 256 * 256) + 256;   // gathered positions / scores (bode_svgd_peer_gather) + tickets
   return b + 1024;
 }
 
 namespace {
 struct Ws {
   float* d2; float* part; unsigned long long* hist; SelState* st; float* mu; PeerFlags* flags; void* ops;
+  float* gath[2]; unsigned int* tickets;
 };
 Ws carve(void* ws, int nr, int nc, int d) {
   Ws w;
@@ -496,6 +498,12 @@ Ws carve(void* ws, int nr, int nc, int d) {
   w.mu = (float*)p; p += 256;
   w.flags = (PeerFlags*)p; p += 256;
   w.ops = p;
+  p += svgd_tc2_carved_bytes(nr, nc);
+  p = (char*)(((uintptr_t)p + 255) / 256 * 256);
+  const size_t gb = (((size_t)nc * d * sizeof(float)) + 255) / 256 * 256;
+  w.gath[0] = (float*)p; p += gb;
+  w.gath[1] = (float*)p; p += gb;
+  w.tickets = (unsigned int*)p;
   return w;
 }
 // workspace -> peer mapping (bode_svgd_set_peers); absent = single rank
@@ -537,6 +545,92 @@ extern "C" int bode_svgd_set_peers(void* workspace, int32_t n_rows, int32_t n_co
   p.table_off = (unsigned long long)((char*)svgd_tc2_table(w.ops, n_rows, n_cols) - (char*)workspace);
   p.flag_off = (unsigned long long)((char*)w.flags - (char*)workspace);
   g_peers[workspace] = p;
+  return BODE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// All-gather over peer memory (the SVGD data-path exchange of SURVEY.md 8(e), without a collective launch).  Every rank PUSHES
+// its rows into the gather buffer of every rank's workspace (posted NVLink writes) between two flag barriers:
+//   entry  every rank has reached this gather, i.e. finished the kernels of the previous step that read the buffer;
+//   exit   every rank's rows have landed everywhere (release / acquire at system scope).
+// The barriers use their own flag block per buffer (block 0 belongs to the median kernels, which run on another stream).  The
+// first CTA to start signals the entry, the last CTA to finish pushing signals the exit and waits: the kernel does not retire
+// before the gathered buffer is complete, so the consumers simply follow it in stream order.
+__device__ __forceinline__ void peer_signal(const PeerInfo& p, int fb, unsigned int e) {
+  __threadfence_system();
+  for (int q = 0; q < p.world; ++q) {
+    unsigned int* f = &reinterpret_cast<PeerFlags*>(p.base[q] + p.flag_off + 64 * fb)->arrived[p.rank];
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(f), "r"(e) : "memory");
+  }
+}
+__device__ __forceinline__ void peer_wait(const PeerInfo& p, PeerFlags* mine, unsigned int e) {
+  for (int q = 0; q < p.world; ++q) {
+    unsigned int v;
+    long long spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(&mine->arrived[q]) : "memory");
+    } while ((int)(v - e) < 0 && ++spins < (1ll << 24));
+    if ((int)(v - e) < 0) mine->timed_out = 1u;
+  }
+}
+
+__global__ void __launch_bounds__(256) peer_gather_kernel(const float* __restrict__ src, long long ld, int n_rows, int d, const PeerInfo peer,
+                                                          unsigned long long gath_off, int fb, unsigned int* tickets) {
+  PeerFlags* mine = reinterpret_cast<PeerFlags*>(peer.base[peer.rank] + peer.flag_off + 64 * fb);
+  __shared__ unsigned int e_s;
+  if (threadIdx.x == 0) {
+    const unsigned int e = *reinterpret_cast<volatile unsigned int*>(&mine->epoch) + 1u;
+    if (atomicAdd(tickets + 2 * fb, 1u) == 0u) peer_signal(peer, fb, e);
+    peer_wait(peer, mine, e);
+    e_s = e;
+  }
+  __syncthreads();
+  const long long n = (long long)n_rows * d;
+  const unsigned long long dst_off = gath_off + (unsigned long long)peer.rank * n * sizeof(float);
+  if (ld == d && (n & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+    const float4* s4 = reinterpret_cast<const float4*>(src);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < (n >> 2); i += (long long)gridDim.x * blockDim.x) {
+      const float4 v = __ldg(s4 + i);
+      for (int q = 0; q < peer.world; ++q) reinterpret_cast<float4*>(peer.base[q] + dst_off)[i] = v;
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+      const float v = __ldg(src + (i / d) * ld + (i % d));
+      for (int q = 0; q < peer.world; ++q) reinterpret_cast<float*>(peer.base[q] + dst_off)[i] = v;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (atomicAdd(tickets + 2 * fb + 1, 1u) == gridDim.x - 1) {            // every CTA of this rank has pushed (and fenced) its part
+      const unsigned int e = e_s + 1u;
+      tickets[2 * fb] = 0u;
+      tickets[2 * fb + 1] = 0u;
+      mine->epoch = e;
+      peer_signal(peer, fb, e);
+      peer_wait(peer, mine, e);
+    }
+  }
+}
+
+/* which = 0: particle positions, 1: scores.  rows[n_rows, d] (leading dimension ld) of this rank -> *gathered_out = the
+ * [n_cols, d] buffer (contiguous, rank-major) inside this rank's workspace, complete when the launch retires.  Needs
+ * bode_svgd_set_peers and n_cols == world * n_rows; every rank must issue the same sequence of gathers per buffer. */
+extern "C" int bode_svgd_peer_gather(int32_t which, const float* rows, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
+                                     float** gathered_out, bode_stream_t stream) {
+  BODE_REQUIRE(workspace && rows && gathered_out && (which == 0 || which == 1), "bad args");
+  const PeerInfo peer = peers_of(workspace);
+  BODE_REQUIRE(peer.world > 1, "workspace has no peers (bode_svgd_set_peers)");
+  BODE_REQUIRE((long long)peer.world * n_rows == n_cols, "n_cols must be world * n_rows");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  const unsigned long long off = (unsigned long long)((char*)w.gath[which] - (char*)workspace);
+  const long long n4 = ((long long)n_rows * d + 3) / 4;
+  int blocks = (int)((n4 + 255) / 256);
+  if (blocks > 32) blocks = 32;                      // all CTAs poll the entry flags: keep them few and co-resident
+  if (blocks < 1) blocks = 1;
+  peer_gather_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, ld, n_rows, d, peer, off, 1 + which, w.tickets);
+  BODE_CUDA(cudaGetLastError());
+  *gathered_out = w.gath[which];
   return BODE_OK;
 }
 
@@ -611,6 +705,7 @@ extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t 
   BODE_CUDA(cudaMemsetAsync(w.hist, 0, 2 * 2048 * sizeof(unsigned long long), (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(w.st, 0, 256, (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(w.flags, 0, 256, (cudaStream_t)stream));
+  BODE_CUDA(cudaMemsetAsync(w.tickets, 0, 256, (cudaStream_t)stream));
   BODE_CUDA(cudaMemsetAsync(svgd_tc2_table(w.ops, n_rows, n_cols), 0, 2 * (size_t)(WIN_TABLE + 1) * sizeof(unsigned long long) + 512, (cudaStream_t)stream));
   return BODE_OK;
 }

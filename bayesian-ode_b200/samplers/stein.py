@@ -95,6 +95,7 @@ class _Workspace:
         self.med_gamma = torch.zeros(2, dtype=torch.float32, device=device)
         self.hist_ptr = C.c_void_p()
         self._hist = None
+        self._gath = [None, None]
         self._dims = (nr, nc, d)
         _lib.check(lib.bode_svgd_workspace_init(nr, nc, d, C.c_void_p(self.base.data_ptr()), nbytes, _lib.stream_ptr()))
         tp, tn = C.c_void_p(), C.c_size_t()
@@ -190,6 +191,20 @@ class _Workspace:
                     lambda ps: _lib.check(lib.bode_svgd_select_digit(ps, nr, nc, d, w, _lib.stream_ptr())))
         _lib.check(lib.bode_svgd_gamma(n_total, float(sigma or 0.0), nr, nc, d, w, _lib.ptr(self.med_gamma), _lib.stream_ptr()))
 
+    def peer_gather(self, which, X):
+        """All-gather of this rank's rows over peer memory (``bode_svgd_peer_gather``: one push kernel between two flag barriers,
+        no collective).  which = 0 positions, 1 scores.  Returns the [n_cols, d] buffer inside the workspace."""
+        lib = _lib.load()
+        nr, nc, d = self._dims
+        xp, xs = _lib.rows(X, d)
+        out = C.c_void_p()
+        _lib.check(lib.bode_svgd_peer_gather(int(which), xp, xs, nr, nc, d, C.c_void_p(self.base.data_ptr()), C.byref(out),
+                                             _lib.stream_ptr()))
+        if self._gath[which] is None:
+            off = out.value - self.base.data_ptr()
+            self._gath[which] = self.base[off:off + nc * d * 4].view(torch.float32).view(nc, d)
+        return self._gath[which]
+
     def d2(self, nr, nc):
         """The squared-distance block as a [nr, nc] matrix (a view when the workspace holds it row-major, a gathered copy when
         it is stored as [nr/128][nc/32][128][32] tiles, ``bode_svgd_d2_tiled``)."""
@@ -221,7 +236,7 @@ class SVGD(Sampler):
     """
 
     def __init__(self, params, optimizer=None, kernel=None, num_particles=None, particle_init_fn=None, overlap="gram", side_sms=40,
-                 median_comm="p2p", **kwargs):
+                 median_comm="p2p", gather_comm="p2p", **kwargs):
         defaults = kwargs
         if "lr" not in defaults:
             defaults["lr"] = 1e-4                        # stein.py:40-41
@@ -244,8 +259,13 @@ class SVGD(Sampler):
                    and bool(_lib.load().bode_svgd_staged_supported(self.n_total, self.d)))
         self._ws = _Workspace(self.P_local, self.n_total, self.d, dev, peers=(self.rank, self.world) if use_p2p else None)
         self.median_comm = "p2p" if self._ws.p2p else ("nccl" if self.world > 1 else "local")
+        # the data-path exchange: "p2p" = push kernels over the peer-mapped workspaces (needs the mapping above), "nccl" = all-gather
+        if gather_comm not in ("p2p", "nccl"):
+            raise ValueError("gather_comm must be 'p2p' or 'nccl'")
+        self.gather_comm = "p2p" if (self._ws.p2p and gather_comm == "p2p") else ("nccl" if self.world > 1 else "local")
         self.phi_buf = torch.empty_like(self._flat)
-        if self.world > 1:
+        self._Xall = None
+        if self.world > 1 and self.gather_comm != "p2p":
             self._gath = torch.empty(2, self.n_total, self.d, dtype=torch.float32, device=dev)
         if overlap is True:
             overlap = "operands"
@@ -257,11 +277,17 @@ class SVGD(Sampler):
         self._prefetched = False
         self._saved_cta_limit = None
 
+    def _gather(self, which, X):
+        """The data-path exchange: rows of every rank -> [n_total, d] (which = 0 positions, 1 scores)."""
+        if self.world == 1:
+            return X
+        if self.gather_comm == "p2p":
+            return self._ws.peer_gather(which, X)
+        torch.distributed.all_gather_into_tensor(self._gath[which], X if X.is_contiguous() else X.contiguous())
+        return self._gath[which]
+
     def _gather_positions(self, X):
-        if self.world > 1:
-            torch.distributed.all_gather_into_tensor(self._gath[0], X)
-            return self._gath[0]
-        return X
+        return self._gather(0, X)
 
     def prefetch(self):
         """Fork the position-only part of the interaction (all-gather of the positions, pre-split Gram operands and, with
@@ -274,13 +300,15 @@ class SVGD(Sampler):
         self._side.wait_stream(cur)
         nl, nt, d = self.P_local, self.n_total, self.d
         with torch.cuda.stream(self._side):
-            Xall = self._gather_positions(self._flat)
-            self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
+            Xall = self._Xall = self._gather_positions(self._flat)
+            # the local rows as a block of the gathered columns: the Gram kernel then reuses the column operands for them
+            Xloc = Xall[self.rank * nl:(self.rank + 1) * nl] if self.world > 1 else self._flat
+            self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
             if self.overlap == "gram":
                 # finer Gram CTAs (two column tiles each): the pass shares the GPU with the solve, a one-wave grid would
                 # leave a long tail on the few SMs it gets (measured on B200: 147 -> 143 us per c3 step)
                 old_split = lib.bode_svgd_set_gram_split(16)
-                self._ws.sqdist(self._flat, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
+                self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
                 lib.bode_svgd_set_gram_split(old_split)
                 if self.world == 1 or self._ws.p2p:
                     self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=None)
@@ -313,12 +341,9 @@ class SVGD(Sampler):
             cur.wait_stream(self._side)                     # prefetched for other positions: drop it
         self._prefetched = False
         # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
-        Xall = (self._gath[0] if self.world > 1 else X) if prefetched else self._gather_positions(X)
-        if self.world > 1:
-            torch.distributed.all_gather_into_tensor(self._gath[1], G)
-            Gall = self._gath[1]
-        else:
-            Gall = G
+        Xall = self._Xall if (prefetched and self.world > 1) else self._gather_positions(X)
+        Gall = self._gather(1, G)
+        Xloc = Xall[self.rank * nl:(self.rank + 1) * nl] if self.world > 1 else X
         xr, xrs = _lib.rows(X, d)
         xc, xcs = _lib.rows(Xall, d)
         sc, scs = _lib.rows(Gall, d)
@@ -336,11 +361,11 @@ class SVGD(Sampler):
                 ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True)
             phi_stage(_lib.SVGD_COMPUTE)
         elif prefetched:
-            ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
+            ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
             ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
             phi_stage(both)
         else:
-            ws.sqdist(X, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=both)
+            ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=both)
             ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True if self.world > 1 else None)
             phi_stage(both)
         return self.phi_buf

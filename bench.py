@@ -10,7 +10,8 @@ Workloads:
   c3 (default)  Van der Pol npde, 5x5 inducing grid, SVGD, 4096 particles per GPU, N=5, T=40 -> 39 rk4 (3/8) steps
   c2            Van der Pol npde, pSGLD, 1024 independent chains per GPU, T=101 -> 100 rk4 steps
   c1            1 chain SGLD (the reference's own CPU-runnable case; parity-sized)
-One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); the only data-path collective is the SVGD all-gather.
+One process per GPU (torchrun sets RANK/LOCAL_RANK/WORLD_SIZE); the only data-path exchange is the SVGD all-gather of positions and scores
+(push kernels over NVLink peer memory; NCCL when the workspaces cannot be peer-mapped).
 """
 import argparse
 import json
@@ -252,6 +253,8 @@ def run_b200(args, wl):
             smp.step(use_ctl=True)
 
     launches_per_step = 7 if wl["sampler"] == "svgd" else 3
+    if wl["sampler"] == "svgd" and world > 1 and smp.gather_comm == "p2p":
+        launches_per_step += 2              # the two push-kernel all-gathers (positions, scores); with "nccl" they are NCCL's kernels
     peaks = measure_peaks(torch, bode)
 
     # eager warm-up (allocates every buffer), then capture one step in a CUDA graph (single-GPU path)
@@ -432,6 +435,10 @@ def run_b200(args, wl):
                    "parallelism": "particles sharded, dp%d" % world, "cuda_graph": bool(use_graph),
                    "streams": ("SVGD operands + Gram + exact median on a side stream beside the fused solve (solve packed into %d CTAs, %d SMs left "
                                "to the Gram pass)" % (148 - smp.side_sms, smp.side_sms)) if wl["sampler"] == "svgd" and smp.overlap == "gram" else "single",
+                   "exchange": ("none (one GPU)" if world == 1 else
+                                "positions + scores gathered by %s; exact median via %s" % (
+                                    "push kernels over NVLink peer memory (flag barriers, no collective)" if smp.gather_comm == "p2p" else "NCCL all-gather",
+                                    "peer reads + flag barriers" if smp.median_comm == "p2p" else "NCCL all-reduce")) if wl["sampler"] == "svgd" else "none (independent chains)",
                    "l2": "256 MiB memset between timed steps (outside the event brackets); working set < L2"},
         "roofline": roofline, "kernels": kernels, "peaks": peaks,
         "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clk,

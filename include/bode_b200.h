@@ -364,6 +364,14 @@ int bode_peer_export(void* ptr, void* handle64);
 int bode_peer_import(const void* handle64, void** out);
 int bode_peer_release(void* imported);
 int bode_svgd_set_peers(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, void* const* bases, int32_t rank, int32_t world);
+/* The data-path exchange itself over peer memory (the all-gather of particle positions and scores, which the
+ * reference, a single-process program, does not have): every rank pushes its rows[n_rows, d] into the gather buffer of every
+ * rank's workspace between two flag barriers, in ONE launch and without a collective.  which = 0 positions, 1 scores (separate
+ * buffers and barrier flags, so the two gathers may run on different streams).  *gathered_out = the [n_cols, d] rank-major
+ * buffer in THIS rank's workspace, complete when the launch retires.  Needs bode_svgd_set_peers and n_cols == world * n_rows;
+ * every rank issues the same sequence of gathers per buffer. */
+int bode_svgd_peer_gather(int32_t which, const float* rows, int64_t ld, int32_t n_rows, int32_t n_cols, int32_t d, void* workspace,
+                          float** gathered_out, bode_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -29,13 +29,14 @@ def _worker():
     U = U0[None] + 0.1 * torch.randn(P, 25, 2, generator=torch.Generator().manual_seed(3), dtype=torch.float64)
     lo, hi = rank * P // world, (rank + 1) * P // world
 
-    def run(Uslice, distributed, median_comm="p2p"):
+    def run(Uslice, distributed, median_comm="p2p", gather_comm="p2p"):
         f = bode.NPDEField(Uslice, Z, 1.0, 0.75, 0.1)
         post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
         f.bind_flat_grads()
-        smp = SVGD([f.U, f.logsn], lr=1e-4, median_comm=median_comm)
+        smp = SVGD([f.U, f.logsn], lr=1e-4, median_comm=median_comm, gather_comm=gather_comm)
         if distributed:
             assert smp.median_comm == median_comm, smp.median_comm
+            assert smp.gather_comm == (gather_comm if median_comm == "p2p" else "nccl"), smp.gather_comm
         if not distributed:
             smp.world, smp.rank, smp.n_total = 1, 0, smp.P_local
         for it in range(3):
@@ -45,9 +46,11 @@ def _worker():
             smp.phi(update_lr=1e-4)
         return f.theta.clone(), smp._ws.med_gamma.clone()
 
-    th_d, mg_d = run(U[lo:hi], True, "p2p")          # peer-mapped workspaces: NVLink reads + flag barriers in the median kernels
-    th_n, mg_n = run(U[lo:hi], True, "nccl")         # collective protocol
+    th_d, mg_d = run(U[lo:hi], True, "p2p")          # peer-mapped workspaces: push-kernel gathers, NVLink reads + flag barriers in the median kernels
+    th_g, mg_g = run(U[lo:hi], True, "p2p", "nccl")  # peer-memory median, NCCL all-gathers
+    th_n, mg_n = run(U[lo:hi], True, "nccl")         # collective protocol throughout
     assert torch.equal(mg_d, mg_n) and torch.equal(th_d, th_n)
+    assert torch.equal(mg_d, mg_g) and torch.equal(th_d, th_g)
     # single-GPU reference on every rank (world forced to 1 before the workspace is built)
     f = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
     post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
