@@ -32,9 +32,23 @@ __global__ void __launch_bounds__(256) peak_ex2_kernel(float* out, int iters) {
   if (s == 123.456f) out[0] = s;
 }
 
+__global__ void stamp_kernel(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *slot = t;
+}
+
 }  // namespace bode
 
 using namespace bode;
+
+/* Measurement aid: one thread writes the GPU's nanosecond timer to *slot when the stream reaches this point.  Unlike an event
+ * record it is a kernel node, so it can sit inside a captured CUDA graph (tools/step_timeline.py). */
+extern "C" int bode_stamp(unsigned long long* slot, bode_stream_t stream) {
+  BODE_REQUIRE(slot, "null slot");
+  stamp_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(slot);
+  return check_cuda(cudaGetLastError(), "stamp launch");
+}
 
 /* kind 0: dependent-FMA chains (16 per thread) -> flops = 2*16*iters per thread; kind 1: MUFU.EX2 chains (8 per thread).
  * Launches `ctas` CTAs of 256 threads; the caller times it with events and divides. */

@@ -135,17 +135,35 @@ __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X
 // that the lanes' 16-byte stores fall into distinct banks) and one lane issues a 2-D tensor store, which also clips the ragged
 // edges.  (The same data written with st.global -- 8 row segments of 64 bytes per warp instruction -- kept the LSU busy for 40 % of
 // the kernel: 158 -> 94 us at 4096 x 32768 with the stores removed.)
-__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
-               "r"(smem_u32(src_smem))
-               : "memory");
+// `policy` != 0: an L2 evict-first policy (l2_evict_first()).  A d2 block that cannot stay in L2 anyway (several ranks: 134 MB and
+// up) is streamed through it, so that it does not push out what the kernels running beside the Gram pass keep there -- the fused
+// solve's stage checkpoints (its launch took 103 instead of 91 us next to an unhinted 4096 x 8192 Gram pass) and the V operand tiles.
+__device__ __forceinline__ uint64_t l2_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1, uint64_t policy) {
+  if (policy)
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2}], [%3], %4;" ::"l"(tmap), "r"(c0),
+                 "r"(c1), "r"(smem_u32(src_smem)), "l"(policy)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(smem_u32(src_smem))
+                 : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 // the same store into the tiled d2 layout [row block][column stage][128][32] (see svgd_tc2_d2_tiled)
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c0), "r"(c1),
-               "r"(c2), "r"(c3), "r"(smem_u32(src_smem))
-               : "memory");
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tmap, const void* src_smem, int c0, int c1, int c2, int c3, uint64_t policy) {
+  if (policy)
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group.L2::cache_hint [%0, {%1, %2, %3, %4}], [%5], %6;" ::"l"(tmap),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(src_smem)), "l"(policy)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(smem_u32(src_smem))
+                 : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
@@ -154,7 +172,7 @@ __device__ __forceinline__ void bulk_wait_all0() { asm volatile("cp.async.bulk.w
 template <bool FULL, bool DIAG>
 __device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* ncs, unsigned char* stage, const CUtensorMap* tmD2, float nrow,
                                             int lane, int dcol, int row, int nr, int colbase, int nc, int grow0, unsigned int wlo,
-                                            unsigned int wspan, unsigned long long* table, unsigned int& below, bool tiled) {
+                                            unsigned int wspan, unsigned long long* table, unsigned int& below, bool tiled, uint64_t policy) {
   const uint32_t sw = (uint32_t)(lane >> 1) & 3u;                // 64-byte swizzle: 16-byte chunk c of row r sits at chunk c ^ ((r / 2) % 4)
   unsigned char* myrow = stage + lane * 64;
 #pragma unroll
@@ -188,8 +206,8 @@ __device__ __forceinline__ void gram2_chunk(const float (&s)[32], const float* n
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) {
-      if (tiled) tma_store_4d(tmD2, stage, 16 * hf, grow0 & (BLK - 1), colbase / PK2, grow0 / BLK);   // a chunk is one column stage wide
-      else tma_store_2d(tmD2, stage, colbase + 16 * hf, grow0);
+      if (tiled) tma_store_4d(tmD2, stage, 16 * hf, grow0 & (BLK - 1), colbase / PK2, grow0 / BLK, policy);   // a chunk is one column stage wide
+      else tma_store_2d(tmD2, stage, colbase + 16 * hf, grow0, policy);
     }
     while (hits) {                                               // the lane's own staged row still holds the values
       const int b = __ffs(hits) - 1;
@@ -216,7 +234,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constan
                                                         const float* __restrict__ nrm_r, int nr, int row_offset,
                                                         const float* __restrict__ XcH, const float* __restrict__ XcL,
                                                         const float* __restrict__ nrm_c, int nc, int tiles_per_cta,
-                                                        SelState* __restrict__ st, unsigned long long* __restrict__ table, int tiled) {
+                                                        SelState* __restrict__ st, unsigned long long* __restrict__ table, int tiled, int stream_d2) {
   extern __shared__ unsigned char sm_raw_g[];
   unsigned char* sm = sm_raw_g + ((1024u - (smem_u32(sm_raw_g) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sm + Gram2Smem::BARS);
@@ -311,6 +329,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constan
     const unsigned int wlo = win ? st->win_lo : 0x80000000u;
     const unsigned int wspan = win ? WIN_SPAN : 0u;
     unsigned int below = 0;
+    const uint64_t policy = stream_d2 ? l2_evict_first() : 0ull;
     const int cb = 32 * cq;                                        // first tile column of this warp
     float nreg = __ldg(nrm_c + ct0 * BLK + cb + lane);
     for (int t = 0; t < nt; ++t) {
@@ -329,9 +348,9 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) gram2_kernel(const __grid_constan
       const int dtile = rb * BLK + 32 * q + row_offset - (c0 + cb);  // warp-uniform: diagonal crosses this chunk iff -31 <= dtile <= 31
       const bool diag = dtile > -32 && dtile < 32;
       const int grow0 = rb * BLK + 32 * q, colbase = c0 + cb;
-      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
-      else if (full) gram2_chunk<true, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
-      else gram2_chunk<false, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0);
+      if (full && !diag) gram2_chunk<true, false>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0, policy);
+      else if (full) gram2_chunk<true, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0, policy);
+      else gram2_chunk<false, true>(s, ncs, stage, &tmD2, nrow, lane, dcol, row, nr, colbase, nc, grow0, wlo, wspan, table, below, tiled != 0, policy);
     }
     if (lane == 0) bulk_wait_all0();                               // this warp's tensor stores are complete before the CTA retires
 #pragma unroll
@@ -406,16 +425,29 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
       below = table[WIN_TABLE];
     }
   } else {
+    // all peers' loads are in flight together (one NVLink round trip, not one per rank), then summed in rank order
+    unsigned long long px[MAX_PEERS], py[MAX_PEERS];
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q) {
+      px[q] = py[q] = 0ull;
+      if (q < peer.world) {
+        const unsigned long long* tq = reinterpret_cast<const unsigned long long*>(peer.base[q] + peer.table_off);
+        px[q] = peer_ld_u64(tq + 2 * (c * 1024 + tid));
+        py[q] = peer_ld_u64(tq + 2 * (c * 1024 + tid) + 1);
+      }
+    }
     v = make_ulonglong2(0ull, 0ull);
-    for (int q = 0; q < peer.world; ++q) {
-      const unsigned long long* tq = reinterpret_cast<const unsigned long long*>(peer.base[q] + peer.table_off);
-      v.x += peer_ld_u64(tq + 2 * (c * 1024 + tid));
-      v.y += peer_ld_u64(tq + 2 * (c * 1024 + tid) + 1);
-      if (tid == 0) {
+#pragma unroll
+    for (int q = 0; q < MAX_PEERS; ++q) {
+      v.x += px[q];
+      v.y += py[q];
+    }
+    if (tid == 0)
+      for (int q = 0; q < peer.world; ++q) {
+        const unsigned long long* tq = reinterpret_cast<const unsigned long long*>(peer.base[q] + peer.table_off);
         last += peer_ld_u64(tq + WIN_SPAN);
         below += peer_ld_u64(tq + WIN_TABLE);
       }
-    }
   }
   if (tid == 0 && c == 0) found[0] = found[1] = 0xffffffffu;
   if (!armed) v = make_ulonglong2(0ull, 0ull);
@@ -480,17 +512,31 @@ struct Phi2Smem {
 };
 
 // 2-D tiled TMA load (SASS UTMALDG): box {32 columns, 128 rows} of the row-major d2 matrix, 128-byte swizzle
-__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tma_load_2d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar, uint64_t policy) {
+  if (policy)
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar)), "l"(policy)
+                 : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+                 : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
-                   smem_u32(dst_smem)),
-               "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ void tma_load_4d(void* dst_smem, const CUtensorMap* tmap, int c0, int c1, int c2, int c3, uint64_t* bar,
+                                            uint64_t policy) {
+  if (policy)
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3, %4, %5}], [%6], %7;" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+                 : "memory");
 }
 // D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (one row per TMEM lane, K 32-bit columns) never touches shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -525,7 +571,7 @@ struct Phi2Combine {
 
 __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
                                                        const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
-                                                       float* __restrict__ part, const Phi2Combine cmb, int tiled) {
+                                                       float* __restrict__ part, const Phi2Combine cmb, int tiled, int stream_d2) {
   extern __shared__ unsigned char sm_raw[];
   // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
   unsigned char* sm = sm_raw + ((1024u - (smem_u32(sm_raw) & 1023u)) & 1023u);
@@ -565,6 +611,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
     // It only waits for slots to drain (barKV: the workers consumed raw(t); barM: the MMAs that read V(t-1) retired), so the
     // MMA-issuing thread never spends time on copies.
     if (lane == 0 && nst > 0) {
+      const uint64_t policy = stream_d2 ? l2_evict_first() : 0ull;     // d2 is read once: do not let it displace the V tiles in L2
       auto load_v = [&](int t) {
         const int slot = t % 3;
         unsigned char* dst = sm + Phi2Smem::V + slot * 2 * VST_BYTES;
@@ -577,8 +624,8 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
         if (t < nst) {
           const int slot = t % NRAW;
           mbar_expect_tx(barR + slot, Phi2Smem::RAW_SLOT);             // out-of-range box elements are zero-filled and counted
-          if (tiled) tma_load_4d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, 0, 0, s0 + t, blockIdx.x, barR + slot);
-          else tma_load_2d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, (s0 + t) * PK2, r0, barR + slot);
+          if (tiled) tma_load_4d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, 0, 0, s0 + t, blockIdx.x, barR + slot, policy);
+          else tma_load_2d(sm + Phi2Smem::RAW + slot * Phi2Smem::RAW_SLOT, &tmD2, (s0 + t) * PK2, r0, barR + slot, policy);
         }
       };
       for (int t = 0; t < NRAW; ++t) load_raw(t);
@@ -777,6 +824,8 @@ static int encode_d2_map(CUtensorMap* tm, const float* D2, int nr, int nc, int b
 // is 128 segments of 128 bytes, one per DRAM page: once the block has left L2 (several ranks: 537 MB per rank at 8 x 4096
 // particles) those reads ran at 3.2 TB/s.  The order statistics do not care about the order of the entries.
 int svgd_tc2_d2_tiled(int nr, int nc) { return (nr % BLK == 0 && nc % PK2 == 0) ? 1 : 0; }
+// the d2 block is larger than what L2 can keep between the Gram pass and the K@V pass (126 MB, shared with the solve's checkpoints)
+static int d2_streams(int nr, int nc) { return (size_t)nr * nc * 4 > ((size_t)96 << 20) ? 1 : 0; }
 static int encode_d2_map_tiled(CUtensorMap* tm, const float* D2, int nr, int nc, int bx, int by, CUtensorMapSwizzle swz) {
   EncodeTiledFn enc = encode_tiled_fn();
   BODE_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled is not available from this driver");
@@ -865,7 +914,7 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
                      : encode_d2_map(&tm, D2, nr, nc, 16, 32, CU_TENSOR_MAP_SWIZZLE_64B))
     return rc;
   gram2_kernel<<<grid, NTHR_PHI, Gram2Smem::TOTAL, stream>>>(tm, rH, rL, rN, nr, row_offset, o.XcH, o.XcL, o.nrm_c, nc, tiles_per, st, o.table,
-                                                             tiled);
+                                                             tiled, d2_streams(nr, nc));
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
@@ -935,7 +984,7 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb, tiled));
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb, tiled, d2_streams(nr, nc)));
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 

@@ -58,6 +58,9 @@ int bode_device_sm_count(void);
 /* Measurement aid: register-resident chains for the non-tensor fp32 FMA peak (kind 0: 32*iters flop per thread)
  * and the MUFU.EX2 peak (kind 1: 8*iters ex2 per thread); `ctas` CTAs of 256 threads.  Timed by the caller. */
 int bode_peak_kernel(int32_t kind, int32_t ctas, int32_t iters, float* scratch, bode_stream_t stream);
+/* Measurement aid: writes the GPU nanosecond timer (%globaltimer) to *slot (device memory) when `stream` reaches this point; a
+ * kernel node, so it can be captured in a CUDA graph where event records cannot be read back (tools/step_timeline.py). */
+int bode_stamp(unsigned long long* slot, bode_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * npde field description: KernelRegression (gp.py:56-71) for P particles sharing Z/sf/ell.
