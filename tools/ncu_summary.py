@@ -43,11 +43,11 @@ keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "sm__inst_executed_pipe_xu.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum", "smsp__cycles_active.avg",
         "sm__cycles_elapsed.max"]
 traffic = {}
+seen = set()          # a kernel is reported from the FIRST capture that holds it: list the newest capture first
 for rep in reps:
     csvtxt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rr = list(csv.reader(csvtxt.splitlines()))
     h, units = rr[0], rr[1]
-    seen = set()
     for r in rr[2:]:
         name = r[h.index("Kernel Name")].split("(")[0].replace("void ", "").replace("bode::", "")
         if name in seen:
