@@ -658,6 +658,9 @@ extern "C" int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64
   BODE_REQUIRE(n_rows > 0 && n_cols > 0 && d > 0 && d <= 512, "bad sizes");
   BODE_REQUIRE(workspace_bytes >= bode_svgd_workspace_bytes(n_rows, n_cols, d), "workspace too small");
   BODE_REQUIRE(((uintptr_t)workspace & 255) == 0, "workspace must be 256-byte aligned");
+  // unrelated row and column sets: no entry is a cdist(x, x) diagonal.  The kernels force d2 = 0 where row + row_offset == column,
+  // which for the documented -1 would have hit the first sub-diagonal; move the "diagonal" out of every matrix instead.
+  if (row_offset < 0) row_offset = -(1 << 30);
   Ws w = carve(workspace, n_rows, n_cols, d);
   cudaStream_t st = (cudaStream_t)stream;
   const size_t smem = 2 * (size_t)TS * (d | 1) * sizeof(float);

@@ -819,11 +819,11 @@ static int encode_d2_map(CUtensorMap* tm, const float* D2, int nr, int nc, int b
   return BODE_OK;
 }
 
-// d2 layout inside the workspace.  Row-major [nr][nc] in general; when both edges are whole tiles the block is stored as
+// d2 layout inside the workspace.  Row-major [nr][nc] in general; when both edges are whole 128 x 128 Gram tiles the block is stored as
 // [nr / 128][nc / 32][128][32], i.e. every 16 KB tile a K@V stage consumes is CONTIGUOUS.  A stage tile of the row-major matrix
 // is 128 segments of 128 bytes, one per DRAM page: once the block has left L2 (several ranks: 537 MB per rank at 8 x 4096
 // particles) those reads ran at 3.2 TB/s.  The order statistics do not care about the order of the entries.
-int svgd_tc2_d2_tiled(int nr, int nc) { return (nr % BLK == 0 && nc % PK2 == 0) ? 1 : 0; }
+int svgd_tc2_d2_tiled(int nr, int nc) { return (nr % BLK == 0 && nc % BLK == 0) ? 1 : 0; }
 // the d2 block is larger than what L2 can keep between the Gram pass and the K@V pass (126 MB, shared with the solve's checkpoints)
 static int d2_streams(int nr, int nc) { return (size_t)nr * nc * 4 > ((size_t)96 << 20) ? 1 : 0; }
 static int encode_d2_map_tiled(CUtensorMap* tm, const float* D2, int nr, int nc, int bx, int by, CUtensorMapSwizzle swz) {

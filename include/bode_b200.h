@@ -292,7 +292,8 @@ size_t bode_svgd_workspace_bytes(int32_t n_rows, int32_t n_cols, int32_t d);
 int bode_svgd_sqdist(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
                      int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
                      size_t workspace_bytes, void** hist_out, bode_stream_t stream);
-/* row_offset = index of local row 0 among the columns (rank * P_local); -1 when rows and columns are unrelated sets.
+/* row_offset = index of local row 0 among the columns (rank * P_local): d2 is forced to 0 where row + row_offset == column, like
+ * cdist(x, x); -1 (any negative value) when rows and columns are unrelated sets: nothing is forced.
  * bode_svgd_set_tensor_cores(1) (default) runs the two contractions as 3xTF32 tcgen05.mma (d <= 56); 0 selects the FP32-pipe
  * kernels.  Returns the previous setting. */
 int bode_svgd_set_tensor_cores(int32_t on);
@@ -337,7 +338,7 @@ int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const flo
 int bode_svgd_staged_supported(int32_t n_cols, int32_t d);
 /* Layout of the d2 block at the start of the workspace (internal to sqdist -> median -> phi; exposed for tests and for
  * RBFKernel.forward, stein.py:22-32, which returns the kernel matrix).  0: row-major [n_rows][n_cols].  1: tiles
- * [n_rows / 128][n_cols / 32][128][32] -- chosen by the pipelined tensor-core kernels when both edges are whole tiles, so that
+ * [n_rows / 128][n_cols / 32][128][32] -- chosen by the pipelined tensor-core kernels when n_rows and n_cols are multiples of 128, so that
  * every 16 KB tile the K@V pass consumes is contiguous in HBM.  The layout must not change between a bode_svgd_sqdist and the
  * bode_svgd_phi that consumes it (i.e. no bode_svgd_set_tensor_cores in between). */
 int bode_svgd_d2_tiled(int32_t n_rows, int32_t n_cols, int32_t d);

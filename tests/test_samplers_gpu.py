@@ -297,6 +297,36 @@ def test_median_window_path_is_bit_exact_and_falls_back():
         assert np.float32(float(ws.med_gamma[0])) == np.median(ws.d2(n, 256).cpu().numpy())
 
 
+def test_tiled_d2_layout_rectangular_blocks():
+    """Blocks whose edges are whole 128 x 128 Gram tiles are stored as [rows/128][cols/32][128][32] tiles (bode_svgd_d2_tiled),
+    the others row-major; the accessor must return the same matrix as the float64 oracle either way -- for rows at an offset among
+    the columns (rank > 0 of a sharded job: the diagonal of cdist(x, x) is forced to zero at row_offset), for column counts that
+    are not a multiple of the Gram tile, and for unrelated row / column sets (row_offset = -1: NO entry is forced to zero)."""
+    from bayesian_ode_b200 import _lib
+    from bayesian_ode_b200.samplers.stein import _Workspace
+    from oracle import samplers as osamp
+    rng = np.random.default_rng(23)
+    d = 52
+    cases = ((128, 160, 0, 0), (128, 160, 32, 0), (256, 512, 256, 1), (128, 96, -1, 0), (128, 256, 128, 1), (256, 384, 0, 1),
+             (128, 256, -1, 1))
+    for nr, nc, off, tiled in cases:
+        Xc = (rng.standard_normal((nc, d)) * 0.3 + 1.5).astype(np.float32)
+        Xr = Xc[off:off + nr] if off >= 0 else (rng.standard_normal((nr, d)) * 0.3 + 1.5).astype(np.float32)
+        Xcd = torch.from_numpy(Xc).cuda()
+        Xrd = Xcd[off:off + nr] if off >= 0 else torch.from_numpy(Xr).cuda()
+        ws = _Workspace(nr, nc, d, Xcd.device)
+        assert _lib.load().bode_svgd_d2_tiled(nr, nc, d) == tiled, (nr, nc)
+        ref = osamp.sq_dists(Xr.astype(np.float64), Xc.astype(np.float64))
+        for _ in range(2):                                        # second call: armed window
+            ws.sqdist(Xrd, nr, Xcd, nc, d, nr * nc, row_offset=off)
+            ws.median(nr, nc, d, nc)
+            d2 = ws.d2(nr, nc).cpu().numpy()
+            assert np.abs(d2 - ref).max() < 2e-5 * ref.max(), (nr, nc, off)
+            if off >= 0:
+                assert np.all(d2[np.arange(nr), off + np.arange(nr)] == 0)
+            assert np.float32(float(ws.med_gamma[0])) == np.median(d2), (nr, nc, off)
+
+
 def test_svgd_stream_overlap_is_bit_identical_and_graph_capturable():
     """prefetch()/phi() fork the position-only operands and the V operand onto a side stream (same kernels, same inputs):
     the particles must come out bit-identical to the serial order, eagerly and when the step is replayed from one CUDA graph."""
