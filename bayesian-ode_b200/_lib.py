@@ -111,6 +111,7 @@ SYMBOLS = {
     "bode_svgd_d2_tiled": (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     "bode_svgd_peer_gather": (C.c_int, [C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
                                         C.POINTER(C.c_void_p), C.c_void_p]),
+    "bode_svgd_peer_status": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.POINTER(C.c_int32)]),
     "bode_peer_alloc": (C.c_int, [C.c_size_t, C.POINTER(C.c_void_p)]),
     "bode_peer_free": (C.c_int, [_P]),
     "bode_peer_export": (C.c_int, [_P, _P]),

@@ -634,6 +634,25 @@ extern "C" int bode_svgd_peer_gather(int32_t which, const float* rows, int64_t l
   return BODE_OK;
 }
 
+/* Host-side check of the flag barriers (median kernels, position gather, score gather): *timed_out = 1 when one of them gave up
+ * waiting for a peer (PeerFlags::timed_out, svgd_state.cuh) since bode_svgd_workspace_init -- the results of that step are then
+ * invalid.  Blocking copy: call it after synchronising the streams that use the workspace. */
+extern "C" int bode_svgd_peer_status(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, int32_t* timed_out) {
+  BODE_REQUIRE(workspace && timed_out, "null pointer");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  unsigned int h[64];
+  static_assert(sizeof(PeerFlags) <= 64 && sizeof(h) == 256, "three 64-byte flag blocks inside the 256-byte flag region");
+  BODE_CUDA(cudaMemcpy(h, w.flags, sizeof(h), cudaMemcpyDeviceToHost));
+  int t = 0;
+  for (int k = 0; k < 3; ++k) {
+    PeerFlags f;
+    memcpy(&f, reinterpret_cast<const char*>(h) + 64 * k, sizeof(f));
+    t |= f.timed_out != 0u;
+  }
+  *timed_out = t;
+  return BODE_OK;
+}
+
 extern "C" int bode_svgd_set_gram_split(int32_t column_splits) { return svgd_tc2_set_gram_split(column_splits); }
 
 extern "C" int bode_svgd_staged_supported(int32_t n_cols, int32_t d) {

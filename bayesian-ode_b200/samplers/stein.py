@@ -382,6 +382,17 @@ class SVGD(Sampler):
         self._step_index += 1
         return self.loss
 
+    def check(self):
+        """NaN report of the base class, plus: did a flag barrier of the peer-memory exchange give up on a peer?"""
+        super().check()
+        if self._ws.p2p:
+            torch.cuda.synchronize()
+            t = C.c_int32(0)
+            _lib.check(_lib.load().bode_svgd_peer_status(C.c_void_p(self._ws.base.data_ptr()), self.P_local, self.n_total, self.d,
+                                                         C.byref(t)))
+            if t.value:
+                raise _lib.BodeError("SVGD: a peer flag barrier timed out (a rank never arrived); the particles are invalid")
+
     def get_particles(self):
         return self._flat
 

@@ -368,6 +368,10 @@ int bode_peer_export(void* ptr, void* handle64);
 int bode_peer_import(const void* handle64, void** out);
 int bode_peer_release(void* imported);
 int bode_svgd_set_peers(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, void* const* bases, int32_t rank, int32_t world);
+/* The flag barriers give up after ~2^24 polls instead of hanging when a peer never arrives; *timed_out = 1 if that has happened on
+ * this workspace since bode_svgd_workspace_init (the results of that step are invalid).  Blocking device-to-host copy: synchronise
+ * the streams that use the workspace first. */
+int bode_svgd_peer_status(void* workspace, int32_t n_rows, int32_t n_cols, int32_t d, int32_t* timed_out);
 /* The data-path exchange itself over peer memory (the all-gather of particle positions and scores, which the
  * reference, a single-process program, does not have): every rank pushes its rows[n_rows, d] into the gather buffer of every
  * rank's workspace between two flag barriers, in ONE launch and without a collective.  which = 0 positions, 1 scores (separate
