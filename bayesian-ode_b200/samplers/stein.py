@@ -62,6 +62,12 @@ def shard_range(n, rank, world):
     return lo, lo + base + (1 if rank < rem else 0)
 
 
+def untile_d2(flat, nr, nc):
+    """[nr/128][nc/32][128][32] stage tiles (the layout the pipelined kernels keep d2 in when nr and nc are multiples of 128,
+    ``bode_svgd_d2_tiled``; element (i, j) sits in tile (i // 128, j // 32) at (i % 128, j % 32)) -> the [nr, nc] matrix."""
+    return flat.view(nr // 128, nc // 32, 128, 32).permute(0, 2, 1, 3).reshape(nr, nc)
+
+
 class _RawCuda:
     """Zero-copy torch view of a raw device allocation (``torch.as_tensor`` reads ``__cuda_array_interface__``)."""
 
@@ -210,7 +216,7 @@ class _Workspace:
         it is stored as [nr/128][nc/32][128][32] tiles, ``bode_svgd_d2_tiled``)."""
         flat = self.base[:nr * nc * 4].view(torch.float32)
         if _lib.load().bode_svgd_d2_tiled(nr, nc, self._dims[2]):
-            return flat.view(nr // 128, nc // 32, 128, 32).permute(0, 2, 1, 3).reshape(nr, nc)
+            return untile_d2(flat, nr, nc)
         return flat.view(nr, nc)
 
 

@@ -78,6 +78,9 @@ def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the reference arm may use every host thread (the per-chain workers pin
+    # themselves to one thread each, the numpy/BLAS phi runs on all of them).  Must happen before numpy / torch are imported.
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     P_total = (args.particles or wl["P"]) * (args.gpus if args.scaling == "weak" else 1)
     t0 = time.perf_counter()
     steps = max(args.steps, 1)

@@ -58,3 +58,20 @@ def test_grid_must_hit_end_point():
     _grid = _load_grid_module()
     with pytest.raises(AssertionError):
         _grid.build(torch.tensor([0.0, 1.0]), torch.float32, "cpu", grid_constructor=lambda f, y, t: t * 0.5)
+
+
+def test_untile_d2_matches_the_documented_tile_layout():
+    """bode_svgd_d2_tiled layout (include/bode_b200.h): element (i, j) of the block lives in tile (i // 128, j // 32) at
+    (i % 128, j % 32), tiles ordered [row block][column stage]."""
+    import numpy as np
+    import torch
+    from bayesian_ode_b200.samplers.stein import untile_d2
+    nr, nc = 256, 384
+    want = np.arange(nr * nc, dtype=np.float32).reshape(nr, nc)
+    flat = np.empty(nr * nc, dtype=np.float32)
+    for i in range(nr):
+        for j0 in range(0, nc, 32):
+            off = ((i // 128) * (nc // 32) + j0 // 32) * 128 * 32 + (i % 128) * 32
+            flat[off:off + 32] = want[i, j0:j0 + 32]
+    got = untile_d2(torch.from_numpy(flat), nr, nc).numpy()
+    assert np.array_equal(got, want)
