@@ -200,3 +200,61 @@ class HAMCMC:
         self.params.pop(0)
         self.grads.pop(0)
         return new
+
+
+class HAMCMCContiguous(HAMCMC):
+    """HAMCMC2 / HAMCMC3 / HAMCMC4 (samplers/langevin.py:1109-1470): the variants that form (s, y) from CONTIGUOUS samples.  They
+    share ``_compute_vector_prod`` with HAMCMC (``vector_prod`` above) and differ only in the window bookkeeping, restated here
+    bug-compatibly for one chain (``variant`` = 2, 3 or 4; M = memory + 1, langevin.py:645):
+      warm-up  M plain Langevin steps, each storing (theta AFTER the update, gradient BEFORE it) (:1180-1203, :1151-1178); when the
+               M-th lands, the pairs are formed without any curvature filter: variant 2 from entries 1..M-2 -> 2..M-1 (:1173-1178),
+               variant 3 from 0..M-3 -> 1..M-2 (:1355-1359), variant 4 from 0..M-2 -> 1..M-1 (:1462-1466);
+      step     base point = the OLDEST stored theta for variant 2 (:1209), the NEWEST for 3 and 4 (:1368); after the update the new
+               (theta, grad) is appended and ONE pair is added -- between the last two entries for variants 2 and 4 (:1131-1134,
+               :1424-1427), between the two entries BEFORE the last for variant 3 (:1315-1318) -- then the oldest entry of every
+               list is dropped."""
+
+    def __init__(self, variant, memory=5, H_gamma=1.0, trust_reg=1.0):
+        assert variant in (2, 3, 4)
+        super().__init__(memory=memory, H_gamma=H_gamma, trust_reg=trust_reg)
+        self.variant = variant
+
+    def _pair(self, a, b):
+        si = -self.params[a] + self.params[b]
+        yi = -self.grads[a] + self.grads[b] + self.trust_reg * si
+        self.s.append(si)
+        self.y.append(yi)
+
+    def step_without_metric(self, theta, grad, lr, xi, add_noise=True, update_metric=True):
+        new = theta + (-lr) * grad
+        if add_noise:
+            new = new + (-lr) * (xi * (1.0 / np.sqrt(0.5 * lr)))
+        if update_metric:
+            self.params.append(new.copy())
+            self.grads.append(grad.copy())
+            M = self.M
+            if len(self.params) >= M:
+                if self.variant == 2:
+                    for j in range(M - 2):
+                        self._pair(j + 1, j + 2)
+                else:
+                    for i in range(M - 2 if self.variant == 3 else M - 1):
+                        self._pair(i, i + 1)
+        return new
+
+    def step(self, grad, lr, xi, add_noise=True):
+        base = self.params[0] if self.variant == 2 else self.params[-1]
+        noise = xi * (1.0 / np.sqrt(0.5 * lr))
+        Hg, Sn = self.vector_prod(grad, noise)
+        new = base + (-lr) * Hg
+        if add_noise:
+            new = new + (-lr) * Sn
+        self.params.append(new.copy())
+        self.grads.append(grad.copy())
+        if self.variant == 3:
+            self._pair(len(self.params) - 3, len(self.params) - 2)
+        else:
+            self._pair(len(self.params) - 2, len(self.params) - 1)
+        for lst in (self.params, self.grads, self.s, self.y):
+            lst.pop(0)
+        return new

@@ -639,7 +639,68 @@ def gen_predictive(data):
     save("predictive", **out)
 
 
+def gen_hamcmc_contiguous():
+    """HAMCMC2 / HAMCMC3 / HAMCMC4 (langevin.py:1109-1470) on the convex quadratic of gen_hamcmc; noise replayed per step.
+    M warm-up steps (sample(): i < self.memory, :1254) then metric steps, driven step by step like ``sample`` does."""
+    import io, contextlib, warnings
+    from samplers import langevin
+    from oracle import samplers as osamp
+    out = {}
+    for variant in (2, 3, 4):
+        g = torch.Generator().manual_seed(5)
+        d = 10
+        Q = torch.randn(d, d, generator=g)
+        Aq = Q @ Q.t() / d + 0.5 * torch.eye(d)
+        a = torch.nn.Parameter(torch.randn(3, 2, generator=g))
+        b = torch.nn.Parameter(torch.randn(4, generator=g))
+
+        def closure(add_prior=True):
+            th = torch.cat([a.reshape(-1), b.reshape(-1)])
+            return 0.5 * th @ (Aq @ th)
+
+        memory = 3
+        cls = getattr(langevin, "HAMCMC%d" % variant)
+        with contextlib.redirect_stdout(io.StringIO()):
+            smp = cls([a, b], memory=memory, lr0=2e-2, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3, H_gamma=1.0, trust_reg=1.0)
+        M = memory + 1
+        nsteps = M + 10
+        thetas, grads, xis, lrs = [torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).clone()], [], [], []
+        with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for i in range(nsteps):
+                smp.zero_grad()
+                smp.loss = closure()
+                smp.loss.backward()
+                grads.append(torch.cat([a.grad.reshape(-1), b.grad.reshape(-1)]).clone())
+                lr = smp.get_lr(i)
+                torch.manual_seed(9000 + 100 * variant + i)
+                if i < M:
+                    smp.step_without_metric(lr=lr, add_noise=True)
+                else:
+                    smp.step(lr=lr, add_noise=True)
+                torch.manual_seed(9000 + 100 * variant + i)
+                xis.append(torch.randn(d))
+                lrs.append(lr)
+                thetas.append(torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).clone())
+        th_all, gr_all, xi_all = torch.stack(thetas), torch.stack(grads), torch.stack(xis)
+        assert bool(torch.isfinite(th_all).all())
+        # pin the oracle restatement (and the noise replay) right here
+        orc = osamp.HAMCMCContiguous(variant, memory=memory, H_gamma=1.0, trust_reg=1.0)
+        for i in range(nsteps):
+            th, gr, xi = th_all[i].numpy(), gr_all[i].numpy(), xi_all[i].numpy()
+            new = orc.step_without_metric(th, gr, lrs[i], xi) if i < M else orc.step(gr, lrs[i], xi)
+            err = np.abs(new - th_all[i + 1].numpy()).max() / max(1.0, np.abs(th_all[i + 1].numpy()).max())
+            assert err < 1e-10, ("hamcmc%d oracle mismatch" % variant, i, err)
+        out.update({"theta%d" % variant: th_all, "grad%d" % variant: gr_all, "xi%d" % variant: xi_all, "lr%d" % variant: np.array(lrs)})
+        out["A"] = Aq
+        out["memory"] = memory
+    save("hamcmc_contiguous", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "hamcmc_contiguous":
+        gen_hamcmc_contiguous()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predictive":
         gen_predictive(make_data())
         sys.exit(0)
@@ -659,6 +720,7 @@ if __name__ == "__main__":
     gen_mlp(data)
     gen_dopri5(data)
     gen_hamcmc()
+    gen_hamcmc_contiguous()
     gen_mala()
     gen_cyclical(data)
     gen_predictive(data)

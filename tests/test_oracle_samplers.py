@@ -96,6 +96,31 @@ def test_hamcmc_oracle_matches_reference_run():
     assert len(orc.s) == int(g["n_pairs"])
 
 
+def test_hamcmc_contiguous_oracle_matches_reference_runs():
+    """HAMCMC2 / HAMCMC3 / HAMCMC4 (langevin.py:1109-1470): M warm-up steps, then 10 metric steps of each variant recorded from the
+    reference; the three differ only in which stored samples form the (s, y) pairs and in the base point of the update."""
+    g = load_golden("hamcmc_contiguous")
+    memory = int(g["memory"])
+    M = memory + 1
+    finals = {}
+    for variant in (2, 3, 4):
+        orc = osamp.HAMCMCContiguous(variant, memory=memory, H_gamma=1.0, trust_reg=1.0)
+        th, gr, xi, lr = (g["%s%d" % (k, variant)] for k in ("theta", "grad", "xi", "lr"))
+        for i in range(gr.shape[0]):
+            new = orc.step_without_metric(th[i], gr[i], float(lr[i]), xi[i]) if i < M else orc.step(gr[i], float(lr[i]), xi[i])
+            assert relerr(new, th[i + 1]) < 1e-10, (variant, i)
+        assert len(orc.params) == M and len(orc.s) == (M - 1 if variant == 4 else M - 2)      # the reference's own asserts
+        finals[variant] = new
+    # the variants are genuinely different samplers, and none of them is the wrong restatement of another
+    g2 = osamp.HAMCMCContiguous(3, memory=memory)
+    th, gr, xi, lr = (g["%s2" % k] for k in ("theta", "grad", "xi", "lr"))
+    bad = 0.0
+    for i in range(gr.shape[0]):
+        new = g2.step_without_metric(th[i], gr[i], float(lr[i]), xi[i]) if i < M else g2.step(gr[i], float(lr[i]), xi[i])
+        bad = max(bad, relerr(new, th[i + 1]))
+    assert bad > 1e-6
+
+
 def test_mala_oracle_explains_reference_decisions():
     """langevin.py:57-95: the oracle's aliased-state ratio reproduces every accept/reject decision of the reference run in the
     fixture; the textbook ratio (aliased=False) does not (that is the quirk the fixture pins)."""
