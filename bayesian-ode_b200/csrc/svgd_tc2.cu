@@ -6,7 +6,9 @@
 //   gram2_kernel                    d2 = |xc_i|^2 + |xc_j|^2 - 2 xc_i.xc_j   (stein.py:22).  One CTA keeps its 128-row A tile
 //                                   resident and walks 128-column B tiles through a 2-slot ring; the accumulator is
 //                                   double-buffered in TMEM (2 x 128 columns) so tile t+1's MMAs run under tile t's epilogue.
-//                                   The epilogue also counts the window of the exact median selection (svgd_state.cuh).
+//                                   The epilogue also counts the window of the exact median selection (svgd_state.cuh) and
+//                                   hands the d2 tile to the TMA engine (tensor stores from swizzled per-warp staging); d2 is
+//                                   row-major, or [rows/128][cols/32][128][32] stage tiles when both edges are whole tiles.
 //   phi2_kernel                     part[i,:] = sum_j 2^(-g d2_ij) [ -grad_j | xc_j | 1 ]   (stein.py:75-86).  d2 tiles arrive
 //                                   by 2-D TMA six stages ahead, V^T tiles by bulk copy, the exp/split of stage t runs
 //                                   under the MMAs of stage t-1.
