@@ -86,6 +86,10 @@ SYMBOLS = {
     "bode_hamcmc_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
     "bode_hamcmc_step": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P, C.c_int64, _P,
                                     C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32, C.c_uint64, C.c_uint32, _P, _P]),
+    "bode_hamcmc_contig_floats": (C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "bode_hamcmc_contig_step": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.c_int64, _P,
+                                          C.c_int64, _P, C.c_float, C.c_float, C.c_float, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_uint64, C.c_uint32, _P, _P]),
     "bode_axpy": (C.c_int, [_P, _P, C.c_float, C.c_int64, _P, _P, _P]),
     "bode_sampler_schedule": (C.c_int, [_P, C.c_int32, C.c_double, C.c_double, C.c_double, C.c_double, C.c_uint32, C.c_uint32, _P]),
     "bode_fill_normal": (C.c_int, [_P, C.c_int64, C.c_uint64, C.c_uint32, _P]),

@@ -432,3 +432,96 @@ class HAMCMC(_LangevinBase):
                 else:
                     print("{} iter {:04d}".format(tag, k))
         return chain, logp_array
+
+
+class _HAMCMCContiguous(HAMCMC):
+    """langevin.py:1109-1470: HAMCMC2 / HAMCMC3 / HAMCMC4, the variants that build the L-BFGS pairs from contiguous samples
+    (``bode_hamcmc_contig_step``; bookkeeping restated in oracle/samplers.py::HAMCMCContiguous, which is pinned to reference runs of
+    all three).  Same constructor and stepping API as the reference classes: the first ``self.memory`` iterations of ``sample``
+    are plain Langevin steps that fill the window (:1254), every later one is a metric step.
+    STATUS: not yet run on a GPU (the kernel was written after round 1's GPU budget was spent); see DESIGN.md section 7."""
+
+    _variant = None
+
+    def _state(self, P, d, dev):
+        if self._hs is None:
+            lib = _lib.load()
+            z = lambda w: torch.zeros(lib.bode_hamcmc_contig_floats(P, d, self._user_memory, w), dtype=torch.float32, device=dev)
+            self._hs = dict(ht=z(0), hg=z(0), ps=z(1), py=z(1), wk=z(2), meta=torch.zeros(P, 4, dtype=torch.int32, device=dev))
+        return self._hs
+
+    def _launch(self, lr, metric, add_params, add_noise, noise):
+        lib = _lib.load()
+        th, gr, scatter = self._chain_buffers()
+        P, d = th.shape
+        hs = self._state(P, d, th.device)
+        g0 = self.param_groups[0]
+        xi = None
+        if noise is not None:
+            xi = torch.as_tensor(noise).to(th.device, torch.float32).reshape(P, d).contiguous()
+        _lib.check(lib.bode_hamcmc_contig_step(int(self._variant), P, d, self._user_memory, _lib.ptr(hs["ht"]), _lib.ptr(hs["hg"]),
+                                               _lib.ptr(hs["ps"]), _lib.ptr(hs["py"]), _lib.ptr(hs["wk"]), _lib.ptr(hs["meta"]),
+                                               _lib.ptr(th), d, _lib.ptr(gr), d, _lib.ptr(xi), float(lr), float(g0["H_gamma"]),
+                                               float(g0["trust_reg"]), int(metric), int(add_params), int(add_noise), self.seed,
+                                               self._step_index, _lib.ptr(self._status), _lib.stream_ptr()))
+        if scatter is not None:
+            scatter()
+        self._after_step()
+
+    def step_without_metric(self, lr, update_metric=True, add_noise=True, noise=None):
+        self._launch(lr, False, update_metric, add_noise, noise)
+
+    def step(self, lr, use_old_lbfgs=False, add_noise=True, noise=None):
+        if use_old_lbfgs:
+            raise NotImplementedError("the dense-BFGS + Cholesky variant (langevin.py:669-715) is not built")
+        self._launch(lr, True, False, add_noise, noise)
+
+    def sample(self, closure, num_samples=1000, burn_in=100, print_loss=False, use_metric=True, use_old_lbfgs=False, add_noise=True,
+               print_iters=True, thinning=1):
+        """langevin.py:1243-1290; returns (chain, logp_array) like the reference."""
+        chain = self.samples
+        logp_array = []
+        fused = hasattr(closure, "loss_and_grad_") and self._flat is not None
+        if fused:
+            if self._grad_flat() is None and hasattr(closure.field, "bind_flat_grads"):
+                closure.field.bind_flat_grads()
+            chain.reserve((num_samples + thinning - 1) // thinning, self._flat, self._plist)
+        for i in range(burn_in + num_samples):
+            if fused:
+                self.loss = closure.loss_and_grad_()[0]
+            else:
+                self.zero_grad()
+                self.loss = closure()
+                self._backward(self.loss)
+            lr = self.get_lr(i)
+            if i < burn_in and i < self.memory:                                  # langevin.py:1254
+                self.step_without_metric(lr=lr, add_noise=add_noise)
+            elif use_metric:
+                self.step(lr=lr, use_old_lbfgs=use_old_lbfgs, add_noise=add_noise)
+            else:
+                self.step_without_metric(lr=lr, update_metric=use_metric, add_noise=add_noise)
+            logp_array.append(-self.loss.detach())
+            if i >= burn_in and (i - burn_in) % thinning == 0:
+                self._record(chain)
+            if print_iters:
+                tag, k = ("Burn-in", i + 1) if i < burn_in else ("Sample", i - burn_in + 1)
+                if print_loss:
+                    print("{} iter {:04d} | loss {:.06f}".format(tag, k, float(closure(add_prior=False).sum())))
+                else:
+                    print("{} iter {:04d}".format(tag, k))
+        return chain, logp_array
+
+
+class HAMCMC2(_HAMCMCContiguous):
+    """langevin.py:1109-1290: theta_t = theta_{t-M} - lr H(theta_{t-M+1:t-1}) grad + noise (base point = the oldest stored sample)."""
+    _variant = 2
+
+
+class HAMCMC3(_HAMCMCContiguous):
+    """langevin.py:1292-1400: base point = the newest stored sample, the pair that joins the window lags one sample behind."""
+    _variant = 3
+
+
+class HAMCMC4(_HAMCMCContiguous):
+    """langevin.py:1402-1470: like HAMCMC3 with the newest pair included (M-1 pairs)."""
+    _variant = 4

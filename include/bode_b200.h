@@ -261,6 +261,20 @@ int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* hist_theta, fl
                      int32_t add_params, int32_t add_noise, uint64_t seed, uint32_t step, int32_t* status,
                      bode_stream_t stream);
 
+/* HAMCMC2 / HAMCMC3 / HAMCMC4, samplers/langevin.py:1109-1470: the variants that form (s, y) from contiguous samples (same
+ * _compute_vector_prod, different window bookkeeping and base point; variant = 2, 3 or 4).  State buffers (caller-owned,
+ * zero-initialised, sizes from bode_hamcmc_contig_floats; meta int32 [P][4]): hist_theta/hist_grad [P][M][d] (M = memory+1),
+ * pair_s/pair_y [P][M-1][d], work [P][4(M-1)+2][d].  metric_step = 0: step_without_metric (:1180-1203), update_metric stores
+ * (theta_new, grad) and forms the pairs when the M-entry window fills (the first M iterations of sample(), :1254);
+ * metric_step = 1: step (:1205-1238, :1364-1397).
+ * STATUS: compiled, oracle pinned to reference runs of all three variants, NOT yet run on a GPU. */
+size_t bode_hamcmc_contig_floats(int32_t P, int32_t d, int32_t memory, int32_t which);
+int bode_hamcmc_contig_step(int32_t variant, int32_t P, int32_t d, int32_t memory, float* hist_theta, float* hist_grad,
+                            float* pair_s, float* pair_y, float* work, int32_t* meta, float* theta, int64_t ld_theta,
+                            const float* grad, int64_t ld_grad, const float* xi, float lr, float H_gamma, float trust_reg,
+                            int32_t metric_step, int32_t update_metric, int32_t add_noise, uint64_t seed, uint32_t step,
+                            int32_t* status, bode_stream_t stream);
+
 /* MALA.accept_or_reject, samplers/langevin.py:57-95, for P chains of d parameters (rows of theta).  The proposal itself is
  * bode_sgld_step (langevin.py:27-54 is the SGLD update).  Per chain:
  *   log_alpha = loss_prev - loss_new - |theta_prev - theta + lr grad_new|^2 / (4 lr) + |theta - theta_prev + lr grad_prev|^2 / (4 lr)

@@ -121,6 +121,88 @@ def test_hamcmc_contiguous_oracle_matches_reference_runs():
     assert bad > 1e-6
 
 
+def test_hamcmc_contig_kernel_ring_bookkeeping_mirror():
+    """csrc/hamcmc_contig.cu keeps the M-entry history and the pair list as RINGS (head / pair_head indices in `meta`) instead of
+    the reference's Python lists.  This is a line-by-line float64 NumPy mirror of the kernel's two modes -- same ring arithmetic,
+    same order of operations -- run on the reference's own HAMCMC2 / HAMCMC3 / HAMCMC4 runs: it pins the index logic of the kernel
+    (which entry is the base point, which two entries form the joining pair, which slots are overwritten) on the CPU."""
+    g = load_golden("hamcmc_contiguous")
+    memory = int(g["memory"]); M = memory + 1; d = 10
+    H_gamma, trust_reg = 1.0, 1.0
+
+    def run(variant):
+        th_ref, gr, xi, lrs = g["theta%d"%variant], g["grad%d"%variant], g["xi%d"%variant], g["lr%d"%variant]
+        ht = np.zeros((M, d)); hg = np.zeros((M, d)); ps = np.zeros((M-1, d)); py = np.zeros((M-1, d))
+        U = np.zeros((M-1, d)); V = np.zeros((M-1, d)); Pp = np.zeros((M-1, d)); Q = np.zeros((M-1, d))
+        meta = [0, 0, 0, 0]
+        th = th_ref[0].copy()
+        worst = 0.0
+        for it in range(gr.shape[0]):
+            lr = float(lrs[it]); gg = gr[it]; nscale = 1.0/np.sqrt(0.5*lr); noise = xi[it]*nscale
+            n_hist0, head, K0, phead = meta
+            if it < M:   # mode 0
+                n_hist, K = n_hist0, K0
+                store = n_hist < M
+                t = th + (-lr)*gg; t = t + (-lr)*noise; th = t.copy()
+                if store:
+                    ht[n_hist] = t; hg[n_hist] = gg; n_hist += 1
+                if store and n_hist == M:
+                    first = 1 if variant == 2 else 0
+                    K = M-1 if variant == 4 else M-2
+                    for i in range(K):
+                        s = ht[first+i+1] - ht[first+i]; y = hg[first+i+1] - hg[first+i] + trust_reg*s
+                        ps[i] = s; py[i] = y
+                meta = [n_hist, 0, K, 0]
+            else:        # mode 1
+                K = K0
+                newest = (head + M - 1) % M; prev = (head + M - 2) % M
+                B0 = 1.0/H_gamma; C0 = np.sqrt(B0); S0 = 1.0/np.sqrt(B0)
+                base = ht[head if variant == 2 else newest].copy()
+                nu = 0
+                for i in range(K):
+                    s = ps[(phead+i) % K]; y = py[(phead+i) % K]
+                    sy = s @ y
+                    if sy < 0: continue
+                    if nu == 0: z = B0*s
+                    else:
+                        z = s.copy()
+                        for j in range(nu-1, -1, -1):
+                            c = z @ V[j]; z = z - c*U[j]
+                        z = z*C0*C0
+                        for j in range(nu):
+                            c = z @ U[j]; z = z - c*V[j]
+                    sBs = s @ z
+                    cq = np.sqrt(sy/sBs); cu = np.sqrt(sBs/sy)
+                    Q[nu] = cq*z - y; Pp[nu] = s/sy; U[nu] = cu + z; V[nu] = s/sBs
+                    nu += 1
+                z = gg.copy(); z2 = S0*noise
+                if nu == 0: z = z/B0
+                else:
+                    for j in range(nu-1, -1, -1):
+                        c = z @ Q[j]; z = z - c*Pp[j]
+                    z = z*S0*S0
+                    for j in range(nu):
+                        c = z @ Pp[j]; z = z - c*Q[j]
+                for j in range(nu):
+                    c = z2 @ Pp[j]; z2 = z2 - c*Q[j]
+                tn, gn, tp, gp = ht[newest].copy(), hg[newest].copy(), ht[prev].copy(), hg[prev].copy()
+                t = base + (-lr)*z; t = t + (-lr)*z2
+                if variant == 3: s = tn - tp; y = gn - gp + trust_reg*s
+                else: s = t - tn; y = gg - gn + trust_reg*s
+                th = t.copy()
+                if K > 0: ps[phead] = s; py[phead] = y
+                ht[head] = t; hg[head] = gg
+                meta = [n_hist0, (head+1) % M, K, (phead+1) % K if K > 0 else 0]
+            err = np.abs(th - th_ref[it+1]).max() / max(1.0, np.abs(th_ref[it+1]).max())
+            worst = max(worst, err)
+        return worst, meta
+
+    for variant in (2, 3, 4):
+        worst, meta = run(variant)
+        assert worst < 1e-10, (variant, worst)
+        assert meta[0] == M and meta[2] == (M - 1 if variant == 4 else M - 2)
+
+
 def test_mala_oracle_explains_reference_decisions():
     """langevin.py:57-95: the oracle's aliased-state ratio reproduces every accept/reject decision of the reference run in the
     fixture; the textbook ratio (aliased=False) does not (that is the quirk the fixture pins)."""
