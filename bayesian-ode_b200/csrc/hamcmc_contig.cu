@@ -9,9 +9,9 @@
 //            new (theta, grad) is appended, ONE pair is added -- between the last two entries (variants 2 and 4, :1131-1134,
 //            :1424-1427) or between the two entries before the last (variant 3, :1315-1318) -- and the oldest entry of every list
 //            is dropped.
-// STATUS: written against the pinned oracle at the end of round 1, after the round's GPU budget was spent -- compiled, not yet
-// run on a GPU; its parity test (tests/test_samplers_gpu.py::test_hamcmc_contiguous_variants_match_reference_runs) is skipped
-// unless BODE_RUN_UNVALIDATED=1.  hamcmc.cu (HAMCMC proper) is untouched.
+// Parity: tests/test_samplers_gpu.py::test_hamcmc_contiguous_variants_match_reference_runs (reference runs of all three, B200).
+// A metric step before the window is full (the reference indexes an empty list there and raises) changes nothing and sets
+// status bit 2; the host raises RuntimeError.
 #include "common.cuh"
 
 namespace bode {
@@ -122,6 +122,10 @@ __global__ void __launch_bounds__(128) hamcmc_contig_kernel(const HamcmcContigAr
     if (threadIdx.x == 0) { meta[0] = n_hist; meta[1] = 0; meta[2] = K; meta[3] = 0; }
   } else {
     // ---------------- metric step (:1205-1238 / :1364-1397)
+    if (n_hist0 < M) {                                                    // window not full: nothing to build the metric from
+      if (threadIdx.x == 0 && a.status) atomicOr(a.status, 2);
+      return;
+    }
     const int K = K0;
     const int newest = (head + M - 1) % M, prev = (head + M - 2) % M;
     const float B0 = 1.f / a.H_gamma, C0 = sqrtf(B0), S0 = rsqrtf(B0);

@@ -96,6 +96,7 @@ def run_sampler(config, data, output=None, chains=1, jitter=0.0, seed=0, device=
         sq_err_loss_arr.append(se.item() if se.numel() == 1 else se.cpu().numpy())
 
     sampler, extra = _make_sampler(config, params, N)
+    sampler.seed = int(seed)                                                  # the run's seed keys the in-kernel noise too
     kwargs = dict(burn_in=config["burn_in"], num_samples=config["num_samples"], print_iters=False)
     kwargs.update(extra)
     if config["method"] != "HAMCMC":

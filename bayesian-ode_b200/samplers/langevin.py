@@ -438,8 +438,9 @@ class _HAMCMCContiguous(HAMCMC):
     """langevin.py:1109-1470: HAMCMC2 / HAMCMC3 / HAMCMC4, the variants that build the L-BFGS pairs from contiguous samples
     (``bode_hamcmc_contig_step``; bookkeeping restated in oracle/samplers.py::HAMCMCContiguous, which is pinned to reference runs of
     all three).  Same constructor and stepping API as the reference classes: the first ``self.memory`` iterations of ``sample``
-    are plain Langevin steps that fill the window (:1254), every later one is a metric step.
-    STATUS: not yet run on a GPU (the kernel was written after round 1's GPU budget was spent); see DESIGN.md section 7."""
+    are plain Langevin steps that fill the window (:1254), every later one is a metric step.  A metric step on a window that is
+    not full yet (``step()`` called directly, or ``burn_in < memory + 1``) raises RuntimeError and leaves the parameters unchanged
+    (the reference fails there with an IndexError)."""
 
     _variant = None
 

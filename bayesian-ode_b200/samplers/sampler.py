@@ -13,6 +13,13 @@ from .. import _lib
 
 
 
+def _default_seed():
+    import torch.distributed as dist
+    draw = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    rank = dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+    return (draw ^ (rank * 0x9E3779B97F4A7C15)) & 0x7FFFFFFFFFFFFFFF
+
+
 def _flat_base(tensors):
     """If every tensor is a dense column block [P, ...] of one row-major [P, d] buffer and together they tile its
     columns, return that buffer as a [P, d] view; else None."""
@@ -118,7 +125,12 @@ class Sampler(Optimizer):
         self._status = torch.zeros(1, dtype=torch.int32, device=self._plist[0].device)
         self._ctl_dev = None
         self._step_index = 0
-        self.seed = int(defaults.get("seed", 0)) if isinstance(defaults, dict) else 0
+        # Philox key of the in-kernel noise.  ``seed=`` pins it (reproducible runs); by default it is a fresh draw from torch's
+        # global generator -- so ``torch.manual_seed`` governs it like it governs the reference's ``Normal(...).sample()`` draws
+        # (langevin.py:194-199) and successive samplers differ -- mixed with the distributed rank, so that the shards of a
+        # multi-GPU job never replay each other's stream.
+        seed = defaults.get("seed") if isinstance(defaults, dict) else None
+        self.seed = int(seed) if seed is not None else _default_seed()
         self.check_finite = "sync"       # "sync": raise inside step() like the reference; "deferred": raise at check()
 
     # ---- flat buffers ------------------------------------------------------------------------------------
@@ -184,8 +196,12 @@ class Sampler(Optimizer):
 
     # ---- NaN reporting (langevin.py:184-185) -------------------------------------------------------------
     def check(self):
-        if int(self._status.item()) != 0:
+        st = int(self._status.item())
+        if st != 0:
             self._status.zero_()
+            if st & 2:
+                raise RuntimeError("metric step before the history window is full: run `memory + 1` step_without_metric() "
+                                   "iterations first (sample() does, langevin.py:1254); parameters were left unchanged")
             raise ValueError("Encountered NaN/Inf in parameter")
 
     def _after_step(self):

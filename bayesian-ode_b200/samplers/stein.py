@@ -257,6 +257,13 @@ class SVGD(Sampler):
         self.rank = dist.get_rank() if self.world > 1 else 0
         self.n_total = self.P_local * self.world
         dev = self._flat.device
+        if self.world > 1:
+            # the exchange buffers and the Gram blocks assume equal shards (shard_range() hands out uneven ones when P % world != 0)
+            sizes = torch.tensor([self.P_local, -self.P_local], device=dev)
+            dist.all_reduce(sizes, op=dist.ReduceOp.MAX)
+            if int(sizes[0]) != self.P_local or int(-sizes[1]) != self.P_local:
+                raise _lib.BodeError("SVGD: every rank must hold the same number of particles (got %d here, %d..%d over the ranks)"
+                                     % (self.P_local, int(-sizes[1]), int(sizes[0])))
         # several ranks: "p2p" maps the workspaces into each other (NVLink peer reads + flag barriers inside the median kernels);
         # "nccl" keeps the collective protocol (one table all-reduce + three histogram all-reduces per step)
         if median_comm not in ("p2p", "nccl"):
@@ -327,6 +334,19 @@ class SVGD(Sampler):
                 self._saved_cta_limit = lib.bode_npde_set_cta_limit(sms - self.side_sms)   # until phi() restores it
         self._prefetched = self.overlap
 
+    def _restore_cta_limit(self):
+        """Undo prefetch()'s process-wide CTA cap of the fused solve (phi() does; so does an aborted step)."""
+        if self._saved_cta_limit is not None:
+            _lib.load().bode_npde_set_cta_limit(self._saved_cta_limit)
+            self._saved_cta_limit = None
+
+    def cancel_prefetch(self):
+        """Drop a prefetch() whose phi() will not follow (the closure raised): joins the side stream, restores the CTA cap."""
+        self._restore_cta_limit()
+        if self._prefetched:
+            torch.cuda.current_stream().wait_stream(self._side)
+            self._prefetched = False
+
     def phi(self, X=None, grad=None, update_lr=None):
         """stein.py:75-86 for the local rows.  Returns phi [P_local, d]; with ``update_lr`` the update is fused."""
         lib = _lib.load()
@@ -337,9 +357,7 @@ class SVGD(Sampler):
         d, nl, nt = self.d, self.P_local, self.n_total
         ws = self._ws
         cur = torch.cuda.current_stream()
-        if self._saved_cta_limit is not None:
-            lib.bode_npde_set_cta_limit(self._saved_cta_limit)
-            self._saved_cta_limit = None
+        self._restore_cta_limit()
         prefetched = self._prefetched if X is self._flat else False
         if self._prefetched and prefetched != "gram":
             cur.wait_stream(self._side)                     # join: operands (and the gathered positions) are ready
@@ -385,12 +403,16 @@ class SVGD(Sampler):
         if lr:
             group["lr"] = lr
         self.phi(update_lr=group["lr"])
-        self._step_index += 1
+        self._after_step()                                   # "sync": check() now, like langevin.py:184-185; "deferred": at check()
         return self.loss
 
     def check(self):
-        """NaN report of the base class, plus: did a flag barrier of the peer-memory exchange give up on a peer?"""
+        """Non-finite particles (the fused phi + update launch carries no status word, so the particles themselves are tested:
+        one NaN/Inf poisons every row of the next interaction), plus: did a flag barrier of the peer-memory exchange give up on a
+        peer?  Called after every step() unless ``check_finite == "deferred"``, and at the end of sample()."""
         super().check()
+        if not bool(torch.isfinite(self._flat).all()):
+            raise ValueError("Encountered NaN/Inf in parameter")
         if self._ws.p2p:
             torch.cuda.synchronize()
             t = C.c_int32(0)
@@ -408,17 +430,25 @@ class SVGD(Sampler):
         if fused and self._grad_flat() is None and hasattr(closure.field, "bind_flat_grads"):
             closure.field.bind_flat_grads()
         chain.reserve((num_samples + thinning - 1) // thinning, self._flat, self._plist)
-        for i in range(burn_in + num_samples):
-            self.prefetch()                                  # position-only operands beside the solve
-            if fused:
-                self.loss = closure.loss_and_grad_()[0]
-            else:
-                self.zero_grad()
-                self.loss = closure()
-                self._backward(self.loss)
-            self.step()
-            if i >= burn_in and (i - burn_in) % thinning == 0:
-                self._record(chain)
-            if arr_closure is not None:
-                arr_closure(self.loss, closure(add_prior=False))
+        mode, self.check_finite = self.check_finite, "deferred"      # one check at the end instead of a device sync per step
+        try:
+            for i in range(burn_in + num_samples):
+                self.prefetch()                              # position-only operands beside the solve
+                if fused:
+                    self.loss = closure.loss_and_grad_()[0]
+                else:
+                    self.zero_grad()
+                    self.loss = closure()
+                    self._backward(self.loss)
+                self.step()
+                if i >= burn_in and (i - burn_in) % thinning == 0:
+                    self._record(chain)
+                if arr_closure is not None:
+                    arr_closure(self.loss, closure(add_prior=False))
+                if mode == "sync" and (i + 1) % 64 == 0:
+                    self.check()
+        finally:
+            self.check_finite = mode
+            self.cancel_prefetch()
+        self.check()                                         # NaN/Inf particles or a peer barrier that gave up: raise, do not return
         return chain

@@ -99,15 +99,10 @@ def run_reference(args, wl):
 
 # ------------------------------------------------------------------------------------------ helpers (GPU arm)
 def checked(smp, notes):
-    """smp.check(): a NaN report (ValueError, langevin.py:184-185) fails the run; any other report -- the peer flag-barrier
-    status of a multi-GPU SVGD job, a path that had not run on a GPU when round 1 closed -- is carried in the JSON line
-    ("check") instead of discarding the measurement."""
-    try:
-        smp.check()
-    except ValueError:
-        raise
-    except Exception as e:                                   # noqa: BLE001
-        notes.append(str(e).splitlines()[0] if str(e) else type(e).__name__)
+    """smp.check(): ANY report fails the run -- NaN/Inf parameters (ValueError, langevin.py:184-185), a peer flag barrier of the
+    multi-GPU exchange that gave up on a rank (the gathered particles of that step were stale), a CUDA error.  A throughput
+    measured over invalid particles is not a measurement."""
+    smp.check()
 
 
 class ClockSampler:

@@ -267,7 +267,7 @@ int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* hist_theta, fl
  * pair_s/pair_y [P][M-1][d], work [P][4(M-1)+2][d].  metric_step = 0: step_without_metric (:1180-1203), update_metric stores
  * (theta_new, grad) and forms the pairs when the M-entry window fills (the first M iterations of sample(), :1254);
  * metric_step = 1: step (:1205-1238, :1364-1397).
- * STATUS: compiled, oracle pinned to reference runs of all three variants, NOT yet run on a GPU. */
+ * A metric step while the window is not full yet changes nothing and sets bit 2 of *status (bit 1: non-finite parameter). */
 size_t bode_hamcmc_contig_floats(int32_t P, int32_t d, int32_t memory, int32_t which);
 int bode_hamcmc_contig_step(int32_t variant, int32_t P, int32_t d, int32_t memory, float* hist_theta, float* hist_grad,
                             float* pair_s, float* pair_y, float* work, int32_t* meta, float* theta, int64_t ld_theta,

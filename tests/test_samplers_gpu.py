@@ -421,18 +421,24 @@ def test_hamcmc_matches_reference_run():
     assert int(smp.n_pairs()[0]) == int(g["n_pairs"])
 
 
-@pytest.mark.skipif(os.environ.get("BODE_RUN_UNVALIDATED") != "1",
-                    reason="hamcmc_contig.cu was written after round 1's GPU budget was spent: enable once it has run on a B200")
 def test_hamcmc_contiguous_variants_match_reference_runs():
     """HAMCMC2 / HAMCMC3 / HAMCMC4 on the reference's own runs (tests/golden/hamcmc_contiguous.npz: M warm-up + 10 metric steps
-    each, injected noise, gradients of the same quadratic by autograd on the device)."""
+    each, injected noise, gradients of the same quadratic by autograd on the device).
+    Tolerance per step: the fixture's runs are ill-conditioned in places (HAMCMC2's last step multiplies |theta| by 370, HAMCMC4
+    grows to 1.6e6 -- the reference diverges on this quadratic), so the bar is tied to the step's MEASURED conditioning: the float64
+    oracle re-run on the float32-rounded inputs (theta_0, A, xi) deviates from the reference by dev_i through input rounding alone
+    (4e-8 on a well-conditioned step, 9e-4 on HAMCMC2's last one); the fp32 kernel must stay within max(2e-5, 40 dev_i)."""
     from bayesian_ode_b200 import samplers
+    from oracle import samplers as osamp
     g = load_golden("hamcmc_contiguous")
     memory = int(g["memory"])
     M = memory + 1
     A = torch.from_numpy(g["A"]).float().cuda()
+    A32 = g["A"].astype(np.float32).astype(np.float64)
     for variant in (2, 3, 4):
         th_ref, xi, lrs = g["theta%d" % variant], g["xi%d" % variant], g["lr%d" % variant]
+        orc = osamp.HAMCMCContiguous(variant, memory=memory, H_gamma=1.0, trust_reg=1.0)
+        th_o = th_ref[0].astype(np.float32).astype(np.float64)
         th0 = torch.from_numpy(th_ref[0]).float().cuda()
         a = torch.nn.Parameter(th0[:6].reshape(3, 2).clone())
         b = torch.nn.Parameter(th0[6:].clone())
@@ -444,14 +450,30 @@ def test_hamcmc_contiguous_variants_match_reference_runs():
             (0.5 * th @ (A @ th)).backward()
             lr = smp.get_lr(i)
             assert lr == float(lrs[i])
+            x64 = xi[i].astype(np.float32).astype(np.float64)
             if i < M:
                 smp.step_without_metric(lr=lr, noise=xi[i])
+                th_o = orc.step_without_metric(th_o, A32 @ th_o, float(np.float32(lr)), x64)
             else:
                 smp.step(lr=lr, noise=xi[i])
+                th_o = orc.step(A32 @ th_o, float(np.float32(lr)), x64)
+            dev = relerr(th_o, th_ref[i + 1])
             got = torch.cat([a.detach().reshape(-1), b.detach().reshape(-1)]).cpu().numpy()
-            # fp32 against the fp64 reference; HAMCMC3/4 amplify (they diverge on this quadratic in the reference too)
-            assert relerr(got, th_ref[i + 1]) < (2e-5 if i < M else 2e-3), (variant, i)
+            assert relerr(got, th_ref[i + 1]) < max(2e-5, 40.0 * dev), (variant, i, dev)
         assert int(smp.n_pairs()[0]) == (M - 1 if variant == 4 else M - 2)
+
+
+def test_hamcmc_contiguous_metric_step_on_partial_window_raises():
+    """langevin.py:1205-1238 indexes the pair lists of a window that does not exist yet; the kernel leaves theta alone and reports."""
+    from bayesian_ode_b200.samplers import HAMCMC4
+    a = torch.nn.Parameter(torch.randn(6, device="cuda"))
+    a.grad = torch.randn(6, device="cuda")
+    smp = HAMCMC4([a], memory=3, lr0=1e-2, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3)
+    smp.step_without_metric(lr=1e-2)
+    before = a.detach().clone()
+    with pytest.raises(RuntimeError, match="history window"):
+        smp.step(lr=1e-2)
+    assert torch.equal(a.detach(), before)
 
 
 def test_hamcmc_batched_chains_on_npde():
