@@ -34,7 +34,8 @@ class MlpFieldStruct(C.Structure):
 
 class Dopri5Opts(C.Structure):
     _fields_ = [("t", C.c_void_p), ("rtol", C.c_double), ("atol", C.c_double), ("safety", C.c_double), ("ifactor", C.c_double),
-                ("dfactor", C.c_double), ("max_num_steps", C.c_int32), ("user_first_step", C.c_int32), ("stats", C.c_void_p)]
+                ("dfactor", C.c_double), ("max_num_steps", C.c_int32), ("user_first_step", C.c_int32), ("stats", C.c_void_p),
+                ("controller", C.c_int32)]
 
 
 class GridStruct(C.Structure):

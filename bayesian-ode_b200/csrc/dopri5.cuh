@@ -8,6 +8,14 @@
 //   step-size controller           misc.py:160-170 (float64 t, dt; applied after accepted AND rejected steps)
 //   dense output                   interp.py:5-65  (outputs are interpolated; dt is never clipped to hit t[i])
 // t and dt are float64 like the reference's controller; the state is fp32.
+//
+// Controller granularity (Dopri5Params::pool).  torchdiffeq keeps ONE controller per odeint call and pools the error over every
+// element of y0 (misc.py:146-157: mean over the whole tensor; the initial-step norms of misc.py:116-143 likewise).  The notebook
+// integrates one trajectory row per call (nn.ipynb cell 10), gp.py integrates all N rows in one call (gp.py:346, 452):
+//   pool = 0  one controller per (particle, trajectory) pair   == one reference call per row
+//   pool = 1  one controller per particle, error pooled over its N trajectories x 2 components  == one reference call with y0 [N, 2]
+// In pooled mode the N pairs of a particle advance in lock-step (same dt, same accept / reject); their squared error terms meet
+// in shared memory (CtrlPool) and every thread of the particle adds them in the same fixed order.
 #pragma once
 #include "npde_solve.cuh"
 
@@ -20,9 +28,36 @@ struct Dopri5Params {
   double safety, ifactor, dfactor;
   int max_num_steps;
   int* stats;             // [P*N][3]: accepted, rejected, status bits (1 max_num_steps, 2 dt underflow, 4 non-finite state)
+  int pool;               // 0: controller per pair, 1: per particle (see above)
+};
+
+// Pooled controller: sum of one float per pair (and OR of one flag) over the N pairs of a particle.  Geometry comes from plan()
+// (npde.cu) / the MLP launchers: G == 1 -> 32-thread CTAs holding floor(32 / N) particles, so a particle's lanes share a warp and
+// synchronise with __syncwarp on their own lane mask (particles of one warp take different numbers of attempts); G == 32 -> one
+// particle per CTA (N warps), __syncthreads.  Two alternating buffers: one barrier per reduction.
+template <int G>
+struct CtrlPool {
+  float (*buf)[2][64];
+  int flip, pairl, first, N;
+  unsigned mask;
+  __device__ __forceinline__ void init(float (*b)[2][64], int pairl_, int pl, int N_) {
+    buf = b; flip = 0; pairl = pairl_; N = N_; first = pl * N_;
+    mask = G == 1 ? (((N_ >= 32 ? 0u : (1u << N_)) - 1u) << (first & 31)) : 0xffffffffu;
+  }
+  __device__ __forceinline__ float sum(float v, int lane, int flag, int* any) {
+    float(*b)[64] = buf[flip];
+    flip ^= 1;
+    if (lane == 0) { b[0][pairl] = v; b[1][pairl] = flag ? 1.f : 0.f; }
+    if (G == 1) __syncwarp(mask); else __syncthreads();
+    float s = 0.f, f = 0.f;
+    for (int n = 0; n < N; ++n) { s += b[0][first + n]; f += b[1][first + n]; }
+    *any = f != 0.f;
+    return s;
+  }
 };
 
 __device__ __forceinline__ float rms2(float2 v) { return sqrtf(0.5f * (v.x * v.x + v.y * v.y)); }
+__device__ __forceinline__ float ss2(float2 v) { return v.x * v.x + v.y * v.y; }
 __device__ __forceinline__ float2 div2(float2 a, float2 b) { return f2(a.x / b.x, a.y / b.y); }
 
 template <class Field>
@@ -35,7 +70,12 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
   const int pairl = tid / G, lane = tid % G;
   const int pl = pairl / prm.N, n = pairl % prm.N;
   const int p = blockIdx.x * prm.ppc + pl;
+  __shared__ float pool_buf[2][2][64];
   if (pl >= prm.ppc || p >= prm.P) return;
+  CtrlPool<G> cp;
+  cp.init(pool_buf, pairl, pl, prm.N);
+  const float inv_n = 1.f / (2.f * (float)prm.N);
+  int any = 0;
   Field fld;
   fld.load(prm, smem, pl, pairl, lane);
   const long long pair = (long long)p * prm.N + n;
@@ -65,10 +105,15 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
       dt = 0.01;
     } else {
       const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
-      const float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
+      float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
+      if (dp.pool) {                                       // norms over the whole y0 tensor of the call (misc.py:116-118)
+        d0 = sqrtf(cp.sum(ss2(div2(y, scale)), lane, 0, &any) * inv_n);
+        d1 = sqrtf(cp.sum(ss2(div2(f, scale)), lane, 0, &any) * inv_n);
+      }
       const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
       const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
-      const float d2 = rms2(div2(f1 - f, scale)) / h0;
+      float d2 = rms2(div2(f1 - f, scale)) / h0;
+      if (dp.pool) d2 = sqrtf(cp.sum(ss2(div2(f1 - f, scale)), lane, 0, &any) * inv_n) / h0;
       float h1;
       if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
       else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
@@ -83,7 +128,8 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
         if (n_steps >= dp.max_num_steps) { status |= 1; break; }
         const double ts = t1;                            // start of the attempted step
         if (!(ts + dt > ts)) { status |= 2; break; }
-        if (!(fabsf(y.x) <= 3.4028234e38f && fabsf(y.y) <= 3.4028234e38f)) { status |= 4; break; }
+        const bool nonfin = !(fabsf(y.x) <= 3.4028234e38f && fabsf(y.y) <= 3.4028234e38f);
+        if (nonfin && !dp.pool) { status |= 4; break; }     // pooled: reported after the reduction below, by the whole particle
         const float h = (float)dt;
         const float2 k1 = f;
         const float2 k2 = sg * fld.eval(prm, fma2(h * B21, k1, y));
@@ -96,7 +142,11 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
         const float2 err = fma2(h * E7, k7, fma2(h * E6, k6, fma2(h * E5, k5, fma2(h * E4, k4, fma2(h * E3, k3, (h * E1) * k1)))));
         const float2 tol = f2(dp.atol + dp.rtol * fmaxf(fabsf(y.x), fabsf(y1.x)), dp.atol + dp.rtol * fmaxf(fabsf(y.y), fabsf(y1.y)));
         const float2 er = div2(err, tol);
-        const float ratio = 0.5f * (er.x * er.x + er.y * er.y);
+        float ratio = 0.5f * (er.x * er.x + er.y * er.y);
+        if (dp.pool) {                                     // misc.py:151-157: mean over ALL elements of the state tensor
+          ratio = cp.sum(er.x * er.x + er.y * er.y, lane, nonfin, &any) * inv_n;
+          if (any) { status |= 4; break; }
+        }
         const bool accept = ratio <= 1.f;
         if (accept) {
           const float2 ymid = fma2(h * M7, k7, fma2(h * M6, k6, fma2(h * M5, k5, fma2(h * M4, k4, fma2(h * M3, k3, fma2(h * M1, k1, y))))));
@@ -173,6 +223,11 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
   const int pl = pairl / N, n = pairl % N;
   const int p = blockIdx.x * prm.ppc + pl;
   const bool active = pl < prm.ppc && p < prm.P;
+  __shared__ float pool_buf[2][2][64];
+  CtrlPool<G> cp;
+  cp.init(pool_buf, active ? pairl : 0, active ? pl : 0, N);
+  const float inv_n = 1.f / (2.f * (float)N);
+  int any = 0;
   float r2x = 0.f, r2y = 0.f;
   Field fld;
   fld.zero_grad();
@@ -214,10 +269,15 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
         dt = 0.01;
       } else {
         const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
-        const float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
+        float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
+        if (dp.pool) {                                       // norms over the whole y0 tensor of the call (misc.py:116-118)
+          d0 = sqrtf(cp.sum(ss2(div2(y, scale)), lane, 0, &any) * inv_n);
+          d1 = sqrtf(cp.sum(ss2(div2(f, scale)), lane, 0, &any) * inv_n);
+        }
         const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
         const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
-        const float d2 = rms2(div2(f1 - f, scale)) / h0;
+        float d2 = rms2(div2(f1 - f, scale)) / h0;
+        if (dp.pool) d2 = sqrtf(cp.sum(ss2(div2(f1 - f, scale)), lane, 0, &any) * inv_n) / h0;
         float h1;
         if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
         else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
@@ -232,7 +292,8 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
           if (n_steps >= dp.max_num_steps) { status |= 1; break; }
           const double ts = t1;
           if (!(ts + dt > ts)) { status |= 2; break; }
-          if (!(fabsf(y.x) <= 3.4028234e38f && fabsf(y.y) <= 3.4028234e38f)) { status |= 4; break; }
+          const bool nonfin = !(fabsf(y.x) <= 3.4028234e38f && fabsf(y.y) <= 3.4028234e38f);
+          if (nonfin && !dp.pool) { status |= 4; break; }
           const float h = (float)dt;
           const float2 k1 = f;
           const float2 p2 = fma2(h * B21, k1, y);
@@ -250,7 +311,11 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
           const float2 err = fma2(h * E7, k7, fma2(h * E6, k6, fma2(h * E5, k5, fma2(h * E4, k4, fma2(h * E3, k3, (h * E1) * k1)))));
           const float2 tol = f2(dp.atol + dp.rtol * fmaxf(fabsf(y.x), fabsf(y1.x)), dp.atol + dp.rtol * fmaxf(fabsf(y.y), fabsf(y1.y)));
           const float2 er = div2(err, tol);
-          const float ratio = 0.5f * (er.x * er.x + er.y * er.y);
+          float ratio = 0.5f * (er.x * er.x + er.y * er.y);
+          if (dp.pool) {
+            ratio = cp.sum(er.x * er.x + er.y * er.y, lane, nonfin, &any) * inv_n;
+            if (any) { status |= 4; break; }
+          }
           if (ratio <= 1.f) {
             const float2 ymid = fma2(h * M7, k7, fma2(h * M6, k6, fma2(h * M5, k5, fma2(h * M4, k4, fma2(h * M3, k3, fma2(h * M1, k1, y))))));
             ca = fma2(16.f, ymid, fma2(-8.f, y1, fma2(-8.f, y, fma2(2.f * h, k7, (-2.f * h) * k1))));

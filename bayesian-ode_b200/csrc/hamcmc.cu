@@ -25,22 +25,26 @@ struct HamcmcArgs {
   int* status;
 };
 
-__device__ __forceinline__ float block_sum(float v, float* red) {
+// Dot products accumulate in float64 (the product of two floats is exact there, so a length-d dot is rounded ONCE, when it is
+// returned): the product-form BFGS recursion subtracts projections of nearly parallel vectors and pairs whose curvature differs
+// by 1e7 are common on the 16 x 16 npde posterior -- fp32 accumulation cost two digits of the update there.  The vectors stay fp32
+// (HBM traffic unchanged); ~50 dots of d <= 514 per chain and step are nothing against the FP64 rate.  Fixed order: deterministic.
+__device__ __forceinline__ double block_sum(double v, double* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[w] = v;
   __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nw; ++i) t += red[i];       // fixed order: deterministic
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
   return t;
 }
 
-__device__ __forceinline__ float bdot(const float* a, const float* b, int d, float* red) {
-  float acc = 0.f;
-  for (int e = threadIdx.x; e < d; e += blockDim.x) acc = fmaf(a[e], b[e], acc);
-  return block_sum(acc, red);
+__device__ __forceinline__ float bdot(const float* a, const float* b, int d, double* red) {
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) acc = fma((double)a[e], (double)b[e], acc);
+  return (float)block_sum(acc, red);
 }
 
 // minimal Philox for in-kernel noise (same generator as samplers.cu)
@@ -62,7 +66,7 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
 }
 
 __global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
-  __shared__ float red[8];
+  __shared__ double red[8];
   const int p = blockIdx.x, d = a.d, M = a.M, cap = 2 * M - 1;
   float* ht = a.hist_theta + (long long)p * cap * d;
   float* hg = a.hist_grad + (long long)p * cap * d;
@@ -102,16 +106,16 @@ __global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
       __syncthreads();
       K = 0;
       for (int i = 0; i < M - 1; ++i) {
-        float sy = 0.f, ss = 0.f;
+        double sy = 0.0, ss = 0.0;
         for (int e = threadIdx.x; e < d; e += blockDim.x) {
           const float s = ht[(long long)(i + M) * d + e] - ht[(long long)i * d + e];
           const float y = hg[(long long)(i + M) * d + e] - hg[(long long)i * d + e] + a.trust_reg * s;
           z[e] = s; z2[e] = y;
-          sy = fmaf(s, y, sy); ss = fmaf(s, s, ss);
+          sy = fma((double)s, (double)y, sy); ss = fma((double)s, (double)s, ss);
         }
         sy = block_sum(sy, red);
         ss = block_sum(ss, red);
-        if (sy > 1e-4f * ss) {
+        if (sy > 1e-4 * ss) {
           for (int e = threadIdx.x; e < d; e += blockDim.x) { ps[(long long)K * d + e] = z[e]; py[(long long)K * d + e] = z2[e]; }
           ++K;
         }
@@ -175,7 +179,7 @@ __global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
       for (int e = threadIdx.x; e < d; e += blockDim.x) z2[e] = fmaf(-c, Q[(long long)j * d + e], z2[e]);
     }
     // theta_new = base - lr Hg - lr Sn ; s/y of the refresh pair (:862-873)
-    float sy = 0.f, ss = 0.f;
+    double sy = 0.0, ss = 0.0;
     for (int e = threadIdx.x; e < d; e += blockDim.x) {
       float t = fmaf(-a.lr, z[e], base[e]);
       if (a.add_noise) t = fmaf(-a.lr, z2[e], t);
@@ -184,12 +188,12 @@ __global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
       const float y = g[e] - gbase[e] + a.trust_reg * s;
       z[e] = s; z2[e] = y;
       th[e] = t;
-      sy = fmaf(s, y, sy); ss = fmaf(s, s, ss);
+      sy = fma((double)s, (double)y, sy); ss = fma((double)s, (double)s, ss);
     }
     sy = block_sum(sy, red);
     ss = block_sum(ss, red);
     int np_head = phead;
-    if (sy > 1e-8f * ss && K > 0) {                                      // append + pop(0): the oldest pair is replaced
+    if (sy > 1e-8 * ss && K > 0) {                                      // append + pop(0): the oldest pair is replaced
       for (int e = threadIdx.x; e < d; e += blockDim.x) { ps[(long long)phead * d + e] = z[e]; py[(long long)phead * d + e] = z2[e]; }
       np_head = (phead + 1) % K;
     }

@@ -31,22 +31,26 @@ struct HamcmcContigArgs {
   int* status;
 };
 
-__device__ __forceinline__ float hc_block_sum(float v, float* red) {
+// Dot products accumulate in float64 (the product of two floats is exact there, so a length-d dot is rounded ONCE, when it is
+// returned): the product-form BFGS recursion subtracts projections of nearly parallel vectors and pairs whose curvature differs
+// by 1e7 are common on the 16 x 16 npde posterior -- fp32 accumulation cost two digits of the update there.  The vectors stay fp32
+// (HBM traffic unchanged); ~50 dots of d <= 514 per chain and step are nothing against the FP64 rate.  Fixed order: deterministic.
+__device__ __forceinline__ double hc_block_sum(double v, double* red) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
   __syncthreads();
   if ((threadIdx.x & 31) == 0) red[w] = v;
   __syncthreads();
-  float t = 0.f;
-  for (int i = 0; i < nw; ++i) t += red[i];       // fixed order: deterministic
+  double t = 0.0;
+  for (int i = 0; i < nw; ++i) t += red[i];
   return t;
 }
 
-__device__ __forceinline__ float hc_dot(const float* a, const float* b, int d, float* red) {
-  float acc = 0.f;
-  for (int e = threadIdx.x; e < d; e += blockDim.x) acc = fmaf(a[e], b[e], acc);
-  return hc_block_sum(acc, red);
+__device__ __forceinline__ float hc_dot(const float* a, const float* b, int d, double* red) {
+  double acc = 0.0;
+  for (int e = threadIdx.x; e < d; e += blockDim.x) acc = fma((double)a[e], (double)b[e], acc);
+  return (float)hc_block_sum(acc, red);
 }
 
 // the Philox stream of hamcmc.cu / samplers.cu
@@ -70,7 +74,7 @@ __device__ __forceinline__ float hc_philox_normal(unsigned long long seed, unsig
 // Every thread owns the elements e = threadIdx.x + k blockDim.x of every length-d vector: elementwise updates need no barrier,
 // only the dot products synchronise the CTA.
 __global__ void __launch_bounds__(128) hamcmc_contig_kernel(const HamcmcContigArgs a) {
-  __shared__ float red[8];
+  __shared__ double red[8];
   const int p = blockIdx.x, d = a.d, M = a.M;
   float* ht = a.hist_theta + (long long)p * M * d;
   float* hg = a.hist_grad + (long long)p * M * d;

@@ -301,6 +301,8 @@ int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o) {
   dp.safety = o->safety; dp.ifactor = o->ifactor; dp.dfactor = o->dfactor;
   dp.max_num_steps = o->max_num_steps > 0 ? o->max_num_steps : 2147483647;
   dp.stats = o->stats;
+  BODE_REQUIRE(o->controller == 0 || o->controller == 1, "dopri5 controller must be 0 (per pair) or 1 (per particle, pooled)");
+  dp.pool = o->controller;
   return BODE_OK;
 }
 

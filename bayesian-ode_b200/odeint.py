@@ -148,10 +148,21 @@ def last_dopri5_stats():
 DOPRI5_MAX_REC_STEPS = 256      # accepted steps recorded per (particle, trajectory) pair for the gradient
 
 
-def dopri5_setup(func, y0, t, rtol, atol, options):
-    """Normalise the dopri5 call (dopri5.py:60-75 options, misc.py:184-187 time reversal) into the C-ABI structures."""
+CONTROLLERS = {"pair": 0, "batch": 1}
+
+
+def dopri5_setup(func, y0, t, rtol, atol, options, controller="batch"):
+    """Normalise the dopri5 call (dopri5.py:60-75 options, misc.py:184-187 time reversal) into the C-ABI structures.
+
+    ``options['controller']`` (an extension; every other unknown key warns like misc.py:79-81) picks what ONE reference call is:
+      "batch" (default of ``odeint`` / ``odeint_adjoint``)  the whole ``y0 [N, 2]`` of a particle is one call -- one step-size
+               controller per particle, error ratio and initial-step norms pooled over all N x 2 elements (misc.py:146-157);
+      "pair"   one call per trajectory row, as nn.ipynb cell 10 integrates (``MLPPosterior``'s default)."""
     import warnings
     options = dict(options or {})
+    controller = options.pop("controller", controller)
+    if controller not in CONTROLLERS:
+        raise ValueError("options['controller'] must be 'batch' or 'pair'")
     known = {k: options.pop(k) for k in ("first_step", "safety", "ifactor", "dfactor", "max_num_steps") if k in options}
     if len(options) > 0:
         warnings.warn("Dopri5Solver: Unexpected arguments {}".format(options))          # misc.py:79-81
@@ -171,6 +182,7 @@ def dopri5_setup(func, y0, t, rtol, atol, options):
     o.max_num_steps = int(min(known.get("max_num_steps", 2 ** 31 - 1), 2 ** 31 - 1))
     o.user_first_step = int(known.get("first_step") is not None)
     o.stats = stats.data_ptr()
+    o.controller = CONTROLLERS[controller]
     return dict(o=o, tdev=tdev, T=int(t64.numel()), sign=sign, y0=y0c, batched=batched, N=N, stats=stats)
 
 
@@ -241,7 +253,7 @@ class _Dopri5Odeint(torch.autograd.Function):
 
 
 def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
-    """Dopri5Solver (dopri5.py:58-122) with one controller per (particle, trajectory) pair."""
+    """Dopri5Solver (dopri5.py:58-122); controller granularity per ``options['controller']`` (see dopri5_setup)."""
     cfg = dopri5_setup(func, y0, t, rtol, atol, options)
     params = [func.U] if isinstance(func, NPDEField) else [getattr(func, k) for k in func._blocks()]
     sol = _Dopri5Odeint.apply(cfg["y0"], func, cfg, *params)

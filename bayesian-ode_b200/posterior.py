@@ -59,6 +59,7 @@ class NPDEPosterior:
             raise ValueError("Y must be [N, T, 2]")
         if method == "dopri5":
             self.grid = None
+            self.options.setdefault("controller", "batch")           # gp.py:346: ONE odeint call with y0 [N, 2]
             self._d5 = _om.dopri5_setup(field, self.x0, self.t, rtol, atol, self.options)
         else:
             opts = _grid.split_options("NPDEPosterior", self.options)
@@ -172,6 +173,7 @@ class MLPPosterior:
             raise ValueError("X must be [N, T, 2]")
         if method == "dopri5":
             self.grid = None
+            self.options.setdefault("controller", "pair")            # nn.ipynb cell 10: one odeint call per trajectory row
             self._d5 = _om.dopri5_setup(field, self.x0, self.t, rtol, atol, self.options)
         else:
             opts = _grid.split_options("MLPPosterior", self.options)

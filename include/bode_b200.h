@@ -111,6 +111,11 @@ typedef struct bode_dopri5_opts {
   double rtol, atol, safety, ifactor, dfactor;
   int32_t max_num_steps, user_first_step;
   int32_t* stats;
+  /* Controller granularity.  0: one step-size controller per (particle, trajectory) pair == one reference odeint call per
+   * trajectory row (nn.ipynb cell 10).  1: one controller per particle with the error ratio (misc.py:146-157) and the
+   * initial-step norms (misc.py:116-143) pooled over its N trajectories x 2 components == one reference odeint call with
+   * y0 [N, 2] (gp.py:346, 452).  stats then repeats the particle's counts for each of its pairs. */
+  int32_t controller;
 } bode_dopri5_opts;
 
 int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,

@@ -697,9 +697,86 @@ def gen_hamcmc_contiguous():
     save("hamcmc_contiguous", **out)
 
 
+def gen_dopri5_batched(data):
+    """Adaptive dopri5 through the reference with the WHOLE y0 [N, 2] in one odeint call: one controller, error ratio and
+    initial-step norms pooled over all N x 2 elements (misc.py:146-157, 116-143) -- what gp.py:346 / 452
+    run.  The accept / reject sequence is recorded by wrapping (not changing) Dopri5Solver._adaptive_dopri5_step.  The MLP is the
+    notebook's layers applied row-wise (nn.ipynb's NN.forward flattens its input, so it only takes one row per call)."""
+    from torchdiffeq._impl import dopri5 as ref_d5
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    x0, t = data["x0"], data["t"]
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    torch.manual_seed(120)
+    net = NN(2, 20)
+    for m_ in net.modules():
+        if isinstance(m_, torch.nn.Linear):
+            torch.nn.init.uniform_(m_.weight, a=-0.5, b=0.5)
+
+    class RowWise(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, t, x):
+            return self.inner.layers(x)
+
+    accepts = []
+    orig = ref_d5.Dopri5Solver._adaptive_dopri5_step
+
+    def recording(self, rk_state):
+        new = orig(self, rk_state)
+        accepts.append((bool(new.t1 > rk_state.t1), float(rk_state.dt)))
+        return new
+    ref_d5.Dopri5Solver._adaptive_dopri5_step = recording
+    out = dict(x0=x0, t=t, U=U0, Z=Zt, theta=torch.cat([q.detach().reshape(-1) for q in net.parameters()]))
+    cases = {"default": dict(), "loose": dict(rtol=1e-5, atol=1e-7), "firststep": dict(rtol=1e-5, atol=1e-7, options=dict(first_step=0.5))}
+    try:
+        for name, kw in cases.items():
+            for fname, fobj in (("npde", kreg), ("mlp", RowWise(net))):
+                cf = _Counted(fobj)
+                del accepts[:]
+                with torch.no_grad():
+                    sol = torchdiffeq.odeint(cf, x0, t, method="dopri5" if "options" in kw else None, **kw)
+                out[f"{name}_{fname}_sol"] = sol                                   # [T,N,2]
+                out[f"{name}_{fname}_nfe"] = np.array(cf.nfe)
+                out[f"{name}_{fname}_accept"] = np.array([a for a, _ in accepts], dtype=np.int8)
+                out[f"{name}_{fname}_dt"] = np.array([d for _, d in accepts])
+                assert cf.nfe == (1 if "options" in kw else 2) + 6 * len(accepts)
+        # closure gradients through the reference's adjoint, one batched call (rtol 1e-7 / atol 1e-9)
+        kreg.zero_grad()
+        xode = torchdiffeq.odeint_adjoint(kreg, x0, t, rtol=1e-7, atol=1e-9, method="dopri5").permute(1, 0, 2)
+        loss = torch.sum((Yt - xode) ** 2 / (2 * torch.exp(kreg.logsn) ** 2)) + torch.numel(Yt) * torch.sum(kreg.logsn) / 2
+        loss = loss + torch.sum(torch.diag(torch.mm(kreg.U.t(), torch.mm(kreg.Kzzinv, kreg.U)))) / 2
+        loss.backward()
+        out.update(npde_loss=loss.detach(), npde_gU_adjoint=kreg.U.grad.clone(), npde_glogsn_adjoint=kreg.logsn.grad.clone(), Y=Yt)
+        rw = RowWise(net)
+        Xt = torch.from_numpy(data["X"])
+        for q in net.parameters():
+            q.grad = None
+        xode = torchdiffeq.odeint_adjoint(rw, x0, t, rtol=1e-7, atol=1e-9, method="dopri5").permute(1, 0, 2)
+        sq = torch.sum((Xt - xode) ** 2)
+        loss = sq + 0.5 * sum([torch.sum(q ** 2) for q in net.parameters()])
+        loss.backward()
+        out.update(mlp_sqerr=sq.detach(), mlp_loss=loss.detach(), mlp_grad_adjoint=torch.cat([q.grad.reshape(-1) for q in net.parameters()]), X=Xt)
+    finally:
+        ref_d5.Dopri5Solver._adaptive_dopri5_step = orig
+    # pin the oracle's pooled controller (oracle/dopri5.py takes any y0 shape and pools like misc.py:146-157) right here
+    from oracle import dopri5 as od5, npde as onpde
+    fo = onpde.NPDEField(U0.numpy()[None], Zt.numpy(), 1.0, 0.75)
+    so, st = od5.odeint_dopri5(lambda y: fo.f(y[None])[0], x0.numpy(), t.numpy().astype(np.float64), rtol=1e-5, atol=1e-7)
+    na = int(out["loose_npde_accept"].sum())
+    assert (st["accepted"], st["rejected"]) == (na, len(out["loose_npde_accept"]) - na), (st, na)
+    assert np.abs(so - out["loose_npde_sol"].numpy()).max() < 1e-9
+    save("dopri5_batched", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hamcmc_contiguous":
         gen_hamcmc_contiguous()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "dopri5_batched":
+        gen_dopri5_batched(make_data())
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predictive":
         gen_predictive(make_data())
@@ -719,6 +796,7 @@ if __name__ == "__main__":
     gen_svgd(data)
     gen_mlp(data)
     gen_dopri5(data)
+    gen_dopri5_batched(data)
     gen_hamcmc()
     gen_hamcmc_contiguous()
     gen_mala()

@@ -128,3 +128,20 @@ def test_dopri5_oracle_reversed_time():
     for r in range(5):
         sol, _ = dopri5.odeint_dopri5(lambda y: fn.f(y[None, None])[0, 0], g["x0"][r], g["rev_t"], rtol=1e-5, atol=1e-7)
         assert relerr(sol, g["rev_npde_sol"][:, r]) < 1e-8
+
+
+def test_oracle_dopri5_pooled_controller_matches_reference_batched_call():
+    """oracle/dopri5.py with y0 [N, 2] pools the error ratio and the initial-step norms over the whole tensor like misc.py:116-157;
+    fixture: the reference's batched odeint call with its accept / reject sequence recorded (dopri5_batched.npz)."""
+    from oracle import dopri5, mlp, npde
+    g = load_golden("dopri5_batched")
+    fo = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    fm = mlp.MLPField(g["theta"][None], 20)
+    t = g["t"].astype(np.float64)
+    for case, kw in (("default", {}), ("loose", dict(rtol=1e-5, atol=1e-7)), ("firststep", dict(rtol=1e-5, atol=1e-7, first_step=0.5))):
+        for fname, f in (("npde", lambda y: fo.f(y[None])[0]), ("mlp", lambda y: fm.f(y[None])[0])):
+            sol, st = dopri5.odeint_dopri5(f, g["x0"], t, **kw)
+            acc = g[f"{case}_{fname}_accept"]
+            assert (st["accepted"], st["rejected"]) == (int(acc.sum()), int(len(acc) - acc.sum())), (case, fname)
+            assert st["nfe"] == int(g[f"{case}_{fname}_nfe"])
+            assert relerr(sol, g[f"{case}_{fname}_sol"]) < 1e-9, (case, fname)
