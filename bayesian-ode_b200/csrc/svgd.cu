@@ -732,6 +732,16 @@ extern "C" int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t 
   return BODE_OK;
 }
 
+/* Disarm the median window: the next selection takes the radix passes (what the first call of a run, or a step that moves the
+ * median by more than the window's +-0.2 %, pays).  Used to MEASURE that path (bench.py median_fallback_ms) and by callers that
+ * replace the particles wholesale.  Every rank of a peer-mapped job must call it (all ranks must take the same path). */
+extern "C" int bode_svgd_window_disarm(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
+  BODE_REQUIRE(workspace && n_rows > 0 && n_cols > 0 && d > 0, "bad args");
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  BODE_CUDA(cudaMemsetAsync(&w.st->win_valid, 0, sizeof(unsigned int), (cudaStream_t)stream));
+  return BODE_OK;
+}
+
 /* Median window (svgd_state.cuh): *table_out = device address of WIN_TABLE+1 uint64 counters filled by bode_svgd_sqdist
  * (multi-rank callers all-reduce them); bode_svgd_window_select then reads the median off the table when both middle
  * ranks fall inside the window, which turns the following bode_svgd_hist_pass / bode_svgd_select_digit calls into no-ops. */

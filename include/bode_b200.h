@@ -328,6 +328,9 @@ int bode_svgd_set_tensor_cores(int32_t on);
 int bode_svgd_workspace_init(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, size_t workspace_bytes, bode_stream_t stream);
 int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, void** table_out, size_t* count_out);
 int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
+/* Disarm the median window (next selection = the 3-pass radix select over the stored d2).  For measuring that path and for
+ * callers that replace the particles wholesale; every rank of a peer-mapped job must call it. */
+int bode_svgd_window_disarm(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream);
 /* single-rank: the three radix passes fused into one cooperative launch (a no-op after a window hit); with med_gamma != NULL it
  * also writes med_gamma[0] = median, med_gamma[1] = gamma (median heuristic, n = n_total) and arms the next window, i.e. it
  * replaces the bode_svgd_gamma call */

