@@ -63,7 +63,10 @@ def parse():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--particles", type=int, default=None, help="override particles per GPU")
     ap.add_argument("--tol", default="tight", choices=sorted(TOLS), help="c4: dopri5 tolerances")
-    ap.add_argument("--init-scale", type=float, default=1.0, help="c4: scale of the U(-0.5, 0.5) weight draw (nn.ipynb cell 4)")
+    ap.add_argument("--init-scale", type=float, default=0.3,
+                    help="c4: scale of the U(-0.5, 0.5) weight draw of nn.ipynb cell 4.  The notebook's net has H = 20; the same draw at H = 64 "
+                         "has sqrt(64/20) = 1.8x the layer gain, its trajectories grow like e^(5t) and aSGHMC at the notebook's lr = 1e-2 turns the "
+                         "chains non-finite within a few iterations (in the reference as well).  0.3 ~ sqrt(20/64) / 2 keeps the ensemble bounded.")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling sub-record")
