@@ -11,10 +11,10 @@ All compute runs in hand-written CUDA behind the C ABI of include/bode_b200.h; t
 """
 from . import _lib
 from .fields import KernelRegression, MLPField, NPDEField, rbf_kernel
-from .odeint import last_dopri5_stats, odeint, odeint_adjoint
+from .odeint import TupleField, last_dopri5_stats, odeint, odeint_adjoint
 from .posterior import MLPPosterior, NPDEPosterior
 from . import samplers
 from .predictive import ensemble_trajectories, posterior_predictive
 from . import driver
 
-__all__ = ["odeint", "odeint_adjoint", "NPDEField", "KernelRegression", "NPDEPosterior", "MLPField", "MLPPosterior", "rbf_kernel", "samplers", "ensemble_trajectories", "posterior_predictive", "driver", "_lib"]
+__all__ = ["odeint", "odeint_adjoint", "TupleField", "NPDEField", "KernelRegression", "NPDEPosterior", "MLPField", "MLPPosterior", "rbf_kernel", "samplers", "ensemble_trajectories", "posterior_predictive", "driver", "_lib"]

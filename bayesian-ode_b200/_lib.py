@@ -35,7 +35,7 @@ class MlpFieldStruct(C.Structure):
 class Dopri5Opts(C.Structure):
     _fields_ = [("t", C.c_void_p), ("rtol", C.c_double), ("atol", C.c_double), ("safety", C.c_double), ("ifactor", C.c_double),
                 ("dfactor", C.c_double), ("max_num_steps", C.c_int32), ("user_first_step", C.c_int32), ("stats", C.c_void_p),
-                ("controller", C.c_int32)]
+                ("controller", C.c_int32), ("n_groups", C.c_int32), ("group_end", C.c_int32 * 4)]
 
 
 class GridStruct(C.Structure):
@@ -137,11 +137,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("BODE_LIB_PATH", LIB_PATH)          # developer aid: load an experimental build of the same ABI
+    if not os.path.exists(path):
         raise BodeError(
             f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "or `make -C bayesian-ode_b200/csrc`. There is no CPU fallback.")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     for name, (res, args) in SYMBOLS.items():
         fn = getattr(lib, name)
         fn.restype = res

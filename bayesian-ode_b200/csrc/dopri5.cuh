@@ -29,7 +29,17 @@ struct Dopri5Params {
   int max_num_steps;
   int* stats;             // [P*N][3]: accepted, rejected, status bits (1 max_num_steps, 2 dt underflow, 4 non-finite state)
   int pool;               // 0: controller per pair, 1: per particle (see above)
+  // Tuple states (misc.py:175-182): the N trajectories of a particle are the concatenation of ngroups state tensors, group g =
+  // trajectories [gend[g-1], gend[g]).  torchdiffeq pools the error PER TENSOR and takes the maximum over the tuple (accept iff
+  // every tensor's mean ratio <= 1, dopri5.py:108-109; _optimal_step_size uses max(ratios), misc.py:161; the initial-step norms
+  // likewise, misc.py:125-141).  ngroups <= 1: one tensor.
+  int ngroups;
+  int gend[4];
 };
+
+__device__ __forceinline__ float rms2(float2 v) { return sqrtf(0.5f * (v.x * v.x + v.y * v.y)); }
+__device__ __forceinline__ float ss2(float2 v) { return v.x * v.x + v.y * v.y; }
+__device__ __forceinline__ float2 div2(float2 a, float2 b) { return f2(a.x / b.x, a.y / b.y); }
 
 // Pooled controller: sum of one float per pair (and OR of one flag) over the N pairs of a particle.  Geometry comes from plan()
 // (npde.cu) / the MLP launchers: G == 1 -> 32-thread CTAs holding floor(32 / N) particles, so a particle's lanes share a warp and
@@ -38,27 +48,77 @@ struct Dopri5Params {
 template <int G>
 struct CtrlPool {
   float (*buf)[2][64];
-  int flip, pairl, first, N;
+  int flip, pairl, first, N, ng;
+  int ge[4];
   unsigned mask;
-  __device__ __forceinline__ void init(float (*b)[2][64], int pairl_, int pl, int N_) {
+  __device__ __forceinline__ void init(float (*b)[2][64], int pairl_, int pl, int N_, const Dopri5Params& dp) {
     buf = b; flip = 0; pairl = pairl_; N = N_; first = pl * N_;
+    ng = dp.ngroups > 1 ? dp.ngroups : 1;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) ge[g] = dp.ngroups > 1 ? dp.gend[g] : N_;
     mask = G == 1 ? (((N_ >= 32 ? 0u : (1u << N_)) - 1u) << (first & 31)) : 0xffffffffu;
   }
-  __device__ __forceinline__ float sum(float v, int lane, int flag, int* any) {
+  // gm[g] = mean over the elements of state tensor g of v (v = this pair's sum over its 2 components); *any = OR of the flags
+  __device__ __forceinline__ void means(float v, int lane, int flag, int* any, float (&gm)[4]) {
     float(*b)[64] = buf[flip];
     flip ^= 1;
     if (lane == 0) { b[0][pairl] = v; b[1][pairl] = flag ? 1.f : 0.f; }
     if (G == 1) __syncwarp(mask); else __syncthreads();
-    float s = 0.f, f = 0.f;
-    for (int n = 0; n < N; ++n) { s += b[0][first + n]; f += b[1][first + n]; }
+    float f = 0.f;
+    int n = 0;
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float s = 0.f;
+      const int n0 = n;
+      if (g < ng)
+        for (; n < ge[g]; ++n) { s += b[0][first + n]; f += b[1][first + n]; }
+      gm[g] = (g < ng && n > n0) ? s / (2.f * (float)(n - n0)) : 0.f;
+    }
     *any = f != 0.f;
-    return s;
+  }
+  __device__ __forceinline__ float max_mean(float v, int lane, int flag, int* any) {
+    float gm[4];
+    means(v, lane, flag, any, gm);
+    return fmaxf(fmaxf(gm[0], gm[1]), fmaxf(gm[2], gm[3]));      // unused groups are 0 and every mean is >= 0
   }
 };
 
-__device__ __forceinline__ float rms2(float2 v) { return sqrtf(0.5f * (v.x * v.x + v.y * v.y)); }
-__device__ __forceinline__ float ss2(float2 v) { return v.x * v.x + v.y * v.y; }
-__device__ __forceinline__ float2 div2(float2 a, float2 b) { return f2(a.x / b.x, a.y / b.y); }
+// misc.py:84-143 (_select_initial_step, order 4) in the state dtype; pooled mode forms the norms per state tensor and combines them
+// as the reference does for tuples (max of the norms; h0 from the largest d0 / d1 ratio).
+template <class Field, int G>
+__device__ __forceinline__ double dopri5_first_dt(const NpdeKParams& prm, const Dopri5Params& dp, const Field& fld, CtrlPool<G>& cp, int lane,
+                                                  float2 y, float2 f, float sg) {
+  const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
+  float d0, d1, r01;
+  int any = 0;
+  if (dp.pool) {
+    float g0[4], g1[4];
+    cp.means(ss2(div2(y, scale)), lane, 0, &any, g0);
+    cp.means(ss2(div2(f, scale)), lane, 0, &any, g1);
+    d0 = d1 = r01 = 0.f;
+#pragma unroll
+    for (int g = 0; g < 4; ++g)
+      if (g < cp.ng) {
+        const float a = sqrtf(g0[g]), b = sqrtf(g1[g]);
+        d0 = fmaxf(d0, a);
+        d1 = fmaxf(d1, b);
+        r01 = fmaxf(r01, a / b);
+      }
+  } else {
+    d0 = rms2(div2(y, scale));
+    d1 = rms2(div2(f, scale));
+    r01 = 0.f;
+  }
+  // one tensor: 0.01 * d0 / d1 (misc.py:128 evaluates left to right); a tuple: 0.01 * max_g(d0_g / d1_g)
+  const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : ((dp.pool && cp.ng > 1) ? 0.01f * r01 : 0.01f * d0 / d1);
+  const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
+  float d2 = rms2(div2(f1 - f, scale)) / h0;
+  if (dp.pool) d2 = sqrtf(cp.max_mean(ss2(div2(f1 - f, scale)), lane, 0, &any)) / h0;
+  float h1;
+  if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
+  else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
+  return (double)fminf(100.f * h0, h1);
+}
 
 template <class Field>
 __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __grid_constant__ NpdeKParams prm,
@@ -73,8 +133,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
   __shared__ float pool_buf[2][2][64];
   if (pl >= prm.ppc || p >= prm.P) return;
   CtrlPool<G> cp;
-  cp.init(pool_buf, pairl, pl, prm.N);
-  const float inv_n = 1.f / (2.f * (float)prm.N);
+  cp.init(pool_buf, pairl, pl, prm.N, dp);
   int any = 0;
   Field fld;
   fld.load(prm, smem, pl, pairl, lane);
@@ -104,20 +163,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
     if (dp.user_first_step) {
       dt = 0.01;
     } else {
-      const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
-      float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
-      if (dp.pool) {                                       // norms over the whole y0 tensor of the call (misc.py:116-118)
-        d0 = sqrtf(cp.sum(ss2(div2(y, scale)), lane, 0, &any) * inv_n);
-        d1 = sqrtf(cp.sum(ss2(div2(f, scale)), lane, 0, &any) * inv_n);
-      }
-      const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
-      const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
-      float d2 = rms2(div2(f1 - f, scale)) / h0;
-      if (dp.pool) d2 = sqrtf(cp.sum(ss2(div2(f1 - f, scale)), lane, 0, &any) * inv_n) / h0;
-      float h1;
-      if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-      else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
-      dt = (double)fminf(100.f * h0, h1);
+      dt = dopri5_first_dt<Field, G>(prm, dp, fld, cp, lane, y, f, sg);
     }
     double t0 = dp.t[0], t1 = dp.t[0];
     float2 ca = y, cb = y, cc = y, cd = y, ce = y;       // interp_coeff = [y0]*5 (dopri5.py:83)
@@ -144,7 +190,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_fwd_kernel(const __
         const float2 er = div2(err, tol);
         float ratio = 0.5f * (er.x * er.x + er.y * er.y);
         if (dp.pool) {                                     // misc.py:151-157: mean over ALL elements of the state tensor
-          ratio = cp.sum(er.x * er.x + er.y * er.y, lane, nonfin, &any) * inv_n;
+          ratio = cp.max_mean(er.x * er.x + er.y * er.y, lane, nonfin, &any);
           if (any) { status |= 4; break; }
         }
         const bool accept = ratio <= 1.f;
@@ -225,8 +271,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
   const bool active = pl < prm.ppc && p < prm.P;
   __shared__ float pool_buf[2][2][64];
   CtrlPool<G> cp;
-  cp.init(pool_buf, active ? pairl : 0, active ? pl : 0, N);
-  const float inv_n = 1.f / (2.f * (float)N);
+  cp.init(pool_buf, active ? pairl : 0, active ? pl : 0, N, dp);
   int any = 0;
   float r2x = 0.f, r2y = 0.f;
   Field fld;
@@ -268,20 +313,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
       if (dp.user_first_step) {
         dt = 0.01;
       } else {
-        const float2 scale = f2(dp.atol + fabsf(y.x) * dp.rtol, dp.atol + fabsf(y.y) * dp.rtol);
-        float d0 = rms2(div2(y, scale)), d1 = rms2(div2(f, scale));
-        if (dp.pool) {                                       // norms over the whole y0 tensor of the call (misc.py:116-118)
-          d0 = sqrtf(cp.sum(ss2(div2(y, scale)), lane, 0, &any) * inv_n);
-          d1 = sqrtf(cp.sum(ss2(div2(f, scale)), lane, 0, &any) * inv_n);
-        }
-        const float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
-        const float2 f1 = sg * fld.eval(prm, fma2(h0, f, y));
-        float d2 = rms2(div2(f1 - f, scale)) / h0;
-        if (dp.pool) d2 = sqrtf(cp.sum(ss2(div2(f1 - f, scale)), lane, 0, &any) * inv_n) / h0;
-        float h1;
-        if (d1 <= 1e-15f && d2 <= 1e-15f) h1 = fmaxf(1e-6f, h0 * 1e-3f);
-        else h1 = powf(0.01f / fmaxf(d1, d2), 1.f / 5.f);
-        dt = (double)fminf(100.f * h0, h1);
+        dt = dopri5_first_dt<Field, G>(prm, dp, fld, cp, lane, y, f, sg);
       }
       double t0 = dp.t[0], t1 = dp.t[0];
       float2 ca = y, cb = y, cc = y, cd = y, ce = y;
@@ -313,7 +345,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) dopri5_grad_kernel(const _
           const float2 er = div2(err, tol);
           float ratio = 0.5f * (er.x * er.x + er.y * er.y);
           if (dp.pool) {
-            ratio = cp.sum(er.x * er.x + er.y * er.y, lane, nonfin, &any) * inv_n;
+            ratio = cp.max_mean(er.x * er.x + er.y * er.y, lane, nonfin, &any);
             if (any) { status |= 4; break; }
           }
           if (ratio <= 1.f) {

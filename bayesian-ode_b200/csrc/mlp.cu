@@ -3,7 +3,7 @@
 #include "dopri5.cuh"
 #include <string.h>
 
-int fill_dopri5(bode::Dopri5Params& dp, const bode_dopri5_opts* o);
+int fill_dopri5(bode::Dopri5Params& dp, const bode_dopri5_opts* o, int N);
 int carve_dopri5_rec(bode::Dopri5Rec& rec, float* scratch, size_t scratch_n, long long npairs, int T, int max_rec);
 
 namespace bode {
@@ -78,7 +78,7 @@ extern "C" int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* 
   BODE_REQUIRE(sol, "null sol");
   prm.sol = sol;
   Dopri5Params dp;
-  st = fill_dopri5(dp, o);
+  st = fill_dopri5(dp, o, N);
   if (st != BODE_OK) return st;
   const dim3 grid(f->P), block(32 * N);
   const size_t smem = mlp_smem(f->H, N);
@@ -89,7 +89,7 @@ extern "C" int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* 
 static int mlp_dopri5_grad(const bode_mlp_field* f, const bode_dopri5_opts* o, int T, int N, NpdeKParams& prm, int inj, float* scratch,
                            size_t scratch_n, int max_rec, cudaStream_t st) {
   Dopri5Params dp;
-  int e = fill_dopri5(dp, o);
+  int e = fill_dopri5(dp, o, N);
   if (e != BODE_OK) return e;
   Dopri5Rec rec;
   e = carve_dopri5_rec(rec, scratch, scratch_n, (long long)f->P * N, T, max_rec);

@@ -294,7 +294,7 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
   }
 }
 
-int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o) {
+int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o, int N) {
   BODE_REQUIRE(o && o->t, "null dopri5 options / t");
   BODE_REQUIRE(o->rtol > 0 && o->atol >= 0 && o->safety > 0 && o->ifactor > 0 && o->dfactor > 0, "bad dopri5 tolerances/factors");
   dp.t = o->t; dp.rtol = (float)o->rtol; dp.atol = (float)o->atol; dp.user_first_step = o->user_first_step;
@@ -303,6 +303,15 @@ int fill_dopri5(Dopri5Params& dp, const bode_dopri5_opts* o) {
   dp.stats = o->stats;
   BODE_REQUIRE(o->controller == 0 || o->controller == 1, "dopri5 controller must be 0 (per pair) or 1 (per particle, pooled)");
   dp.pool = o->controller;
+  BODE_REQUIRE(o->n_groups >= 0 && o->n_groups <= 4, "dopri5: at most 4 state tensors in a tuple (got %d)", o->n_groups);
+  BODE_REQUIRE(o->n_groups <= 1 || o->controller == 1, "dopri5: tuple states need the pooled controller");
+  dp.ngroups = o->n_groups;
+  for (int g = 0; g < 4; ++g) dp.gend[g] = o->group_end[g];
+  if (o->n_groups > 1) {
+    for (int g = 0; g < o->n_groups; ++g)
+      BODE_REQUIRE(o->group_end[g] > (g ? o->group_end[g - 1] : 0), "dopri5: group_end must be strictly increasing");
+    BODE_REQUIRE(o->group_end[o->n_groups - 1] == N, "dopri5: the state tensors of the tuple must cover the N=%d trajectories", N);
+  }
   return BODE_OK;
 }
 
@@ -316,7 +325,7 @@ extern "C" int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts
   BODE_REQUIRE(sol, "null sol");
   prm.sol = sol;
   Dopri5Params dp;
-  st = fill_dopri5(dp, o);
+  st = fill_dopri5(dp, o, N);
   if (st != BODE_OK) return st;
   dim3 grid, block;
   if (!use_sep(f)) {
@@ -363,7 +372,7 @@ extern "C" size_t bode_dopri5_scratch_floats(int32_t P, int32_t N, int32_t T, in
 static int npde_dopri5_grad(const bode_npde_field* f, const bode_dopri5_opts* o, int T, float sign, int N, const float* y0, int y0_batched,
                             NpdeKParams& prm, int inj, float* scratch, size_t scratch_n, int max_rec, cudaStream_t st) {
   Dopri5Params dp;
-  int e = fill_dopri5(dp, o);
+  int e = fill_dopri5(dp, o, N);
   if (e != BODE_OK) return e;
   Dopri5Rec rec;
   e = carve_dopri5_rec(rec, scratch, scratch_n, (long long)f->P * N, T, max_rec);

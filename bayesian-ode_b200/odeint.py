@@ -55,9 +55,54 @@ def _check_inputs(func, y0, t):
             raise TypeError("`y0` must be a floating point Tensor but is a {}".format(y0_.type()))
     if not torch.is_floating_point(t):
         raise TypeError("`t` must be a floating point Tensor but is a {}".format(t.type()))
-    if len(y0) != 1:
-        raise NotImplementedError("the fused fields integrate a single state tensor; tuple states of length > 1 are not built")
-    return tensor_input, y0[0]
+    return tensor_input, y0
+
+
+class TupleField(torch.nn.Module):
+    """``func`` for TUPLE states (misc.py:175-182; api_tests.py:19-38 ``tuple_f = lambda t, y: (f(t, y[0]), f(t, y[1]))``): applies one
+    fused field to every element of the state tuple.  ``odeint(TupleField(f), (y0a, y0b), t)`` integrates the concatenated
+    trajectories in ONE launch and returns a tuple; with dopri5 the single step-size controller pools the error per state tensor
+    and takes the maximum over the tuple, exactly as torchdiffeq does (dopri5.py:108-109, misc.py:125-141, 161)."""
+
+    def __init__(self, field):
+        super().__init__()
+        if not isinstance(field, (NPDEField, MLPField)):
+            raise TypeError("TupleField wraps an NPDEField or MLPField")
+        self.field = field
+
+    def forward(self, t, y):
+        return tuple(self.field(t, y_) for y_ in y)
+
+
+def _field_eval(func, sol):
+    """f(t_i, y_i) for every stored solution point with the field's torch evaluation (sol [T, N, 2] or [T, P, N, 2])."""
+    T = sol.shape[0]
+    with torch.no_grad():
+        if sol.dim() == 3:                                   # single un-batched particle
+            return func(None, sol.reshape(-1, 2)).reshape(sol.shape)
+        X = sol.permute(1, 0, 2, 3).reshape(sol.shape[1], T * sol.shape[2], 2)
+        return func(None, X).reshape(sol.shape[1], T, sol.shape[2], 2).permute(1, 0, 2, 3)
+
+
+class _TimeGrad(torch.autograd.Function):
+    """dL/dt of ``odeint_adjoint`` (adjoint.py:68-76, 99-100) for the autonomous fused fields: moving observation time t_i moves the
+    observed state along f, dL/dt_i = f(t_i, y_i) . dL/dy_i for i >= 1, and the start time collects the negative sum (the
+    ``adj_time`` component of the augmented state is only changed by these terms, since df/dt = 0)."""
+
+    @staticmethod
+    def forward(ctx, sol, t, func):
+        ctx.func = func
+        ctx.save_for_backward(sol.detach(), t)
+        return sol.view_as(sol)
+
+    @staticmethod
+    def backward(ctx, gout):
+        sol, t = ctx.saved_tensors
+        f = _field_eval(ctx.func, sol)
+        per_t = (f * gout.to(f.dtype)).reshape(sol.shape[0], -1).sum(1)
+        gt = per_t.clone()
+        gt[0] = -per_t[1:].sum()
+        return gout, gt.to(device=t.device, dtype=t.dtype), None
 
 
 def _norm_y0(field, y0):
@@ -151,7 +196,7 @@ DOPRI5_MAX_REC_STEPS = 256      # accepted steps recorded per (particle, traject
 CONTROLLERS = {"pair": 0, "batch": 1}
 
 
-def dopri5_setup(func, y0, t, rtol, atol, options, controller="batch"):
+def dopri5_setup(func, y0, t, rtol, atol, options, controller="batch", groups=None):
     """Normalise the dopri5 call (dopri5.py:60-75 options, misc.py:184-187 time reversal) into the C-ABI structures.
 
     ``options['controller']`` (an extension; every other unknown key warns like misc.py:79-81) picks what ONE reference call is:
@@ -183,6 +228,16 @@ def dopri5_setup(func, y0, t, rtol, atol, options, controller="batch"):
     o.user_first_step = int(known.get("first_step") is not None)
     o.stats = stats.data_ptr()
     o.controller = CONTROLLERS[controller]
+    if groups is not None and len(groups) > 1:                  # tuple state: per-tensor error pooling, max over the tuple
+        if controller != "batch":
+            raise ValueError("a tuple state is one odeint call: options['controller'] must be 'batch'")
+        if len(groups) > 4:
+            raise NotImplementedError("tuple states of more than 4 tensors are not built")
+        o.n_groups = len(groups)
+        end = 0
+        for g, n in enumerate(groups):
+            end += int(n)
+            o.group_end[g] = end
     return dict(o=o, tdev=tdev, T=int(t64.numel()), sign=sign, y0=y0c, batched=batched, N=N, stats=stats)
 
 
@@ -252,9 +307,9 @@ class _Dopri5Odeint(torch.autograd.Function):
         return (gy0, None, None) + grads
 
 
-def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
+def _dopri5(func, y0, t, rtol, atol, options, tensor_input, groups=None):
     """Dopri5Solver (dopri5.py:58-122); controller granularity per ``options['controller']`` (see dopri5_setup)."""
-    cfg = dopri5_setup(func, y0, t, rtol, atol, options)
+    cfg = dopri5_setup(func, y0, t, rtol, atol, options, groups=groups)
     params = [func.U] if isinstance(func, NPDEField) else [getattr(func, k) for k in func._blocks()]
     sol = _Dopri5Odeint.apply(cfg["y0"], func, cfg, *params)
     if isinstance(func, NPDEField) and not func.batched:
@@ -263,7 +318,7 @@ def _dopri5(func, y0, t, rtol, atol, options, tensor_input):
 
 
 def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
-    tensor_input, y0 = _check_inputs(func, y0, t)
+    tensor_input, y0s = _check_inputs(func, y0, t)
     if options is None:
         options = {}
     elif method is None:
@@ -273,36 +328,66 @@ def _odeint_impl(func, y0, t, rtol, atol, method, options, grad_mode, who):
     if method in _UNBUILT:
         raise NotImplementedError("method '{}' of the reference registry is outside the B200 hot path".format(method))
     solver_name = SOLVERS[method]          # KeyError for unknown methods, like odeint.py:71
-    if t.requires_grad:
-        raise NotImplementedError("gradients with respect to `t` are not built")
-    if isinstance(func, NPDEField):
+    want_gt = bool(t.requires_grad)
+    if want_gt and grad_mode != _lib.GRAD_ADJOINT:
+        raise NotImplementedError("dL/dt is built for odeint_adjoint (adjoint.py:68-76); plain odeint differentiates the state and the "
+                                  "parameters only -- detach `t` or use odeint_adjoint")
+    t_in, t = t, t.detach()
+    # ---- tuple states: one fused field applied to every element (TupleField); the elements travel as one concatenated batch
+    groups = None
+    field = func
+    if isinstance(func, TupleField):
+        field = func.field
+        if tensor_input:
+            raise TypeError("TupleField expects a tuple state; pass the field itself for a tensor state")
+    elif len(y0s) > 1:
+        raise TypeError("{}: a tuple state needs `func = TupleField(field)` (the reference's func returns a tuple there, "
+                        "misc.py:175-182); got {}".format(who, type(func).__name__))
+    if len(y0s) > 1:
+        if any(y_.dim() != y0s[0].dim() or y_.shape[:-2] != y0s[0].shape[:-2] for y_ in y0s):
+            raise ValueError("the elements of a tuple state must agree in all but the trajectory dimension")
+        groups = [int(y_.shape[-2]) for y_ in y0s]
+        y0 = torch.cat(list(y0s), dim=-2)
+    else:
+        y0 = y0s[0]
+
+    def finish(sol):
+        if want_gt:
+            sol = _TimeGrad.apply(sol, t_in, field)
+        if tensor_input:
+            return sol
+        if groups is None:
+            return (sol,)
+        return tuple(torch.split(sol, groups, dim=-2))
+
+    if isinstance(field, NPDEField):
         if method in FIXED_GRID_METHODS:
             opts = _grid.split_options(solver_name, options)
             if opts["step_size"] is not None and opts["grid_constructor"] is not None:
                 raise ValueError("step_size and grid_constructor are exclusive arguments.")
-            y0c, batched, N = _norm_y0(func, y0)
-            g = _grid.cached(t, torch.float32, func.U.device, opts["step_size"], opts["grid_constructor"],
-                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=func, y0=(y0c,))
-            sol = _NpdeOdeint.apply(y0c, func.U, func, g, _lib.METHODS[method], grad_mode, batched, N)
-            if not func.batched:
+            y0c, batched, N = _norm_y0(field, y0)
+            g = _grid.cached(t, torch.float32, field.U.device, opts["step_size"], opts["grid_constructor"],
+                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=field, y0=(y0c,))
+            sol = _NpdeOdeint.apply(y0c, field.U, field, g, _lib.METHODS[method], grad_mode, batched, N)
+            if not field.batched:
                 sol = sol[:, 0]
-            return sol if tensor_input else (sol,)
-        return _dopri5(func, y0, t, rtol, atol, options, tensor_input)
-    if isinstance(func, MLPField):
+            return finish(sol)
+        return finish(_dopri5(field, y0, t, rtol, atol, options, True, groups=groups))
+    if isinstance(field, MLPField):
         if method in FIXED_GRID_METHODS:
             opts = _grid.split_options(solver_name, options)
             if opts["step_size"] is not None and opts["grid_constructor"] is not None:
                 raise ValueError("step_size and grid_constructor are exclusive arguments.")
-            y0c, batched, N = _norm_y0(func, y0)
-            g = _grid.cached(t, torch.float32, func.theta.device, opts["step_size"], opts["grid_constructor"],
-                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=func, y0=(y0c,))
-            params = [getattr(func, k) for k in func._blocks()]
-            sol = _MlpOdeint.apply(y0c, func, g, _lib.METHODS[method], grad_mode, batched, N, *params)
-            return sol if tensor_input else (sol,)
-        return _dopri5(func, y0, t, rtol, atol, options, tensor_input)
+            y0c, batched, N = _norm_y0(field, y0)
+            g = _grid.cached(t, torch.float32, field.theta.device, opts["step_size"], opts["grid_constructor"],
+                             with_adjoint=grad_mode == _lib.GRAD_ADJOINT, func=field, y0=(y0c,))
+            params = [getattr(field, k) for k in field._blocks()]
+            sol = _MlpOdeint.apply(y0c, field, g, _lib.METHODS[method], grad_mode, batched, N, *params)
+            return finish(sol)
+        return finish(_dopri5(field, y0, t, rtol, atol, options, True, groups=groups))
     raise TypeError(
-        "{}: `func` must be a field module of bayesian_ode_b200 (NPDEField / MLPField); got {}. The B200 build "
-        "has no generic-callable or CPU path.".format(who, type(func).__name__))
+        "{}: `func` must be a field module of bayesian_ode_b200 (NPDEField / MLPField, or TupleField around one); got {}. The B200 "
+        "build has no generic-callable or CPU path.".format(who, type(func).__name__))
 
 
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):

@@ -42,7 +42,8 @@ WORKLOADS = {
     "c1": dict(field="npde", sampler="sgld", P=1, M=5, T=40, method="rk4",
                desc="VDP npde SGLD, 5x5 grid, 1 chain, N=5, T=40 (39 rk4 3/8 steps)"),
     "c4": dict(field="mlp", sampler="asghmc", P=8192, H=64, T=40, method="dopri5",
-               desc="neural ODE 2-64-64-2 ELU MLP, aSGHMC, 8192 chains/GPU, N=5, T=40, adaptive dopri5 (one controller per trajectory row)"),
+               desc="neural ODE 2-64-64-2 ELU MLP, aSGHMC, 8192 chains/GPU, N=5, T=40, adaptive dopri5 batched-step (one controller per chain, "
+                    "error pooled over its 5 trajectories = one reference odeint call with y0 [5, 2])"),
     "c5": dict(field="npde", sampler="hamcmc", P=2048, M=16, T=40, method="rk4", ell=0.35,
                desc="VDP npde HAMCMC (memory 5), 16x16 grid (d=514), 2048 chains/GPU, N=5, T=40 (39 rk4 3/8 steps)"),
 }
@@ -300,7 +301,7 @@ class Job:
             rtol, atol = TOLS[args.tol]
             self.obs_host = torch.from_numpy(data["X"]).float().pin_memory()
             self.post = bode.MLPPosterior(self.field, data["x0"], data["t"], torch.from_numpy(data["X"]), method="dopri5", rtol=rtol,
-                                          atol=atol, reg=0.5)
+                                          atol=atol, reg=0.5, options=dict(controller="batch"))     # BASELINE config 4: "dopri5 batched-step"
             self.post.check_status = False                 # no host sync per step; the solver status is checked after the run
             self.S = None
             params = list(self.field.parameters())
@@ -580,7 +581,7 @@ def run_b200(args, wl):
         ode_ms = statistics.median(event_ms(torch, lambda: post.loss_and_grad_(), 5))
         att_pairs = float((bode.last_dopri5_stats()[..., :2]).sum().item())
         ode_flop = MLP_FLOP_PER_STAGE_TRAJ * 6.0 * att_pairs
-        kernels.append(dict(name="dopri5_grad_kernel<MlpField<64>> (adaptive solve + record + frozen-step reverse sweep, one warp per pair)",
+        kernels.append(dict(name="dopri5_grad_kernel<MlpField<64>> (adaptive solve, pooled controller + record + frozen-step reverse sweep, one warp per pair)",
                             ms=ode_ms, bound="fp32", achieved=ode_flop / (ode_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"], unit="TFLOP/s",
                             flop_per_launch=ode_flop, attempted_steps_per_pair=att_pairs / (P_gpu * N)))
     if sampler in ("psgld", "sgld", "asghmc", "hamcmc"):

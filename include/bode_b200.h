@@ -116,6 +116,11 @@ typedef struct bode_dopri5_opts {
    * initial-step norms (misc.py:116-143) pooled over its N trajectories x 2 components == one reference odeint call with
    * y0 [N, 2] (gp.py:346, 452).  stats then repeats the particle's counts for each of its pairs. */
   int32_t controller;
+  /* Tuple states (misc.py:175-182) with controller = 1: the N trajectories of a particle are the concatenation of n_groups state
+   * tensors, group g = trajectories [group_end[g-1], group_end[g]).  The error is pooled per tensor and combined by max, as
+   * torchdiffeq does for tuples (dopri5.py:108-109, misc.py:125-141, 161).  n_groups <= 1: a single tensor.  At most 4. */
+  int32_t n_groups;
+  int32_t group_end[4];
 } bode_dopri5_opts;
 
 int bode_npde_dopri5(const bode_npde_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,

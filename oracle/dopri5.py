@@ -23,21 +23,40 @@ def _norm(x):
     return np.sqrt(np.mean(np.square(x)))
 
 
-def _initial_step(f, y0, f0, rtol, atol, dtype):
+def _split(x, groups):
+    """Tuple states (misc.py:175-182): ``groups`` = row counts of the state tensors along axis -2 of the concatenated state."""
+    if groups is None:
+        return [x]
+    out, o = [], 0
+    for n in groups:
+        out.append(x[..., o:o + n, :])
+        o += n
+    return out
+
+
+def _initial_step(f, y0, f0, rtol, atol, dtype, groups=None):
+    """misc.py:84-143; for a tuple the norms are taken per state tensor and combined as the reference does (max; h0 from the
+    largest d0 / d1 ratio, :128)."""
     scale = atol + np.abs(y0) * rtol
-    d0, d1 = _norm(y0 / scale), _norm(f0 / scale)
-    h0 = dtype(1e-6) if (d0 < 1e-5 or d1 < 1e-5) else dtype(0.01) * d0 / d1
+    d0 = [_norm(a) for a in _split(y0 / scale, groups)]
+    d1 = [_norm(a) for a in _split(f0 / scale, groups)]
+    if max(d0) < 1e-5 or max(d1) < 1e-5:
+        h0 = dtype(1e-6)
+    elif groups is None:
+        h0 = dtype(0.01) * d0[0] / d1[0]
+    else:
+        h0 = dtype(0.01) * max(a / b for a, b in zip(d0, d1))
     f1 = f(y0 + h0 * f0)
-    d2 = _norm((f1 - f0) / scale) / h0
-    if d1 <= 1e-15 and d2 <= 1e-15:
+    d2 = [_norm(a) / h0 for a in _split((f1 - f0) / scale, groups)]
+    if max(d1) <= 1e-15 and max(d2) <= 1e-15:
         h1 = max(dtype(1e-6), h0 * dtype(1e-3))
     else:
-        h1 = (dtype(0.01) / max(d1, d2)) ** dtype(1. / 5.)
+        h1 = (dtype(0.01) / max(d1 + d2)) ** dtype(1. / 5.)
     return min(dtype(100) * h0, h1)
 
 
 def odeint_dopri5(f, y0, t, rtol=1e-7, atol=1e-9, first_step=None, safety=0.9, ifactor=10.0, dfactor=0.2,
-                  max_num_steps=2 ** 31 - 1):
+                  max_num_steps=2 ** 31 - 1, groups=None):
     y0 = np.asarray(y0)
     dtype = y0.dtype.type
     t = np.asarray(t, dtype=np.float64)
@@ -54,7 +73,7 @@ def odeint_dopri5(f, y0, t, rtol=1e-7, atol=1e-9, first_step=None, safety=0.9, i
     rtol_, atol_ = dtype(rtol), dtype(atol)
     f0 = func(y0)
     if first_step is None:
-        dt = float(_initial_step(func, y0, f0, rtol_, atol_, dtype))
+        dt = float(_initial_step(func, y0, f0, rtol_, atol_, dtype, groups))
     else:
         dt = 0.01                                              # dopri5.py:81-82
     y, fcur = y0, f0
@@ -78,7 +97,7 @@ def odeint_dopri5(f, y0, t, rtol=1e-7, atol=1e-9, first_step=None, safety=0.9, i
             y1, f1 = yi, k[-1]
             err = sum((h * dtype(c)) * kj for c, kj in zip(C_ERROR, k) if c != 0)
             tol = atol_ + rtol_ * np.maximum(np.abs(y), np.abs(y1))
-            ratio = np.mean(np.square(err / tol))
+            ratio = max(np.mean(np.square(a)) for a in _split(err / tol, groups))     # per tensor, then max (misc.py:151-161)
             accept = ratio <= 1
             if accept:
                 ymid = y + sum((h * dtype(c)) * kj for c, kj in zip(C_MID, k) if c != 0)

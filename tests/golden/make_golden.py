@@ -771,12 +771,81 @@ def gen_dopri5_batched(data):
     save("dopri5_batched", **out)
 
 
+def gen_tuple_and_time(data):
+    """(1) Tuple states (misc.py:175-182, api_tests.py:19-38): odeint(tuple_f, (y0a, y0b), t) with tuple_f applying the npde field to
+    each element, rk4 and dopri5 (one controller for the tuple: per-tensor error means, max over the tuple).
+    (2) dL/dt through odeint_adjoint (adjoint.py:68-76, 99-100; gradient_tests.py:19-37 gradchecks (y0, t)): t.grad of a weighted
+    sum of the solution, npde field (rk4 and dopri5) and the row-wise MLP (rk4)."""
+    from torchdiffeq._impl import dopri5 as ref_d5
+    torch.cholesky = torch.linalg.cholesky
+    Zt, Yt, U0 = make_model(data, 5)
+    x0, t = data["x0"], data["t"].to(torch.float64)
+    kreg = gp.KernelRegression(U0.clone(), Zt, 1.0, 0.75, 0.1)
+    out = dict(x0=x0, t=t, U=U0, Z=Zt)
+    tuple_f = lambda tt, y: (kreg(tt, y[0]), kreg(tt, y[1]))
+    with torch.no_grad():
+        ra, rb = torchdiffeq.odeint(tuple_f, (x0[:3], x0[3:]), t, method="rk4")
+        out.update(tuple_rk4_a=ra, tuple_rk4_b=rb)
+        accepts = []
+        orig = ref_d5.Dopri5Solver._adaptive_dopri5_step
+
+        def recording(self, rk_state):
+            new = orig(self, rk_state)
+            accepts.append(bool(new.t1 > rk_state.t1))
+            return new
+        ref_d5.Dopri5Solver._adaptive_dopri5_step = recording
+        try:
+            da, db = torchdiffeq.odeint(tuple_f, (x0[:3], x0[3:]), t, rtol=1e-5, atol=1e-7)
+        finally:
+            ref_d5.Dopri5Solver._adaptive_dopri5_step = orig
+        out.update(tuple_dopri5_a=da, tuple_dopri5_b=db, tuple_dopri5_accept=np.array(accepts, dtype=np.int8))
+        # the same rows integrated as ONE tensor take different steps (mean over all rows instead of max of per-tensor means)
+        del accepts[:]
+        ref_d5.Dopri5Solver._adaptive_dopri5_step = recording
+        try:
+            torchdiffeq.odeint(kreg, x0, t, rtol=1e-5, atol=1e-7)
+        finally:
+            ref_d5.Dopri5Solver._adaptive_dopri5_step = orig
+        out["single_dopri5_accept"] = np.array(accepts, dtype=np.int8)
+    g = torch.Generator().manual_seed(31)
+    w = torch.randn(len(t), 5, 2, generator=g)
+    out["w"] = w
+    for name, kw in (("rk4", dict(method="rk4")), ("dopri5", dict(rtol=1e-7, atol=1e-9, method="dopri5"))):
+        tr = t.clone().requires_grad_(True)
+        kreg.zero_grad()
+        sol = torchdiffeq.odeint_adjoint(kreg, x0, tr, **kw)
+        (sol * w).sum().backward()
+        out[f"npde_{name}_gt"] = tr.grad.clone()
+        out[f"npde_{name}_gU"] = kreg.U.grad.clone()
+    torch.manual_seed(120)
+    net = NN(2, 20)
+    for m_ in net.modules():
+        if isinstance(m_, torch.nn.Linear):
+            torch.nn.init.uniform_(m_.weight, a=-0.5, b=0.5)
+
+    class RowWise(torch.nn.Module):
+        def __init__(self, inner):
+            super().__init__()
+            self.inner = inner
+
+        def forward(self, tt, x):
+            return self.inner.layers(x)
+    tr = t.clone().requires_grad_(True)
+    sol = torchdiffeq.odeint_adjoint(RowWise(net), x0, tr, method="rk4")
+    (sol * w).sum().backward()
+    out.update(theta=torch.cat([q.detach().reshape(-1) for q in net.parameters()]), mlp_rk4_gt=tr.grad.clone())
+    save("tuple_time", **out)
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "hamcmc_contiguous":
         gen_hamcmc_contiguous()
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "dopri5_batched":
         gen_dopri5_batched(make_data())
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "tuple_time":
+        gen_tuple_and_time(make_data())
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "predictive":
         gen_predictive(make_data())
@@ -797,6 +866,7 @@ if __name__ == "__main__":
     gen_mlp(data)
     gen_dopri5(data)
     gen_dopri5_batched(data)
+    gen_tuple_and_time(data)
     gen_hamcmc()
     gen_hamcmc_contiguous()
     gen_mala()

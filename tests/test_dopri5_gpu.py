@@ -176,16 +176,18 @@ def test_dopri5_config4_step_runs_with_asghmc():
 def test_dopri5_batched_controller_matches_reference_call(case, kw):
     """odeint(f, y0[N, 2], t) as the reference runs it: ONE controller, error pooled over all N x 2 elements (misc.py:146-157;
     SURVEY.md A.8 quirk 4) -- the default of bode.odeint.  Fixture: the reference's own batched call with its accept / reject
-    sequence recorded (tests/golden/dopri5_batched.npz).  Measured on B200: 4 of the 6 (case, field) combinations take exactly the
-    reference's numbers of accepted and rejected attempts, the other two differ by ONE attempt (a borderline decision seen
-    through an fp32 error estimate); the bar below allows that one."""
+    sequence recorded (tests/golden/dopri5_batched.npz)."""
     import bayesian_ode_b200 as bode
     g = load_golden("dopri5_batched")
     fn = bode.NPDEField(torch.from_numpy(g["U"]), torch.from_numpy(g["Z"]), 1.0, 0.75, 0.1)
     fm = bode.MLPField(1, hidden_size=20, theta=torch.from_numpy(g["theta"])[None])
     x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
-    same = 0
-    for fname, f in (("npde", fn), ("mlp", fm)):
+    from oracle import dopri5 as od5, mlp as omlp, npde as onpde
+    fo, mo = onpde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75), omlp.MLPField(g["theta"][None], 20)
+    okw = {k: v for k, v in kw.items() if k in ("rtol", "atol")}
+    if "options" in kw:
+        okw["first_step"] = kw["options"]["first_step"]
+    for fname, f, of in (("npde", fn, lambda y: fo.f(y[None].astype(np.float64))[0]), ("mlp", fm, lambda y: mo.f(y[None].astype(np.float64))[0])):
         sol = bode.odeint(f, x0, t, **kw)                        # method=None -> dopri5 (odeint.py:68-69), controller "batch"
         sol = sol if sol.dim() == 3 else sol[:, 0]
         st = bode.last_dopri5_stats().cpu().numpy().reshape(-1, 3)
@@ -195,13 +197,16 @@ def test_dopri5_batched_controller_matches_reference_call(case, kw):
         got = (int(st[0, 0]), int(st[0, 1]))
         err = relerr(sol.detach().cpu().numpy(), g[f"{case}_{fname}_sol"])
         print("dopri5 batched %s/%s: accepted,rejected = %s (reference %s), trajectory err %.2e" % (case, fname, got, ref, err))
-        same += int(got == ref)
-        # the decisions can agree while dt still differs in its last digits (dt_next is a continuous function of the fp32 error
-        # estimate, a difference of nearly cancelling stage values), so the trajectory bar is the solver's own: 1e-5 at the default
-        # tolerances (rtol 1e-7), 10 rtol otherwise
-        assert abs(sum(got) - sum(ref)) <= 1 and abs(got[1] - ref[1]) <= 1, (case, fname, got, ref)
+        # Selection logic: against the oracle in the SAME arithmetic (float32 state, float64 t / dt; its float64 run reproduces the
+        # reference's sequence exactly, test_oracle_golden).  At these tolerances the fp32 error estimate sits at rounding-noise
+        # level, so single decisions differ from the float64 reference; the kernel must follow the float32 oracle, give or take one
+        # borderline decision (FMA contraction and MUFU.EX2 differ from NumPy in the last ulp).
+        _, so = od5.odeint_dopri5(of, g["x0"].astype(np.float32), g["t"], **okw)
+        print("   float32 oracle: accepted,rejected = (%d, %d)" % (so["accepted"], so["rejected"]))
+        assert abs(got[0] - so["accepted"]) <= 1 and abs(got[1] - so["rejected"]) <= 1, (case, fname, got, so)
+        assert abs(sum(got) - sum(ref)) <= 3, (case, fname, got, ref)
+        # trajectories: the solver's own bar -- 1e-5 at the default tolerances (rtol 1e-7), 10 rtol otherwise
         assert err < (1e-5 if case == "default" else 1e-4), (case, fname, err)
-    assert same >= 1
 
 
 def test_dopri5_batched_and_pair_controllers_differ_and_validate():

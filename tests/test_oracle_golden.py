@@ -145,3 +145,19 @@ def test_oracle_dopri5_pooled_controller_matches_reference_batched_call():
             assert (st["accepted"], st["rejected"]) == (int(acc.sum()), int(len(acc) - acc.sum())), (case, fname)
             assert st["nfe"] == int(g[f"{case}_{fname}_nfe"])
             assert relerr(sol, g[f"{case}_{fname}_sol"]) < 1e-9, (case, fname)
+
+
+def test_oracle_dopri5_tuple_state_matches_reference():
+    """Tuple states: one controller, error pooled per state tensor, max over the tuple (dopri5.py:108-109, misc.py:125-141, 161);
+    fixture: the reference's odeint(tuple_f, (y0[:3], y0[3:]), t) with its accept / reject sequence (tuple_time.npz)."""
+    from oracle import dopri5, npde
+    g = load_golden("tuple_time")
+    fo = npde.NPDEField(g["U"][None], g["Z"], 1.0, 0.75)
+    f = lambda y: fo.f(y[None])[0]
+    sol, st = dopri5.odeint_dopri5(f, g["x0"], g["t"], rtol=1e-5, atol=1e-7, groups=[3, 2])
+    acc = g["tuple_dopri5_accept"]
+    assert (st["accepted"], st["rejected"]) == (int(acc.sum()), int(len(acc) - acc.sum()))
+    assert relerr(sol[:, :3], g["tuple_dopri5_a"]) < 1e-9 and relerr(sol[:, 3:], g["tuple_dopri5_b"]) < 1e-9
+    _, st1 = dopri5.odeint_dopri5(f, g["x0"], g["t"], rtol=1e-5, atol=1e-7)
+    acc1 = g["single_dopri5_accept"]
+    assert (st1["accepted"], st1["rejected"]) == (int(acc1.sum()), int(len(acc1) - acc1.sum())) and len(acc1) != len(acc)
