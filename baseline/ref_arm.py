@@ -180,7 +180,10 @@ def chain_worker(args):
             net = NN(2, H)                                                                   # not a usable gradient (SURVEY hard part 6)
             for m_ in net.modules():
                 if isinstance(m_, torch.nn.Linear):
-                    torch.nn.init.uniform_(m_.weight, a=-0.5 * wl["init_scale"], b=0.5 * wl["init_scale"])
+                    torch.nn.init.uniform_(m_.weight, a=-0.5, b=0.5)                          # nn.ipynb cell 4
+            with torch.no_grad():
+                for q in net.parameters():
+                    q.mul_(wl["init_scale"])                                                 # same scaling as the GPU arm (bench.py --init-scale)
             cnet = Counted(net)
             params = list(net.parameters())
             smp = hamiltonian.aSGHMC(params, lr=1e-2, mom_decay=5e-2, lambda_=1e-5)

@@ -105,6 +105,7 @@ SYMBOLS = {
     "bode_svgd_workspace_init": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_size_t, _P]),
     "bode_svgd_window_table": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)]),
     "bode_svgd_window_select": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
+    "bode_mlp_set_tensor_cores": (C.c_int, [C.c_int32]),
     "bode_svgd_window_disarm": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bode_svgd_radix_fallback": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_svgd_hist_pass": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_int32, _P, _P]),

@@ -16,6 +16,12 @@ namespace bode {
                                  size_t smem, cudaStream_t st);
 BODE_DECL_MLP(20)
 BODE_DECL_MLP(64)
+BODE_DECL_MLP(64tc)
+
+// H = 64: the 64 x 64 layer runs on the tensor cores (mlp_tc.cuh) whenever the trajectories of a particle advance in lock-step --
+// fixed-grid solvers, or dopri5 with the pooled controller -- and 4 <= N <= 8.  0 forces the FP32-pipe kernels (MlpField).
+static int g_mlp_tc = 1;
+static bool mlp_use_tc(const bode_mlp_field* f, int N, bool lockstep) { return g_mlp_tc && f->H == 64 && N >= 4 && N <= 8 && lockstep; }
 
 static int mlp_fill(NpdeKParams& prm, const bode_mlp_field* f, const bode_grid* g, int method, int N, const float* y0, int y0_batched) {
   BODE_REQUIRE(f && g, "null field/grid");
@@ -35,7 +41,7 @@ static int mlp_fill(NpdeKParams& prm, const bode_mlp_field* f, const bode_grid* 
   return BODE_OK;
 }
 
-static size_t mlp_smem(int H, int N) { return H == 20 ? mlp_smem_bytes_20(N) : mlp_smem_bytes_64(N); }
+static size_t mlp_smem(int H, int N, bool tc = false) { return tc ? mlp_smem_bytes_64tc(N) : (H == 20 ? mlp_smem_bytes_20(N) : mlp_smem_bytes_64(N)); }
 
 static int mlp_grad(const bode_mlp_field* f, const bode_grid* g, int method, int grad_mode, int inj, int N, NpdeKParams& prm,
                     float* scratch, size_t scratch_n, cudaStream_t st) {
@@ -46,14 +52,23 @@ static int mlp_grad(const bode_mlp_field* f, const bode_grid* g, int method, int
   prm.ck = reinterpret_cast<float2*>(scratch);
   prm.npairs = (long long)f->P * N;
   const dim3 grid(f->P), block(32 * N);
-  prm.stage_off = (int)((mlp_smem(f->H, N) / sizeof(float) + 3) & ~(size_t)3);
+  const bool tc = mlp_use_tc(f, N, true);
+  prm.stage_off = (int)((mlp_smem(f->H, N, tc) / sizeof(float) + 3) & ~(size_t)3);
   const size_t smem = sizeof(float) * ((size_t)prm.stage_off + ((2 * (size_t)prm.S + 2) & ~(size_t)1) + 2 * (size_t)N * prm.T + 2);
+  if (tc) return launch_mlp_grad_64tc(prm, method, inj, grad_mode, grid, block, smem, st);
   if (f->H == 20) return launch_mlp_grad_20(prm, method, inj, grad_mode, grid, block, smem, st);
   return launch_mlp_grad_64(prm, method, inj, grad_mode, grid, block, smem, st);
 }
 }  // namespace bode
 
 using namespace bode;
+
+/* 1 (default): tensor-core kernels for H = 64 where the trajectories advance in lock-step; 0: FP32-pipe kernels.  Returns the old value. */
+extern "C" int bode_mlp_set_tensor_cores(int32_t on) {
+  const int old = g_mlp_tc;
+  g_mlp_tc = on ? 1 : 0;
+  return old;
+}
 
 extern "C" int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
                                int32_t y0_batched, float* sol, bode_stream_t stream) {
@@ -63,7 +78,9 @@ extern "C" int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int3
   BODE_REQUIRE(sol, "null sol");
   prm.sol = sol;
   const dim3 grid(f->P), block(32 * N);
-  const size_t smem = mlp_smem(f->H, N);
+  const bool tc = mlp_use_tc(f, N, true);
+  const size_t smem = mlp_smem(f->H, N, tc);
+  if (tc) return launch_mlp_fwd_64tc(prm, method, grid, block, smem, (cudaStream_t)stream);
   if (f->H == 20) return launch_mlp_fwd_20(prm, method, grid, block, smem, (cudaStream_t)stream);
   return launch_mlp_fwd_64(prm, method, grid, block, smem, (cudaStream_t)stream);
 }
@@ -81,7 +98,9 @@ extern "C" int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* 
   st = fill_dopri5(dp, o, N);
   if (st != BODE_OK) return st;
   const dim3 grid(f->P), block(32 * N);
-  const size_t smem = mlp_smem(f->H, N);
+  const bool tc = mlp_use_tc(f, N, dp.pool != 0);
+  const size_t smem = mlp_smem(f->H, N, tc);
+  if (tc) return launch_mlp_dopri5_64tc(prm, dp, grid, block, smem, (cudaStream_t)stream);
   if (f->H == 20) return launch_mlp_dopri5_20(prm, dp, grid, block, smem, (cudaStream_t)stream);
   return launch_mlp_dopri5_64(prm, dp, grid, block, smem, (cudaStream_t)stream);
 }
@@ -96,7 +115,9 @@ static int mlp_dopri5_grad(const bode_mlp_field* f, const bode_dopri5_opts* o, i
   if (e != BODE_OK) return e;
   prm.npairs = (long long)f->P * N;
   const dim3 grid(f->P), block(32 * N);
-  const size_t smem = mlp_smem(f->H, N);
+  const bool tc = mlp_use_tc(f, N, dp.pool != 0);
+  const size_t smem = mlp_smem(f->H, N, tc);
+  if (tc) return launch_mlp_dopri5_grad_64tc(prm, dp, rec, inj, grid, block, smem, st);
   if (f->H == 20) return launch_mlp_dopri5_grad_20(prm, dp, rec, inj, grid, block, smem, st);
   return launch_mlp_dopri5_grad_64(prm, dp, rec, inj, grid, block, smem, st);
 }

@@ -1,13 +1,20 @@
 // Instantiates the solver kernels for the MLP field with hidden width BODE_H (compiled once per width).
+// BODE_MF / BODE_SFX select another field type and symbol suffix (mlp_h64tc.cu: the tensor-core field MlpTcField, suffix 64tc).
 #include "npde_solve.cuh"
 #include "mlp_field.cuh"
+#include "mlp_tc.cuh"
 #include "dopri5.cuh"
 
 namespace bode {
 
 #define BODE_CAT_(a, b) a##b
 #define BODE_CAT(a, b) BODE_CAT_(a, b)
+#ifdef BODE_MF
+using MF = BODE_MF;
+#else
 using MF = MlpField<BODE_H>;
+#define BODE_SFX BODE_H
+#endif
 
 template <int METHOD>
 static int mlp_launch_fwd(const NpdeKParams& prm, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
@@ -29,7 +36,7 @@ static int mlp_launch_grad(const NpdeKParams& prm, dim3 grid, dim3 block, size_t
   return check_cuda(cudaGetLastError(), "mlp grad launch");
 }
 
-int BODE_CAT(launch_mlp_dopri5_, BODE_H)(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem,
+int BODE_CAT(launch_mlp_dopri5_, BODE_SFX)(const NpdeKParams& prm, const Dopri5Params& dp, dim3 grid, dim3 block, size_t smem,
                                          cudaStream_t st) {
   if (smem > 48 * 1024) {
     int e = check_cuda(cudaFuncSetAttribute(dopri5_fwd_kernel<MF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
@@ -39,7 +46,7 @@ int BODE_CAT(launch_mlp_dopri5_, BODE_H)(const NpdeKParams& prm, const Dopri5Par
   return check_cuda(cudaGetLastError(), "mlp dopri5 launch");
 }
 
-int BODE_CAT(launch_mlp_dopri5_grad_, BODE_H)(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid,
+int BODE_CAT(launch_mlp_dopri5_grad_, BODE_SFX)(const NpdeKParams& prm, const Dopri5Params& dp, const Dopri5Rec& rec, int inj, dim3 grid,
                                               dim3 block, size_t smem, cudaStream_t st) {
   if (smem > 48 * 1024) {
     int e = check_cuda(cudaFuncSetAttribute(dopri5_grad_kernel<MF, INJ_LIK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem), "smem attr");
@@ -52,9 +59,9 @@ int BODE_CAT(launch_mlp_dopri5_grad_, BODE_H)(const NpdeKParams& prm, const Dopr
   return check_cuda(cudaGetLastError(), "mlp dopri5 grad launch");
 }
 
-size_t BODE_CAT(mlp_smem_bytes_, BODE_H)(int N) { return sizeof(float) * (size_t)MF::smem_floats(N); }
+size_t BODE_CAT(mlp_smem_bytes_, BODE_SFX)(int N) { return sizeof(float) * (size_t)MF::smem_floats(N); }
 
-int BODE_CAT(launch_mlp_fwd_, BODE_H)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+int BODE_CAT(launch_mlp_fwd_, BODE_SFX)(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
   switch (method) {
     case BODE_EULER: return mlp_launch_fwd<BODE_EULER>(prm, grid, block, smem, st);
     case BODE_MIDPOINT: return mlp_launch_fwd<BODE_MIDPOINT>(prm, grid, block, smem, st);
@@ -72,7 +79,7 @@ static int mlp_launch_grad_m(const NpdeKParams& prm, int inj, int adj, dim3 grid
   return mlp_launch_grad<METHOD, INJ_GOUT, BODE_GRAD_ADJOINT>(prm, grid, block, smem, st);
 }
 
-int BODE_CAT(launch_mlp_grad_, BODE_H)(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem,
+int BODE_CAT(launch_mlp_grad_, BODE_SFX)(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem,
                                        cudaStream_t st) {
   switch (method) {
     case BODE_EULER: return mlp_launch_grad_m<BODE_EULER>(prm, inj, adj, grid, block, smem, st);

@@ -68,6 +68,7 @@ def parse():
                     help="c4: scale of the U(-0.5, 0.5) weight draw of nn.ipynb cell 4.  The notebook's net has H = 20; the same draw at H = 64 "
                          "has sqrt(64/20) = 1.8x the layer gain, its trajectories grow like e^(5t) and aSGHMC at the notebook's lr = 1e-2 turns the "
                          "chains non-finite within a few iterations (in the reference as well).  0.3 ~ sqrt(20/64) / 2 keeps the ensemble bounded.")
+    ap.add_argument("--no-mlp-tc", action="store_true", help="c4: FP32-pipe MLP kernels instead of the tensor-core ones (comparison runs)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling sub-record")
@@ -537,6 +538,8 @@ def run_b200(args, wl):
 
     cfg = config_of(args, wl, world)
     P_gpu, P_total = cfg["particles_per_gpu"], cfg["total_particles"]
+    if args.no_mlp_tc:
+        bode._lib.load().bode_mlp_set_tensor_cores(0)
     job = Job(args, wl, P_gpu, rank, world, torch, bode)
     smp, post, field = job.smp, job.post, job.field
     N = job.N
@@ -581,7 +584,9 @@ def run_b200(args, wl):
         ode_ms = statistics.median(event_ms(torch, lambda: post.loss_and_grad_(), 5))
         att_pairs = float((bode.last_dopri5_stats()[..., :2]).sum().item())
         ode_flop = MLP_FLOP_PER_STAGE_TRAJ * 6.0 * att_pairs
-        kernels.append(dict(name="dopri5_grad_kernel<MlpField<64>> (adaptive solve, pooled controller + record + frozen-step reverse sweep, one warp per pair)",
+        kernels.append(dict(name=("dopri5_grad_kernel<MlpField<64>> (FP32 pipe; " if args.no_mlp_tc else
+                                  "dopri5_grad_kernel<MlpTcField> (64x64 layer on mma.sync tf32 3x split; ") +
+                            "adaptive solve, pooled controller + record + frozen-step reverse sweep)",
                             ms=ode_ms, bound="fp32", achieved=ode_flop / (ode_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"], unit="TFLOP/s",
                             flop_per_launch=ode_flop, attempted_steps_per_pair=att_pairs / (P_gpu * N)))
     if sampler in ("psgld", "sgld", "asghmc", "hamcmc"):

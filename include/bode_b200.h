@@ -202,6 +202,10 @@ typedef struct bode_mlp_field {
 /* odeint(net, x0, t, method) forward for every particle and trajectory row (nn.ipynb cell 10 loops rows) */
 int bode_mlp_odeint(const bode_mlp_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,
                     int32_t y0_batched, float* sol, bode_stream_t stream);
+/* H = 64: the 64 x 64 hidden layer runs on the tensor cores (mma.sync tf32, 3x split: fp32-level accuracy) whenever the
+ * trajectories of a particle advance in lock-step -- fixed-grid solvers, dopri5 with controller = 1 -- and 4 <= N <= 8.
+ * on = 0 forces the FP32-pipe kernels everywhere.  Returns the previous setting. */
+int bode_mlp_set_tensor_cores(int32_t on);
 /* odeint(net, x0, t, method='dopri5') forward, per-pair controller (see bode_dopri5_opts) */
 int bode_mlp_dopri5(const bode_mlp_field* f, const bode_dopri5_opts* o, int32_t T, float sign, int32_t N,
                     const float* y0, int32_t y0_batched, float* sol, bode_stream_t stream);
