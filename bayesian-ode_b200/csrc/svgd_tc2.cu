@@ -1,4 +1,5 @@
-// Pipelined SVGD contractions on tcgen05 (3xTF32, TMEM accumulators) for shapes whose column count is a multiple of 4.
+// Pipelined SVGD contractions on tcgen05 (3xTF32 Gram; K @ V as TF32 hi.hi + ONE bf16 product for both correction terms; TMEM
+// accumulators) for shapes whose column count is a multiple of 4.
 //
 //   prep_x_kernel / prep_v_kernel   centre, split (hi = top 19 bits, lo = x - hi) and store the operands ONCE per step in global
 //                                   memory, already in the canonical no-swizzle K-major UMMA layout, so that every later
@@ -17,6 +18,7 @@
 #include "tc_ptx.cuh"
 #include "svgd_state.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cooperative_groups.h>
 
 namespace bode {
@@ -106,15 +108,23 @@ __global__ void __launch_bounds__(256) prep_x_kernel(const float* __restrict__ X
   }
 }
 
-// VH/VL[j/4][f][j%4] : K-major (K = particle index j) core matrices of V^T, zero padded to n_pad particles (multiple of 32)
+// VH[j/4][f][j%4] : K-major (K = particle index j) tf32 core matrices of V^T (hi parts), zero padded to n_pad particles (multiple of 32).
+// VC: the B operand of the CORRECTION product.  K V = K_hi V_hi + (K_hi V_lo + K_lo V_hi) + O(2^-22); the bracket only needs 2^-9
+// relative accuracy, so it is ONE bf16 product of twice the K extent, [bf16 K | bf16 K_lo] . [bf16 V_lo ; bf16 V_hi]: per 32-particle
+// stage 64 bf16 rows -- rows 0..31 = V_lo[j], rows 32..63 = V_hi[j] -- as 8 K-chunks of 8 bf16 (16 bytes) x 112 features, i.e. the
+// same 14336 bytes, LBO and SBO as a tf32 stage.  8 instead of 12 MMA slots per stage, error ~2^-19.
+__device__ __forceinline__ uint2 pack_bf16x4(const float (&v)[4]) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);   // .x = low half = lower k
+  return make_uint2(*reinterpret_cast<const unsigned int*>(&a), *reinterpret_cast<const unsigned int*>(&b));
+}
 __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
                                                      int n, int d, const float* __restrict__ mu, float gsign, int n_pad,
-                                                     float* __restrict__ VH, float* __restrict__ VL) {
+                                                     float* __restrict__ VH, float* __restrict__ VC) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(n_pad / 4) * NF2) return;
   const int f = (int)(idx % NF2);
   const long long jq = idx / NF2;
-  float h[4], l[4];
+  float h[4], l[4], full[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     const long long j = 4 * jq + e;
@@ -124,10 +134,16 @@ __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X
       else if (f < 2 * d) v = __ldg(X + j * ldx + (f - d)) - __ldg(mu + f - d);
       else if (f == 2 * d) v = 1.f;
     }
+    full[e] = v;
     split_tf32(v, h[e], l[e]);
   }
   *reinterpret_cast<float4*>(VH + idx * 4) = make_float4(h[0], h[1], h[2], h[3]);
-  *reinterpret_cast<float4*>(VL + idx * 4) = make_float4(l[0], l[1], l[2], l[3]);
+  // stage s = j / 32; inside it this thread's 4 particles are half (jq % 2) of K-chunk (jq % 8) / 2 (V_lo) and of chunk 4 + that (V_hi)
+  const long long s = jq >> 3;
+  const int c = (int)(jq & 7) >> 1, half = (int)(jq & 1);
+  unsigned char* base = reinterpret_cast<unsigned char*>(VC) + s * VST_BYTES + (long long)f * 16 + half * 8;
+  *reinterpret_cast<uint2*>(base + (long long)c * (NF2 * 16)) = pack_bf16x4(l);
+  *reinterpret_cast<uint2*>(base + (long long)(c + 4) * (NF2 * 16)) = pack_bf16x4(full);
 }
 
 // ---------------------------------------------------------------- Gram tiles + window count
@@ -557,6 +573,25 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
+}
+// D[tmem] += A[tmem, bf16 pairs per 32-bit column] * B[smem desc, bf16], fp32 accumulate; warp-uniform issue (see umma_tf32_ts_w)
+__device__ __forceinline__ void umma_bf16_ts_w(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, q;\n\t"
+      "elect.sync _|q, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// instruction descriptor, kind::f16: c = F32 [4,6), a = BF16 (1) [7,10), b = BF16 (1) [10,13), K-major both, N>>3 [17,23), M>>4 [24,29)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // Arguments of the fused combine.
 constexpr int ACC_PITCH = NF2 + 1;   // odd pitch: a warp's 32 rows hit 32 banks
 struct Phi2Combine {
@@ -572,7 +607,7 @@ struct Phi2Combine {
 };
 
 __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant__ CUtensorMap tmD2, int nr, int nc, const float* __restrict__ VH,
-                                                       const float* __restrict__ VL, int d, const float* __restrict__ gam, int jsplit,
+                                                       const float* __restrict__ VC, int d, const float* __restrict__ gam, int jsplit,
                                                        float* __restrict__ part, const Phi2Combine cmb, int tiled, int stream_d2) {
   extern __shared__ unsigned char sm_raw[];
   // 1024-byte alignment for the swizzled TMA tiles, computed as an OFFSET so the pointer stays in the shared address space
@@ -592,7 +627,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   const int s0 = blockIdx.y * per;
   const int nst = min(per, nst_all - s0);                              // stages of this CTA (may be <= 0)
 
-  // TMEM columns: [0,112) accumulator, [128 + 64 s, +32) K_hi and [+32, +64) K_lo of slot s = 0..2
+  // TMEM columns: [0,112) accumulator; slot s = 0..2: [128 + 64 s, +32) K_hi (tf32), [+32, +48) bf16 pairs of K, [+48, +64) of K_lo
   if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) mbar_init(barM + i, 1);
@@ -603,7 +638,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
-  constexpr uint32_t idesc = idesc_tf32(BLK, NF2, 0, 0);
+  constexpr uint32_t idesc = idesc_tf32(BLK, NF2, 0, 0), idesc_c = idesc_bf16(BLK, NF2);
   constexpr uint32_t B_LBO = NF2 * 16, SBO = 128;
 
   // No CTA-wide barrier inside the stage loop: the warps only meet through mbarriers, so a slow warp delays nobody but the MMA
@@ -620,7 +655,7 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
         const long long src = (long long)(s0 + t) * (VST_BYTES / 4);
         mbar_expect_tx(barKV + t % 6, 2 * VST_BYTES);
         bulk_g2s(dst, VH + src, VST_BYTES, barKV + t % 6);
-        bulk_g2s(dst + VST_BYTES, VL + src, VST_BYTES, barKV + t % 6);
+        bulk_g2s(dst + VST_BYTES, VC + src, VST_BYTES, barKV + t % 6);
       };
       auto load_raw = [&](int t) {
         if (t < nst) {
@@ -652,16 +687,15 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       mbar_wait(barKV + 0, 0);
       for (int t = 0; t < nst; ++t) {
         tc_fence_after();
-        const uint32_t ah = tmem + 128 + (t % 3) * 64, al = ah + 32;         // K_hi / K_lo of this stage in TMEM
-        const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bl = bh + (VST_BYTES >> 4);
+        const uint32_t ah = tmem + 128 + (t % 3) * 64, ac = ah + 32;         // K_hi (tf32) / [bf16 K | bf16 K_lo] of this stage in TMEM
+        const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bc = bh + (VST_BYTES >> 4);
 #pragma unroll
         for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
-#pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, ah + ks * 8, bl + ks * BK, idesc, 1u);
-        // the wait for the NEXT stage is taken while eight MMAs of this one are queued on the tensor core
+        // the wait for the NEXT stage is taken while the MMAs of this one are queued on the tensor core
         if (t + 1 < nst) mbar_wait(barKV + (t + 1) % 6, ((t + 1) / 6) & 1);
+        // corrections K_hi V_lo + K_lo V_hi: ONE bf16 product over 64 K rows = four K = 16 MMAs (8 TMEM columns / 2 chunks each)
 #pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, al + ks * 8, bh + ks * BK, idesc, 1u);
+        for (int q = 0; q < 4; ++q) umma_bf16_ts_w(tmem, ac + q * 8, bc + q * BK, idesc_c, 1u);
         umma_commit_w(barM + t % 3);
       }
     }
@@ -688,12 +722,21 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       float h[8], l[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) split_tf32(kv[e], h[e], l[e]);
+      // correction operand: bf16 pairs (low half = lower k) of K at columns 32 + 4 qd .., of K_lo at 48 + 4 qd ..
+      uint32_t ck[4], cl[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(kv[2 * e], kv[2 * e + 1]), b = __floats2bfloat162_rn(l[2 * e], l[2 * e + 1]);
+        ck[e] = *reinterpret_cast<const unsigned int*>(&a);
+        cl[e] = *reinterpret_cast<const unsigned int*>(&b);
+      }
       if (t >= 3) {                                                    // K slot t % 3 was read by stage t-3's MMAs
         mbar_wait(barM + t % 3, ((t - 3) / 3) & 1);
         tc_fence_after();
       }
       tmem_st8(klane + (t % 3) * 64, h);
-      tmem_st8(klane + (t % 3) * 64 + 32, l);
+      tmem_st4u(klane - 8 * qd + (t % 3) * 64 + 32 + 4 * qd, ck);
+      tmem_st4u(klane - 8 * qd + (t % 3) * 64 + 48 + 4 * qd, cl);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       tc_fence_before();
       __syncwarp();
@@ -772,7 +815,7 @@ size_t svgd_tc2_operand_bytes(int nr, int nc) {
 }
 
 struct Tc2Ops {
-  float *XrH, *XrL, *nrm_r, *XcH, *XcL, *nrm_c, *VH, *VL;
+  float *XrH, *XrL, *nrm_r, *XcH, *XcL, *nrm_c, *VH, *VC;
   unsigned long long* table;
 };
 Tc2Ops svgd_tc2_carve(void* base, int nr, int nc) {
@@ -782,7 +825,7 @@ Tc2Ops svgd_tc2_carve(void* base, int nr, int nc) {
   auto take = [&](size_t bytes) { char* q = p; p += (bytes + 255) / 256 * 256; return q; };
   o.XrH = (float*)take(nrp * KP2 * 4); o.XrL = (float*)take(nrp * KP2 * 4); o.nrm_r = (float*)take(nrp * 4);
   o.XcH = (float*)take(ncp * KP2 * 4); o.XcL = (float*)take(ncp * KP2 * 4); o.nrm_c = (float*)take(ncp * 4);
-  o.VH = (float*)take(ncp * NF2 * 4); o.VL = (float*)take(ncp * NF2 * 4);
+  o.VH = (float*)take(ncp * NF2 * 4); o.VC = (float*)take(ncp * NF2 * 4);
   o.table = (unsigned long long*)take(2 * (size_t)(WIN_TABLE + 1) * 8 + 512);
   return o;
 }
@@ -955,7 +998,7 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   if (js > 8) js = 8;                                                  // portable cluster size
   *jsplit_out = js;
   if (stages & 1) {   // V^T = [-G | X - mu | 1] operand tiles: needs positions and scores, not d2 or gamma
-    prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VL);
+    prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VC);
     BODE_CUDA(cudaGetLastError());
   }
   if (!(stages & 2)) return BODE_OK;
@@ -986,7 +1029,7 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VL, d, gam, js, part, cmb, tiled, d2_streams(nr, nc)));
+  BODE_CUDA(cudaLaunchKernelEx(&cfg, phi2_kernel, tm, nr, nc, (const float*)o.VH, (const float*)o.VC, d, gam, js, part, cmb, tiled, d2_streams(nr, nc)));
   return check_cuda(cudaGetLastError(), "phi2 launch");
 }
 

@@ -649,7 +649,7 @@ def run_b200(args, wl):
         if med_ms is not None:
             kernels.append(dict(name="svgd exact median: window_select + radix fallback (no-op after a window hit) + gamma", ms=med_ms, bound="hbm",
                                 achieved=(2 * 16384 + 2) * 8 * 2 / (med_ms * 1e-3) / 1e9, peak=hbm_peak, unit="GB/s"))
-        kernels.append(dict(name=("svgd phi: prep_v + phi2 K@[S|X|1] (3xTF32 tcgen05, TMA d2 tiles) + cluster combine, %s" % shape) if tc else "svgd phi_partial+combine (K@[S|X])",
+        kernels.append(dict(name=("svgd phi: prep_v + phi2 K@[S|X|1] (tcgen05: TF32 hi.hi + one bf16 product for both correction terms, TMA d2 tiles) + cluster combine, %s" % shape) if tc else "svgd phi_partial+combine (K@[S|X])",
                             ms=phi_ms, bound="tensor" if tc else "fp32", achieved=4.0 * nl * nt * d / (phi_ms * 1e-3) / 1e12,
                             peak=tpeak if tc else peaks["fp32_fma_tflops"], unit="TFLOP/s"))
         # one step whose median window MISSES (what the first step of a run, or a step that moves the median by > 0.2 %, pays):
@@ -685,7 +685,7 @@ def run_b200(args, wl):
                     kernel=dom["name"], kernel_ms=dom["ms"], share_of_step=dom["ms"] / ms_per_step,
                     peak_source=("fp32 FMA-chain microbenchmark run by this bench (MEASURED_PEAKS.json has no fp32 figure)"
                                  if dom["bound"] == "fp32" else (("half of %s bf16_tflops (tf32 dense rate); algorithmic flops, "
-                                                                  "the kernel issues 3 MMAs per product" % peak_src) if dom["bound"] == "tensor" else peak_src)))
+                                                                  "the kernels issue 2 - 3 MMA passes per product" % peak_src) if dom["bound"] == "tensor" else peak_src)))
 
     # ---- end to end through the public API with HOST buffers: H2D of this step's observations, step, D2H of the loss
     loss_host = torch.empty(P_gpu, dtype=torch.float32).pin_memory()
