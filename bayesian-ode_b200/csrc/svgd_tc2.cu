@@ -524,8 +524,8 @@ struct Phi2Smem {
   static constexpr uint32_t RAW = 0;
   static constexpr uint32_t RAW_SLOT = BLK * PK2 * 4;                  // 16384 (1024-byte aligned)
   static constexpr uint32_t V = RAW + NRAW * RAW_SLOT;                 // 3 slots x (hi | lo); the K tile (A operand) lives in TMEM
-  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[3], barR[NRAW], barKV[6]
-  static constexpr uint32_t TSLOT = BARS + 16 * 8;
+  static constexpr uint32_t BARS = V + 6 * VST_BYTES;                  // barM[3], barR[NRAW], barKV[6], barF[2], barD[2]
+  static constexpr uint32_t TSLOT = BARS + 24 * 8;
   static constexpr uint32_t TOTAL = TSLOT + 16 + 1024;                 // + slack to align the dynamic base to 1024 bytes
 };
 
@@ -573,6 +573,13 @@ __device__ __forceinline__ void tmem_st8(uint32_t taddr, const float (&v)[8]) {
                : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld4_add(uint32_t taddr, float* acc) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i] += __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_st4u(uint32_t taddr, const uint32_t (&v)[4]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]) : "memory");
 }
@@ -619,6 +626,15 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   constexpr int NRAW = Phi2Smem::NRAW;
   uint64_t* barR = bars + 3;      // [NRAW] d2 tile landed
   uint64_t* barKV = bars + 3 + NRAW;   // [6] stage t ready for the tensor core (count NWARP + 1 arrivals, + the V bytes)
+  // Two-level accumulation.  The tensor core adds every MMA into its fp32 accumulator with TRUNCATION, so a long chain into one
+  // growing sum is biased by ~half an ulp of that sum per MMA: measured 2e-5 (4096 columns) -> 5e-4 (32768 columns) relative error
+  // of phi on B200 (tools/phi_accuracy.py), linear in the number of accumulated stages.  The MMAs therefore accumulate CHUNKS of
+  // ACC_G stages into two alternating TMEM accumulators (small partial sums: small ulps) and the worker warps drain each finished
+  // chunk into fp32 registers with round-to-nearest adds (28 columns of its row per thread, +7 % worker instructions).
+  uint64_t* barF = barKV + 6;          // [2] chunk accumulator complete (tcgen05.commit after the chunk's last MMA)
+  uint64_t* barD = barF + 2;           // [2] chunk accumulator drained by all NWARP worker warps: the MMA warp may overwrite it
+  constexpr int ACC_G = 8;
+  constexpr uint32_t ACC_B = 384;      // second accumulator: TMEM columns [384, 496)
   uint32_t* tslot = reinterpret_cast<uint32_t*>(sm + Phi2Smem::TSLOT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int r0 = blockIdx.x * BLK;
@@ -627,12 +643,13 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
   const int s0 = blockIdx.y * per;
   const int nst = min(per, nst_all - s0);                              // stages of this CTA (may be <= 0)
 
-  // TMEM columns: [0,112) accumulator; slot s = 0..2: [128 + 64 s, +32) K_hi (tf32), [+32, +48) bf16 pairs of K, [+48, +64) of K_lo
+  // TMEM columns: [0,112) and [384,496) the two chunk accumulators; slot s = 0..2: [128 + 64 s, +32) K_hi (tf32), [+32, +48) bf16 pairs of K, [+48, +64) of K_lo
   if (warp == 0) tmem_alloc(tslot, 512);
   if (tid == 0) {
     for (int i = 0; i < 3; ++i) mbar_init(barM + i, 1);
     for (int i = 0; i < NRAW; ++i) mbar_init(barR + i, 1);
     for (int i = 0; i < 6; ++i) mbar_init(barKV + i, NWARP + 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(barF + i, 1); mbar_init(barD + i, NWARP); }
   }
   tc_fence_before();
   __syncthreads();
@@ -687,15 +704,23 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       mbar_wait(barKV + 0, 0);
       for (int t = 0; t < nst; ++t) {
         tc_fence_after();
+        const int c = t / ACC_G;                                       // chunk of this stage and its accumulator
+        const uint32_t acc = tmem + ((c & 1) ? ACC_B : 0u);
+        const bool first = (t % ACC_G) == 0;
+        if (first && c >= 2) {                                         // chunk c-2 (same accumulator) has been drained
+          mbar_wait(barD + (c & 1), ((c >> 1) - 1) & 1);
+          tc_fence_after();
+        }
         const uint32_t ah = tmem + 128 + (t % 3) * 64, ac = ah + 32;         // K_hi (tf32) / [bf16 K | bf16 K_lo] of this stage in TMEM
         const uint64_t bh = dV + (uint64_t)((t % 3) * ((2 * VST_BYTES) >> 4)), bc = bh + (VST_BYTES >> 4);
 #pragma unroll
-        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(tmem, ah + ks * 8, bh + ks * BK, idesc, (t > 0 || ks > 0) ? 1u : 0u);
+        for (int ks = 0; ks < PK2 / 8; ++ks) umma_tf32_ts_w(acc, ah + ks * 8, bh + ks * BK, idesc, (!first || ks > 0) ? 1u : 0u);
         // the wait for the NEXT stage is taken while the MMAs of this one are queued on the tensor core
         if (t + 1 < nst) mbar_wait(barKV + (t + 1) % 6, ((t + 1) / 6) & 1);
         // corrections K_hi V_lo + K_lo V_hi: ONE bf16 product over 64 K rows = four K = 16 MMAs (8 TMEM columns / 2 chunks each)
 #pragma unroll
-        for (int q = 0; q < 4; ++q) umma_bf16_ts_w(tmem, ac + q * 8, bc + q * BK, idesc_c, 1u);
+        for (int q = 0; q < 4; ++q) umma_bf16_ts_w(acc, ac + q * 8, bc + q * BK, idesc_c, 1u);
+        if ((t % ACC_G) == ACC_G - 1 || t == nst - 1) umma_commit_w(barF + (c & 1));
         umma_commit_w(barM + t % 3);
       }
     }
@@ -707,7 +732,24 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
     const uint32_t klane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 128 + 8 * qd;   // this thread's row (TMEM lane), its 8 K columns of slot 0
     // 128-byte swizzle of the TMA tile: 16-byte chunk c of row r sits at chunk c ^ (r % 8)
     const uint32_t roff0 = rl * 128 + (((2 * qd) ^ (rl & 7)) << 4), roff1 = rl * 128 + (((2 * qd + 1) ^ (rl & 7)) << 4);
+    // this thread's share of the fp32 result: row rl, columns [28 qd, 28 qd + 28) (4 threads per row: the 4 warps of a TMEM lane quarter)
+    float racc[28];
+#pragma unroll
+    for (int i = 0; i < 28; ++i) racc[i] = 0.f;
+    const uint32_t alane = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 28 * qd;
+    int next_drain = 0;
+    auto drain = [&](int c) {                                          // chunk c's accumulator -> registers (round-to-nearest adds)
+      mbar_wait(barF + (c & 1), (c >> 1) & 1);
+      tc_fence_after();
+      const uint32_t a0 = alane + ((c & 1) ? ACC_B : 0u);
+#pragma unroll
+      for (int i = 0; i < 7; ++i) tmem_ld4_add(a0 + 4 * i, racc + 4 * i);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(barD + (c & 1));
+    };
     for (int t = 0; t < nst; ++t) {
+      if ((next_drain + 1) * ACC_G + 1 <= t) drain(next_drain++);      // one stage after the chunk closed: its MMAs have retired
       mbar_wait(barR + (t % NRAW), (t / NRAW) & 1);                    // d2 tile of this stage has landed
       const unsigned char* raw = sm + Phi2Smem::RAW + (t % NRAW) * Phi2Smem::RAW_SLOT;
       const float4 dv0 = *reinterpret_cast<const float4*>(raw + roff0), dv1 = *reinterpret_cast<const float4*>(raw + roff1);
@@ -742,25 +784,17 @@ __global__ void __launch_bounds__(NTHR_PHI, 1) phi2_kernel(const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive(barKV + t % 6);
     }
-    // ---------------- epilogue: one TMEM lane per thread = one output row; warps 4..7 take the upper feature half.  The partial
-    // tile goes to shared memory (the drained d2 / V pipeline buffers) for the cluster-wide split-K reduction below.
-    const int half = qd;
+    // ---------------- epilogue: drain the remaining chunks, then every thread parks its 28 columns of the partial tile in shared
+    // memory (the drained d2 / V pipeline buffers: all MMAs have retired, hence every warp has consumed its last raw tile) for the
+    // cluster-wide split-K reduction below.
     float* acc_s = reinterpret_cast<float*>(sm);                       // [BLK][ACC_PITCH]
-    if (nst > 0 && warp < 8) {
-      mbar_wait(barM + (nst - 1) % 3, ((nst - 1) / 3) & 1);
-      tc_fence_after();
-      const int cbeg = half * (NF2 / 2);
-#pragma unroll 1
-      for (int cb = cbeg; cb < cbeg + NF2 / 2; cb += 8) {
-        float s[8];
-        tmem_ld8(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cb, s);
-#pragma unroll
-        for (int qq = 0; qq < 8; ++qq)
-          if (cb + qq <= 2 * d) acc_s[rl * ACC_PITCH + cb + qq] = s[qq];
-      }
-    } else if (nst <= 0 && half == 0) {
-      for (int f = 0; f <= 2 * d; ++f) acc_s[rl * ACC_PITCH + f] = 0.f;
+    if (nst > 0) {
+      const int nchunks = (nst + ACC_G - 1) / ACC_G;
+      while (next_drain < nchunks) drain(next_drain++);
     }
+#pragma unroll
+    for (int i = 0; i < 28; ++i)
+      if (28 * qd + i <= 2 * d) acc_s[rl * ACC_PITCH + 28 * qd + i] = racc[i];
   }
   tc_fence_before();
   __syncthreads();
