@@ -69,6 +69,7 @@ def parse():
                          "has sqrt(64/20) = 1.8x the layer gain, its trajectories grow like e^(5t) and aSGHMC at the notebook's lr = 1e-2 turns the "
                          "chains non-finite within a few iterations (in the reference as well).  0.3 ~ sqrt(20/64) / 2 keeps the ensemble bounded.")
     ap.add_argument("--no-mlp-tc", action="store_true", help="c4: FP32-pipe MLP kernels instead of the tensor-core ones (comparison runs)")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"], help="c3, N>1: exchange of positions / scores")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling sub-record")
@@ -309,7 +310,7 @@ class Job:
         self.field.bind_flat_grads()
         s = wl["sampler"]
         if s == "svgd":
-            self.smp = SVGD(params, lr=1e-4)
+            self.smp = SVGD(params, lr=1e-4, gather_comm=args.gather)
         elif s == "psgld":
             self.smp = pSGLD(params, lr0=5e-3, lr_gamma=0.51, lr_t0=100, lr_alpha=0.1, lambda_=1e-8, alpha=0.99, N=self.N, seed=7 + rank)
             self.post.scale = 1.0 / self.N
@@ -762,7 +763,8 @@ def run_b200(args, wl):
     if sampler == "svgd":
         cfg["streams"] = "SVGD operands + Gram + exact median on a side stream beside the fused solve"
         cfg["exchange"] = "none (one GPU)" if world == 1 else (
-            "positions + scores: push kernels over NVLink peer memory (flag barriers, no collective); exact median via peer reads")
+            ("positions + scores: push kernels over NVLink peer memory (flag barriers, no collective)" if args.gather == "p2p" else
+             "positions + scores: NCCL all-gather") + "; exact median via peer reads")
     else:
         cfg["exchange"] = "none (independent chains)"
     launches = {"svgd": 7 + (2 if world > 1 else 0), "psgld": 3, "sgld": 3, "asghmc": 2, "hamcmc": 2}[sampler]

@@ -8,7 +8,7 @@ import subprocess
 import sys
 
 tag, launches, reps = sys.argv[1], sys.argv[2], sys.argv[3:]
-out = ["# Round-1 ncu evidence, final kernels (B200, sm_100a, driver 580, CUDA 12.9)", "",
+out = ["# Round-%s ncu evidence (B200, sm_100a, driver 580, CUDA 12.9)" % ("2" if "r02" in tag else "1"), "",
        "Command (run plain first, then under ncu): `python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-graph`",
        "Launch list: `profiles/launches_%s.csv` (`ncu --metrics gpu__time_duration.sum --clock-control none`).  Per-launch times are "
        "cold-cache and serialised (ncu flushes caches between replays): compare SHARES, not absolutes." % tag, ""]
@@ -19,7 +19,7 @@ seq = [(r[ix["Kernel Name"]].split("(")[0].replace("void ", "").replace("bode::"
        for r in rows[1:] if r[ix["Metric Name"]] == "gpu__time_duration.sum"]
 # one step = from one npde grad launch to the next; take the LAST complete step of the eager loop
 idx = [i for i, (n, _) in enumerate(seq) if "npde_pair_grad" in n or "npde_grad_kernel" in n]
-step = None
+step = []
 for a, b in zip(idx[:-1], idx[1:]):
     names = [n for n, _ in seq[a:b]]
     if any("phi2" in n or "phi_tc" in n or "phi_partial" in n for n in names) and any("gram" in n or "sqdist" in n for n in names):
