@@ -859,7 +859,7 @@ if __name__ == "__main__":
     data = make_data()
     save("vdp_data", x0=data["x0"], t=data["t"], X=data["X"], Y=data["Y"])
     gen_npde(data, 5, 4, "npde_m5")
-    gen_npde(data, 3, 2, "npde_m3", methods=("rk4",))
+    gen_npde(data, 3, 2, "npde_m3")
     gen_grid_options(data)
     gen_sampler_steps(data)
     gen_svgd(data)
