@@ -25,6 +25,7 @@ class NpdeFieldStruct(C.Structure):
         ("P", C.c_int32), ("m", C.c_int32), ("grid_mx", C.c_int32), ("grid_my", C.c_int32),
         ("gx", C.c_double * 32), ("gy", C.c_double * 32), ("ell", C.c_double * 2),
         ("Z", C.c_void_p), ("A", C.c_void_p), ("Ksym", C.c_void_p), ("U", C.c_void_p), ("U_stride", C.c_int64),
+        ("AT", C.c_void_p),
     ]
 
 
@@ -56,6 +57,7 @@ SYMBOLS = {
     "bode_peak_kernel": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bode_stamp": (C.c_int, [_P, _P]),
     "bode_npde_scratch_floats": (C.c_size_t, [C.c_int32] * 6),
+    "bode_npde_scratch_floats_m": (C.c_size_t, [C.c_int32] * 7),
     "bode_npde_odeint": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),
     "bode_npde_odeint_backward": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, C.c_int32,
                                              _P, C.c_int32, _P, _P, C.c_int64, _P, _P, C.c_size_t, _P]),

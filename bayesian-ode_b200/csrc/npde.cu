@@ -4,6 +4,9 @@
 #include <math.h>
 
 namespace bode {
+int launch_proj_W(const float* AT, const float* U, long long U_stride, int P, int m, float* W, cudaStream_t st);
+int launch_proj_back(const float* A, const float* Ksym, const float* U, long long U_stride, float* gU, long long gU_stride, float* loss,
+                     float scale, int add_prior, int P, int m, cudaStream_t st);
 
 // one translation unit per grid size keeps the build parallel; see npde_inst.cuh
 #define BODE_DECL_SEP(M)                                                                               \
@@ -54,7 +57,7 @@ static int fill_common(NpdeKParams& prm, const bode_npde_field* f, const bode_gr
   const double c0 = sqrt(0.5 * LOG2E) / f->ell[0], c1 = sqrt(0.5 * LOG2E) / f->ell[1];
   prm.c0 = (float)c0; prm.c1 = (float)c1;
   prm.k0 = (float)(2.0 * LN2 * c0); prm.k1 = (float)(2.0 * LN2 * c1);
-  prm.U = f->U; prm.A = f->A; prm.Ksym = f->Ksym; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
+  prm.U = f->U; prm.A = f->A; prm.AT = f->AT; prm.Ksym = f->Ksym; prm.y0 = y0; prm.dt = g->dt; prm.obs_ptr = g->obs_ptr;
   prm.adj_dt = g->adj_dt; prm.adj_ptr = g->adj_ptr; prm.Z = f->Z;
   BODE_REQUIRE(f->U_stride >= 2 * f->m && (f->U_stride % 2) == 0, "U_stride=%lld must be even and >= 2m", (long long)f->U_stride);
   prm.U_stride = f->U_stride;
@@ -227,12 +230,29 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
   prm.stage_off = (int)(((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2 + 3) & ~(size_t)3);
   const size_t smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
   BODE_REQUIRE(smem <= 48 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
-  switch (gen_jpl(f->m)) {
-    case 1: return launch_gen_grad_1(prm, method, inj, grad_mode, grid, block, smem, st);
-    case 2: return launch_gen_grad_2(prm, method, inj, grad_mode, grid, block, smem, st);
-    case 4: return launch_gen_grad_4(prm, method, inj, grad_mode, grid, block, smem, st);
-    default: return launch_gen_grad_8(prm, method, inj, grad_mode, grid, block, smem, st);
+  // Large inducing sets: the projections W = A U and gU = A^T gW + Ksym U as panel GEMMs over all particles (npde_proj.cu) around
+  // the solve -- three launches instead of one -- when the caller's scratch holds the P x 2m projected values behind the checkpoints
+  // (bode_npde_scratch_floats_m); the prior then enters the loss in proj_back_kernel.
+  const size_t w_off = (need + 3) & ~(size_t)3;
+  const bool split = f->m >= 64 && f->AT && scratch_n >= w_off + (size_t)f->P * 2 * f->m;
+  const int add_prior = prm.add_prior;
+  if (split) {
+    float* Wpre = scratch + w_off;
+    st_ = launch_proj_W(f->AT, f->U, f->U_stride, f->P, f->m, Wpre, st);
+    if (st_ != BODE_OK) return st_;
+    prm.Wpre = Wpre;
+    prm.split = 1;
+    prm.add_prior = 0;
   }
+  switch (gen_jpl(f->m)) {
+    case 1: st_ = launch_gen_grad_1(prm, method, inj, grad_mode, grid, block, smem, st); break;
+    case 2: st_ = launch_gen_grad_2(prm, method, inj, grad_mode, grid, block, smem, st); break;
+    case 4: st_ = launch_gen_grad_4(prm, method, inj, grad_mode, grid, block, smem, st); break;
+    default: st_ = launch_gen_grad_8(prm, method, inj, grad_mode, grid, block, smem, st); break;
+  }
+  if (st_ != BODE_OK || !split) return st_;
+  return launch_proj_back(f->A, f->Ksym, f->U, f->U_stride, prm.gU, prm.gU_stride, inj == INJ_LIK ? prm.loss : nullptr, prm.scale, add_prior,
+                          f->P, f->m, st);
 }
 
 }  // namespace bode
@@ -256,6 +276,12 @@ extern "C" int bode_npde_set_cta_limit(int32_t max_ctas) {
 
 extern "C" size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode) {
   return scratch_floats(P, N, S, T, method, grad_mode);
+}
+/* ... plus room for the projected values W = A U of all particles when m >= 64: the gradient entry points then run the
+ * projections as panel GEMMs around the solve (npde_proj.cu) instead of inside it. */
+extern "C" size_t bode_npde_scratch_floats_m(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode, int32_t m) {
+  const size_t base = (scratch_floats(P, N, S, T, method, grad_mode) + 3) & ~(size_t)3;
+  return base + (m >= 64 ? (size_t)P * 2 * (size_t)m : 0);
 }
 
 extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, int32_t method, int32_t N, const float* y0,

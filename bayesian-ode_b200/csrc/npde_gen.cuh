@@ -30,6 +30,14 @@ struct GenField {
     float* Us = smem;
     float* Ws = smem + nout;
     const int p0 = blockIdx.x * prm.ppc;
+    if (prm.Wpre) {                                  // split mode: the projection was done for all particles by proj_W_kernel
+      for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
+        const int q = idx / m2, r = idx - q * m2;
+        Ws[idx] = (p0 + q < prm.P) ? __ldg(prm.Wpre + (long long)(p0 + q) * m2 + r) : 0.f;
+      }
+      __syncthreads();
+      return;
+    }
     for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
       const int q = idx / m2, r = idx - q * m2;
       Us[idx] = (p0 + q < prm.P) ? __ldg(prm.U + (long long)(p0 + q) * prm.U_stride + r) : 0.f;
@@ -38,9 +46,14 @@ struct GenField {
     for (int idx = threadIdx.x; idx < nout; idx += blockDim.x) {
       const int q = idx / m2, r = idx - q * m2, j = r >> 1, d = r & 1;
       const float* Uq = Us + q * m2 + d;
-      const float* Aj = prm.A + (long long)j * m;
       float acc = 0.f;
-      for (int k = 0; k < m; ++k) acc = fmaf(__ldg(Aj + k), Uq[2 * k], acc);
+      if (prm.AT) {                                  // threads run over j: AT[k][j] is one cache line per warp load, A[j][k] sixteen
+        const float* Atj = prm.AT + j;
+        for (int k = 0; k < m; ++k) acc = fmaf(__ldg(Atj + (long long)k * m), Uq[2 * k], acc);
+      } else {
+        const float* Aj = prm.A + (long long)j * m;
+        for (int k = 0; k < m; ++k) acc = fmaf(__ldg(Aj + k), Uq[2 * k], acc);
+      }
       Ws[idx] = acc;
     }
     __syncthreads();

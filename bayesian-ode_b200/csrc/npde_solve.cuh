@@ -25,7 +25,8 @@ __device__ __forceinline__ void project_W(const NpdeKParams& prm, float* Us, flo
     const int q = idx / m2, r = idx - q * m2, j = r >> 1, d = r & 1;
     const float* Uq = Us + q * m2 + d;
     float acc = 0.f;
-    for (int k = 0; k < m; ++k) acc = fmaf(__ldg(prm.A + j * m + k), Uq[2 * k], acc);
+    if (prm.AT) for (int k = 0; k < m; ++k) acc = fmaf(__ldg(prm.AT + k * m + j), Uq[2 * k], acc);
+    else for (int k = 0; k < m; ++k) acc = fmaf(__ldg(prm.A + j * m + k), Uq[2 * k], acc);
     Ws[idx] = acc;
   }
   __syncthreads();
@@ -173,13 +174,19 @@ __device__ __forceinline__ void npde_epilogue(const NpdeKParams& prm, float* sme
     const int q = idx / m2, r = idx - q * m2, k = r >> 1, d = r & 1;
     const int pp = blockIdx.x * ppc + q;
     if (pp >= prm.P) { pri[idx] = 0.f; continue; }
+    if (prm.split) {                     // split mode: sum_n gW goes out unprojected; proj_back_kernel finishes gU and the prior
+      pri[idx] = 0.f;
+      prm.gU[(long long)pp * prm.gU_stride + r] = Ws[idx];
+      continue;
+    }
     float acc = 0.f;
     const float* Wq = Ws + q * m2 + d;
     for (int j = 0; j < m; ++j) acc = fmaf(__ldg(prm.A + j * m + k), Wq[2 * j], acc);
     float pr = 0.f;
     if (prm.add_prior) {
       const float* Uq = Us + q * m2 + d;
-      for (int j = 0; j < m; ++j) pr = fmaf(__ldg(prm.Ksym + k * m + j), Uq[2 * j], pr);
+      // Ksym is symmetric bit for bit ((a + b) / 2 commutes): row j, column k -- the thread index k is then the fast one (coalesced)
+      for (int j = 0; j < m; ++j) pr = fmaf(__ldg(prm.Ksym + j * m + k), Uq[2 * j], pr);
       acc += pr;
       pr *= 0.5f * Us[idx];
     }

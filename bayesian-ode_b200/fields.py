@@ -99,6 +99,7 @@ class NPDEField(torch.nn.Module):
             self.Kzzinv = self.Kzz.inverse()               # gp.py:65
             self.KzzinvL = torch.mm(self.Kzzinv, self.L)   # gp.py:67
         self._A = (self.sf ** 2 * self.KzzinvL).to(device, torch.float32).contiguous()
+        self._AT = self._A.t().contiguous()                # coalesced reads for the W = A U projection (bode_npde_field.AT)
         self._Ksym = (0.5 * (self.Kzzinv + self.Kzzinv.t())).to(device, torch.float32).contiguous()
         self._Zdev = Z64.to(device, torch.float32).contiguous()
         self.grid_axes = _detect_grid(Z64.numpy())
@@ -129,6 +130,7 @@ class NPDEField(torch.nn.Module):
         fs.ell[0], fs.ell[1] = self._ell2
         fs.Z = self._Zdev.data_ptr()
         fs.A = self._A.data_ptr()
+        fs.AT = self._AT.data_ptr()
         fs.Ksym = self._Ksym.data_ptr()
         U = self.U if U is None else U
         p, stride = _lib.rows(U, 2 * self.m)

@@ -136,7 +136,7 @@ class _NpdeOdeint(torch.autograd.Function):
         gout = gout.to(torch.float32).contiguous()
         gU = torch.empty((field.P, field.m, 2), dtype=torch.float32, device=U.device)
         gy0 = torch.empty((field.P, N, 2), dtype=torch.float32, device=U.device)
-        nsc = lib.bode_npde_scratch_floats(field.P, N, g.S, g.T, method, grad_mode)
+        nsc = lib.bode_npde_scratch_floats_m(field.P, N, g.S, g.T, method, grad_mode, field.m)
         sc = _scratch(U.device, nsc)
         fs = field.c_struct(U.detach())
         gs = _grid_struct(g, grad_mode == _lib.GRAD_ADJOINT)

@@ -106,7 +106,7 @@ class NPDEPosterior:
                 _om.DOPRI5_MAX_REC_STEPS, _lib.stream_ptr()))
             _om.dopri5_check(c["stats"], sync=self.check_status)
             return loss, gU, gl
-        nsc = lib.bode_npde_scratch_floats(f.P, self.N, self.grid.S, self.grid.T, _lib.METHODS[self.method], self.grad_mode)
+        nsc = lib.bode_npde_scratch_floats_m(f.P, self.N, self.grid.S, self.grid.T, _lib.METHODS[self.method], self.grad_mode, f.m)
         sc = _scratch(U.device, nsc)
         gs = _grid_struct(self.grid, self.grad_mode == _lib.GRAD_ADJOINT)
         _lib.check(lib.bode_npde_nlp_grad(

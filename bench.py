@@ -577,8 +577,16 @@ def run_b200(args, wl):
         ode_flop = FLOP_PER_EVAL * STAGES * N * M * M * job.S * P_gpu
         kname = ("npde_pair_grad_kernel / npde_grad_kernel<Sep> (fused rk4 solve + closure + discrete adjoint; %s)" % ode_cfg) if M <= 6 else \
             "npde_grad_kernel<GenField> (general-Z field, one warp per (particle, trajectory) pair, m = %d)" % (M * M)
+        extra = {}
+        if M * M >= 64:
+            # the closure is three launches here: W = A U and gU = A^T gW + Ksym U as panel GEMMs around the solve (csrc/npde_proj.cu);
+            # ms covers all three, the flop count adds their 3 x 2 m^2 x 2 per particle
+            proj_flop = 3 * 2 * (M * M) ** 2 * 2 * P_gpu
+            ode_flop += proj_flop
+            kname = "proj_W_kernel + " + kname + " + proj_back_kernel (one closure call, three launches)"
+            extra = dict(projection_flop=proj_flop)
         kernels.append(dict(name=kname, ms=ode_ms, bound="fp32", achieved=ode_flop / (ode_ms * 1e-3) / 1e12, peak=peaks["fp32_fma_tflops"],
-                            unit="TFLOP/s", ms_one_cta_per_sm=ode_all_ms, flop_per_launch=ode_flop))
+                            unit="TFLOP/s", ms_one_cta_per_sm=ode_all_ms, flop_per_launch=ode_flop, **extra))
     else:
         post.loss_and_grad_()
         torch.cuda.synchronize()
@@ -768,6 +776,8 @@ def run_b200(args, wl):
     else:
         cfg["exchange"] = "none (independent chains)"
     launches = {"svgd": 7 + (2 if world > 1 else 0), "psgld": 3, "sgld": 3, "asghmc": 2, "hamcmc": 2}[sampler]
+    if wl["field"] == "npde" and wl["M"] ** 2 >= 64:
+        launches += 2                                        # proj_W_kernel, proj_back_kernel around the solve
     line = {
         "metric": "particle*RK-steps/sec (fwd+grad)", "value": value, "unit": "particle*RK-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": n_pre_main, "ms_per_step": ms_per_step, "higher_is_better": True,

@@ -80,6 +80,9 @@ typedef struct bode_npde_field {
   const float* Ksym;    /* [m,m]  (may be NULL when no prior term is requested) */
   const float* U;       /* [P,m,2], particle p at U + p*U_stride */
   int64_t U_stride;     /* floats between consecutive particles (>= 2m) */
+  const float* AT;      /* optional [m,m]: A transposed.  The projection W = A U_p (gp.py:70, hoisted to once per solve) reads A
+                           with the output index fastest; with AT those loads are coalesced (m = 256: 16 cache lines -> 1 per warp
+                           load).  NULL: A itself is read. */
 } bode_npde_field;
 
 /* Solver grid, precomputed on the host exactly as FixedGridODESolver.integrate does
@@ -151,6 +154,10 @@ int bode_npde_set_lanes_per_pair(int32_t lanes);
  * The solve is latency-bound at three warps per scheduler either way.  0 = every SM.  Returns the previous setting. */
 int bode_npde_set_cta_limit(int32_t max_ctas);
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
+/* The same plus P x 2m floats for m >= 64 inducing points: with that much scratch (and bode_npde_field.AT set) the gradient entry
+ * points run the projections W = A U and gU = A^T gW + Ksym U (gp.py:70, 350) as panel GEMMs over all particles around the solve
+ * instead of per-particle loops inside it (three launches; BASELINE config 5, m = 256). */
+size_t bode_npde_scratch_floats_m(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode, int32_t m);
 
 /* odeint(func=KernelRegression, y0, t, method in {euler,midpoint,rk4}) forward
  * replaces torchdiffeq/_impl/odeint.py:20-76 + solvers.py:79-99 + fixed_grid.py for the npde field.

@@ -29,8 +29,8 @@ def test_header_symbols_are_exported_and_bound():
 
 def test_struct_layout_matches_header():
     import bayesian_ode_b200 as bode
-    # 4 int32 + 66 doubles + 4 pointers + int64; 3 x 4 bytes (+pad) + 4 pointers
-    assert ctypes.sizeof(bode._lib.NpdeFieldStruct) == 16 + 66 * 8 + 5 * 8
+    # 4 int32 + 66 doubles + 4 pointers + int64 + AT pointer; 3 x 4 bytes (+pad) + 4 pointers
+    assert ctypes.sizeof(bode._lib.NpdeFieldStruct) == 16 + 66 * 8 + 6 * 8
     assert ctypes.sizeof(bode._lib.GridStruct) == 16 + 4 * 8
 
 

@@ -220,3 +220,47 @@ def test_16x16_grid_config5_shape():
     err = np.abs(gU.cpu().numpy() - ogU).max(axis=(1, 2)) / np.abs(ogU).max(axis=(1, 2))
     assert err.max() < 1e-3, err            # fp32 A = Kzz^-1 L with entries ~1e3: the looser bar is the conditioning, not the kernel
     assert f.d == 514
+
+
+@pytest.mark.parametrize("M", [8, 16])
+def test_large_m_split_projection_matches_fused_kernel(M):
+    """m >= 64: the projections W = A U and gU = A^T gW + Ksym U run as panel GEMMs around the solve (csrc/npde_proj.cu) when the
+    scratch from bode_npde_scratch_floats_m is passed.  With the plain bode_npde_scratch_floats size the SAME entry point keeps the
+    projections inside the solve kernel: both paths on the same particles (P = 37: a ragged last panel), through the posterior
+    closure and through odeint + autograd.  Same summation order => W and gU agree to rounding of the final scale; the loss adds
+    the prior after instead of before the scale."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200 import _lib
+    from oracle import npde
+    g = load_golden("npde_m5")
+    ell = 0.75 * 5 / M + 0.1
+    Z = npde.inducing_grid(g["Y"], M)
+    rng = np.random.default_rng(21)
+    P = 37
+    U = 0.3 * rng.standard_normal((P, M * M, 2))
+    f = bode.NPDEField(torch.from_numpy(U), torch.from_numpy(Z), 1.0, ell, 0.1, stable_solve=True)
+    x0, t, Y = (torch.from_numpy(g[k]) for k in ("x0", "t", "Y"))
+    lib = _lib.load()
+    real = lib.bode_npde_scratch_floats_m
+    out = {}
+    for split in (True, False):
+        if not split:
+            lib.bode_npde_scratch_floats_m = lambda P_, N, S, T, me, gm, m: lib.bode_npde_scratch_floats(P_, N, S, T, me, gm)
+        try:
+            res = []
+            for mode in ("discrete", "adjoint"):
+                post = bode.NPDEPosterior(f, x0, t, Y, grad_mode=mode)
+                loss, gU, gl = post.loss_and_grad_()
+                res += [loss.clone(), gU.clone(), gl.clone()]
+            for p in f.parameters():
+                p.grad = None
+            sol = bode.odeint(f, x0, t, method="rk4")
+            (sol ** 2).sum().backward()
+            res += [sol.detach().clone(), f.U.grad.clone()]
+            f.U.grad = None
+        finally:
+            lib.bode_npde_scratch_floats_m = real
+        out[split] = res
+    for a, b in zip(out[True], out[False]):
+        assert a.shape == b.shape and bool(torch.isfinite(a).all())
+        assert relerr(a.double().cpu().numpy(), b.double().cpu().numpy()) < 2e-6
