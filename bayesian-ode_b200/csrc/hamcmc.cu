@@ -6,6 +6,7 @@
 // The reference materialises d x d outer products and B0 = eye(d)/H_gamma; here every operator is applied as dot + axpy over
 // length-d vectors (O(K^2 d) per step), each thread owning a fixed strided slice so elementwise updates need no barrier and
 // only the dot products synchronise the CTA.
+#include <cstdlib>
 #include "common.cuh"
 
 namespace bode {
@@ -65,7 +66,7 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
   return (idx & 1) ? r * s : r * c;
 }
 
-__global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
+__global__ void __launch_bounds__(128) hamcmc_generic_kernel(const HamcmcArgs a) {
   __shared__ double red[8];
   const int p = blockIdx.x, d = a.d, M = a.M, cap = 2 * M - 1;
   float* ht = a.hist_theta + (long long)p * cap * d;
@@ -207,6 +208,234 @@ __global__ void __launch_bounds__(128) hamcmc_kernel(const HamcmcArgs a) {
   if (bad && a.status) atomicOr(a.status, 1);
 }
 
+
+// ------------------------------------------------------------------ register-sliced kernel (d <= NT * EPT)
+// The ~50 dot + axpy pairs of a metric step are ONE dependent chain per sampler chain.  In the generic kernel above every link is a
+// strided loop over global memory: ncu (profiles/ncu_summary_r02.md, hamcmc) counted 76 M warp instructions per launch at d = 514 --
+// 17 per element and link, most of them 64-bit address arithmetic -- for 0.18 ms per step, 4 % of the HBM roofline.  Here thread t
+// owns elements t, t + NT, ... (EPT of them, compile time): the running vectors z, z2 and the current pair (s, y) stay in
+// REGISTERS, the product-form vectors u, v, p, q (rebuilt on every step, never read by another launch) in shared memory at
+// constant offsets from one base, and a block-wide sum costs one barrier (the partial sums alternate between two buffers).
+// Element ownership, accumulation order (per-thread sequential in float64, xor tree, warps in order) and every elementwise
+// expression are those of the generic kernel.
+template <int EPT, int NT>
+struct Sliced {
+  int tid, d;
+  double* red;      // [2][NT / 32]
+  int par;
+  __device__ __forceinline__ bool ok(int i) const { return tid + NT * i < d; }
+  __device__ __forceinline__ double bsum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    constexpr int NW = NT / 32;
+    if (NW == 1) return 0.0 + v;
+    if ((tid & 31) == 0) red[par * NW + (tid >> 5)] = v;
+    __syncthreads();
+    double t = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) t += red[par * NW + i];
+    par ^= 1;
+    return t;
+  }
+  __device__ __forceinline__ void load(float (&r)[EPT], const float* src) const {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) r[i] = ok(i) ? src[tid + NT * i] : 0.f;
+  }
+  __device__ __forceinline__ void store(float* dst, const float (&r)[EPT]) const {
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (ok(i)) dst[tid + NT * i] = r[i];
+  }
+  __device__ __forceinline__ float dot(const float (&x)[EPT], const float (&y)[EPT]) {
+    double acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i)
+      if (ok(i)) acc = fma((double)x[i], (double)y[i], acc);
+    return (float)bsum(acc);
+  }
+  // z <- z - (z . x) y   with x, y in (shared) memory
+  __device__ __forceinline__ void project(float (&z)[EPT], const float* x, const float* y) {
+    float xv[EPT], yv[EPT];
+    load(xv, x);
+    load(yv, y);
+    const float c = dot(z, xv);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) z[i] = fmaf(-c, yv[i], z[i]);
+  }
+};
+
+template <int EPT, int NT>
+__global__ void __launch_bounds__(NT) hamcmc_kernel(const HamcmcArgs a) {
+  __shared__ double red[2 * (NT / 32)];
+  extern __shared__ __align__(16) float wsm[];          // u, v, p, q: [4][M-1][d]
+  const int p = blockIdx.x, d = a.d, M = a.M, cap = 2 * M - 1;
+  float* ht = a.hist_theta + (long long)p * cap * d;
+  float* hg = a.hist_grad + (long long)p * cap * d;
+  float* ps = a.pair_s + (long long)p * (M - 1) * d;
+  float* py = a.pair_y + (long long)p * (M - 1) * d;
+  float *U = wsm, *V = wsm + (M - 1) * d, *Pp = wsm + 2 * (M - 1) * d, *Q = wsm + 3 * (M - 1) * d;
+  int* meta = a.meta + 4 * p;
+  float* th = a.theta + (long long)p * a.ld_theta;
+  const float* g = a.grad + (long long)p * a.ld_grad;
+  const float nscale = rsqrtf(0.5f * a.lr);
+  Sliced<EPT, NT> sl{(int)threadIdx.x, d, red, 0};
+  const int tid = threadIdx.x;
+  int bad = 0;
+  auto noise_at = [&](int e) -> float {
+    const float x = a.xi ? a.xi[(long long)p * d + e] : philox_normal(a.seed, (unsigned)(p * d + e), a.step);
+    return x * nscale;
+  };
+  float gv[EPT];
+  sl.load(gv, g);
+
+  if (a.mode == 0) {
+    // ---------------- step_without_metric (:941-964)
+    const int n_hist0 = meta[0];
+    int n_hist = n_hist0;
+    const bool keep = a.add_params && n_hist < cap;
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      if (!sl.ok(i)) continue;
+      const int e = tid + NT * i;
+      float t = th[e];
+      bad |= !(fabsf(t) <= 3.4028234e38f);
+      t = fmaf(-a.lr, gv[i], t);
+      if (a.add_noise) t = fmaf(-a.lr, noise_at(e), t);
+      th[e] = t;
+      if (keep) {
+        ht[(long long)n_hist * d + e] = t;          // theta AFTER the update, gradient from BEFORE it (:954-961)
+        hg[(long long)n_hist * d + e] = gv[i];
+      }
+    }
+    if (keep) ++n_hist;
+    int K = meta[2];
+    if (a.add_params && n_hist == cap && n_hist0 == cap - 1) {
+      // history just became full: start-up pairs i <-> i+M with the 1e-4 curvature filter (:924-935); own elements only, so the
+      // slot written above is read back by the thread that wrote it
+      K = 0;
+      for (int i = 0; i < M - 1; ++i) {
+        float t1[EPT], t0[EPT], g1[EPT], g0[EPT], sv[EPT], yv[EPT];
+        sl.load(t1, ht + (long long)(i + M) * d);
+        sl.load(t0, ht + (long long)i * d);
+        sl.load(g1, hg + (long long)(i + M) * d);
+        sl.load(g0, hg + (long long)i * d);
+        double sy = 0.0, ss = 0.0;
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          sv[k] = t1[k] - t0[k];
+          yv[k] = g1[k] - g0[k] + a.trust_reg * sv[k];
+          if (sl.ok(k)) { sy = fma((double)sv[k], (double)yv[k], sy); ss = fma((double)sv[k], (double)sv[k], ss); }
+        }
+        sy = sl.bsum(sy);
+        ss = sl.bsum(ss);
+        if (sy > 1e-4 * ss) {
+          sl.store(ps + (long long)K * d, sv);
+          sl.store(py + (long long)K * d, yv);
+          ++K;
+        }
+      }
+    }
+    __syncthreads();                                  // every thread has read meta
+    if (tid == 0) { meta[0] = n_hist; meta[1] = 0; meta[2] = K; meta[3] = 0; }
+  } else {
+    // ---------------- metric step (:966-1000)
+    const int head = meta[1], K = meta[2], phead = meta[3];
+    const float B0 = 1.f / a.H_gamma, C0 = sqrtf(B0), S0 = rsqrtf(B0);
+    const float* base = ht + (long long)((head + M - 1) % cap) * d;
+    const float* gbase = hg + (long long)((head + M - 1) % cap) * d;
+    float bv[EPT], gbv[EPT], z[EPT], z2[EPT];
+    sl.load(bv, base);                                // requested now, used after the recursion
+    sl.load(gbv, gbase);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) z2[i] = sl.ok(i) ? S0 * noise_at(tid + NT * i) : 0.f;
+    int nu = 0;
+    int slot = phead;
+    for (int i = 0; i < K; ++i) {
+      float sv[EPT], yv[EPT];
+      sl.load(sv, ps + (long long)slot * d);
+      sl.load(yv, py + (long long)slot * d);
+      slot = slot + 1 == K ? 0 : slot + 1;
+      const float sy = sl.dot(sv, yv);
+      if (sy < 0.f) continue;                                           // :825-829
+      if (nu == 0) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) z[k] = B0 * sv[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) z[k] = sv[k];
+        for (int j = nu - 1; j >= 0; --j) sl.project(z, V + j * d, U + j * d);      // C^T z (:760-777)
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) z[k] *= C0 * C0;                  // C0 applied by C^T and again by C (:751,776)
+        for (int j = 0; j < nu; ++j) sl.project(z, U + j * d, V + j * d);           // C z (:750-757)
+      }
+      const float sBs = sl.dot(sv, z);
+      const float cq = sqrtf(sy / sBs), cu = sqrtf(sBs / sy), isy = 1.f / sy, isBs = 1.f / sBs;
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        if (!sl.ok(k)) continue;
+        const int e = tid + NT * k;
+        Q[nu * d + e] = cq * z[k] - yv[k];
+        Pp[nu * d + e] = sv[k] * isy;
+        U[nu * d + e] = cu + z[k];                                       // scalar + vector (:846)
+        V[nu * d + e] = sv[k] * isBs;
+      }
+      ++nu;
+    }
+    // Hg = S (S^T g)   (:808-815) ; Sn = S n (:856)
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) z[k] = gv[k];
+    if (nu == 0) {
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) z[k] = z[k] / B0;
+    } else {
+      for (int j = nu - 1; j >= 0; --j) sl.project(z, Q + j * d, Pp + j * d);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) z[k] *= S0 * S0;
+      for (int j = 0; j < nu; ++j) sl.project(z, Pp + j * d, Q + j * d);
+    }
+    for (int j = 0; j < nu; ++j) sl.project(z2, Pp + j * d, Q + j * d);
+    // theta_new = base - lr Hg - lr Sn ; s/y of the refresh pair (:862-873)
+    double sy = 0.0, ss = 0.0;
+    float tv[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      float t = fmaf(-a.lr, z[k], bv[k]);
+      if (a.add_noise) t = fmaf(-a.lr, z2[k], t);
+      if (sl.ok(k)) bad |= !(fabsf(t) <= 3.4028234e38f);
+      const float s = t - bv[k];
+      const float y = gv[k] - gbv[k] + a.trust_reg * s;
+      z[k] = s; z2[k] = y; tv[k] = t;
+      if (sl.ok(k)) { sy = fma((double)s, (double)y, sy); ss = fma((double)s, (double)s, ss); }
+    }
+    sl.store(th, tv);
+    sy = sl.bsum(sy);
+    ss = sl.bsum(ss);
+    int np_head = phead;
+    if (sy > 1e-8 * ss && K > 0) {                                      // append + pop(0): the oldest pair is replaced
+      sl.store(ps + (long long)phead * d, z);
+      sl.store(py + (long long)phead * d, z2);
+      np_head = (phead + 1) % K;
+    }
+    sl.store(ht + (long long)head * d, tv);                             // history: append new, pop oldest (own elements: base was
+    sl.store(hg + (long long)head * d, gv);                             // read into registers by the same thread)
+    __syncthreads();                                                    // every thread has read meta
+    if (tid == 0) { meta[1] = (head + 1) % cap; meta[3] = np_head; }
+  }
+  if (bad && a.status) atomicOr(a.status, 1);
+}
+
+template <int EPT, int NT>
+static int launch_sliced(const HamcmcArgs& a, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(hamcmc_kernel<EPT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024), "hamcmc smem attr");
+    if (e != BODE_OK) return e;
+    attr_set = true;
+  }
+  hamcmc_kernel<EPT, NT><<<a.P, NT, smem, st>>>(a);
+  return check_cuda(cudaGetLastError(), "hamcmc launch");
+}
+
 }  // namespace bode
 
 using namespace bode;
@@ -232,6 +461,20 @@ extern "C" int bode_hamcmc_step(int32_t P, int32_t d, int32_t memory, float* his
   a.work = work; a.meta = meta; a.theta = theta; a.ld_theta = ld_theta; a.grad = grad; a.ld_grad = ld_grad; a.xi = xi;
   a.lr = lr; a.H_gamma = H_gamma; a.trust_reg = trust_reg; a.mode = metric_step ? 1 : 0; a.add_params = add_params;
   a.add_noise = add_noise; a.seed = seed; a.step = step; a.status = status;
-  hamcmc_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(a);
+  // d <= 1024 with the product-form vectors (4 * memory * d floats) within 100 KB of shared memory: the register-sliced kernel;
+  // anything larger: the generic kernel over the global work buffer (BODE_HAMCMC_GENERIC=1 forces it: the test that compares the
+  // two).  Measured at d = 514, 2048 chains (c5): 128 threads x 5 elements 0.116 ms, 64 x 9 0.122, 32 x 17 0.165, generic 0.187.
+  const size_t wbytes = sizeof(float) * (size_t)(4 * memory) * d;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (wbytes <= 100 * 1024 && !getenv("BODE_HAMCMC_GENERIC")) {
+    if (d <= 32) return launch_sliced<1, 32>(a, wbytes, st);
+    if (d <= 64) return launch_sliced<1, 64>(a, wbytes, st);
+    if (d <= 128) return launch_sliced<1, 128>(a, wbytes, st);
+    if (d <= 256) return launch_sliced<2, 128>(a, wbytes, st);
+    if (d <= 384) return launch_sliced<3, 128>(a, wbytes, st);
+    if (d <= 640) return launch_sliced<5, 128>(a, wbytes, st);
+    if (d <= 1024) return launch_sliced<8, 128>(a, wbytes, st);
+  }
+  hamcmc_generic_kernel<<<P, 128, 0, st>>>(a);
   return check_cuda(cudaGetLastError(), "hamcmc launch");
 }

@@ -476,6 +476,48 @@ def test_hamcmc_contiguous_metric_step_on_partial_window_raises():
     assert torch.equal(a.detach(), before)
 
 
+@pytest.mark.parametrize("d", [9, 52, 100, 300, 514, 900])
+def test_hamcmc_register_sliced_kernel_equals_generic_kernel(d, monkeypatch):
+    """hamcmc.cu has two kernels: the register-sliced one (d <= 1024, product-form vectors in shared memory) and the generic one
+    over the global work buffer (BODE_HAMCMC_GENERIC=1 forces it).  Same element ownership where both run 128 threads, float64 dot
+    products in both: 24 warm-up + metric steps from the same state and the same injected noise agree to 1e-6 of |theta| (bit-identical
+    for d > 64) and build the same number of curvature pairs.  d spans every instantiation."""
+    from bayesian_ode_b200.samplers import HAMCMC
+    P, memory = 33, 3
+    gen = torch.Generator().manual_seed(d)
+    A = torch.randn(P, d, d, generator=gen) / d ** 0.5
+    A = (A @ A.transpose(1, 2) + 0.5 * torch.eye(d)).cuda()
+    th0 = torch.randn(P, d, generator=gen).cuda()
+    xi = torch.randn(24, P, d, generator=gen)
+    out = {}
+    for generic in (0, 1):
+        if generic:
+            monkeypatch.setenv("BODE_HAMCMC_GENERIC", "1")
+        else:
+            monkeypatch.delenv("BODE_HAMCMC_GENERIC", raising=False)
+        th = torch.nn.Parameter(th0.clone())
+        smp = HAMCMC([th], memory=memory, lr0=2e-3, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3, H_gamma=1.0, trust_reg=1.0)
+        smp.check_finite = "deferred"                      # the reference's metric step can blow a chain up; both kernels must agree on it
+        traj = []
+        for i in range(24):
+            th.grad = torch.einsum("pij,pj->pi", A, th.detach())
+            lr = smp.get_lr(i)
+            if i < 2 * (memory + 1) - 1:
+                smp.step_without_metric(lr=lr, add_params=True, noise=xi[i])
+            else:
+                smp.step(lr=lr, noise=xi[i])
+            traj.append(th.detach().clone())
+        out[generic] = (torch.stack(traj), smp.n_pairs().clone())
+    a, b = out[0][0], out[1][0]
+    fin = torch.isfinite(a).all(dim=(0, 2))
+    assert torch.equal(fin, torch.isfinite(b).all(dim=(0, 2))) and int(fin.sum()) >= P // 2
+    assert torch.equal(out[0][1], out[1][1]) and int(out[0][1].max()) >= 1
+    if d > 64:
+        assert torch.equal(a[:, fin], b[:, fin])
+    else:
+        assert float((a[:, fin] - b[:, fin]).abs().max()) <= 1e-5 * float(b[:, fin].abs().max())
+
+
 def test_hamcmc_batched_chains_on_npde():
     """P chains on the flat theta buffer: sample() drives warm-up -> metric steps through the fused closure."""
     import bayesian_ode_b200 as bode
