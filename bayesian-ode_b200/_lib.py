@@ -56,6 +56,7 @@ SYMBOLS = {
     "bode_device_sm_count": (C.c_int, []),
     "bode_peak_kernel": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, _P]),
     "bode_stamp": (C.c_int, [_P, _P]),
+    "bode_npde_set_row_kernel": (C.c_int, [C.c_int32]),
     "bode_npde_scratch_floats": (C.c_size_t, [C.c_int32] * 6),
     "bode_npde_scratch_floats_m": (C.c_size_t, [C.c_int32] * 7),
     "bode_npde_odeint": (C.c_int, [C.POINTER(NpdeFieldStruct), C.POINTER(GridStruct), C.c_int32, C.c_int32, _P, C.c_int32, _P, _P]),

@@ -4,6 +4,12 @@
 #include <math.h>
 
 namespace bode {
+#define BODE_DECL_ROW(MY)                                                                                                   \
+  int launch_row_fwd_##MY(const NpdeKParams& prm, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st);           \
+  int launch_row_grad_##MY(const NpdeKParams& prm, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st);
+BODE_DECL_ROW(8)
+BODE_DECL_ROW(12)
+BODE_DECL_ROW(16)
 int launch_proj_W(const float* AT, const float* U, long long U_stride, int P, int m, float* W, cudaStream_t st);
 int launch_proj_back(const float* A, const float* Ksym, const float* U, long long U_stride, float* gU, long long gU_stride, float* loss,
                      float scale, int add_prior, int P, int m, cudaStream_t st);
@@ -37,6 +43,12 @@ static bool use_sep(const bode_npde_field* f) {
   return f->grid_mx == f->grid_my && f->grid_mx >= 3 && f->grid_mx <= 6 && f->grid_mx * f->grid_my == f->m;
 }
 static int gen_jpl(int m) { return m <= 32 ? 1 : (m <= 64 ? 2 : (m <= 128 ? 4 : 8)); }
+// Tensor grids beyond the one-thread separable kernels (7x7 .. 16x16): row-sliced separable field, 16 lanes per pair (npde_row.cuh)
+static int g_row_kernel = 1;
+static bool use_row(const bode_npde_field* f, int N) {
+  return g_row_kernel && !use_sep(f) && f->grid_mx >= 7 && f->grid_mx <= 16 && f->grid_my >= 7 && f->grid_my <= 16 &&
+         f->grid_mx * f->grid_my == f->m && N <= 10;          // RowField::MAX_THREADS = 160
+}
 
 static int stages_of(int method) { return method == BODE_RK4 ? 4 : (method == BODE_MIDPOINT ? 2 : 1); }
 
@@ -85,6 +97,38 @@ static int plan(NpdeKParams& prm, int G, int max_threads, dim3* grid, dim3* bloc
   *block = dim3(threads);
   *grid = dim3((prm.P + ppc - 1) / ppc);
   return BODE_OK;
+}
+
+// Row-sliced field: 16 lanes per pair; two particles per CTA when one particle would leave half a warp idle.
+static int plan_row(NpdeKParams& prm, const bode_npde_field* f, dim3* grid, dim3* block) {
+  const double LOG2E = 1.4426950408889634074;
+  const double c0 = sqrt(0.5 * LOG2E) / f->ell[0], c1 = sqrt(0.5 * LOG2E) / f->ell[1];
+  for (int a = 0; a < f->grid_mx; ++a) prm.gxs[a] = (float)(c0 * f->gx[a]);
+  for (int b = 0; b < f->grid_my; ++b) prm.gys[b] = (float)(c1 * f->gy[b]);
+  prm.gmx = f->grid_mx;
+  prm.gmy = f->grid_my;
+  int ppc = 1;
+  if (prm.N == 1) ppc = 2;
+  else if ((prm.N & 1) && 2 * prm.N * 16 <= 160) ppc = 2;
+  prm.ppc = ppc;
+  *block = dim3(((ppc * prm.N * 16 + 31) / 32) * 32);
+  *grid = dim3((prm.P + ppc - 1) / ppc);
+  return BODE_OK;
+}
+static int row_my(const bode_npde_field* f) { return f->grid_my <= 8 ? 8 : (f->grid_my <= 12 ? 12 : 16); }
+static int dispatch_row_fwd(const NpdeKParams& prm, int my, int method, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  switch (my) {
+    case 8: return launch_row_fwd_8(prm, method, grid, block, smem, st);
+    case 12: return launch_row_fwd_12(prm, method, grid, block, smem, st);
+    default: return launch_row_fwd_16(prm, method, grid, block, smem, st);
+  }
+}
+static int dispatch_row_grad(const NpdeKParams& prm, int my, int method, int inj, int adj, dim3 grid, dim3 block, size_t smem, cudaStream_t st) {
+  switch (my) {
+    case 8: return launch_row_grad_8(prm, method, inj, adj, grid, block, smem, st);
+    case 12: return launch_row_grad_12(prm, method, inj, adj, grid, block, smem, st);
+    default: return launch_row_grad_16(prm, method, inj, adj, grid, block, smem, st);
+  }
 }
 
 // Component-split kernels (npde_pair.cuh): ppc particles x N trajectories x 2 lanes per CTA.  ppc is sized so that the
@@ -225,10 +269,18 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
   }
   // general inducing locations (or a grid outside 3x3..6x6): lane-sliced kernel, one warp per (particle, trajectory)
   BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
-  int st_ = plan(prm, 32, 256, &grid, &block);
+  bool row = use_row(f, N);
+  int st_ = row ? plan_row(prm, f, &grid, &block) : plan(prm, 32, 256, &grid, &block);
   if (st_ != BODE_OK) return st_;
   prm.stage_off = (int)(((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2 + 3) & ~(size_t)3);
-  const size_t smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
+  size_t smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
+  if (row && smem > 48 * 1024) {          // two particles per CTA do not fit next to a long solver grid: the general-Z kernel
+    row = false;
+    st_ = plan(prm, 32, 256, &grid, &block);
+    if (st_ != BODE_OK) return st_;
+    prm.stage_off = (int)(((size_t)prm.ppc * 2 * prm.m * (2 + N) + (size_t)prm.ppc * N * 2 + 3) & ~(size_t)3);
+    smem = sizeof(float) * ((size_t)prm.stage_off + stage_floats(prm));
+  }
   BODE_REQUIRE(smem <= 48 * 1024, "solver grid too long to stage in shared memory (S=%d)", prm.S);
   // Large inducing sets: the projections W = A U and gU = A^T gW + Ksym U as panel GEMMs over all particles (npde_proj.cu) around
   // the solve -- three launches instead of one -- when the caller's scratch holds the P x 2m projected values behind the checkpoints
@@ -244,7 +296,8 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
     prm.split = 1;
     prm.add_prior = 0;
   }
-  switch (gen_jpl(f->m)) {
+  if (row) st_ = dispatch_row_grad(prm, row_my(f), method, inj, grad_mode, grid, block, smem, st);
+  else switch (gen_jpl(f->m)) {
     case 1: st_ = launch_gen_grad_1(prm, method, inj, grad_mode, grid, block, smem, st); break;
     case 2: st_ = launch_gen_grad_2(prm, method, inj, grad_mode, grid, block, smem, st); break;
     case 4: st_ = launch_gen_grad_4(prm, method, inj, grad_mode, grid, block, smem, st); break;
@@ -271,6 +324,12 @@ extern "C" int bode_npde_set_lanes_per_pair(int32_t lanes) {
 extern "C" int bode_npde_set_cta_limit(int32_t max_ctas) {
   const int old = g_cta_limit;
   g_cta_limit = max_ctas > 0 ? max_ctas : 0;
+  return old;
+}
+
+extern "C" int bode_npde_set_row_kernel(int32_t on) {
+  const int old = g_row_kernel;
+  g_row_kernel = on ? 1 : 0;
   return old;
 }
 
@@ -309,9 +368,11 @@ extern "C" int bode_npde_odeint(const bode_npde_field* f, const bode_grid* g, in
     return dispatch_fwd(prm, f->grid_mx, method, grid, block, smem, (cudaStream_t)stream);
   }
   BODE_REQUIRE(f->Z && f->m <= 256, "general-Z npde kernel needs Z and m <= 256 (got m=%d)", f->m);
-  st = plan(prm, 32, 256, &grid, &block);
+  const bool row = use_row(f, N);
+  st = row ? plan_row(prm, f, &grid, &block) : plan(prm, 32, 256, &grid, &block);
   if (st != BODE_OK) return st;
   const size_t smem = sizeof(float) * (size_t)prm.ppc * 2 * prm.m * 2;
+  if (row) return dispatch_row_fwd(prm, row_my(f), method, grid, block, smem, (cudaStream_t)stream);
   switch (gen_jpl(f->m)) {
     case 1: return launch_gen_fwd_1(prm, method, grid, block, smem, (cudaStream_t)stream);
     case 2: return launch_gen_fwd_2(prm, method, grid, block, smem, (cudaStream_t)stream);

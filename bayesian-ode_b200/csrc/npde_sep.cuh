@@ -20,6 +20,7 @@ struct NpdeKParams {
   float c0, c1;   // sqrt(log2(e)/2) / ell_d
   float k0, k1;   // 2 ln2 c_d     (d kappa / dx = -k * delta * kappa)
   float gxs[16], gys[16];  // c0*gx[a], c1*gy[b]
+  int gmx, gmy;            // grid size for the row-sliced field (npde_row.cuh)
   const float *U, *logsn, *A, *Ksym, *y0, *dt, *Y, *gout, *adj_dt, *Z;
   const float* AT;    // optional transpose of A (coalesced projection), may be null
   const float* Wpre;  // split mode (npde_proj.cu): W = A U precomputed for all particles [P][2m]; the epilogue then leaves sum_n gW in gU

@@ -7,8 +7,13 @@
 // RHS / VJP for one pair; G = Field::G lanes cooperate on one pair (G = 1 for the separable field).
 #pragma once
 #include "npde_sep.cuh"
+#include <type_traits>
 
 namespace bode {
+
+// optional Field::MIN_BLOCKS: resident CTAs per SM the register allocation must allow (second __launch_bounds__ argument)
+template <class F, class = void> struct MinBlocks { static constexpr int value = 1; };
+template <class F> struct MinBlocks<F, std::void_t<decltype(F::MIN_BLOCKS)>> { static constexpr int value = F::MIN_BLOCKS; };
 
 template <int METHOD> struct Stages { static constexpr int value = METHOD == BODE_RK4 ? 4 : (METHOD == BODE_MIDPOINT ? 2 : 1); };
 
@@ -229,7 +234,7 @@ __device__ __forceinline__ void SepField<MX, MY>::epilogue(const NpdeKParams& pr
 
 // ------------------------------------------------------------------ forward-only kernel: sol[T,P,N,2]
 template <class Field, int METHOD>
-__global__ void __launch_bounds__(Field::MAX_THREADS) npde_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
+__global__ void __launch_bounds__(Field::MAX_THREADS, MinBlocks<Field>::value) npde_fwd_kernel(const __grid_constant__ NpdeKParams prm) {
   extern __shared__ __align__(16) float smem[];
   constexpr int G = Field::G;
   Field::prologue(prm, smem);
@@ -255,7 +260,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_fwd_kernel(const __gr
 
 // ------------------------------------------------------------------ fused forward + closure + gradient kernel
 template <class Field, int METHOD, int INJ, int ADJ>
-__global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __grid_constant__ NpdeKParams prm) {
+__global__ void __launch_bounds__(Field::MAX_THREADS, MinBlocks<Field>::value) npde_grad_kernel(const __grid_constant__ NpdeKParams prm) {
   extern __shared__ __align__(16) float smem[];
   constexpr int G = Field::G;
   constexpr int STG = Stages<METHOD>::value;
@@ -275,6 +280,8 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
   const int pl = pairl / N, n = pairl % N;
   const int p = blockIdx.x * ppc + pl;
   const bool active = pl < ppc && p < prm.P;
+  // the lanes of this pair (a warp may hold an active and an inactive pair when G < 32)
+  const unsigned gmask = G >= 32 ? 0xffffffffu : (((1u << (G & 31)) - 1u) << (((tid & 31) / G) * G));
   float r2x = 0.f, r2y = 0.f;
   Field fld;
   fld.zero_grad();
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
     if (ADJ == BODE_GRAD_DISCRETE) {
       float2 yend = y;
       float2 ys[STG], yn[STG];
-      if (G > 1) __syncwarp();
+      if (G > 1) __syncwarp(gmask);
       if (prm.S > 0) load_stage_points<METHOD>(ys, ck + (long long)(prm.S - 1) * STG * stride, stride);
       for (int s = prm.S - 1; s >= 0; --s) {
         // software prefetch: the stage points of step s-1 travel from L2 while step s is differentiated
@@ -344,7 +351,7 @@ __global__ void __launch_bounds__(Field::MAX_THREADS) npde_grad_kernel(const __g
       }
     } else {
       // continuous adjoint, adjoint.py:57-95: restart from the stored forward value at every t[i]
-      if (G > 1) __syncwarp();
+      if (G > 1) __syncwarp(gmask);
       const float s_in = -prm.sign;
       {
         const float2 yT = ck[(long long)(prm.T - 1) * stride];

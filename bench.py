@@ -576,7 +576,7 @@ def run_b200(args, wl):
             ode_cfg = "as launched in the step: at most %d CTAs, timed alone" % (lib.bode_device_sm_count() - smp.side_sms)
         ode_flop = FLOP_PER_EVAL * STAGES * N * M * M * job.S * P_gpu
         kname = ("npde_pair_grad_kernel / npde_grad_kernel<Sep> (fused rk4 solve + closure + discrete adjoint; %s)" % ode_cfg) if M <= 6 else \
-            "npde_grad_kernel<GenField> (general-Z field, one warp per (particle, trajectory) pair, m = %d)" % (M * M)
+            "npde_grad_kernel<RowField> (row-sliced separable field, 16 lanes per (particle, trajectory) pair, m = %d)" % (M * M)
         extra = {}
         if M * M >= 64:
             # the closure is three launches here: W = A U and gU = A^T gW + Ksym U as panel GEMMs around the solve (csrc/npde_proj.cu);
@@ -679,7 +679,7 @@ def run_b200(args, wl):
     # DRAM traffic of the dominant kernel per launch: dram__bytes_read.sum + dram__bytes_write.sum of the committed
     # `ncu --set full` capture (profiles/traffic_r*.json, written by tools/ncu_summary.py); not measurable from here
     traffic = None
-    keys = {"npde_pair": "npde_pair_grad_kernel", "GenField": "npde_grad_kernel", "dopri5": "dopri5_grad_kernel", "sqdist": "gram2_kernel",
+    keys = {"npde_pair": "npde_pair_grad_kernel", "RowField": "npde_grad_kernel<RowField", "dopri5": "dopri5_grad_kernel", "sqdist": "gram2_kernel",
             "svgd phi": "phi2_kernel", "sampler_kernel": "sampler_kernel", "hamcmc": "hamcmc_kernel"}
     for tname in ("traffic_r02.json", "traffic_r01_final.json"):
         tpath = os.path.join(ROOT, "profiles", tname)

@@ -153,6 +153,10 @@ int bode_npde_set_lanes_per_pair(int32_t lanes);
  * position-only half of the SVGD interaction (bode_svgd_sqdist_staged + median), whose CTAs cannot share an SM with the solver's.
  * The solve is latency-bound at three warps per scheduler either way.  0 = every SM.  Returns the previous setting. */
 int bode_npde_set_cta_limit(int32_t max_ctas);
+/* Tensor grids of 7x7 .. 16x16 inducing points run the row-sliced separable kernels (csrc/npde_row.cuh: Mx + My exponentials per
+ * evaluation, 16 lanes per pair) in the fixed-step entry points; 0 sends them through the general-Z kernels instead (what
+ * non-grid Z always uses) -- the parity tests compare the two.  Returns the previous setting. */
+int bode_npde_set_row_kernel(int32_t on);
 size_t bode_npde_scratch_floats(int32_t P, int32_t N, int32_t S, int32_t T, int32_t method, int32_t grad_mode);
 /* The same plus P x 2m floats for m >= 64 inducing points: with that much scratch (and bode_npde_field.AT set) the gradient entry
  * points run the projections W = A U and gU = A^T gW + Ksym U (gp.py:70, 350) as panel GEMMs over all particles around the solve

@@ -264,3 +264,58 @@ def test_large_m_split_projection_matches_fused_kernel(M):
     for a, b in zip(out[True], out[False]):
         assert a.shape == b.shape and bool(torch.isfinite(a).all())
         assert relerr(a.double().cpu().numpy(), b.double().cpu().numpy()) < 2e-6
+
+
+@pytest.mark.parametrize("Mx,My,N", [(16, 16, 5), (8, 8, 4), (7, 9, 1), (12, 10, 3)])
+def test_row_sliced_grid_kernels_match_general_Z_kernels(Mx, My, N):
+    """Tensor grids of 7x7 .. 16x16 inducing points take the row-sliced separable kernels (csrc/npde_row.cuh: 16 lanes per pair,
+    Mx + My exponentials per evaluation); bode_npde_set_row_kernel(0) sends the same field through the general-Z kernels, which
+    the oracle tests above pin.  Every method, both gradient definitions, odeint + autograd, P = 7 (ragged last CTA when two
+    particles share one), square and non-square grids, every columns-per-lane instantiation (8 / 12 / 16)."""
+    import bayesian_ode_b200 as bode
+    from bayesian_ode_b200 import _lib
+    g = load_golden("npde_m5")
+    lib = _lib.load()
+    rng = np.random.default_rng(100 * Mx + My)
+    lo, hi = g["Y"].min(axis=(0, 1)), g["Y"].max(axis=(0, 1))
+    gx, gy = np.linspace(lo[0], hi[0], Mx), np.linspace(lo[1], hi[1], My)
+    Z = np.stack([np.repeat(gx, My), np.tile(gy, Mx)], 1)
+    ell = 0.9 * max(gx[1] - gx[0], gy[1] - gy[0])          # well-conditioned Kzz: the two kernels differ by fp32 rounding only
+    P = 7
+    U = 0.3 * rng.standard_normal((P, Mx * My, 2))
+    f = bode.NPDEField(torch.from_numpy(U), torch.from_numpy(Z), 1.0, float(ell), 0.1, stable_solve=True)
+    assert f.grid_axes is not None and len(f.grid_axes[0]) == Mx and len(f.grid_axes[1]) == My
+    x0 = torch.from_numpy(g["x0"][:N])
+    t = torch.from_numpy(g["t"])
+    Y = torch.from_numpy(g["Y"][:N])
+    out = {}
+    for rowk in (1, 0):
+        old = lib.bode_npde_set_row_kernel(rowk)
+        try:
+            res = {}
+            for method in ("euler", "midpoint", "rk4"):
+                with torch.no_grad():
+                    res["sol_" + method] = bode.odeint(f, x0, t, method=method).clone()
+                for mode in ("discrete", "adjoint"):
+                    post = bode.NPDEPosterior(f, x0, t, Y, method=method, grad_mode=mode)
+                    loss, gU, gl = post.loss_and_grad_()
+                    res[f"loss_{method}_{mode}"], res[f"gU_{method}_{mode}"], res[f"gl_{method}_{mode}"] = loss.clone(), gU.clone(), gl.clone()
+            for p in f.parameters():
+                p.grad = None
+            sol = bode.odeint(f, x0, t, method="rk4")
+            (sol ** 2).sum().backward()
+            res["autograd_gU"] = f.U.grad.clone()
+            f.U.grad = None
+        finally:
+            lib.bode_npde_set_row_kernel(old)
+        out[rowk] = res
+    for k in out[1]:
+        a, b = out[1][k].double().cpu().numpy(), out[0][k].double().cpu().numpy()
+        assert np.isfinite(a).all(), k
+        if k.startswith("gU") or k.startswith("autograd"):
+            # gU = A^T gW: A = Kzz^-1 L has entries ~1e3 on the 16 x 16 grid, which amplifies the fp32 rounding of the two
+            # summation orders (the oracle test of this grid allows 1e-3 for the same reason)
+            err, tol = (np.abs(a - b).max(axis=(1, 2)) / np.abs(b).max(axis=(1, 2))).max(), 1e-4
+        else:
+            err, tol = relerr(a, b), 2e-5
+        assert err < tol, (k, err)

@@ -2,7 +2,7 @@ import sys, os, numpy as np, torch
 sys.path.insert(0, "/root/repo")
 import bayesian_ode_b200 as bode
 from bayesian_ode_b200 import problems
-for M, ell in ((16, 0.35), (5, 0.75)):
+for M, ell in ((16, 0.35),):
     for T in (2, 11, 40):
         data = problems.make_dataset("VDP", seed=0, N=5, R=3.0, T=T, t_end=7.0 * (T - 1) / 39.0, noise=0.1)
         Z = problems.inducing_grid(data["Y"], M)
