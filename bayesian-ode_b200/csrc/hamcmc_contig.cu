@@ -12,7 +12,9 @@
 // Parity: tests/test_samplers_gpu.py::test_hamcmc_contiguous_variants_match_reference_runs (reference runs of all three, B200).
 // A metric step before the window is full (the reference indexes an empty list there and raises) changes nothing and sets
 // status bit 2; the host raises RuntimeError.
+#include <cstdlib>
 #include "common.cuh"
+#include "hamcmc_sliced.cuh"
 
 namespace bode {
 
@@ -73,7 +75,7 @@ __device__ __forceinline__ float hc_philox_normal(unsigned long long seed, unsig
 
 // Every thread owns the elements e = threadIdx.x + k blockDim.x of every length-d vector: elementwise updates need no barrier,
 // only the dot products synchronise the CTA.
-__global__ void __launch_bounds__(128) hamcmc_contig_kernel(const HamcmcContigArgs a) {
+__global__ void __launch_bounds__(128) hamcmc_contig_generic_kernel(const HamcmcContigArgs a) {
   __shared__ double red[8];
   const int p = blockIdx.x, d = a.d, M = a.M;
   float* ht = a.hist_theta + (long long)p * M * d;
@@ -214,6 +216,136 @@ __global__ void __launch_bounds__(128) hamcmc_contig_kernel(const HamcmcContigAr
   if (bad && a.status) atomicOr(a.status, 1);
 }
 
+
+// ------------------------------------------------------------------ register-sliced kernel (d <= NT * EPT), see hamcmc.cu
+template <int EPT, int NT>
+__global__ void __launch_bounds__(NT) hamcmc_contig_kernel(const HamcmcContigArgs a) {
+  __shared__ double red[2 * (NT / 32)];
+  extern __shared__ __align__(16) float wsm[];          // u, v, p, q: [4][M-1][d]
+  const int p = blockIdx.x, d = a.d, M = a.M;
+  float* ht = a.hist_theta + (long long)p * M * d;
+  float* hg = a.hist_grad + (long long)p * M * d;
+  float* ps = a.pair_s + (long long)p * (M - 1) * d;
+  float* py = a.pair_y + (long long)p * (M - 1) * d;
+  int* meta = a.meta + 4 * p;
+  float* th = a.theta + (long long)p * a.ld_theta;
+  const float* g = a.grad + (long long)p * a.ld_grad;
+  const float nscale = rsqrtf(0.5f * a.lr);
+  Sliced<EPT, NT> sl{(int)threadIdx.x, d, red, 0};
+  const int tid = threadIdx.x;
+  int bad = 0;
+  auto noise_at = [&](int e) -> float {
+    const float x = a.xi ? a.xi[(long long)p * d + e] : hc_philox_normal(a.seed, (unsigned)(p * d + e), a.step);
+    return x * nscale;
+  };
+  const int n_hist0 = meta[0], head = meta[1], K0 = meta[2], phead = meta[3];
+  float gv[EPT];
+  sl.load(gv, g);
+
+  if (a.mode == 0) {
+    // ---------------- step_without_metric (:1180-1203) + _add_to_memory
+    int n_hist = n_hist0, K = K0;
+    const bool store = a.update_metric && n_hist < M;
+    float tv[EPT];
+    sl.load(tv, th);
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) {
+      if (!sl.ok(i)) continue;
+      float t = tv[i];
+      bad |= !(fabsf(t) <= 3.4028234e38f);
+      t = fmaf(-a.lr, gv[i], t);
+      if (a.add_noise) t = fmaf(-a.lr, noise_at(tid + NT * i), t);
+      tv[i] = t;
+    }
+    sl.store(th, tv);
+    if (store) {
+      sl.store(ht + (long long)n_hist * d, tv);          // theta AFTER the update, gradient from BEFORE it
+      sl.store(hg + (long long)n_hist * d, gv);
+      ++n_hist;
+    }
+    if (store && n_hist == M) {
+      // the window just became full: contiguous pairs, no curvature filter (own elements only: no barrier needed)
+      const int first = a.variant == 2 ? 1 : 0;
+      K = a.variant == 4 ? M - 1 : M - 2;
+      for (int i = 0; i < K; ++i) {
+        float t1[EPT], t0[EPT], g1[EPT], g0[EPT], sv[EPT], yv[EPT];
+        sl.load(t1, ht + (long long)(first + i + 1) * d);
+        sl.load(t0, ht + (long long)(first + i) * d);
+        sl.load(g1, hg + (long long)(first + i + 1) * d);
+        sl.load(g0, hg + (long long)(first + i) * d);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          sv[k] = t1[k] - t0[k];
+          yv[k] = g1[k] - g0[k] + a.trust_reg * sv[k];
+        }
+        sl.store(ps + (long long)i * d, sv);
+        sl.store(py + (long long)i * d, yv);
+      }
+    }
+    __syncthreads();                                 // every thread has read meta
+    if (tid == 0) { meta[0] = n_hist; meta[1] = 0; meta[2] = K; meta[3] = 0; }
+  } else {
+    // ---------------- metric step (:1205-1238 / :1364-1397)
+    if (n_hist0 < M) {                                                    // window not full: nothing to build the metric from
+      if (tid == 0 && a.status) atomicOr(a.status, 2);
+      return;
+    }
+    const int K = K0;
+    const int newest = (head + M - 1) % M, prev = (head + M - 2) % M;
+    const float S0 = rsqrtf(1.f / a.H_gamma);
+    float bv[EPT], tn[EPT], gn[EPT], tp[EPT], gp[EPT], z[EPT], z2[EPT];
+    sl.load(bv, ht + (long long)(a.variant == 2 ? head : newest) * d);   // requested now, used after the recursion
+    sl.load(tn, ht + (long long)newest * d);
+    sl.load(gn, hg + (long long)newest * d);
+    if (a.variant == 3) {
+      sl.load(tp, ht + (long long)prev * d);
+      sl.load(gp, hg + (long long)prev * d);
+    }
+#pragma unroll
+    for (int i = 0; i < EPT; ++i) z2[i] = sl.ok(i) ? S0 * noise_at(tid + NT * i) : 0.f;
+    sliced_metric(sl, ps, py, K, phead, d, M, wsm, a.H_gamma, gv, z, z2);
+    // theta_new = base - lr Hg - lr Sn; the pair that joins the window; then the rings move (own elements only)
+    float tv[EPT], sv[EPT], yv[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      float t = fmaf(-a.lr, z[k], bv[k]);
+      if (a.add_noise) t = fmaf(-a.lr, z2[k], t);
+      if (sl.ok(k)) bad |= !(fabsf(t) <= 3.4028234e38f);
+      if (a.variant == 3) {                                              // between the two entries BEFORE the new one
+        sv[k] = tn[k] - tp[k];
+        yv[k] = gn[k] - gp[k] + a.trust_reg * sv[k];
+      } else {                                                           // between the newest stored entry and the new one
+        sv[k] = t - tn[k];
+        yv[k] = gv[k] - gn[k] + a.trust_reg * sv[k];
+      }
+      tv[k] = t;
+    }
+    sl.store(th, tv);
+    if (K > 0) {                                                         // append + pop(0): the oldest pair is replaced
+      sl.store(ps + (long long)phead * d, sv);
+      sl.store(py + (long long)phead * d, yv);
+    }
+    sl.store(ht + (long long)head * d, tv);                              // history: append new, pop oldest
+    sl.store(hg + (long long)head * d, gv);
+    __syncthreads();                                                     // every thread has read meta
+    if (tid == 0) { meta[1] = (head + 1) % M; meta[3] = K > 0 ? (phead + 1) % K : 0; }
+  }
+  if (bad && a.status) atomicOr(a.status, 1);
+}
+
+template <int EPT, int NT>
+static int launch_contig_sliced(const HamcmcContigArgs& a, size_t smem, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    int e = check_cuda(cudaFuncSetAttribute(hamcmc_contig_kernel<EPT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024),
+                       "hamcmc contiguous-variant smem attr");
+    if (e != BODE_OK) return e;
+    attr_set = true;
+  }
+  hamcmc_contig_kernel<EPT, NT><<<a.P, NT, smem, st>>>(a);
+  return check_cuda(cudaGetLastError(), "hamcmc contiguous-variant launch");
+}
+
 }  // namespace bode
 
 using namespace bode;
@@ -240,6 +372,17 @@ extern "C" int bode_hamcmc_contig_step(int32_t variant, int32_t P, int32_t d, in
   a.pair_y = pair_y; a.work = work; a.meta = meta; a.theta = theta; a.ld_theta = ld_theta; a.grad = grad; a.ld_grad = ld_grad;
   a.xi = xi; a.lr = lr; a.H_gamma = H_gamma; a.trust_reg = trust_reg; a.mode = metric_step ? 1 : 0; a.update_metric = update_metric;
   a.add_noise = add_noise; a.seed = seed; a.step = step; a.status = status;
-  hamcmc_contig_kernel<<<P, 128, 0, (cudaStream_t)stream>>>(a);
+  const size_t wbytes = sizeof(float) * (size_t)(4 * memory) * d;
+  const cudaStream_t st = (cudaStream_t)stream;
+  if (wbytes <= 100 * 1024 && !getenv("BODE_HAMCMC_GENERIC")) {          // as in bode_hamcmc_step
+    if (d <= 32) return launch_contig_sliced<1, 32>(a, wbytes, st);
+    if (d <= 64) return launch_contig_sliced<1, 64>(a, wbytes, st);
+    if (d <= 128) return launch_contig_sliced<1, 128>(a, wbytes, st);
+    if (d <= 256) return launch_contig_sliced<2, 128>(a, wbytes, st);
+    if (d <= 384) return launch_contig_sliced<3, 128>(a, wbytes, st);
+    if (d <= 640) return launch_contig_sliced<5, 128>(a, wbytes, st);
+    if (d <= 1024) return launch_contig_sliced<8, 128>(a, wbytes, st);
+  }
+  hamcmc_contig_generic_kernel<<<P, 128, 0, st>>>(a);
   return check_cuda(cudaGetLastError(), "hamcmc contiguous-variant launch");
 }

@@ -7,8 +7,8 @@
 // pairs per warp: lane a holds row a of W (My float2 values, as packed pairs for FFMA2) and of the gradient accumulator, computes
 // kx_a and -- acting as column index b = a -- ky_b and ky_b (u1 - gy_b); the column factors are exchanged through a double-buffered
 // shared-memory line (one store, one group barrier, My/4 vector loads, instead of My shuffles) and the sums over a are completed
-// with a 4-round butterfly inside the half-warp.  Per lane and evaluation (My = 16): ~46 instructions forward, ~125 reverse, for
-// two pairs; the general-Z kernel needs 68 / 120-140 for one.
+// with a 4-round butterfly inside the half-warp.  Per lane and evaluation (My = 16): ~95 SASS instructions forward and ~120 reverse
+// for TWO pairs; the general-Z kernel needs 68 / 120-140 for one.
 //   f(x)        = sum_a kx_a sum_b ky_b W_ab
 //   (J^T a)_0   = -k0 sum_a kx_a dx_a sum_b ky_b (a . W_ab)          dx_a = c0 (x0 - gx_a)
 //   (J^T a)_1   = -k1 sum_a kx_a      sum_b ky_b dy_b (a . W_ab)     dy_b = c1 (x1 - gy_b)
@@ -117,8 +117,9 @@ struct RowField {
     const float4* kp = reinterpret_cast<const float4*>(xb + (threadIdx.x & ~15));
     const float4* dp = reinterpret_cast<const float4*>(xb + 256 + (threadIdx.x & ~15));
     const f32x2 kxaw = pk(kx * (av.x * wg), kx * (av.y * wg));
-    float S1[2] = {0.f, 0.f}, S2[2] = {0.f, 0.f};                  // two independent chains each
-    f32x2 q[2] = {pk(0.f, 0.f), pk(0.f, 0.f)};
+    // sum_b ky_b (a . W_ab) = a . q with q = sum_b ky_b W_ab (the forward contraction), likewise r = sum_b ky_b dy_b W_ab:
+    // three FFMA2 per inducing point (q, r, gW) instead of five scalar instructions
+    f32x2 q[2] = {pk(0.f, 0.f), pk(0.f, 0.f)}, r[2] = {pk(0.f, 0.f), pk(0.f, 0.f)};          // two independent chains each
 #pragma unroll
     for (int b4 = 0; b4 < MY / 4; ++b4) {
       const float4 k4 = kp[b4], d4 = dp[b4];
@@ -126,22 +127,20 @@ struct RowField {
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int b = 4 * b4 + i;
-        float wx, wy;
-        upk(W[b], wx, wy);
-        const float aW = fmaf(av.y, wy, av.x * wx);
-        S1[i & 1] = fmaf(kk[i], aW, S1[i & 1]);
-        S2[i & 1] = fmaf(kd[i], aW, S2[i & 1]);
+        q[i & 1] = fma2x(W[b], pk(kk[i], kk[i]), q[i & 1]);
+        r[i & 1] = fma2x(W[b], pk(kd[i], kd[i]), r[i & 1]);
         gW[b] = fma2x(kxaw, pk(kk[i], kk[i]), gW[b]);
-        if (WITH_F) q[i & 1] = fma2x(W[b], pk(kk[i], kk[i]), q[i & 1]);
       }
     }
-    if (WITH_F) {
-      float qx, qy, rx, ry;
-      upk(q[0], qx, qy);
-      upk(q[1], rx, ry);
-      *fout = f2(gsum(kx * (qx + rx)), gsum(kx * (qy + ry)));
-    }
-    return f2(-prm.k0 * gsum(kx * dx * (S1[0] + S1[1])), -prm.k1 * gsum(kx * (S2[0] + S2[1])));
+    float qx, qy, q1x, q1y, rx, ry, r1x, r1y;
+    upk(q[0], qx, qy);
+    upk(q[1], q1x, q1y);
+    upk(r[0], rx, ry);
+    upk(r[1], r1x, r1y);
+    qx += q1x; qy += q1y; rx += r1x; ry += r1y;
+    if (WITH_F) *fout = f2(gsum(kx * qx), gsum(kx * qy));
+    const float S1 = fmaf(av.y, qy, av.x * qx), S2 = fmaf(av.y, ry, av.x * rx);
+    return f2(-prm.k0 * gsum(kx * dx * S1), -prm.k1 * gsum(kx * S2));
   }
 };
 

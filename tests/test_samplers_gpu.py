@@ -518,6 +518,49 @@ def test_hamcmc_register_sliced_kernel_equals_generic_kernel(d, monkeypatch):
         assert float((a[:, fin] - b[:, fin]).abs().max()) <= 1e-5 * float(b[:, fin].abs().max())
 
 
+@pytest.mark.parametrize("variant", [2, 3, 4])
+@pytest.mark.parametrize("d", [20, 130, 514])
+def test_hamcmc_contiguous_register_sliced_kernel_equals_generic_kernel(variant, d, monkeypatch):
+    """hamcmc_contig.cu: register-sliced kernel vs the generic one (BODE_HAMCMC_GENERIC=1) for HAMCMC2 / 3 / 4 -- window fill, the
+    contiguous pairs, ten metric steps, rings wrapping around; same state, same injected noise."""
+    from bayesian_ode_b200 import samplers
+    P, memory = 19, 3
+    M = memory + 1
+    gen = torch.Generator().manual_seed(10 * d + variant)
+    A = torch.randn(P, d, d, generator=gen) / d ** 0.5
+    A = (A @ A.transpose(1, 2) + 0.5 * torch.eye(d)).cuda()
+    th0 = torch.randn(P, d, generator=gen).cuda()
+    xi = torch.randn(M + 10, P, d, generator=gen)
+    out = {}
+    for generic in (0, 1):
+        if generic:
+            monkeypatch.setenv("BODE_HAMCMC_GENERIC", "1")
+        else:
+            monkeypatch.delenv("BODE_HAMCMC_GENERIC", raising=False)
+        th = torch.nn.Parameter(th0.clone())
+        smp = getattr(samplers, "HAMCMC%d" % variant)([th], memory=memory, lr0=2e-3, lr_gamma=0.55, lr_t0=100, lr_alpha=0.3,
+                                                       H_gamma=1.0, trust_reg=1.0)
+        smp.check_finite = "deferred"
+        traj = []
+        for i in range(M + 10):
+            th.grad = torch.einsum("pij,pj->pi", A, th.detach())
+            lr = smp.get_lr(i)
+            if i < M:
+                smp.step_without_metric(lr=lr, noise=xi[i])
+            else:
+                smp.step(lr=lr, noise=xi[i])
+            traj.append(th.detach().clone())
+        out[generic] = (torch.stack(traj), smp.n_pairs().clone())
+    a, b = out[0][0], out[1][0]
+    fin = torch.isfinite(a).all(dim=(0, 2))
+    assert torch.equal(fin, torch.isfinite(b).all(dim=(0, 2))) and int(fin.sum()) >= P // 2
+    assert torch.equal(out[0][1], out[1][1])
+    if d > 64:
+        assert torch.equal(a[:, fin], b[:, fin])
+    else:
+        assert float((a[:, fin] - b[:, fin]).abs().max()) <= 1e-5 * float(b[:, fin].abs().max())
+
+
 def test_hamcmc_batched_chains_on_npde():
     """P chains on the flat theta buffer: sample() drives warm-up -> metric steps through the fused closure."""
     import bayesian_ode_b200 as bode
