@@ -97,7 +97,9 @@ class SGLD(_LangevinBase):
         ctl = self.ctl() if use_ctl else None
         for k, (p, g) in enumerate(self._tensors_for_launch()):
             xi = _flat_noise(noise, self, k, p)
-            _lib.check(lib.bode_sgld_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(xi), p.numel(), float(group["lr"]),
+            # with use_ctl the kernel takes the step size from the device schedule (schedule_()): no host value is needed
+            _lib.check(lib.bode_sgld_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(xi), p.numel(),
+                                          float(group.get("lr", 0.0) if use_ctl else group["lr"]),
                                           int(bool(group["add_noise"])), self.seed + k, self._step_index,
                                           _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
@@ -317,7 +319,7 @@ class pSGLD(_LangevinBase):
                 self._V[key] = torch.zeros_like(p)          # langevin.py:474-475
             xi = _flat_noise(noise, self, k, p)
             _lib.check(lib.bode_psgld_step(_lib.ptr(p), _lib.ptr(g), _lib.ptr(self._V[key]), _lib.ptr(xi), p.numel(),
-                                           float(group["lr"]), float(group["alpha"]), float(group["lambda_"]),
+                                           float(group.get("lr", 0.0) if use_ctl else group["lr"]), float(group["alpha"]), float(group["lambda_"]),
                                            int(bool(group["add_noise"])), self.seed + k, self._step_index,
                                            _lib.ptr(self._status), _lib.ptr(ctl), _lib.stream_ptr()))
         self._after_step()
