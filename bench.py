@@ -696,26 +696,118 @@ def run_b200(args, wl):
                                  if dom["bound"] == "fp32" else (("half of %s bf16_tflops (tf32 dense rate); algorithmic flops, "
                                                                   "the kernels issue 2 - 3 MMA passes per product" % peak_src) if dom["bound"] == "tensor" else peak_src)))
 
-    # ---- end to end through the public API with HOST buffers: H2D of this step's observations, step, D2H of the loss
-    loss_host = torch.empty(P_gpu, dtype=torch.float32).pin_memory()
-
-    def e2e_step():
-        post.set_data(x0=job.x0_host, Y=job.obs_host)
+    # ---- the same steps back to back (no L2 flush, no host wait in between): what a sampling loop sustains, launch gaps included
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nb = min(args.steps, 200) if not job.dopri5 else min(args.steps, 5)
+    a.record()
+    for _ in range(nb):
         run()
-        loss_host.copy_(post.loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-    for _ in range(3):
-        e2e_step()
+    b.record()
+    barrier()
+    b2b_ms = a.elapsed_time(b) / nb
+
+    # ---- end to end through the public API with HOST buffers.  Every step copies ITS observations from pinned host memory (H2D),
+    # runs, and copies its per-particle loss back (D2H), written the way a sampling loop with a data loader is written so that the
+    # GPU never waits for a copy engine or for the host:
+    #   * the observations of step i+1 travel on a copy stream into the second of two device buffers while step i runs (the
+    #     posterior is pointed at buffer i % 2: two captured graphs where the step replays as a CUDA graph);
+    #   * the loss of step i is parked in a device staging buffer by the step and copied to one of two pinned host buffers on the
+    #     copy stream; the host READS it one step later (loss_ready event), the last one inside the timed region.
+    cs = torch.cuda.Stream()
+    main = torch.cuda.current_stream()
+    res_x0, res_Y = post.x0, post.Y
+    stage_in = [(torch.empty_like(post.x0), torch.empty_like(post.Y)) for _ in range(2)]
+    stage_loss = [torch.empty_like(post.loss) for _ in range(2)]
+    loss_host = [torch.empty(P_gpu, dtype=torch.float32).pin_memory() for _ in range(2)]
+    h2d_done = [torch.cuda.Event() for _ in range(2)]
+    step_done = [torch.cuda.Event() for _ in range(2)]
+    loss_ready = [torch.cuda.Event() for _ in range(2)]
+
+    def e2e_body(k):
+        post.x0, post.Y = stage_in[k]
+        job.step()
+        stage_loss[k].copy_(post.loss)
+
+    e2e_graphs = None
+    if use_graph:
+        try:
+            gs = []
+            for k in range(2):
+                for t_, h_ in zip(stage_in[k], (job.x0_host, job.obs_host)):
+                    t_.copy_(h_)
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2):
+                    e2e_body(k)
+                gs.append(g2)
+            e2e_graphs = gs
+        except Exception as e:
+            print("e2e graph capture failed (%s); the e2e steps launch eagerly" % str(e).splitlines()[0], file=sys.stderr)
+            torch.cuda.synchronize()
+    if world > 1:
+        flag = torch.tensor([int(e2e_graphs is not None)], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            e2e_graphs = None
+    host_sum = [0.0]
+
+    def issue_h2d(i):                                      # observations of step i -> device buffer i % 2, on the copy stream
+        k = i & 1
+        cs.wait_event(step_done[k])                        # step i-2 has finished reading that buffer
+        with torch.cuda.stream(cs):
+            stage_in[k][0].copy_(job.x0_host, non_blocking=True)
+            stage_in[k][1].copy_(job.obs_host, non_blocking=True)
+            h2d_done[k].record(cs)
+
+    def consume(i):                                        # the host-side read of step i's result
+        loss_ready[i & 1].synchronize()
+        host_sum[0] += float(loss_host[i & 1][0])
+
+    def e2e_step(i, last):
+        k = i & 1
+        if not last:
+            issue_h2d(i + 1)
+        main.wait_event(h2d_done[k])
+        if e2e_graphs is not None:
+            e2e_graphs[k].replay()
+        else:
+            e2e_body(k)
+        step_done[k].record(main)
+        cs.wait_event(step_done[k])
+        with torch.cuda.stream(cs):
+            loss_host[k].copy_(stage_loss[k], non_blocking=True)
+            loss_ready[k].record(cs)
+        if i > 0:
+            consume(i - 1)
+
+    def e2e_run(n):
+        for k in range(2):
+            step_done[k].record(main)
+        issue_h2d(0)
+        for i in range(n):
+            e2e_step(i, i == n - 1)
+        consume(n - 1)                                     # the last result has reached the host
+        main.wait_stream(cs)
+
+    e2e_run(3)
     barrier()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_units = 0.0
     a.record()
-    for _ in range(args.steps):
-        e2e_step()
-        if job.dopri5:
+    if job.dopri5:
+        for k in range(2):
+            step_done[k].record(main)
+        issue_h2d(0)
+        for i in range(args.steps):
+            e2e_step(i, i == args.steps - 1)
             e2e_units += job.units_per_step()
+        consume(args.steps - 1)
+        main.wait_stream(cs)
+    else:
+        e2e_run(args.steps)
     b.record()
     barrier()
+    post.x0, post.Y = res_x0, res_Y
     if not job.dopri5:
         e2e_units = job.units_per_step() * args.steps
     e2e_ms = a.elapsed_time(b)
@@ -727,7 +819,10 @@ def run_b200(args, wl):
         e2e_ms, e2e_units = float(mx[0].item()), float(tt[1].item())
     e2e = dict(value=e2e_units / (e2e_ms * 1e-3), unit="particle*RK-steps/s",
                h2d_bytes_per_step=int(job.x0_host.numel() * 4 + job.obs_host.numel() * 4), d2h_bytes_per_step=int(P_gpu * 4),
-               ms_per_step=e2e_ms / args.steps)
+               ms_per_step=e2e_ms / args.steps, cuda_graph=e2e_graphs is not None,
+               pipeline="observations of step i+1 copied (H2D, copy stream, second device buffer) while step i runs; loss of step i "
+                        "copied D2H on the copy stream and read on the host one step later; first H2D and last read inside the timed region; "
+                        "no L2 flush between e2e steps (value / ms_per_step are the flushed per-step figures)")
     job.final_checks()
 
     # ---- N > 1: correctness of the sharded interaction, and BASELINE config 3 as written (4096 particles in total)
@@ -784,7 +879,7 @@ def run_b200(args, wl):
         "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg,
         "roofline": roofline, "kernels": kernels, "peaks": peaks,
         "cpu_baseline": cb, "e2e": e2e, "gpu_launches": launches * args.steps, "clocks": clk_main,
-        "wall_s_timed_region": t_wall_main, "check": "ok", "finite_chain_fraction": finite_frac,
+        "wall_s_timed_region": t_wall_main, "back_to_back_ms_per_step": b2b_ms, "check": "ok", "finite_chain_fraction": finite_frac,
     }
     if median_fallback_ms is not None:
         line["median_fallback_ms"] = median_fallback_ms
