@@ -158,21 +158,24 @@ class _MlpOdeint(torch.autograd.Function):
         fs = field.c_struct()
         gs = _grid_struct(g, False)
         _lib.check(lib.bode_mlp_odeint(fs, gs, method, N, _lib.ptr(y0), int(batched), _lib.ptr(sol), _lib.stream_ptr()))
+        # the parameters AS THEY ARE NOW: the sampler kernels update theta through raw pointers (no autograd version bump), so a
+        # backward() after an in-place update would otherwise differentiate a different solve
+        theta0 = field.theta.detach().clone() if any(ctx.needs_input_grad) else None
         ctx.save_for_backward(y0)
-        ctx.misc = (field, g, method, grad_mode, batched, N)
+        ctx.misc = (field, g, method, grad_mode, batched, N, theta0)
         return sol
 
     @staticmethod
     def backward(ctx, gout):
         (y0,) = ctx.saved_tensors
-        field, g, method, grad_mode, batched, N = ctx.misc
+        field, g, method, grad_mode, batched, N, theta0 = ctx.misc
         lib = _lib.load()
         gout = gout.to(torch.float32).contiguous()
         gth = torch.empty((field.P, field.d), dtype=torch.float32, device=y0.device)
         gy0 = torch.empty((field.P, N, 2), dtype=torch.float32, device=y0.device)
         nsc = lib.bode_npde_scratch_floats(field.P, N, g.S, g.T, method, grad_mode)
         sc = _scratch(y0.device, nsc)
-        fs = field.c_struct()
+        fs = field.c_struct(theta0)
         gs = _grid_struct(g, grad_mode == _lib.GRAD_ADJOINT)
         _lib.check(lib.bode_mlp_odeint_backward(fs, gs, method, grad_mode, N, _lib.ptr(y0), int(batched), _lib.ptr(gout),
                                                 _lib.ptr(gth), field.d, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), _lib.stream_ptr()))
@@ -275,13 +278,17 @@ class _Dopri5Odeint(torch.autograd.Function):
         _lib.check(st)
         dopri5_check(cfg["stats"])
         ctx.save_for_backward(y0c)
-        ctx.misc = (func, cfg)
+        # forward-time parameters for the backward re-solve (see _MlpOdeint.forward)
+        p0 = None
+        if any(ctx.needs_input_grad):
+            p0 = (func.U if isinstance(func, NPDEField) else func.theta).detach().clone()
+        ctx.misc = (func, cfg, p0)
         return sol
 
     @staticmethod
     def backward(ctx, gout):
         (y0c,) = ctx.saved_tensors
-        func, cfg = ctx.misc
+        func, cfg, p0 = ctx.misc
         lib = _lib.load()
         T, N = cfg["T"], cfg["N"]
         gout = gout.to(torch.float32).contiguous()
@@ -290,13 +297,13 @@ class _Dopri5Odeint(torch.autograd.Function):
         sc = _scratch(y0c.device, nsc)
         if isinstance(func, NPDEField):
             g = torch.empty((func.P, func.m, 2), dtype=torch.float32, device=y0c.device)
-            st = lib.bode_npde_dopri5_backward(func.c_struct(func.U.detach()), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]),
+            st = lib.bode_npde_dopri5_backward(func.c_struct(p0), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]),
                                                _lib.ptr(gout), _lib.ptr(g), 2 * func.m, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(),
                                                DOPRI5_MAX_REC_STEPS, _lib.stream_ptr())
             grads = (g,)
         else:
             g = torch.empty((func.P, func.d), dtype=torch.float32, device=y0c.device)
-            st = lib.bode_mlp_dopri5_backward(func.c_struct(), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]), _lib.ptr(gout),
+            st = lib.bode_mlp_dopri5_backward(func.c_struct(p0), cfg["o"], T, cfg["sign"], N, _lib.ptr(y0c), int(cfg["batched"]), _lib.ptr(gout),
                                               _lib.ptr(g), func.d, _lib.ptr(gy0), _lib.ptr(sc), sc.numel(), DOPRI5_MAX_REC_STEPS,
                                               _lib.stream_ptr())
             grads = tuple(g[:, o:o + n].view((func.P,) + shp) for (o, n, shp) in func._blocks().values())

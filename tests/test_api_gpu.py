@@ -102,3 +102,39 @@ def test_time_gradient_mlp_and_plain_odeint_policy():
     t2 = torch.from_numpy(g["t"]).clone().requires_grad_(True)
     with pytest.raises(NotImplementedError):                     # plain odeint: no dL/dt (documented; use odeint_adjoint)
         bode.odeint(fm, torch.from_numpy(g["x0"]), t2, method="rk4")
+
+
+@pytest.mark.parametrize("method", ["rk4", None])
+def test_backward_uses_forward_time_parameters(method):
+    """the MLP / dopri5 backward passes re-solve with the parameters.  The samplers update theta through raw pointers (no
+    autograd version bump), so backward() after an in-place update must still differentiate the solve that produced `sol`: the
+    forward-time parameters are snapshotted."""
+    import bayesian_ode_b200 as bode
+    g = load_golden("mlp")
+    th = g["h20_theta"]
+    x0, t = torch.from_numpy(g["x0"]), torch.from_numpy(g["t"])
+    kw = dict(method=method) if method else dict(rtol=1e-6, atol=1e-8)
+    grads = []
+    for poke in (False, True):
+        f = bode.MLPField(th.shape[0], hidden_size=20, theta=torch.from_numpy(th))
+        sol = bode.odeint(f, x0, t, **kw)
+        loss = (sol ** 2).sum()
+        if poke:
+            with torch.no_grad():
+                f.theta.data.mul_(1.5)              # what a sampler step does between closure() and a late backward()
+        loss.backward()
+        grads.append(torch.cat([p.grad.reshape(th.shape[0], -1) for p in f.parameters()], 1).clone())
+    assert torch.equal(grads[0], grads[1])
+    # npde + dopri5 takes the same route
+    gn = load_golden("npde_m5")
+    gU = []
+    for poke in (False, True):
+        f = bode.NPDEField(torch.from_numpy(gn["U"]), torch.from_numpy(gn["Z"]), 1.0, 0.75, 0.1)
+        sol = bode.odeint(f, torch.from_numpy(gn["x0"]), torch.from_numpy(gn["t"]), rtol=1e-6, atol=1e-8)
+        loss = (sol ** 2).sum()
+        if poke:
+            with torch.no_grad():
+                f.U.data.mul_(1.5)
+        loss.backward()
+        gU.append(f.U.grad.clone())
+    assert torch.equal(gU[0], gU[1])
