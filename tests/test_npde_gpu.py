@@ -266,7 +266,7 @@ def test_large_m_split_projection_matches_fused_kernel(M):
         assert relerr(a.double().cpu().numpy(), b.double().cpu().numpy()) < 2e-6
 
 
-@pytest.mark.parametrize("Mx,My,N", [(16, 16, 5), (8, 8, 4), (7, 9, 1), (12, 10, 3)])
+@pytest.mark.parametrize("Mx,My,N", [(16, 16, 5), (8, 8, 4), (7, 9, 1), (12, 10, 3), (9, 9, 7), (8, 8, 8)])
 def test_row_sliced_grid_kernels_match_general_Z_kernels(Mx, My, N):
     """Tensor grids of 7x7 .. 16x16 inducing points take the row-sliced separable kernels (csrc/npde_row.cuh: 16 lanes per pair,
     Mx + My exponentials per evaluation); bode_npde_set_row_kernel(0) sends the same field through the general-Z kernels, which
@@ -285,9 +285,10 @@ def test_row_sliced_grid_kernels_match_general_Z_kernels(Mx, My, N):
     U = 0.3 * rng.standard_normal((P, Mx * My, 2))
     f = bode.NPDEField(torch.from_numpy(U), torch.from_numpy(Z), 1.0, float(ell), 0.1, stable_solve=True)
     assert f.grid_axes is not None and len(f.grid_axes[0]) == Mx and len(f.grid_axes[1]) == My
-    x0 = torch.from_numpy(g["x0"][:N])
+    reps = (N + g["x0"].shape[0] - 1) // g["x0"].shape[0]          # more trajectories than the fixture holds: shifted copies
+    x0 = torch.from_numpy(np.concatenate([g["x0"] + 0.05 * r for r in range(reps)])[:N])
     t = torch.from_numpy(g["t"])
-    Y = torch.from_numpy(g["Y"][:N])
+    Y = torch.from_numpy(np.concatenate([g["Y"] + 0.05 * r for r in range(reps)])[:N])
     out = {}
     for rowk in (1, 0):
         old = lib.bode_npde_set_row_kernel(rowk)
@@ -319,3 +320,30 @@ def test_row_sliced_grid_kernels_match_general_Z_kernels(Mx, My, N):
         else:
             err, tol = relerr(a, b), 2e-5
         assert err < tol, (k, err)
+
+
+def test_row_sliced_kernel_ten_trajectories_against_oracle():
+    """N = 10 trajectories per particle: beyond the general-Z kernel's limit (8 warps per CTA), within the row-sliced one's (ten
+    half-warps).  Checked against the oracle directly."""
+    import bayesian_ode_b200 as bode
+    from oracle import npde
+    g = load_golden("npde_m5")
+    M, N, P = 8, 10, 3
+    Z = npde.inducing_grid(g["Y"], M)
+    ell = 0.9 * float(Z[M, 0] - Z[0, 0])
+    rng = np.random.default_rng(8)
+    U = 0.3 * rng.standard_normal((P, M * M, 2))
+    x0 = np.concatenate([g["x0"], g["x0"] + 0.05])[:N]
+    Y = np.concatenate([g["Y"], g["Y"] + 0.05])[:N]
+    f = bode.NPDEField(torch.from_numpy(U), torch.from_numpy(Z), 1.0, ell, 0.1, stable_solve=True)
+    pre = dict(Kzz=f.Kzz.numpy(), Kzzinv=f.Kzzinv.numpy(), L=f.L.numpy(), KzzinvL=f.KzzinvL.numpy())
+    post = bode.NPDEPosterior(f, torch.from_numpy(x0), torch.from_numpy(g["t"]), torch.from_numpy(Y))
+    loss, gU, gl = post.loss_and_grad_()
+    ol, ogU, ogl, osol = npde.nlp_grad(U, np.full((P, 2), np.log(0.1)), Z, 1.0, ell, x0, g["t"], Y, pre=pre)
+    assert relerr(loss.cpu().numpy(), ol) < 1e-5
+    err = np.abs(gU.cpu().numpy() - ogU).max(axis=(1, 2)) / np.abs(ogU).max(axis=(1, 2))
+    assert err.max() < GRAD_TOL, err
+    assert relerr(gl.cpu().numpy(), ogl) < GRAD_TOL
+    with torch.no_grad():
+        sol = bode.odeint(f, torch.from_numpy(x0), torch.from_numpy(g["t"]), method="rk4")
+    assert relerr(sol.cpu().numpy(), osol) < TRAJ_TOL
