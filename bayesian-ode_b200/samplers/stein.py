@@ -318,9 +318,9 @@ class SVGD(Sampler):
             Xloc = Xall[self.rank * nl:(self.rank + 1) * nl] if self.world > 1 else self._flat
             self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
             if self.overlap == "gram":
-                # finer Gram CTAs (two column tiles each): the pass shares the GPU with the solve, a one-wave grid would
-                # leave a long tail on the few SMs it gets (measured on B200: 147 -> 143 us per c3 step)
-                old_split = lib.bode_svgd_set_gram_split(16)
+                # the pass shares the GPU with the solve: its grid is sized for the side_sms SMs it gets (full waves of CTAs with
+                # as many column tiles each as that allows; a grid sized for the whole GPU leaves a long tail there)
+                old_split = lib.bode_svgd_set_gram_split(self._side_gram_split(nl, nt))
                 self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
                 lib.bode_svgd_set_gram_split(old_split)
                 if self.world == 1 or self._ws.p2p:
@@ -333,6 +333,22 @@ class SVGD(Sampler):
             if sms > self.side_sms:
                 self._saved_cta_limit = lib.bode_npde_set_cta_limit(sms - self.side_sms)   # until phi() restores it
         self._prefetched = self.overlap
+
+    def _side_gram_split(self, nr, nc):
+        """Column chunks per row block for a Gram pass that has ``side_sms`` SMs to itself (one CTA per SM): the cost model of
+        csrc/svgd_tc2.cu (waves x (tiles per CTA + one tile of prologue)) by enumeration.  4096 x 4096 on 40 SMs: 5 chunks of
+        7 tiles = 160 CTAs = 4 full waves (measured: c3 step 142.7 us with 16 chunks, 137.5 us with 4 - 8)."""
+        sms = max(1, self.side_sms)
+        nrb, nct = (nr + 127) // 128, (nc + 127) // 128
+        best, best_cost = 1, None
+        for tp in range(1, nct + 1):
+            chunks = (nct + tp - 1) // tp
+            if chunks > 16:
+                continue
+            cost = ((chunks * nrb + sms - 1) // sms) * (tp + 1)
+            if best_cost is None or cost < best_cost:
+                best, best_cost = chunks, cost
+        return best
 
     def _restore_cta_limit(self):
         """Undo prefetch()'s process-wide CTA cap of the fused solve (phi() does; so does an aborted step)."""
