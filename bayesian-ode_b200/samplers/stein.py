@@ -338,6 +338,10 @@ class SVGD(Sampler):
         """Column chunks per row block for a Gram pass that has ``side_sms`` SMs to itself (one CTA per SM): the cost model of
         csrc/svgd_tc2.cu (waves x (tiles per CTA + one tile of prologue)) by enumeration.  4096 x 4096 on 40 SMs: 5 chunks of
         7 tiles = 160 CTAs = 4 full waves (measured: c3 step 142.7 us with 16 chunks, 137.5 us with 4 - 8)."""
+        if self.world > 1:
+            # several ranks: the rectangular pass outlasts the solve and spreads over the SMs the solve frees -- fine CTAs (16
+            # chunks) follow that change of width best (2 GPUs: 199.2 us per step against 200.9 with the enumeration)
+            return 16
         sms = max(1, self.side_sms)
         nrb, nct = (nr + 127) // 128, (nc + 127) // 128
         best, best_cost = 1, None
