@@ -132,8 +132,11 @@ SYMBOLS = {
                                            _P, C.c_size_t, C.POINTER(C.c_void_p), _P]),
     "bode_svgd_phi_staged": (C.c_int, [C.c_int32, _P, C.c_int64, C.c_int32, _P, C.c_int64, _P, C.c_int64, C.c_float, C.c_int32, C.c_int32,
                                         C.c_int32, _P, _P, _P, C.c_int64, _P, C.c_int64, C.c_float, _P]),
+    "bode_svgd_set_select_ctas": (C.c_int, [C.c_int32]),
+    "bode_svgd_arm_score_tiles": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _P, C.c_float]),
+    "bode_svgd_disarm_score_tiles": (C.c_int, []),
 }
-SVGD_PREPARE, SVGD_COMPUTE = 1, 2
+SVGD_PREPARE, SVGD_COMPUTE, SVGD_PREPARE_POSITIONS = 1, 2, 4
 
 
 def load():

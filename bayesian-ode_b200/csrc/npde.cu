@@ -42,6 +42,19 @@ BODE_DECL_GEN(8)
 static bool use_sep(const bode_npde_field* f) {
   return f->grid_mx == f->grid_my && f->grid_mx >= 3 && f->grid_mx <= 6 && f->grid_mx * f->grid_my == f->m;
 }
+// SVGD score-tile fusion (svgd_tiles.cuh): while armed, the fused likelihood closure of the component-split kernels also writes
+// vsign * (gU | glogsn) of every particle into the interaction's operand tiles; `written` counts such launches.
+static struct { float* VH; float* VC; float sign; int P; int d; int written; } g_score = {nullptr, nullptr, 0.f, 0, 0, 0};
+void npde_arm_score_tiles(float* VH, float* VC, float sign, int P, int d) {
+  g_score.VH = VH; g_score.VC = VC; g_score.sign = sign; g_score.P = P; g_score.d = d; g_score.written = 0;
+}
+int npde_disarm_score_tiles() {
+  const int w = g_score.written;
+  g_score.VH = g_score.VC = nullptr;
+  g_score.written = 0;
+  return w;
+}
+
 static int gen_jpl(int m) { return m <= 32 ? 1 : (m <= 64 ? 2 : (m <= 128 ? 4 : 8)); }
 // Tensor grids beyond the one-thread separable kernels (7x7 .. 16x16): row-sliced separable field, 16 lanes per pair (npde_row.cuh)
 static int g_row_kernel = 1;
@@ -255,6 +268,10 @@ static int run_grad(const bode_npde_field* f, const bode_grid* g, int method, in
     size_t smem = 0;
     st_ = plan_pair(prm, f->grid_mx, true, &grid, &block, &smem);
     if (st_ != BODE_OK) return st_;
+    if (g_score.VH && inj == INJ_LIK && f->P == g_score.P && 2 * f->m + 2 == g_score.d && prm.glogsn && prm.gU) {
+      prm.VH = g_score.VH; prm.VC = g_score.VC; prm.vsign = g_score.sign;
+      ++g_score.written;
+    }
     return dispatch_pair_grad(prm, f->grid_mx, method, inj, grad_mode, grid, block, smem, st);
   }
   if (use_sep(f)) {

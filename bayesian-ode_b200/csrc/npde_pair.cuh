@@ -17,6 +17,7 @@
 // rk_common.py:72-78 (fixed-grid RK), gp.py:342-353 (closure), adjoint.py:23-102 (continuous adjoint).
 #pragma once
 #include "npde_solve.cuh"
+#include "svgd_tiles.cuh"
 
 namespace bode {
 
@@ -342,6 +343,11 @@ __device__ __forceinline__ void pair_epilogue(const NpdeKParams& prm, float* sme
   }
   __syncthreads();
   float* pri = gWs;                      // reuse: prior partials [ppc][m2]
+  // SVGD score tiles (svgd_tiles.cuh): vsign * (gU | glogsn) of the CTA's particles, collected in the free part of gWs and written
+  // four particles at a time (vector stores) for the aligned quads inside the CTA's particle range, element stores at its ends
+  const bool tiles = INJ == INJ_LIK && prm.VH != nullptr;
+  const bool tiles4 = tiles && (N - 1) * nout >= ppc * (m2 + 2);
+  float* gv = gWs + nout;                // [ppc][m2 + 2]
   for (int idx = tid; idx < nout; idx += blockDim.x) {
     const int q = idx / m2, r = idx - q * m2, k = r >> 1, dd = r & 1;
     const int pp = blockIdx.x * ppc + q;
@@ -357,7 +363,12 @@ __device__ __forceinline__ void pair_epilogue(const NpdeKParams& prm, float* sme
       pr *= 0.5f * Us[idx];
     }
     pri[idx] = pr;
-    prm.gU[(long long)pp * prm.gU_stride + r] = prm.scale * acc;
+    const float gval = prm.scale * acc;
+    prm.gU[(long long)pp * prm.gU_stride + r] = gval;
+    if (tiles) {
+      if (tiles4) gv[q * (m2 + 2) + r] = prm.vsign * gval;
+      else score_tile_store(prm.VH, prm.VC, pp, r, prm.vsign * gval);
+    }
   }
   if (INJ == INJ_LIK) {
     __syncthreads();
@@ -375,8 +386,36 @@ __device__ __forceinline__ void pair_epilogue(const NpdeKParams& prm, float* sme
         const float nt = (float)N * (float)prm.T;
         prm.loss[pp] = prm.scale * (0.5f * (sx * ex + sy * ey) + nt * (ls.x + ls.y) + pr);
         prm.sqerr[pp] = sx + sy;
-        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = prm.scale * (nt - sx * ex);
-        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = prm.scale * (nt - sy * ey);
+        const float gl0 = prm.scale * (nt - sx * ex), gl1 = prm.scale * (nt - sy * ey);
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 0] = gl0;
+        prm.glogsn[(long long)pp * prm.glogsn_stride + 1] = gl1;
+        if (tiles) {
+          if (tiles4) {
+            gv[tid * (m2 + 2) + m2] = prm.vsign * gl0;
+            gv[tid * (m2 + 2) + m2 + 1] = prm.vsign * gl1;
+          } else {
+            score_tile_store(prm.VH, prm.VC, pp, m2, prm.vsign * gl0);
+            score_tile_store(prm.VH, prm.VC, pp, m2 + 1, prm.vsign * gl1);
+          }
+        }
+      }
+    }
+    if (tiles4) {
+      __syncthreads();
+      const int nf = m2 + 2;
+      const int p0 = blockIdx.x * ppc, p1 = min(p0 + ppc, prm.P);          // this CTA's particles [p0, p1)
+      const int jq0 = p0 >> 2, nq = ((p1 + 3) >> 2) - jq0;                   // the quads they touch
+      for (int idx = tid; idx < nq * nf; idx += blockDim.x) {
+        const int qi = idx / nf, f = idx - qi * nf;
+        const int pp0 = 4 * (jq0 + qi);
+        if (pp0 >= p0 && pp0 + 4 <= p1) {
+          const float* g0 = gv + (pp0 - p0) * nf + f;
+          const float v[4] = {g0[0], g0[nf], g0[2 * nf], g0[3 * nf]};
+          score_tile_store4(prm.VH, prm.VC, jq0 + qi, f, v);
+        } else {
+          for (int e = 0; e < 4; ++e)
+            if (pp0 + e >= p0 && pp0 + e < p1) score_tile_store(prm.VH, prm.VC, pp0 + e, f, gv[(pp0 + e - p0) * nf + f]);
+        }
       }
     }
   }

@@ -33,6 +33,8 @@ struct NpdeKParams {
   int a_off;          // pair kernels: float offset of the staged A[m,m] | Ksym[m,m]
   float reg, lik_w;   // MLP closure: lik_w * sum (X - x)^2 + reg * sum theta^2
   float *sol, *loss, *sqerr, *gU, *glogsn, *gy0;
+  float *VH, *VC;     // optional: SVGD operand tiles that receive vsign * (gU | glogsn) of every particle (svgd_tiles.cuh)
+  float vsign;
 };
 
 enum { INJ_LIK = 0, INJ_GOUT = 1 };

@@ -34,7 +34,8 @@ int svgd_tc2_d2_tiled(int nr, int nc);
 size_t svgd_tc2_carved_bytes(int nr, int nc);
 int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const float* Xc, long long ldc, int nc, int d, float* mu,
                   void* ops_base, float* D2, SelState* st, unsigned long long total, int sms, int stages, cudaStream_t stream);
-int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, cudaStream_t stream);
+int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, int one_cta, cudaStream_t stream);
+static int g_select_ctas = 0;   // bode_svgd_set_select_ctas
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc);
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
@@ -756,7 +757,7 @@ extern "C" int bode_svgd_window_table(int32_t n_rows, int32_t n_cols, int32_t d,
 extern "C" int bode_svgd_window_select(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, bode_stream_t stream) {
   BODE_REQUIRE(workspace, "null workspace");
   Ws w = carve(workspace, n_rows, n_cols, d);
-  return svgd_tc2_window_select(w.st, w.ops, n_rows, n_cols, peers_of(workspace), (cudaStream_t)stream);
+  return svgd_tc2_window_select(w.st, w.ops, n_rows, n_cols, peers_of(workspace), g_select_ctas > 0 ? 1 : 0, (cudaStream_t)stream);
 }
 
 /* 1 (default): Gram and K@[S|X|1] on tcgen05 tensor cores (3xTF32) when d <= 56; 0: FP32-pipe kernels */
@@ -801,6 +802,16 @@ extern "C" int bode_svgd_select_digit(int32_t pass, int32_t n_rows, int32_t n_co
 /* Single-rank fallback of the exact median: the three radix passes in one cooperative launch (returns immediately when
  * bode_svgd_window_select resolved the median).  With med_gamma != NULL the launch also does bode_svgd_gamma's work for the
  * median heuristic (median -> gamma, next window armed).  Multi-rank callers keep the per-pass calls with their all-reduces. */
+/* Upper bound on the CTAs of the cooperative fallback launch (0 = one per SM slot).  A cooperative grid only starts when ALL its
+ * CTAs can be resident: launched beside a kernel that fills most SMs (the fused solve in the overlapped SVGD step) a full-size grid
+ * waits for that kernel to end -- even when the launch is the no-op it is after a window hit (measured on c3: the median chain ended
+ * 7 us after the solve instead of 15 us before it).  Returns the previous bound. */
+extern "C" int bode_svgd_set_select_ctas(int32_t n) {
+  const int old = g_select_ctas;
+  g_select_ctas = n > 0 ? n : 0;
+  return old;
+}
+
 extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, int32_t n_total, float* med_gamma,
                                         bode_stream_t stream) {
   BODE_REQUIRE(workspace, "null workspace");
@@ -825,7 +836,8 @@ extern "C" int bode_svgd_radix_fallback(int32_t n_rows, int32_t n_cols, int32_t 
   unsigned long long* hsum = svgd_tc2_table(w.ops, n_rows, n_cols) + WIN_TABLE + 1;   // spare half of the table block
   BODE_REQUIRE(peer.world <= 1 || arm, "peer-mapped workspaces need the pipelined tensor-core path (column count a multiple of 4, d <= 55)");
   void* args[] = {(void*)&d2, (void*)&n, (void*)&stp, (void*)&hist, (void*)&hsum, (void*)&ntot, (void*)&arm, (void*)&mg, (void*)&peer};
-  BODE_CUDA(cudaLaunchCooperativeKernel((const void*)radix_fallback_kernel, dim3(grid_blocks), dim3(1024), args, 0, (cudaStream_t)stream));
+  const int gb = (g_select_ctas > 0 && g_select_ctas < grid_blocks) ? g_select_ctas : grid_blocks;
+  BODE_CUDA(cudaLaunchCooperativeKernel((const void*)radix_fallback_kernel, dim3(gb), dim3(1024), args, 0, (cudaStream_t)stream));
   return BODE_OK;
 }
 
@@ -846,10 +858,13 @@ extern "C" int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t 
                                     const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
                                     const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                                     int64_t ld_theta, float step, bode_stream_t stream) {
-  BODE_REQUIRE(Xrows && Xcols && Scols && med_gamma && workspace, "null pointer");
-  BODE_REQUIRE((stages & ~3) == 0 && stages != 0, "stages must be a combination of BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE");
+  BODE_REQUIRE(Xrows && Xcols && med_gamma && workspace, "null pointer");
+  BODE_REQUIRE((stages & ~7) == 0 && stages != 0,
+               "stages must be a combination of BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE | BODE_SVGD_PREPARE_POSITIONS");
+  BODE_REQUIRE(Scols || !(stages & BODE_SVGD_PREPARE), "null scores");
   if (!bode_svgd_staged_supported(n_cols, d)) {
     if (!(stages & BODE_SVGD_COMPUTE)) return BODE_OK;
+    BODE_REQUIRE(Scols, "null scores");
     stages = BODE_SVGD_PREPARE | BODE_SVGD_COMPUTE;
   }
   BODE_REQUIRE(d > 0 && 2 * d + 1 <= 256, "svgd phi kernel supports d <= 127 (got %d)", d);
@@ -897,6 +912,29 @@ extern "C" int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t 
                                                                1.f / (float)n_total, phi, ld_phi, theta, ld_theta, step);
   return check_cuda(cudaGetLastError(), "phi combine launch");
 }
+
+/* Score-tile fusion.  arm: from now until bode_svgd_disarm_score_tiles, every fused likelihood closure of the component-split npde
+ * kernels (bode_npde_nlp_grad on a 3x3 .. 6x6 grid) over exactly n_cols particles with 2m + 2 == d parameters also writes
+ * score_sign * gradient into this workspace's phi operand tiles, so that the interaction needs only
+ * bode_svgd_phi_staged(BODE_SVGD_PREPARE_POSITIONS) (any time after the operands' PREPARE) and ..._staged(BODE_SVGD_COMPUTE).
+ * Returns 1 when armed, 0 when the shapes are outside the pipelined tensor-core path (nothing changes then).
+ * disarm: returns how many closure launches wrote the tiles since arm (0: the caller must run BODE_SVGD_PREPARE itself). */
+namespace bode {
+void npde_arm_score_tiles(float* VH, float* VC, float sign, int P, int d);
+int npde_disarm_score_tiles();
+void svgd_tc2_v_tiles(void* ops_base, int nr, int nc, float** VH, float** VC);
+}
+extern "C" int bode_svgd_arm_score_tiles(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, float score_sign) {
+  if (!workspace || n_rows != n_cols || (n_cols & 3) || !bode_svgd_staged_supported(n_cols, d)) return 0;
+  if (!(g_tensor_cores && svgd_tc_supported(d) && svgd_tc2_supported(d, n_cols))) return 0;
+  if (peers_of(workspace).world > 1) return 0;
+  Ws w = carve(workspace, n_rows, n_cols, d);
+  float *VH = nullptr, *VC = nullptr;
+  svgd_tc2_v_tiles(w.ops, n_rows, n_cols, &VH, &VC);
+  npde_arm_score_tiles(VH, VC, score_sign, n_cols, d);
+  return 1;
+}
+extern "C" int bode_svgd_disarm_score_tiles(void) { return npde_disarm_score_tiles(); }
 
 extern "C" int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_xc,
                              const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,

@@ -16,6 +16,7 @@
 // Warp 16 issues the MMAs (its issue loop is back-pressured by the tensor core), warp 17 the bulk / TMA copies; warps 0-15 (four per
 // SM sub-partition) own the TMEM lanes / operand generation.  Inside the tile loops the warps meet only through mbarriers.
 #include "tc_ptx.cuh"
+#include "svgd_tiles.cuh"
 #include "svgd_state.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
@@ -119,11 +120,14 @@ __device__ __forceinline__ uint2 pack_bf16x4(const float (&v)[4]) {
 }
 __global__ void __launch_bounds__(256) prep_v_kernel(const float* __restrict__ X, long long ldx, const float* __restrict__ G, long long ldg,
                                                      int n, int d, const float* __restrict__ mu, float gsign, int n_pad,
-                                                     float* __restrict__ VH, float* __restrict__ VC) {
+                                                     float* __restrict__ VH, float* __restrict__ VC, int f_lo) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)(n_pad / 4) * NF2) return;
   const int f = (int)(idx % NF2);
   const long long jq = idx / NF2;
+  // f_lo = d: the score columns are written by the closure kernel (svgd_tiles.cuh); only their zero padding (particles >= n,
+  // whole quads: n % 4 == 0 on this path) is kept up here
+  if (f < f_lo && 4 * jq < n) return;
   float h[4], l[4], full[4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -512,6 +516,79 @@ __global__ void __launch_bounds__(1024) window_select_kernel(SelState* st, unsig
     cl.sync();
     *t2 = make_ulonglong2(0ull, 0ull);
     if (c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
+  }
+}
+
+// The same selection by a cluster of FOUR CTAs (single rank), eight bins per thread.  A 16-CTA cluster needs 16 free SMs inside
+// one GPC; beside the fused solve of the overlapped SVGD step (108 of 148 SMs busy) no GPC has that many, so the launch waited for
+// the solve to end and put the median chain -- and phi behind it -- after the solve (tools/step_timeline.py: Gram pass done at
+// 76 us, selection done at 100 us, solve at 97 us).  40 free SMs over 8 GPCs always leave one GPC with five.  (One CTA instead is no
+// answer: a single SM needs ~30 us to move the 262 KB table twice.)
+constexpr int WSEL4 = 4;
+constexpr int WSEL4_V = (int)WIN_SPAN / (WSEL4 * 1024) / 2;            // 16-byte vectors (two bins each) per thread: 4
+__global__ void __launch_bounds__(1024) window_select4_kernel(SelState* st, unsigned long long* table) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cl = cg::this_cluster();
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long segtot[WSEL4];
+  __shared__ unsigned long long mytot, below_s, last_s;
+  __shared__ unsigned int found[2];                                   // meaningful in CTA 0
+  const int tid = threadIdx.x, c = (int)cl.block_rank();
+  const bool armed = st->win_valid != 0;
+  const unsigned long long rr[2] = {st->rank[0], st->rank[1]};
+  ulonglong2* t2 = reinterpret_cast<ulonglong2*>(table) + (c * 1024 + tid) * WSEL4_V;
+  ulonglong2 v[WSEL4_V];
+#pragma unroll
+  for (int i = 0; i < WSEL4_V; ++i) v[i] = t2[i];
+#pragma unroll
+  for (int i = 0; i < WSEL4_V; ++i) t2[i] = make_ulonglong2(0ull, 0ull);   // ready for the next call
+  if (tid == 0) {                                                     // every CTA needs `below`; CTA 0 clears it after the barrier
+    below_s = armed ? table[WIN_TABLE] : 0ull;
+    last_s = armed ? table[WIN_SPAN] : 0ull;
+    if (c == 0) found[0] = found[1] = 0xffffffffu;
+  }
+  unsigned long long mine = 0ull;
+#pragma unroll
+  for (int i = 0; i < WSEL4_V; ++i) {
+    if (!armed) v[i] = make_ulonglong2(0ull, 0ull);
+    mine += v[i].x + v[i].y;
+  }
+  const unsigned long long incl = block_incl_scan_u64(mine, wsum, &mytot);
+  __syncthreads();
+  if (tid < WSEL4) cl.map_shared_rank(segtot, tid)[c] = mytot;
+  cl.sync();
+  if (c == 0 && tid == 0) table[WIN_SPAN] = table[WIN_TABLE] = 0ull;
+  unsigned long long run = below_s;
+  for (int i = 0; i < c; ++i) run += segtot[i];
+  run += incl - mine;                                                 // entries before this thread's first bin
+  const unsigned int b0 = (unsigned int)((c * 1024 + tid) * 2 * WSEL4_V);
+  unsigned int* f0 = cl.map_shared_rank(found, 0);
+  if (mine) {
+#pragma unroll
+    for (int i = 0; i < WSEL4_V; ++i) {
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        if (rr[which] >= run && rr[which] < run + v[i].x) f0[which] = b0 + 2 * i;
+        else if (rr[which] >= run + v[i].x && rr[which] < run + v[i].x + v[i].y) f0[which] = b0 + 2 * i + 1;
+      }
+      run += v[i].x + v[i].y;
+    }
+  }
+  if (c == WSEL4 - 1 && tid == 0 && last_s) {                         // the closing bin of the window
+    unsigned long long tot = below_s;
+    for (int i = 0; i < WSEL4; ++i) tot += segtot[i];
+#pragma unroll
+    for (int which = 0; which < 2; ++which)
+      if (rr[which] >= tot && rr[which] < tot + last_s) f0[which] = WIN_SPAN;
+  }
+  cl.sync();
+  if (c == 0 && tid == 0) {
+    const bool hit = armed && found[0] != 0xffffffffu && found[1] != 0xffffffffu;
+    if (hit) {
+      st->prefix[0] = st->win_lo + found[0];
+      st->prefix[1] = st->win_lo + found[1];
+    }
+    st->hit = hit ? 1u : 0u;
   }
 }
 
@@ -997,8 +1074,24 @@ int svgd_tc2_gram(const float* Xr, long long ldr, int nr, int row_offset, const 
   return check_cuda(cudaGetLastError(), "gram2 launch");
 }
 
-int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, cudaStream_t stream) {
+int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const PeerInfo& peer, int one_cta, cudaStream_t stream) {
   const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
+  if (one_cta && peer.world <= 1) {                      // small cluster: schedulable beside a kernel that fills most SMs
+    cudaLaunchConfig_t cfg4 = {};
+    cfg4.gridDim = dim3(WSEL4);
+    cfg4.blockDim = dim3(1024);
+    cfg4.dynamicSmemBytes = 0;
+    cfg4.stream = stream;
+    cudaLaunchAttribute at4[1];
+    at4[0].id = cudaLaunchAttributeClusterDimension;
+    at4[0].val.clusterDim.x = WSEL4;
+    at4[0].val.clusterDim.y = 1;
+    at4[0].val.clusterDim.z = 1;
+    cfg4.attrs = at4;
+    cfg4.numAttrs = 1;
+    BODE_CUDA(cudaLaunchKernelEx(&cfg4, window_select4_kernel, st, o.table));
+    return BODE_OK;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     BODE_CUDA(cudaFuncSetAttribute(window_select_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -1021,6 +1114,12 @@ int svgd_tc2_window_select(SelState* st, void* ops_base, int nr, int nc, const P
 }
 
 unsigned long long* svgd_tc2_table(void* ops_base, int nr, int nc) { return svgd_tc2_carve(ops_base, nr, nc).table; }
+void svgd_tc2_v_tiles(void* ops_base, int nr, int nc, float** VH, float** VC) {
+  const Tc2Ops o = svgd_tc2_carve(ops_base, nr, nc);
+  *VH = o.VH;
+  *VC = o.VC;
+}
+static_assert(NF2 == SV_NF && PK2 == SV_PK && VST_BYTES == SV_VST_BYTES, "svgd_tiles.cuh must describe the layout prep_v_kernel writes");
 
 int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx, const float* Gc, long long ldg, int d, const float* mu,
                  const float* gam, float gsign, void* ops_base, int* jsplit_out, float* part, int sms, int stages, const float* Xr,
@@ -1031,8 +1130,9 @@ int svgd_tc2_phi(const float* D2, int nr, int nc, const float* Xc, long long ldx
   int js = split_for(nrb, nst, sms);
   if (js > 8) js = 8;                                                  // portable cluster size
   *jsplit_out = js;
-  if (stages & 1) {   // V^T = [-G | X - mu | 1] operand tiles: needs positions and scores, not d2 or gamma
-    prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VC);
+  if (stages & 5) {   // V^T = [-G | X - mu | 1] operand tiles: needs positions and scores, not d2 or gamma; bit 2 alone: without the scores
+    prep_v_kernel<<<(int)(((long long)(ncp / 4) * NF2 + 255) / 256), 256, 0, stream>>>(Xc, ldx, Gc, ldg, nc, d, mu, gsign, ncp, o.VH, o.VC,
+                                                                                          (stages & 1) ? 0 : d);
     BODE_CUDA(cudaGetLastError());
   }
   if (!(stages & 2)) return BODE_OK;

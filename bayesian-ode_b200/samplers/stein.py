@@ -286,7 +286,12 @@ class SVGD(Sampler):
             raise ValueError("overlap must be False, 'operands' or 'gram'")
         self.overlap = overlap if (overlap and _lib.load().bode_svgd_staged_supported(self.n_total, self.d)) else False
         self.side_sms = int(side_sms)
+        self.fuse_scores = True          # let the closure kernel write the score half of the phi operand (single rank, overlap="gram")
+        self._scores_armed = False
+        self._side2_used = False
+        self.last_scores_fused = False
         self._side = torch.cuda.Stream(device=dev) if self.overlap else None
+        self._side2 = torch.cuda.Stream(device=dev) if self.overlap else None     # position half of the phi operand, beside the Gram pass
         self._prefetched = False
         self._saved_cta_limit = None
 
@@ -317,6 +322,18 @@ class SVGD(Sampler):
             # the local rows as a block of the gathered columns: the Gram kernel then reuses the column operands for them
             Xloc = Xall[self.rank * nl:(self.rank + 1) * nl] if self.world > 1 else self._flat
             self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_PREPARE)
+            if self.overlap == "gram" and self.world == 1 and self.fuse_scores:
+                # The position half of the phi operand on a second side stream (it needs the column means just computed, and runs
+                # beside the Gram pass -- behind it, it would lengthen the chain phi() waits for); the score half is written by the
+                # closure's own kernel while armed (bode_svgd_arm_score_tiles): no operand launch between the solve and phi.
+                self._side2.wait_stream(self._side)
+                self._side2_used = True
+                with torch.cuda.stream(self._side2):
+                    xr, xrs = _lib.rows(self._flat, d)
+                    _lib.check(lib.bode_svgd_phi_staged(_lib.SVGD_PREPARE_POSITIONS, xr, xrs, nl, xr, xrs, None, 0, -1.0, nt, d, nt,
+                                                        _lib.ptr(self._ws.med_gamma), C.c_void_p(self._ws.base.data_ptr()), None, d,
+                                                        None, 0, 0.0, _lib.stream_ptr()))
+                self._scores_armed = lib.bode_svgd_arm_score_tiles(nl, nt, d, C.c_void_p(self._ws.base.data_ptr()), -1.0) == 1
             if self.overlap == "gram":
                 # the pass shares the GPU with the solve: its grid is sized for the side_sms SMs it gets (full waves of CTAs with
                 # as many column tiles each as that allows; a grid sized for the whole GPU leaves a long tail there)
@@ -324,7 +341,13 @@ class SVGD(Sampler):
                 self._ws.sqdist(Xloc, nl, Xall, nt, d, nt * nt, row_offset=self.rank * nl, stages=_lib.SVGD_COMPUTE)
                 lib.bode_svgd_set_gram_split(old_split)
                 if self.world == 1 or self._ws.p2p:
+                    # the cooperative fallback launch (a no-op after a window hit) must fit the SMs the solve leaves free, or it
+                    # waits for the solve to end
+                    old_ctas = lib.bode_svgd_set_select_ctas(self.side_sms) if self.side_sms > 0 else None
                     self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=None)
+                    if old_ctas is not None:
+                        lib.bode_svgd_set_select_ctas(old_ctas)
+
                 # collective protocol (median_comm="nccl"): the median's all-reduces are issued by phi() AFTER the all-gather
                 # of the scores -- one communicator executes collectives in issue order, and the scores are ready long
                 # before the Gram pass ends
@@ -360,11 +383,26 @@ class SVGD(Sampler):
             _lib.load().bode_npde_set_cta_limit(self._saved_cta_limit)
             self._saved_cta_limit = None
 
+    def _join_side2(self, cur):
+        if self._side2_used:
+            cur.wait_stream(self._side2)
+            self._side2_used = False
+
+    def _disarm_scores(self):
+        """End the closure kernels' writes into the phi operand tiles; how many launches wrote them since prefetch()."""
+        n = 0
+        if self._scores_armed:
+            n = _lib.load().bode_svgd_disarm_score_tiles()
+            self._scores_armed = False
+        return n
+
     def cancel_prefetch(self):
         """Drop a prefetch() whose phi() will not follow (the closure raised): joins the side stream, restores the CTA cap."""
         self._restore_cta_limit()
+        self._disarm_scores()
         if self._prefetched:
             torch.cuda.current_stream().wait_stream(self._side)
+            self._join_side2(torch.cuda.current_stream())
             self._prefetched = False
 
     def phi(self, X=None, grad=None, update_lr=None):
@@ -378,11 +416,15 @@ class SVGD(Sampler):
         ws = self._ws
         cur = torch.cuda.current_stream()
         self._restore_cta_limit()
+        scores_in_tiles = self._disarm_scores() >= 1 and X is self._flat and grad is None
+        self.last_scores_fused = scores_in_tiles
         prefetched = self._prefetched if X is self._flat else False
         if self._prefetched and prefetched != "gram":
             cur.wait_stream(self._side)                     # join: operands (and the gathered positions) are ready
+            self._join_side2(cur)
         if self._prefetched and not prefetched:
             cur.wait_stream(self._side)                     # prefetched for other positions: drop it
+            self._join_side2(cur)
         self._prefetched = False
         # the one data-path exchange: all-gather of particle positions and loss gradients (NCCL over NVLink)
         Xall = self._Xall if (prefetched and self.world > 1) else self._gather_positions(X)
@@ -399,8 +441,10 @@ class SVGD(Sampler):
                                                 float(update_lr or 0.0), _lib.stream_ptr()))
         both = _lib.SVGD_PREPARE | _lib.SVGD_COMPUTE
         if prefetched == "gram":
-            phi_stage(_lib.SVGD_PREPARE)                    # the V operand needs the scores: here, while the side stream finishes
+            if not scores_in_tiles:
+                phi_stage(_lib.SVGD_PREPARE)                # the V operand needs the scores: here, while the side stream finishes
             cur.wait_stream(self._side)                     # join: d2 (single rank: also median and gamma) are ready
+            self._join_side2(cur)
             if self.world > 1 and not ws.p2p:
                 ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=True)
             phi_stage(_lib.SVGD_COMPUTE)

@@ -377,6 +377,7 @@ int bode_svgd_phi(const float* Xrows, int64_t ld_rows, int32_t n_rows, const flo
  * and COMPUTE alone does all the work, so callers need no second code path. */
 #define BODE_SVGD_PREPARE 1
 #define BODE_SVGD_COMPUTE 2
+#define BODE_SVGD_PREPARE_POSITIONS 4   /* phi_staged only: the [X - mu | 1] columns of V (no scores needed), see bode_svgd_arm_score_tiles */
 int bode_svgd_staged_supported(int32_t n_cols, int32_t d);
 /* Layout of the d2 block at the start of the workspace (internal to sqdist -> median -> phi; exposed for tests and for
  * RBFKernel.forward, stein.py:22-32, which returns the kernel matrix).  0: row-major [n_rows][n_cols].  1: tiles
@@ -387,6 +388,10 @@ int bode_svgd_d2_tiled(int32_t n_rows, int32_t n_cols, int32_t d);
 /* CTA granularity of the Gram kernel: column_splits CTAs per 128-row block (0 = automatic: one wave over all SMs).  A finer
  * split shortens the tail when the Gram pass shares the GPU with the fused solve.  Returns the previous setting. */
 int bode_svgd_set_gram_split(int32_t column_splits);
+/* Upper bound on the CTAs of bode_svgd_radix_fallback's cooperative launch (0 = one per SM slot; returns the previous bound).  A
+ * cooperative grid starts only when all its CTAs can be resident, so beside a kernel that fills most SMs a full-size grid waits for
+ * that kernel to end, even when the launch is the no-op it is after a window hit. */
+int bode_svgd_set_select_ctas(int32_t n);
 int bode_svgd_sqdist_staged(int32_t stages, const float* Xrows, int64_t ld_rows, int32_t n_rows, const float* Xcols, int64_t ld_cols,
                             int32_t n_cols, int32_t d, int32_t row_offset, uint64_t total_entries, void* workspace,
                             size_t workspace_bytes, void** hist_out, bode_stream_t stream);
@@ -394,6 +399,16 @@ int bode_svgd_phi_staged(int32_t stages, const float* Xrows, int64_t ld_rows, in
                          const float* Scols, int64_t ld_sc, float score_sign, int32_t n_cols, int32_t d, int32_t n_total,
                          const float* med_gamma, void* workspace, float* phi, int64_t ld_phi, float* theta,
                          int64_t ld_theta, float step, bode_stream_t stream);
+/* Score-tile fusion (single rank).  stein.py:75-86 consumes score = -grad loss of every particle, the LAST thing the closure's fused
+ * solve produces; between bode_svgd_arm_score_tiles and bode_svgd_disarm_score_tiles every bode_npde_nlp_grad launch of the
+ * component-split kernels (3x3 .. 6x6 grids) over exactly n_cols particles with 2m + 2 == d parameters also writes
+ * score_sign * gradient into this workspace's phi operand tiles, so that the interaction needs only
+ * bode_svgd_phi_staged(BODE_SVGD_PREPARE_POSITIONS) -- any time after the operands' PREPARE, Scols may be NULL -- and
+ * bode_svgd_phi_staged(BODE_SVGD_COMPUTE): no operand launch between the solve and phi.  arm returns 1 when armed, 0 when the
+ * shapes are outside the pipelined tensor-core path or the workspace has peers (nothing changes then); disarm returns how many
+ * closure launches wrote the tiles since arm (0: run BODE_SVGD_PREPARE as usual).  Process-wide state, like bode_npde_set_cta_limit. */
+int bode_svgd_arm_score_tiles(int32_t n_rows, int32_t n_cols, int32_t d, void* workspace, float score_sign);
+int bode_svgd_disarm_score_tiles(void);
 
 /* ---------------------------------------------------------------------------------------
  * Peer-mapped SVGD workspaces (ranks of one NVLink / NVSwitch node).  The reference is a single-process program; this is what

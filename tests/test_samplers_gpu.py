@@ -340,11 +340,12 @@ def test_svgd_stream_overlap_is_bit_identical_and_graph_capturable():
     U0 = problems.gradient_matching_init(data["Y"], data["t"], Z, 1.0, 0.75)
     U = U0[None] + 0.1 * torch.randn(384, 25, 2, generator=torch.Generator().manual_seed(5), dtype=torch.float64)
 
-    def run(overlap, graph):
+    def run(overlap, graph, fuse=True):
         f = bode.NPDEField(U, Z, 1.0, 0.75, 0.1)
         post = bode.NPDEPosterior(f, data["x0"], data["t"], torch.from_numpy(data["Y"]))
         f.bind_flat_grads()
         smp = SVGD([f.U, f.logsn], lr=1e-4, overlap=overlap)
+        smp.fuse_scores = fuse
         assert smp.overlap == overlap
         lib = bode._lib.load()
 
@@ -363,11 +364,15 @@ def test_svgd_stream_overlap_is_bit_identical_and_graph_capturable():
             step()
         torch.cuda.synchronize()
         assert lib.bode_npde_set_cta_limit(0) == 0              # phi() restored the solver's SM budget
+        assert lib.bode_svgd_disarm_score_tiles() == 0          # ... and ended the closure kernel's writes into the phi operand
+        # "gram": the closure kernel itself wrote the score half of the phi operand (bode_svgd_arm_score_tiles), no launch for it
+        assert smp.last_scores_fused == (overlap == "gram" and fuse)
         return f.theta.clone(), smp._ws.med_gamma.clone()
 
     th0, mg0 = run(False, False)
-    for overlap, graph in (("operands", False), ("operands", True), ("gram", False), ("gram", True)):
-        th, mg = run(overlap, graph)
+    for overlap, graph, fuse in (("operands", False, True), ("operands", True, True), ("gram", False, True), ("gram", True, True),
+                                 ("gram", False, False)):
+        th, mg = run(overlap, graph, fuse)
         assert torch.equal(mg, mg0), (overlap, graph)
         # "gram" packs the solver into fewer, larger CTAs: the per-particle reduction over trajectories is unchanged, so the
         # particles still agree bit for bit

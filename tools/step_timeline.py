@@ -64,6 +64,14 @@ def phi_wrapped(stages, *a):
     mark("prep_v" if int(stages) == _lib.SVGD_PREPARE else "phi2")
     return r
 lib.bode_svgd_phi_staged = phi_wrapped
+for _name in ("bode_svgd_window_select", "bode_svgd_radix_fallback"):       # the two launches of the median chain, separately
+    def _mk(fn, tag):
+        def w(*a):
+            r = fn(*a)
+            mark(tag)
+            return r
+        return w
+    setattr(lib, _name, _mk(getattr(lib, _name), _name.replace("bode_svgd_", "")))
 
 
 def step():
