@@ -274,19 +274,26 @@ def test_median_window_path_is_bit_exact_and_falls_back():
     """The warm-workspace path (window table filled by the Gram epilogue, svgd_state.cuh) must return the same order
     statistics, bit for bit, as np.median of the kernel's own d2 -- when the median drifts a little (window hit), when it
     jumps (window miss -> radix fallback), for an odd and an even entry count, and for ragged tile edges (n % 128 != 0)."""
+    from bayesian_ode_b200 import _lib
     from bayesian_ode_b200.samplers.stein import _Workspace
+    lib = _lib.load()
     rng = np.random.default_rng(11)
-    for n in (300, 1024):                                         # n*n even; 300 % 128 != 0 exercises the ragged tiles
+    for n, side in ((300, 0), (1024, 0), (1024, 40)):             # n*n even; 300 % 128 != 0 exercises the ragged tiles
+        # side > 0: the launches of the overlapped step -- 4-CTA selection cluster, cooperative fallback grid of `side` CTAs
         d = 52
         X0 = torch.from_numpy((rng.standard_normal((n, d)) * 0.3 + 1.5).astype(np.float32)).cuda()
         ws = _Workspace(n, n, d, X0.device)
         scales = [1.0, 1.0 + 2e-5, 1.0 - 3e-5, 1.7, 1.7 + 1e-5, 0.2]    # small drifts hit the window, 1.7x / 0.2x jumps miss it
-        for it, sc in enumerate(scales):
-            X = (X0 * sc).contiguous()
-            ws.sqdist(X, n, X, n, d, n * n, row_offset=0)
-            ws.median(n, n, d, n)
-            d2 = ws.d2(n, n).cpu().numpy()
-            assert np.float32(float(ws.med_gamma[0])) == np.median(d2), (n, it)
+        old = lib.bode_svgd_set_select_ctas(side)
+        try:
+            for it, sc in enumerate(scales):
+                X = (X0 * sc).contiguous()
+                ws.sqdist(X, n, X, n, d, n * n, row_offset=0)
+                ws.median(n, n, d, n)
+                d2 = ws.d2(n, n).cpu().numpy()
+                assert np.float32(float(ws.med_gamma[0])) == np.median(d2), (n, side, it)
+        finally:
+            lib.bode_svgd_set_select_ctas(old)
     # rectangular block (rows are a prefix of the columns, as on rank 0 of a sharded job)
     n = 255
     X0 = torch.from_numpy((rng.standard_normal((n, 52)) * 0.3 + 1.5).astype(np.float32)).cuda()
