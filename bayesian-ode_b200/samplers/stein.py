@@ -343,7 +343,8 @@ class SVGD(Sampler):
                 if self.world == 1 or self._ws.p2p:
                     # the cooperative fallback launch (a no-op after a window hit) must fit the SMs the solve leaves free, or it
                     # waits for the solve to end
-                    old_ctas = lib.bode_svgd_set_select_ctas(self.side_sms) if self.side_sms > 0 else None
+                    # (single rank only: with several ranks the Gram pass outlasts the solve and the SMs are free by then)
+                    old_ctas = lib.bode_svgd_set_select_ctas(self.side_sms) if (self.side_sms > 0 and self.world == 1) else None
                     self._ws.median(nl, nt, d, nt, getattr(self.kernel, "sigma", None), group=None)
                     if old_ctas is not None:
                         lib.bode_svgd_set_select_ctas(old_ctas)
