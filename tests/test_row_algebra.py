@@ -51,3 +51,18 @@ def test_row_sliced_formulas_match_oracle_field(Mx, My):
         assert np.allclose(f, f_o, rtol=1e-12, atol=1e-13)
         assert np.allclose(jta, jta_o[0, 0], rtol=1e-11, atol=1e-12)
         assert np.allclose(A.T @ gW, gU_o[0], rtol=1e-11, atol=1e-12)
+
+
+def test_side_gram_split_enumeration():
+    """SVGD._side_gram_split (host logic): column chunks per row block for a Gram pass confined to `side_sms` SMs -- full waves of
+    CTAs with as many tiles each as that allows; several ranks keep the fine 16-way split."""
+    from types import SimpleNamespace
+    from bayesian_ode_b200.samplers.stein import SVGD
+    f = SVGD._side_gram_split
+    assert f(SimpleNamespace(world=1, side_sms=40), 4096, 4096) == 5          # 5 chunks x 32 row blocks = 160 CTAs = 4 waves of 40
+    assert f(SimpleNamespace(world=1, side_sms=32), 4096, 4096) == 1          # one wave of 32 CTAs
+    assert f(SimpleNamespace(world=2, side_sms=40), 4096, 8192) == 16
+    for side in (8, 24, 40, 64):
+        for n in (256, 1000, 4096):
+            c = f(SimpleNamespace(world=1, side_sms=side), n, n)
+            assert 1 <= c <= 16 and c <= (n + 127) // 128
