@@ -75,6 +75,7 @@ def parse():
     ap.add_argument("--no-strong", action="store_true", help="N>1: skip the strong-scaling sub-record")
     ap.add_argument("--no-parity", action="store_true", help="N>1: skip the multi-GPU parity check")
     ap.add_argument("--cpu-steps", type=int, default=4)
+    ap.add_argument("--side-sms", type=int, default=40, help="SVGD: SMs kept free of the fused solve for the position-only side chain")
     a = ap.parse_args()
     if a.steps is None:
         a.steps = 4 if a.impl == "reference" else (20 if a.workload in ("c4", "c5") else 1000)
@@ -310,7 +311,7 @@ class Job:
         self.field.bind_flat_grads()
         s = wl["sampler"]
         if s == "svgd":
-            self.smp = SVGD(params, lr=1e-4, gather_comm=args.gather)
+            self.smp = SVGD(params, lr=1e-4, gather_comm=args.gather, side_sms=args.side_sms)
         elif s == "psgld":
             self.smp = pSGLD(params, lr0=5e-3, lr_gamma=0.51, lr_t0=100, lr_alpha=0.1, lambda_=1e-8, alpha=0.99, N=self.N, seed=7 + rank)
             self.post.scale = 1.0 / self.N
